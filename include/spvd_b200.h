@@ -1,0 +1,180 @@
+/*
+ * spvd_b200.h -- C ABI of libspvd_b200.so: the sm_100a (B200) backend for the hot path of the SPVD
+ * sparse point-voxel denoiser (JohnRomanelis/SPVD).
+ *
+ * This is the drop-in boundary.  The reference obtains these operations from un-vendored Python
+ * packages (torchsparse 2.1.0, torch-scatter 2.1.2); every entry point below names the reference
+ * call site (file:line under the reference checkout) whose backend work it replaces.  A
+ * reference-side binding is a ctypes stub per function; see INTEGRATION.md.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless it says "host"; nothing here allocates or frees;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*); no entry point
+ *     synchronises the device, so calls are CUDA-graph capturable;
+ *   - the return value is SPVD_OK or an SPVD_ERR_* code; spvd_last_error() gives the text
+ *     (thread-local).  Device-side anomalies (coordinate outside the packed range, hash table
+ *     full) are OR-ed into the optional `status` word, which the caller reads whenever it next
+ *     synchronises;
+ *   - coordinates are int32 [N,4] = (batch, x, y, z) (reference: models/sparse_utils.py:44,62,83);
+ *     -32767 <= x,y,z <= 32767 and 0 <= batch <= 65535;
+ *   - row counts: `n_cap` is the host-known number of rows (or an upper bound); when the
+ *     optional `n_dev` (device int32) is non-NULL the kernels use min(*n_dev, n_cap) rows, which
+ *     lets a caller keep true sizes on the device;
+ *   - kernel maps are stored offset-major: map_t[k*ld + o] = input row feeding output row o
+ *     through kernel offset k, or -1; ld >= n_out, a multiple of 128; rows o >= n_out hold -1.
+ *     tile_mask[o/128] has bit k set when any of the tile's 128 output rows uses offset k.
+ */
+#ifndef SPVD_B200_H
+#define SPVD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPVD_ABI_VERSION 1
+
+#define SPVD_OK 0
+#define SPVD_ERR_INVALID 1   /* bad argument */
+#define SPVD_ERR_CUDA 2      /* a CUDA runtime call or launch failed */
+#define SPVD_ERR_WORKSPACE 3 /* workspace too small */
+
+#define SPVD_STATUS_COORD_RANGE 1 /* a coordinate did not fit the 16-bit packed key */
+#define SPVD_STATUS_HASH_FULL 2   /* insertion found no free slot */
+
+#define SPVD_SCALE_MUL 0 /* fl(fl(c*init_res) * fl(1/after_res)): torch-CUDA's division by a scalar */
+#define SPVD_SCALE_DIV 1 /* fl(fl(c*init_res) / after_res):       torch-CPU's                        */
+
+#define SPVD_DOWNSAMPLE_SPCONV 0 /* torchsparse 2.1 default: drop parents above (max_in-1)//2 */
+#define SPVD_DOWNSAMPLE_FLOOR 1  /* keep every floor(c/2) */
+
+#define SPVD_ORDER_BXYZ 0 /* coordinate columns (batch,x,y,z) */
+#define SPVD_ORDER_XYZB 1 /* coordinate columns (x,y,z,batch): what sphashquery passes, models/sparse_utils.py:44,51 */
+
+#define SPVD_CONV_AUTO 0
+#define SPVD_CONV_SIMT 1 /* fp32 FMA reference kernel (any channel count) */
+#define SPVD_CONV_UMMA 2 /* tcgen05 implicit GEMM, TF32 operands, fp32 accumulate in TMEM */
+
+typedef void* spvd_stream_t;
+
+const char* spvd_last_error(void);
+int spvd_abi_version(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * V1  initial_voxelize, coordinate half           reference: models/sparse_utils.py:60-66
+ * pc      [n,4] fp32 = (batch, x, y, z) point coordinates in units of init_res (x.C.float(),
+ *         models/spvd.py:436)
+ * fcoords [n,4] fp32 = (batch, scaled x,y,z)      -> becomes z.C (models/sparse_utils.py:72)
+ * icoords [n,4] int32 = floor(fcoords)            -> new_int_coord (models/sparse_utils.py:65)
+ */
+int spvd_point_voxel_coords(const float* pc, int n, float init_res, float after_res, int scale_mode,
+                            float* fcoords, int32_t* icoords, spvd_stream_t stream);
+
+/* torch.unique(int32[N,4], dim=0) + inverse      reference: models/sparse_utils.py:66-67
+ * out_coords [n_cap,4] sorted lexicographically (first *out_count rows valid), inverse [n_cap]
+ * = row of each input coordinate in out_coords (the idx_query of initial_voxelize). */
+size_t spvd_unique_workspace_bytes(int n_cap);
+int spvd_unique_coords(const int32_t* icoords, int n_cap, const int32_t* n_dev, int32_t* out_coords,
+                       int32_t* inverse, int32_t* out_count, int32_t* status, void* workspace,
+                       size_t workspace_bytes, spvd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * H1  coordinate hash table                      reference: models/sparse_utils.py:36-55
+ * (torchsparse.backend.GPUHashTable: keys int64[capacity] and vals int32[capacity] are the
+ * caller's zero-initialised tensors, models/sparse_utils.py:37-42).  Values are row+1, 0 = absent,
+ * exactly what lookup_coords returns before the reference subtracts 1 (models/sparse_utils.py:49-54).
+ * kernel_size 1, 2 ({0,1}^3, z fastest) or 3 ({-1,0,1}^3, x fastest); out is [m, kernel_size^3].
+ */
+int spvd_hash_build(const int32_t* coords, int n_cap, const int32_t* n_dev, int coord_order,
+                    int64_t* keys, int32_t* vals, int capacity, int32_t* status,
+                    spvd_stream_t stream);
+int spvd_hash_query(const int32_t* query, int m, int coord_order, int kernel_size,
+                    const int64_t* keys, const int32_t* vals, int capacity, int32_t* out,
+                    spvd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * K1  submanifold kernel map, kernel 3 stride 1  reference: spnn.Conv3d(k=3) at models/spvd.py:35,38,
+ *     models/ddpm_unet_attn.py:28 (torchsparse build_kernel_map, frames at
+ *     experiments/ConditionalGeneration.ipynb:449-451)
+ * map_t [27, ld], tile_mask [ld/128].
+ */
+int spvd_kmap_subm3(const int32_t* coords, int n_cap, const int32_t* n_dev, const int64_t* keys,
+                    const int32_t* vals, int capacity, int32_t* map_t, int ld, uint32_t* tile_mask,
+                    spvd_stream_t stream);
+
+/* K2  stride-2 kernel-2 output coordinates       reference: spnn.Conv3d(ni,nf,2,stride=2) at
+ *     models/spvd.py:113 (torchsparse spdownsample; boundary rule: SURVEY.md Appendix B)
+ * out_coords [n_cap,4] sorted (first *out_count valid); parent [n_cap] = coarse row of each fine
+ * voxel or -1 when its parent was dropped; koff [n_cap] = 4*px+2*py+pz parity offset index. */
+size_t spvd_downsample_workspace_bytes(int n_cap);
+int spvd_downsample_coords(const int32_t* coords, int n_cap, const int32_t* n_dev, int mode,
+                           int32_t* out_coords, int32_t* out_count, int32_t* parent, int32_t* koff,
+                           int32_t* status, void* workspace, size_t workspace_bytes,
+                           spvd_stream_t stream);
+/* down map [8, ld_coarse] (coarse <- fine children) and K3 its transpose [8, ld_fine]
+ * (fine <- parent; reference: spnn.Conv3d(..., transposed=True) at models/spvd.py:229).  Either
+ * output may be NULL.  Both are fully written (absent = -1) together with their tile masks. */
+int spvd_kmap_down2(const int32_t* parent, const int32_t* koff, int n_fine_cap,
+                    const int32_t* n_fine_dev, int32_t* map_down_t, int ld_coarse,
+                    uint32_t* tile_mask_down, int32_t* map_up_t, int ld_fine,
+                    uint32_t* tile_mask_up, spvd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * V2  point -> voxel index at tensor stride s    reference: models/sparse_utils.py:79-90
+ * pc [n,4] fp32 = z.C after initial_voxelize (batch, stride-1 voxel coords as floats);
+ * idx [n] = row of voxel (int(batch), floor(xyz / s)) or -1 (the caller clamps, :93). */
+int spvd_point_voxel_query(const float* pc, int n, int stride, const int64_t* keys,
+                           const int32_t* vals, int capacity, int32_t* idx, spvd_stream_t stream);
+
+/* V3  trilinear corner indices + weights          reference: models/sparse_utils.py:108-114
+ * (sphashquery(kernel_size=2) + torchsparse calc_ti_weights(scale=1)); idx8/w8 are [n,8]. */
+int spvd_devox_query(const float* pc, int n, int stride, const int64_t* keys, const int32_t* vals,
+                     int capacity, int32_t* idx8, float* w8, spvd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * torch_scatter.scatter_mean(src, idx, dim=0)     reference: models/sparse_utils.py:69,94
+ * out [nv,c] and counts [nv] are written (zero-filled inside); backward: gsrc = gout[idx]/max(cnt,1).
+ */
+int spvd_scatter_mean_fwd(const float* src, const int32_t* idx, int n, int c, float* out,
+                          float* counts, int nv, spvd_stream_t stream);
+int spvd_scatter_mean_bwd(const float* gout, const int32_t* idx, const float* counts, int n, int c,
+                          float* gsrc, spvd_stream_t stream);
+
+/* torchsparse.nn.functional.spdevoxelize          reference: models/sparse_utils.py:119,128
+ * out[p] = sum_j w8[p,j] * feats[idx8[p,j]] (idx -1 skipped); backward scatter-adds into gfeats
+ * [nv,c] (zero-filled inside). */
+int spvd_devoxelize_fwd(const float* feats, const int32_t* idx8, const float* w8, int n, int c,
+                        float* out, spvd_stream_t stream);
+int spvd_devoxelize_bwd(const float* gout, const int32_t* idx8, const float* w8, int n, int c,
+                        float* gfeats, int nv, spvd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * C1-C4  sparse convolution  out[o] = sum_k in[map_t[k][o]] @ W[k] (+ bias)
+ *     reference: spnn.Conv3d.forward at models/spvd.py:35,38,113,229; models/ddpm_unet_attn.py:28
+ * w        [kvol,cin,cout] fp32, the reference's `kernel` parameter layout
+ * w_packed the same weights in the tensor-core tile image produced by spvd_conv_pack_weights
+ *          (may be NULL when impl == SPVD_CONV_SIMT)
+ * map_t    [kvol, ld] or NULL for the identity map (kernel_size 1)
+ * The UMMA path needs cin % 32 == 0, cout % 16 == 0, cout <= 512 and `in` rounded to TF32
+ * (spvd_round_tf32); SPVD_CONV_AUTO picks it whenever those hold.
+ */
+int spvd_round_tf32(const float* x, float* y, long long count, spvd_stream_t stream);
+/* w_t[k'][co][ci] = w[k][ci][co] with k' = flip ? kvol-1-k : k  (weights of the data gradient) */
+int spvd_conv_transpose_weights(const float* w, int kvol, int cin, int cout, int flip, float* w_t,
+                                spvd_stream_t stream);
+size_t spvd_conv_packed_weight_count(int kvol, int cin, int cout);
+int spvd_conv_pack_weights(const float* w, int kvol, int cin, int cout, float* w_packed,
+                           spvd_stream_t stream);
+int spvd_conv_fwd(const float* in, const float* w, const float* w_packed, const int32_t* map_t,
+                  int ld, const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
+                  const float* bias, float* out, int impl, spvd_stream_t stream);
+/* gw[k] = sum over pairs (i,o) of offset k of in[i]^T gout[o];  gw [kvol,cin,cout] zero-filled inside */
+int spvd_conv_wgrad(const float* in, const float* gout, const int32_t* map_t, int ld, int n_out,
+                    int kvol, int cin, int cout, float* gw, spvd_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPVD_B200_H */
