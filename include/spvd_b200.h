@@ -16,7 +16,7 @@
  *     full) are OR-ed into the optional `status` word, which the caller reads whenever it next
  *     synchronises;
  *   - coordinates are int32 [N,4] = (batch, x, y, z) (reference: models/sparse_utils.py:44,62,83);
- *     -32767 <= x,y,z <= 32767 and 0 <= batch <= 65535;
+ *     -32767 <= x,y,z <= 32767 and 0 <= batch <= 65534;
  *   - row counts: `n_cap` is the host-known number of rows (or an upper bound); when the
  *     optional `n_dev` (device int32) is non-NULL the kernels use min(*n_dev, n_cap) rows, which
  *     lets a caller keep true sizes on the device;
@@ -72,13 +72,15 @@ int spvd_abi_version(void);
 int spvd_point_voxel_coords(const float* pc, int n, float init_res, float after_res, int scale_mode,
                             float* fcoords, int32_t* icoords, spvd_stream_t stream);
 
-/* torch.unique(int32[N,4], dim=0) + inverse      reference: models/sparse_utils.py:66-67
- * out_coords [n_cap,4] sorted lexicographically (first *out_count rows valid), inverse [n_cap]
- * = row of each input coordinate in out_coords (the idx_query of initial_voxelize). */
+/* torch.unique(int32[N,4], dim=0)                reference: models/sparse_utils.py:66
+ * out_coords [n_cap,4] sorted lexicographically by (batch,x,y,z), first *out_count rows valid.  The
+ * inverse index (idx_query of initial_voxelize, models/sparse_utils.py:67) is a kernel_size-1
+ * spvd_hash_query of the points against a table built on out_coords, exactly as the reference
+ * obtains it from sphashquery. */
 size_t spvd_unique_workspace_bytes(int n_cap);
 int spvd_unique_coords(const int32_t* icoords, int n_cap, const int32_t* n_dev, int32_t* out_coords,
-                       int32_t* inverse, int32_t* out_count, int32_t* status, void* workspace,
-                       size_t workspace_bytes, spvd_stream_t stream);
+                       int32_t* out_count, int32_t* status, void* workspace, size_t workspace_bytes,
+                       spvd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * H1  coordinate hash table                      reference: models/sparse_utils.py:36-55
@@ -106,20 +108,20 @@ int spvd_kmap_subm3(const int32_t* coords, int n_cap, const int32_t* n_dev, cons
 
 /* K2  stride-2 kernel-2 output coordinates       reference: spnn.Conv3d(ni,nf,2,stride=2) at
  *     models/spvd.py:113 (torchsparse spdownsample; boundary rule: SURVEY.md Appendix B)
- * out_coords [n_cap,4] sorted (first *out_count valid); parent [n_cap] = coarse row of each fine
- * voxel or -1 when its parent was dropped; koff [n_cap] = 4*px+2*py+pz parity offset index. */
+ * out_coords [n_cap,4] = unique floor(c/2), sorted, first *out_count rows valid. */
 size_t spvd_downsample_workspace_bytes(int n_cap);
 int spvd_downsample_coords(const int32_t* coords, int n_cap, const int32_t* n_dev, int mode,
-                           int32_t* out_coords, int32_t* out_count, int32_t* parent, int32_t* koff,
-                           int32_t* status, void* workspace, size_t workspace_bytes,
-                           spvd_stream_t stream);
-/* down map [8, ld_coarse] (coarse <- fine children) and K3 its transpose [8, ld_fine]
- * (fine <- parent; reference: spnn.Conv3d(..., transposed=True) at models/spvd.py:229).  Either
- * output may be NULL.  Both are fully written (absent = -1) together with their tile masks. */
-int spvd_kmap_down2(const int32_t* parent, const int32_t* koff, int n_fine_cap,
-                    const int32_t* n_fine_dev, int32_t* map_down_t, int ld_coarse,
-                    uint32_t* tile_mask_down, int32_t* map_up_t, int ld_fine,
-                    uint32_t* tile_mask_up, spvd_stream_t stream);
+                           int32_t* out_coords, int32_t* out_count, int32_t* status, void* workspace,
+                           size_t workspace_bytes, spvd_stream_t stream);
+/* down map [8, ld_coarse] (coarse <- fine children, offset = child parity 4*px+2*py+pz) and K3 its
+ * transpose [8, ld_fine] (fine <- parent; reference: spnn.Conv3d(..., transposed=True) at
+ * models/spvd.py:229), from a hash table built on the coarse coordinates.  Any output may be NULL.
+ * Both maps are fully written (absent = -1) together with their tile masks; parent [n_fine_cap] =
+ * coarse row of each fine voxel or -1 when its parent was dropped, koff [n_fine_cap] its offset. */
+int spvd_kmap_down2(const int32_t* fine_coords, int n_fine_cap, const int32_t* n_fine_dev,
+                    const int64_t* keys, const int32_t* vals, int capacity, int32_t* map_down_t,
+                    int ld_coarse, uint32_t* tile_mask_down, int32_t* map_up_t, int ld_fine,
+                    uint32_t* tile_mask_up, int32_t* parent, int32_t* koff, spvd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * V2  point -> voxel index at tensor stride s    reference: models/sparse_utils.py:79-90
@@ -157,8 +159,8 @@ int spvd_devoxelize_bwd(const float* gout, const int32_t* idx8, const float* w8,
  * w_packed the same weights in the tensor-core tile image produced by spvd_conv_pack_weights
  *          (may be NULL when impl == SPVD_CONV_SIMT)
  * map_t    [kvol, ld] or NULL for the identity map (kernel_size 1)
- * The UMMA path needs cin % 32 == 0, cout % 16 == 0, cout <= 512 and `in` rounded to TF32
- * (spvd_round_tf32); SPVD_CONV_AUTO picks it whenever those hold.
+ * The UMMA path needs cin % 32 == 0 and cout % 32 == 0 (operands are rounded to TF32, round-to-nearest,
+ * inside the kernel / the packer); SPVD_CONV_AUTO picks it whenever those hold and w_packed is given.
  */
 int spvd_round_tf32(const float* x, float* y, long long count, spvd_stream_t stream);
 /* w_t[k'][co][ci] = w[k][ci][co] with k' = flip ? kvol-1-k : k  (weights of the data gradient) */
@@ -167,12 +169,36 @@ int spvd_conv_transpose_weights(const float* w, int kvol, int cin, int cout, int
 size_t spvd_conv_packed_weight_count(int kvol, int cin, int cout);
 int spvd_conv_pack_weights(const float* w, int kvol, int cin, int cout, float* w_packed,
                            spvd_stream_t stream);
-int spvd_conv_fwd(const float* in, const float* w, const float* w_packed, const int32_t* map_t,
-                  int ld, const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
+int spvd_conv_umma_supported(int kvol, int cin, int cout);
+int spvd_conv_fwd(const float* in, const float* w, const float* w_packed, const int32_t* map_t, int ld,
+                  const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
                   const float* bias, float* out, int impl, spvd_stream_t stream);
+int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, int ld,
+                       const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
+                       const float* bias, float* out, spvd_stream_t stream);
+/* bn = output-channel slice width per CTA (32,64,96,128,192,256 dividing cout; 0 = choose) */
+int spvd_conv_fwd_umma(const float* in, const float* w_packed, const int32_t* map_t, int ld,
+                       const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
+                       const float* bias, float* out, int bn, spvd_stream_t stream);
 /* gw[k] = sum over pairs (i,o) of offset k of in[i]^T gout[o];  gw [kvol,cin,cout] zero-filled inside */
 int spvd_conv_wgrad(const float* in, const float* gout, const int32_t* map_t, int ld, int n_out,
                     int kvol, int cin, int cout, float* gw, spvd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * C5/M1  inference-time glue fused into single passes
+ * spvd_bn_silu_fwd: y = act(x*scale[c] + shift[c]) -- spnn.BatchNorm (eval: scale = w/sqrt(var+eps),
+ *     shift = b - mean*scale) followed by spnn.SiLU (act = 1) or nothing (act = 0);
+ *     reference: models/ddpm_unet_attn.py:24-28, models/spvd.py:36-37.
+ * spvd_film_fwd: y[i] = (1 + tt[b_i, c]) * x[i, c] + tt[b_i, C + c], b_i = coords[i].batch, tt [B, 2C];
+ *     reference: TimeEmbeddingBlock.message, models/modules/graph.py:35-41.
+ * spvd_batch_counts: counts[b] = number of rows of batch b (what to_dense_batch derives,
+ *     models/modules/transformer.py:12-15). */
+int spvd_bn_silu_fwd(const float* x, const float* scale, const float* shift, long long rows, int c,
+                     int act, float* y, spvd_stream_t stream);
+int spvd_film_fwd(const float* x, const float* tt, const int32_t* coords, long long rows, int c,
+                  float* y, spvd_stream_t stream);
+int spvd_batch_counts(const int32_t* coords, int n_cap, const int32_t* n_dev, int nb, int32_t* counts,
+                      spvd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <limits.h>
 #include <stdio.h>
 
 #include "../../include/spvd_b200.h"
@@ -45,7 +46,7 @@ constexpr int kCoordMax = kCoordBias - 1;
 constexpr unsigned long long kKeySentinel = 0xFFFFFFFFFFFFFFFFull;  // sorts last, never a valid key
 
 __host__ __device__ __forceinline__ bool coord_in_range(int b, int x, int y, int z) {
-  return b >= 0 && b <= 0xFFFF && x >= -kCoordMax && x <= kCoordMax && y >= -kCoordMax &&
+  return b >= 0 && b <= 0xFFFE && x >= -kCoordMax && x <= kCoordMax && y >= -kCoordMax &&
          y <= kCoordMax && z >= -kCoordMax && z <= kCoordMax;
 }
 

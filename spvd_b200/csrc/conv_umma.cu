@@ -1,0 +1,369 @@
+// Sparse convolution on the 5th-generation tensor cores (sm_100a tcgen05 + TMEM), C1-C3.
+//
+//   out[o, :] = sum_k  in[map_t[k][o], :] @ W[k]  (+ bias)          fp32 in/out, TF32 operands,
+//                                                                    fp32 accumulation in TMEM
+// Output-stationary implicit GEMM: one CTA owns a 128-row output tile x BN output channels and
+// walks the (active kernel offset, 32-channel slab) pairs of that tile.  Per step
+//   * 4 producer warps gather the 128 input rows of the slab (128 B each, 16-byte loads, rows with
+//     map -1 are zero-filled without touching memory), round to TF32 (cvt.rna) and store them into
+//     the canonical K-major SWIZZLE_128B shared-memory tile;
+//   * one thread starts a bulk async copy (cp.async.bulk, SASS UBLKCP) of the matching BN x 32
+//     weight tile, which spvd_conv_pack_weights laid out in global memory as the exact
+//     shared-memory image (K-major, 128-byte swizzle, TF32-rounded), completing on the same mbarrier;
+//   * one thread of the MMA warp issues 4 x tcgen05.mma (M=128, N=BN, K=8) into the TMEM accumulator
+//     and commits the stage back to the producers.
+// Offsets with no active row in the tile are skipped through the per-tile bit mask.  The epilogue
+// reads the accumulator with tcgen05.ld (32 lanes x 32 columns per warp), adds the bias and writes
+// 128-byte row segments.
+#include "common.cuh"
+
+namespace spvd {
+
+constexpr int BM = 128;
+constexpr int BK = 32;
+constexpr int kStages = 4;
+constexpr int kProducerThreads = 128;
+constexpr int kUmmaThreads = kProducerThreads + 32;
+constexpr int kATileBytes = BM * BK * 4;  // 16 KB
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t"
+      "}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, SWIZZLE_128B operand tile: rows of 128 bytes, 8-row groups 1024 bytes apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;           // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(1024 >> 4) << 32; // stride byte offset between 8-row groups
+  d |= (uint64_t)1 << 46;           // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;           // SWIZZLE_128B
+  return d;
+}
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+template <int BN>
+struct UmmaCfg {
+  static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int kBTileBytes = BN * BK * 4;
+  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // idesc: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
+  static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                     ((uint32_t)(BM >> 4) << 24);
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __restrict__ in,
+                                                               const float* __restrict__ w_packed,
+                                                               const int* __restrict__ map_t, int ld,
+                                                               const unsigned* __restrict__ tile_mask, int n_out,
+                                                               int kvol, int cin, int cout,
+                                                               const float* __restrict__ bias,
+                                                               float* __restrict__ out) {
+  using Cfg = UmmaCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw = smem_u32(smem_raw);
+  const uint32_t base = (raw + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - raw);
+  const uint32_t bar_base = base + kStages * Cfg::kStageBytes;  // full[kStages], empty[kStages], accum, tmem slot
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 1));
+  int* active_k = reinterpret_cast<int*>(smem + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 1) + 16);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int nchunks = cin / BK;
+
+  unsigned mask = kvol >= 32 ? 0xffffffffu : ((1u << kvol) - 1u);
+  if (tile_mask) mask &= tile_mask[blockIdx.x];
+  const int n_active = __popc(mask);
+  const int num_iters = n_active * nchunks;
+
+  if (tid == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(bar_base + 8 * s, kProducerThreads + 1);
+      mbar_init(bar_base + 8 * (kStages + s), 1);
+    }
+    mbar_init(bar_base + 8 * (2 * kStages), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    int j = 0;
+    for (int k = 0; k < kvol && k < 32; ++k)
+      if ((mask >> k) & 1u) active_k[j++] = k;
+  }
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers
+    const int chunk16 = tid & 7;  // which 16-byte piece of the 128-byte row
+    const int r0 = tid >> 3;      // rows r0 + 16*i
+    int rows[8];
+    for (int it = 0; it < num_iters; ++it) {
+      const int stage = it % kStages;
+      const uint32_t parity = (uint32_t)(it / kStages) & 1u;
+      const int ka = it / nchunks, c = it - ka * nchunks;
+      const int k = active_k[ka];
+      if (c == 0) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) rows[i] = map_t ? __ldg(map_t + (size_t)k * ld + m0 + r0 + 16 * i)
+                                                    : (m0 + r0 + 16 * i < n_out ? m0 + r0 + 16 * i : -1);
+      }
+      mbar_wait(bar_base + 8 * (kStages + stage), parity ^ 1u);
+      const uint32_t a_s = base + stage * Cfg::kStageBytes;
+      if (tid == 0) {
+        mbar_arrive_expect_tx(bar_base + 8 * stage, Cfg::kBTileBytes);
+        const float* src = w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK;
+        bulk_g2s(a_s + kATileBytes, src, Cfg::kBTileBytes, bar_base + 8 * stage);
+      }
+      float4 v[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (rows[i] >= 0)
+          v[i] = __ldg(reinterpret_cast<const float4*>(in + (size_t)rows[i] * cin + c * BK) + chunk16);
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 16 * i;
+        const uint32_t dst = a_s + r * 128 + ((chunk16 ^ (r & 7)) << 4);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(to_tf32(v[i].x)),
+                     "r"(to_tf32(v[i].y)), "r"(to_tf32(v[i].z)), "r"(to_tf32(v[i].w))
+                     : "memory");
+      }
+      fence_proxy_async();
+      mbar_arrive(bar_base + 8 * stage);
+    }
+    // ------------------------------------------------------------------ epilogue
+    const int row = m0 + warp * 32 + lane;
+    if (num_iters > 0) {
+      mbar_wait(bar_base + 8 * (2 * kStages), 0);
+      tc_fence_after();
+    }
+#pragma unroll 1
+    for (int cb = 0; cb < BN / 32; ++cb) {
+      uint32_t r[32];
+      if (num_iters > 0) {
+        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+            : "r"(taddr)
+            : "memory");
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[j] = 0u;
+      }
+      if (row < n_out) {
+        float4* dst = reinterpret_cast<float4*>(out + (size_t)row * cout + n0 + cb * 32);
+        const float4* bp = bias ? reinterpret_cast<const float4*>(bias + n0 + cb * 32) : nullptr;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+          if (bp) {
+            float4 b = __ldg(bp + j);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          dst[j] = o;
+        }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (warp 4)
+    for (int it = 0; it < num_iters; ++it) {
+      const int stage = it % kStages;
+      const uint32_t parity = (uint32_t)(it / kStages) & 1u;
+      mbar_wait(bar_base + 8 * stage, parity);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t a_s = base + stage * Cfg::kStageBytes;
+        const uint64_t adesc = make_desc(a_s);
+        const uint64_t bdesc = make_desc(a_s + kATileBytes);
+#pragma unroll
+        for (int kk = 0; kk < BK / 8; ++kk)
+          umma_tf32(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), Cfg::kIdesc,
+                    (it > 0 || kk > 0) ? 1u : 0u);
+        umma_commit(bar_base + 8 * (kStages + stage));
+        if (it == num_iters - 1) umma_commit(bar_base + 8 * (2 * kStages));
+      }
+      __syncwarp();
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
+                 : "memory");
+  }
+}
+
+// weights [kvol][cin][cout] -> per (k, 32-channel slab) image of the K-major SWIZZLE_128B B tile:
+// element (n, kk) at float offset ((k*nchunks + c)*cout + n)*32 + (((kk>>2) ^ (n&7))<<2) + (kk&3)
+__global__ void k_pack_weights(const float* __restrict__ w, int kvol, int cin, int cout, float* __restrict__ wp) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)kvol * cin * cout;
+  if (t >= total) return;
+  int n = (int)(t % cout);
+  long long q = t / cout;
+  int ci = (int)(q % cin);
+  int k = (int)(q / cin);
+  int c = ci / BK, kk = ci % BK;
+  size_t dst = ((size_t)(k * (cin / BK) + c) * cout + n) * BK + ((((kk >> 2) ^ (n & 7)) << 2) | (kk & 3));
+  wp[dst] = __uint_as_float(to_tf32(w[t]));
+}
+
+template <int BN>
+static int launch_umma(const float* in, const float* wp, const int32_t* map_t, int ld, const uint32_t* tile_mask,
+                       int n_out, int kvol, int cin, int cout, const float* bias, float* out, cudaStream_t s) {
+  using Cfg = UmmaCfg<BN>;
+  static bool configured = false;
+  if (!configured) {
+    SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  dim3 grid(cdiv(n_out, BM), cout / BN);
+  k_conv_fwd_umma<BN><<<grid, kUmmaThreads, Cfg::kSmemBytes, s>>>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout,
+                                                                 bias, out);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+static int pick_bn(int n_tiles, int cout) {
+  // largest slice width that still gives every SM a CTA, among the instantiated widths
+  const int widths[] = {256, 192, 128, 96, 64, 32};
+  int best = 0;
+  for (int w : widths) {
+    if (cout % w) continue;
+    if (!best) best = w;
+    if ((long long)n_tiles * (cout / w) >= 148) return w;
+  }
+  // not enough tiles at any width: take the narrowest that divides cout (most CTAs)
+  for (int i = 5; i >= 0; --i)
+    if (cout % widths[i] == 0) return widths[i];
+  return best;
+}
+
+}  // namespace spvd
+
+using namespace spvd;
+
+extern "C" size_t spvd_conv_packed_weight_count(int kvol, int cin, int cout) { return (size_t)kvol * cin * cout; }
+
+extern "C" int spvd_conv_umma_supported(int kvol, int cin, int cout) {
+  return kvol >= 1 && kvol <= 32 && cin % 32 == 0 && cout % 32 == 0 && cin > 0 && cout > 0;
+}
+
+extern "C" int spvd_conv_pack_weights(const float* w, int kvol, int cin, int cout, float* w_packed,
+                                      spvd_stream_t stream) {
+  SPVD_CHECK_ARG(w && w_packed, "spvd_conv_pack_weights: bad arguments");
+  SPVD_CHECK_ARG(spvd_conv_umma_supported(kvol, cin, cout), "spvd_conv_pack_weights: unsupported shape %dx%dx%d", kvol, cin, cout);
+  long long total = (long long)kvol * cin * cout;
+  k_pack_weights<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, kvol, cin, cout, w_packed);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const int32_t* map_t, int ld,
+                                  const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
+                                  const float* bias, float* out, int bn, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(in && w_packed && out && n_out >= 0, "spvd_conv_fwd_umma: bad arguments");
+  SPVD_CHECK_ARG(spvd_conv_umma_supported(kvol, cin, cout), "spvd_conv_fwd_umma: unsupported shape %dx%dx%d", kvol, cin, cout);
+  SPVD_CHECK_ARG(map_t || kvol == 1, "spvd_conv_fwd_umma: a NULL map needs kvol == 1");
+  SPVD_CHECK_ARG(!map_t || (ld % 128 == 0 && ld >= n_out), "spvd_conv_fwd_umma: ld %d must be a multiple of 128 >= n_out", ld);
+  SPVD_CHECK_ARG(((size_t)in & 15) == 0 && ((size_t)out & 15) == 0 && ((size_t)w_packed & 15) == 0 &&
+                     (!bias || ((size_t)bias & 15) == 0),
+                 "spvd_conv_fwd_umma: pointers must be 16-byte aligned");
+  if (n_out == 0) return SPVD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (bn <= 0) bn = pick_bn(cdiv(n_out, BM), cout);
+  SPVD_CHECK_ARG(cout % bn == 0, "spvd_conv_fwd_umma: slice width %d does not divide cout %d", bn, cout);
+  switch (bn) {
+    case 32: return launch_umma<32>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
+    case 64: return launch_umma<64>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
+    case 96: return launch_umma<96>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
+    case 128: return launch_umma<128>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
+    case 192: return launch_umma<192>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
+    case 256: return launch_umma<256>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
+  }
+  set_error("spvd_conv_fwd_umma: slice width %d is not instantiated", bn);
+  return SPVD_ERR_INVALID;
+}
+
+extern "C" int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, int ld,
+                                  const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
+                                  float* out, spvd_stream_t stream);
+
+extern "C" int spvd_conv_fwd(const float* in, const float* w, const float* w_packed, const int32_t* map_t, int ld,
+                             const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
+                             float* out, int impl, spvd_stream_t stream) {
+  bool umma_ok = w_packed && spvd_conv_umma_supported(kvol, cin, cout) && (!map_t || ld % 128 == 0);
+  if (impl == SPVD_CONV_UMMA || (impl == SPVD_CONV_AUTO && umma_ok)) {
+    SPVD_CHECK_ARG(umma_ok, "spvd_conv_fwd: the tcgen05 path needs packed weights, cin %% 32 == 0 and cout %% 32 == 0");
+    return spvd_conv_fwd_umma(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, 0, stream);
+  }
+  SPVD_CHECK_ARG(w, "spvd_conv_fwd: the SIMT path needs the unpacked weights");
+  return spvd_conv_fwd_simt(in, w, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, stream);
+}

@@ -1,0 +1,434 @@
+// Coordinate work of the SPVD hot path: fp32 coordinate scaling (V1), sorted-unique voxel sets
+// (torch.unique(dim=0), models/sparse_utils.py:66) and the stride-2 coarse coordinate set (K2).
+//
+// Everything is integer/byte work bounded by HBM/L2 bandwidth and launch latency; sizes stay on the
+// device (n_dev) so no entry point synchronises.  The sort is a hand-written LSD radix sort on the
+// packed 64-bit keys: one up-front pass builds all eight digit histograms, passes whose digit is
+// uniform (typically 4 of 8: the high byte of each 16-bit field) are skipped on the device without
+// a host round trip (kernels read SortState::skip / parity and exit).
+#include "common.cuh"
+
+namespace spvd {
+
+typedef unsigned long long u64;
+
+constexpr int kSortThreads = 512;
+constexpr int kSortItems = 8;
+constexpr int kSortTile = kSortThreads * kSortItems;  // 4096 keys per CTA
+constexpr int kSortWarps = kSortThreads / 32;
+
+struct SortState {
+  unsigned hist[8][256];
+  int skip[8];
+  int parity[9];
+  int n;
+  int cmax[3];
+  int pad;
+};
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+struct SortWs {
+  u64* buf[2];
+  unsigned* tile_hist;
+  int* tile_count;
+  SortState* st;
+  int n_tiles;
+};
+
+static size_t sort_ws_bytes(int n_cap) {
+  int n_tiles = cdiv(n_cap > 0 ? n_cap : 1, kSortTile);
+  size_t b = 0;
+  b += align_up((size_t)n_cap * 8, 256) * 2;
+  b += align_up((size_t)256 * n_tiles * 4, 256);
+  b += align_up((size_t)n_tiles * 4, 256);
+  b += align_up(sizeof(SortState), 256);
+  return b + 256;
+}
+
+static SortWs carve_ws(void* ws, int n_cap) {
+  SortWs w;
+  w.n_tiles = cdiv(n_cap > 0 ? n_cap : 1, kSortTile);
+  char* p = (char*)align_up((size_t)ws, 256);
+  w.buf[0] = (u64*)p;
+  p += align_up((size_t)n_cap * 8, 256);
+  w.buf[1] = (u64*)p;
+  p += align_up((size_t)n_cap * 8, 256);
+  w.tile_hist = (unsigned*)p;
+  p += align_up((size_t)256 * w.n_tiles * 4, 256);
+  w.tile_count = (int*)p;
+  p += align_up((size_t)w.n_tiles * 4, 256);
+  w.st = (SortState*)p;
+  return w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// V1: fp32 scaling with the rounding sequence pinned (no FMA contraction, no fast math)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_point_voxel_coords(const float4* __restrict__ pc, int n, float init_res, float after_res,
+                                     float inv_after, int scale_mode, float4* __restrict__ fcoords,
+                                     int4* __restrict__ icoords) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pc[i];
+  float4 f;
+  f.x = p.x;
+  if (scale_mode == SPVD_SCALE_MUL) {
+    f.y = __fmul_rn(__fmul_rn(p.y, init_res), inv_after);
+    f.z = __fmul_rn(__fmul_rn(p.z, init_res), inv_after);
+    f.w = __fmul_rn(__fmul_rn(p.w, init_res), inv_after);
+  } else {
+    f.y = __fdiv_rn(__fmul_rn(p.y, init_res), after_res);
+    f.z = __fdiv_rn(__fmul_rn(p.z, init_res), after_res);
+    f.w = __fdiv_rn(__fmul_rn(p.w, init_res), after_res);
+  }
+  fcoords[i] = f;
+  if (icoords) icoords[i] = make_int4((int)floorf(f.x), (int)floorf(f.y), (int)floorf(f.z), (int)floorf(f.w));
+}
+
+// ---------------------------------------------------------------------------------------------
+// key packing
+// ---------------------------------------------------------------------------------------------
+__global__ void k_state_init(SortState* st, int n_cap, const int* n_dev) {
+  int t = threadIdx.x;
+  unsigned* h = &st->hist[0][0];
+  for (int i = t; i < 8 * 256; i += blockDim.x) h[i] = 0;
+  if (t == 0) {
+    st->n = resolve_n(n_dev, n_cap);
+    st->cmax[0] = st->cmax[1] = st->cmax[2] = INT_MIN;
+  }
+}
+
+__global__ void k_pack_keys(const int4* __restrict__ coords, SortState* st, u64* __restrict__ keys, int* status) {
+  int n = st->n;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 c = coords[i];
+  if (coord_in_range(c.x, c.y, c.z, c.w)) {
+    keys[i] = pack_key(c.x, c.y, c.z, c.w);
+  } else {
+    keys[i] = kKeySentinel;
+    if (status) atomicOr(status, SPVD_STATUS_COORD_RANGE);
+  }
+}
+
+// batch-wide per-axis maximum of the fine coordinates (torchsparse: coords.max(0), frame at
+// experiments/ConditionalGeneration.ipynb:451)
+__global__ void k_coord_max(const int4* __restrict__ coords, SortState* st) {
+  int n = st->n;
+  int mx = INT_MIN, my = INT_MIN, mz = INT_MIN;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int4 c = coords[i];
+    mx = max(mx, c.y);
+    my = max(my, c.z);
+    mz = max(mz, c.w);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    my = max(my, __shfl_xor_sync(0xffffffffu, my, o));
+    mz = max(mz, __shfl_xor_sync(0xffffffffu, mz, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&st->cmax[0], mx);
+    atomicMax(&st->cmax[1], my);
+    atomicMax(&st->cmax[2], mz);
+  }
+}
+
+// parent = floor(c/2); spconv mode drops parents above (max_in - 1) // 2
+__global__ void k_parent_keys(const int4* __restrict__ coords, SortState* st, int mode, u64* __restrict__ keys,
+                              int* status) {
+  int n = st->n;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 c = coords[i];
+  int px = c.y >> 1, py = c.z >> 1, pz = c.w >> 1;
+  bool keep = true;
+  if (mode == SPVD_DOWNSAMPLE_SPCONV)
+    keep = px <= ((st->cmax[0] - 1) >> 1) && py <= ((st->cmax[1] - 1) >> 1) && pz <= ((st->cmax[2] - 1) >> 1);
+  if (!coord_in_range(c.x, px, py, pz)) {
+    keep = false;
+    if (status) atomicOr(status, SPVD_STATUS_COORD_RANGE);
+  }
+  keys[i] = keep ? pack_key(c.x, px, py, pz) : kKeySentinel;
+}
+
+// ---------------------------------------------------------------------------------------------
+// LSD radix sort, 8-bit digits, keys only
+// ---------------------------------------------------------------------------------------------
+__global__ void k_digit_hist(const u64* __restrict__ keys, SortState* st) {
+  __shared__ unsigned h[8 * 256];
+  for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  int n = st->n;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    u64 k = keys[i];
+#pragma unroll
+    for (int p = 0; p < 8; ++p) atomicAdd(&h[p * 256 + (int)((k >> (8 * p)) & 255)], 1u);
+  }
+  __syncthreads();
+  unsigned* g = &st->hist[0][0];
+  for (int i = threadIdx.x; i < 8 * 256; i += blockDim.x)
+    if (h[i]) atomicAdd(g + i, h[i]);
+}
+
+__global__ void k_sort_plan(SortState* st) {
+  __shared__ int uniform[8];
+  if (threadIdx.x < 8) uniform[threadIdx.x] = 0;
+  __syncthreads();
+  unsigned n = (unsigned)st->n;
+  for (int p = 0; p < 8; ++p)
+    if (n == 0 || st->hist[p][threadIdx.x] == n) uniform[p] = 1;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int par = 0;
+    for (int p = 0; p < 8; ++p) {
+      st->skip[p] = uniform[p];
+      st->parity[p] = par;
+      if (!uniform[p]) par ^= 1;
+    }
+    st->parity[8] = par;
+  }
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_tile_hist(const u64* __restrict__ b0, const u64* __restrict__ b1,
+                                                            const SortState* __restrict__ st, int pass, int n_tiles,
+                                                            unsigned* __restrict__ tile_hist) {
+  if (st->skip[pass]) return;
+  __shared__ unsigned h[256];
+  if (threadIdx.x < 256) h[threadIdx.x] = 0;
+  __syncthreads();
+  const u64* src = st->parity[pass] ? b1 : b0;
+  int n = st->n, shift = 8 * pass;
+  int base = blockIdx.x * kSortTile;
+#pragma unroll
+  for (int r = 0; r < kSortItems; ++r) {
+    int i = base + r * kSortThreads + threadIdx.x;
+    if (i < n) atomicAdd(&h[(int)((src[i] >> shift) & 255)], 1u);
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) tile_hist[threadIdx.x * n_tiles + blockIdx.x] = h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_scatter(u64* __restrict__ b0, u64* __restrict__ b1,
+                                                          const SortState* __restrict__ st, int pass, int n_tiles,
+                                                          const unsigned* __restrict__ tile_hist) {
+  if (st->skip[pass]) return;
+  __shared__ unsigned base[256];
+  __shared__ unsigned scan[256];
+  __shared__ unsigned wcount[kSortWarps][256];
+  const u64* src = st->parity[pass] ? b1 : b0;
+  u64* dst = st->parity[pass] ? b0 : b1;
+  const int n = st->n, shift = 8 * pass, tile = blockIdx.x, tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  if (tid < 256) {
+    unsigned total = 0, before = 0;
+    const unsigned* row = tile_hist + tid * n_tiles;
+    for (int t = 0; t < n_tiles; ++t) {
+      unsigned c = row[t];
+      total += c;
+      if (t < tile) before += c;
+    }
+    scan[tid] = total;
+    base[tid] = before;
+  }
+  __syncthreads();
+  if (tid < 32) {  // exclusive scan of the 256 digit totals by one warp (8 per lane)
+    unsigned v[8], s = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[j] = scan[tid * 8 + j];
+      s += v[j];
+    }
+    unsigned incl = s;
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    unsigned run = incl - s;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      scan[tid * 8 + j] = run;
+      run += v[j];
+    }
+  }
+  __syncthreads();
+  if (tid < 256) base[tid] += scan[tid];
+  for (int r = 0; r < kSortItems; ++r) {
+    for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&wcount[0][0])[i] = 0;
+    __syncthreads();
+    int i = tile * kSortTile + r * kSortThreads + tid;
+    bool valid = i < n;
+    u64 key = valid ? src[i] : 0ull;
+    int digit = valid ? (int)((key >> shift) & 255) : 256;
+    unsigned peers = __match_any_sync(0xffffffffu, digit);
+    int rank = __popc(peers & ((1u << lane) - 1u));
+    if (valid && rank == 0) wcount[warp][digit] = __popc(peers);
+    __syncthreads();
+    if (tid < 256) {
+      unsigned run = base[tid];
+#pragma unroll
+      for (int w = 0; w < kSortWarps; ++w) {
+        unsigned c = wcount[w][tid];
+        wcount[w][tid] = run;
+        run += c;
+      }
+      base[tid] = run;
+    }
+    __syncthreads();
+    if (valid) dst[wcount[warp][digit] + rank] = key;
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// unique over the sorted keys (the sentinel, which sorts last, is not a voxel)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int head_flags(const u64* __restrict__ src, int n, int first, u64* k) {
+  int cnt = 0;
+  u64 prev = (first > 0 && first <= n) ? src[first - 1] : kKeySentinel;
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    int i = first + j;
+    k[j] = i < n ? src[i] : kKeySentinel;
+    bool head = k[j] != kKeySentinel && (i == 0 || k[j] != prev);
+    prev = k[j];
+    cnt += head ? 1 : 0;
+  }
+  return cnt;
+}
+
+__device__ __forceinline__ int block_exclusive_scan(int v, int* total) {
+  __shared__ int wsum[kSortWarps];
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  int incl = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  int wbase = 0, tot = 0;
+  for (int w = 0; w < kSortWarps; ++w) {
+    int s = wsum[w];
+    if (w < warp) wbase += s;
+    tot += s;
+  }
+  *total = tot;
+  return wbase + incl - v;
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_unique_count(const u64* __restrict__ b0, const u64* __restrict__ b1,
+                                                               const SortState* __restrict__ st,
+                                                               int* __restrict__ tile_count) {
+  const u64* src = st->parity[8] ? b1 : b0;
+  u64 k[kSortItems];
+  int cnt = head_flags(src, st->n, blockIdx.x * kSortTile + threadIdx.x * kSortItems, k);
+  int total;
+  block_exclusive_scan(cnt, &total);
+  if (threadIdx.x == 0) tile_count[blockIdx.x] = total;
+}
+
+__global__ void __launch_bounds__(kSortThreads) k_unique_write(const u64* __restrict__ b0, const u64* __restrict__ b1,
+                                                               const SortState* __restrict__ st,
+                                                               const int* __restrict__ tile_count, int n_tiles,
+                                                               int4* __restrict__ out_coords,
+                                                               int* __restrict__ out_count) {
+  const u64* src = st->parity[8] ? b1 : b0;
+  __shared__ int s_base;
+  if (threadIdx.x < 32) {
+    int s = 0;
+    for (int t = threadIdx.x; t < (int)blockIdx.x; t += 32) s += tile_count[t];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) s_base = s;
+  }
+  const int n = st->n;
+  const int first = blockIdx.x * kSortTile + threadIdx.x * kSortItems;
+  u64 k[kSortItems];
+  int cnt = head_flags(src, n, first, k);
+  int total;
+  int pos = block_exclusive_scan(cnt, &total);  // contains a __syncthreads: s_base is visible below
+  pos += s_base;
+  u64 prev = (first > 0 && first <= n) ? src[first - 1] : kKeySentinel;
+#pragma unroll
+  for (int j = 0; j < kSortItems; ++j) {
+    bool head = k[j] != kKeySentinel && (first + j == 0 || k[j] != prev);
+    prev = k[j];
+    if (head) out_coords[pos++] = unpack_key(k[j]);
+  }
+  if ((int)blockIdx.x == n_tiles - 1 && threadIdx.x == 0) *out_count = s_base + total;
+}
+
+static int sorted_unique(const SortWs& w, int n_cap, int4* out_coords, int* out_count, cudaStream_t s) {
+  int grid = cdiv(n_cap, 1024);
+  if (grid > 296) grid = 296;
+  if (grid < 1) grid = 1;
+  k_digit_hist<<<grid, 256, 0, s>>>(w.buf[0], w.st);
+  k_sort_plan<<<1, 256, 0, s>>>(w.st);
+  for (int p = 0; p < 8; ++p) {
+    k_tile_hist<<<w.n_tiles, kSortThreads, 0, s>>>(w.buf[0], w.buf[1], w.st, p, w.n_tiles, w.tile_hist);
+    k_scatter<<<w.n_tiles, kSortThreads, 0, s>>>(w.buf[0], w.buf[1], w.st, p, w.n_tiles, w.tile_hist);
+  }
+  k_unique_count<<<w.n_tiles, kSortThreads, 0, s>>>(w.buf[0], w.buf[1], w.st, w.tile_count);
+  k_unique_write<<<w.n_tiles, kSortThreads, 0, s>>>(w.buf[0], w.buf[1], w.st, w.tile_count, w.n_tiles, out_coords,
+                                                    out_count);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+}  // namespace spvd
+
+using namespace spvd;
+
+extern "C" int spvd_point_voxel_coords(const float* pc, int n, float init_res, float after_res, int scale_mode,
+                                       float* fcoords, int32_t* icoords, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(n >= 0 && pc && fcoords, "spvd_point_voxel_coords: bad arguments");
+  SPVD_CHECK_ARG(scale_mode == SPVD_SCALE_MUL || scale_mode == SPVD_SCALE_DIV, "bad scale_mode %d", scale_mode);
+  if (n == 0) return SPVD_OK;
+  volatile float one = 1.0f;
+  float inv = one / after_res;  // fp32 reciprocal, as torch computes it for a CUDA division by a scalar
+  k_point_voxel_coords<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)pc, n, init_res, after_res, inv, scale_mode, (float4*)fcoords, (int4*)icoords);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" size_t spvd_unique_workspace_bytes(int n_cap) { return sort_ws_bytes(n_cap); }
+
+extern "C" int spvd_unique_coords(const int32_t* icoords, int n_cap, const int32_t* n_dev, int32_t* out_coords,
+                                  int32_t* out_count, int32_t* status, void* workspace, size_t workspace_bytes,
+                                  spvd_stream_t stream) {
+  SPVD_CHECK_ARG(n_cap > 0 && icoords && out_coords && out_count && workspace, "spvd_unique_coords: bad arguments");
+  if (workspace_bytes < sort_ws_bytes(n_cap)) {
+    set_error("spvd_unique_coords: workspace %zu < %zu", workspace_bytes, sort_ws_bytes(n_cap));
+    return SPVD_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  SortWs w = carve_ws(workspace, n_cap);
+  k_state_init<<<1, 256, 0, s>>>(w.st, n_cap, n_dev);
+  k_pack_keys<<<cdiv(n_cap, 256), 256, 0, s>>>((const int4*)icoords, w.st, w.buf[0], status);
+  return sorted_unique(w, n_cap, (int4*)out_coords, out_count, s);
+}
+
+extern "C" size_t spvd_downsample_workspace_bytes(int n_cap) { return sort_ws_bytes(n_cap); }
+
+extern "C" int spvd_downsample_coords(const int32_t* coords, int n_cap, const int32_t* n_dev, int mode,
+                                      int32_t* out_coords, int32_t* out_count, int32_t* status, void* workspace,
+                                      size_t workspace_bytes, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(n_cap > 0 && coords && out_coords && out_count && workspace, "spvd_downsample_coords: bad arguments");
+  SPVD_CHECK_ARG(mode == SPVD_DOWNSAMPLE_SPCONV || mode == SPVD_DOWNSAMPLE_FLOOR, "bad downsample mode %d", mode);
+  if (workspace_bytes < sort_ws_bytes(n_cap)) {
+    set_error("spvd_downsample_coords: workspace %zu < %zu", workspace_bytes, sort_ws_bytes(n_cap));
+    return SPVD_ERR_WORKSPACE;
+  }
+  cudaStream_t s = (cudaStream_t)stream;
+  SortWs w = carve_ws(workspace, n_cap);
+  k_state_init<<<1, 256, 0, s>>>(w.st, n_cap, n_dev);
+  if (mode == SPVD_DOWNSAMPLE_SPCONV) {
+    int grid = cdiv(n_cap, 1024);
+    if (grid > 148) grid = 148;
+    k_coord_max<<<grid, 256, 0, s>>>((const int4*)coords, w.st);
+  }
+  k_parent_keys<<<cdiv(n_cap, 256), 256, 0, s>>>((const int4*)coords, w.st, mode, w.buf[0], status);
+  return sorted_unique(w, n_cap, (int4*)out_coords, out_count, s);
+}

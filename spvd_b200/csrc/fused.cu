@@ -1,0 +1,106 @@
+// Small fused elementwise kernels around the sparse convolutions (inference path): BatchNorm folded
+// to a per-channel affine + SiLU (spnn.BatchNorm + spnn.SiLU, models/ddpm_unet_attn.py:24-28), the
+// FiLM time modulation (models/modules/graph.py:19-41) and per-cloud voxel counts (the offsets that
+// models/modules/transformer.py:12-15 gets from to_dense_batch).  HBM-bound, 128-bit accesses.
+#include "common.cuh"
+
+namespace spvd {
+
+__device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+
+// y = act(x * scale[c] + shift[c]);  act: 0 none, 1 SiLU
+__global__ void k_affine_act4(const float4* __restrict__ x, const float4* __restrict__ scale,
+                              const float4* __restrict__ shift, long long total4, int c4, int act,
+                              float4* __restrict__ y) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total4) return;
+  int q = (int)(t % c4);
+  float4 v = x[t], s = __ldg(scale + q), b = __ldg(shift + q);
+  v.x = fmaf(v.x, s.x, b.x);
+  v.y = fmaf(v.y, s.y, b.y);
+  v.z = fmaf(v.z, s.z, b.z);
+  v.w = fmaf(v.w, s.w, b.w);
+  if (act == 1) {
+    v.x = silu(v.x);
+    v.y = silu(v.y);
+    v.z = silu(v.z);
+    v.w = silu(v.w);
+  }
+  y[t] = v;
+}
+
+__global__ void k_affine_act1(const float* __restrict__ x, const float* __restrict__ scale,
+                              const float* __restrict__ shift, long long total, int c, int act,
+                              float* __restrict__ y) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total) return;
+  int q = (int)(t % c);
+  float v = fmaf(x[t], scale[q], shift[q]);
+  y[t] = act == 1 ? silu(v) : v;
+}
+
+// y[i] = (1 + tt[b_i, c]) * x[i, c] + tt[b_i, C + c],  b_i = coords[i].batch
+__global__ void k_film4(const float4* __restrict__ x, const float* __restrict__ tt, const int4* __restrict__ coords,
+                        long long total4, int c4, float4* __restrict__ y) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total4) return;
+  int row = (int)(t / c4), q = (int)(t % c4);
+  int b = coords[row].x;
+  const float4* tb = reinterpret_cast<const float4*>(tt + (size_t)b * c4 * 8);
+  float4 v = x[t], sc = __ldg(tb + q), sh = __ldg(tb + c4 + q);
+  v.x = fmaf(1.f + sc.x, v.x, sh.x);
+  v.y = fmaf(1.f + sc.y, v.y, sh.y);
+  v.z = fmaf(1.f + sc.z, v.z, sh.z);
+  v.w = fmaf(1.f + sc.w, v.w, sh.w);
+  y[t] = v;
+}
+
+__global__ void k_batch_counts(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, int nb,
+                               int* __restrict__ counts) {
+  int n = resolve_n(n_dev, n_cap);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int b = coords[i].x;
+  if (b >= 0 && b < nb) atomicAdd(counts + b, 1);
+}
+
+}  // namespace spvd
+
+using namespace spvd;
+
+extern "C" int spvd_bn_silu_fwd(const float* x, const float* scale, const float* shift, long long rows, int c, int act,
+                                float* y, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && scale && shift && y && rows >= 0 && c > 0, "spvd_bn_silu_fwd: bad arguments");
+  if (rows == 0) return SPVD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  bool v4 = c % 4 == 0 && (((size_t)x | (size_t)y | (size_t)scale | (size_t)shift) & 15) == 0;
+  if (v4)
+    k_affine_act4<<<cdiv(rows * (c / 4), 256), 256, 0, s>>>((const float4*)x, (const float4*)scale, (const float4*)shift,
+                                                          rows * (c / 4), c / 4, act, (float4*)y);
+  else
+    k_affine_act1<<<cdiv(rows * c, 256), 256, 0, s>>>(x, scale, shift, rows * c, c, act, y);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_film_fwd(const float* x, const float* tt, const int32_t* coords, long long rows, int c, float* y,
+                             spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && tt && coords && y && rows >= 0 && c > 0 && c % 4 == 0, "spvd_film_fwd: bad arguments (c %% 4 == 0)");
+  SPVD_CHECK_ARG((((size_t)x | (size_t)y | (size_t)tt) & 15) == 0, "spvd_film_fwd: pointers must be 16-byte aligned");
+  if (rows == 0) return SPVD_OK;
+  k_film4<<<cdiv(rows * (c / 4), 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, tt, (const int4*)coords,
+                                                                      rows * (c / 4), c / 4, (float4*)y);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_batch_counts(const int32_t* coords, int n_cap, const int32_t* n_dev, int nb, int32_t* counts,
+                                 spvd_stream_t stream) {
+  SPVD_CHECK_ARG(coords && counts && n_cap >= 0 && nb > 0, "spvd_batch_counts: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  SPVD_CUDA(cudaMemsetAsync(counts, 0, (size_t)nb * 4, s));
+  if (n_cap == 0) return SPVD_OK;
+  k_batch_counts<<<cdiv(n_cap, 256), 256, 0, s>>>((const int4*)coords, n_cap, n_dev, nb, counts);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}

@@ -1,0 +1,266 @@
+// Coordinate hash table (H1) and everything that probes it: generic neighbourhood queries
+// (torchsparse.backend.GPUHashTable as used by models/sparse_utils.py:36-55), the submanifold
+// kernel map (K1), the stride-2 maps (K2/K3) and the point->voxel / trilinear queries (V2/V3).
+//
+// Open addressing, linear probing, 64-bit packed keys, load factor <= 0.5 (the reference sizes its
+// tables 2*N).  The tables of one forward are a few MB and live in L2; each probe is one 8-byte
+// load in the common case.  All kernels are one thread per query row with offset-major, coalesced
+// stores.
+#include "common.cuh"
+
+namespace spvd {
+
+typedef unsigned long long u64;
+
+__device__ __forceinline__ int4 load_coord(const int* __restrict__ c, int i, int order) {
+  int4 v = reinterpret_cast<const int4*>(c)[i];
+  if (order == SPVD_ORDER_XYZB) return make_int4(v.w, v.x, v.y, v.z);
+  return v;
+}
+
+__global__ void k_hash_insert(const int* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, int order,
+                              u64* keys, int* vals, unsigned cap, int* status) {
+  int n = resolve_n(n_dev, n_cap);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int4 c = load_coord(coords, i, order);
+  if (!coord_in_range(c.x, c.y, c.z, c.w)) {
+    if (status) atomicOr(status, SPVD_STATUS_COORD_RANGE);
+    return;
+  }
+  u64 key = pack_key(c.x, c.y, c.z, c.w);
+  unsigned slot = hash_slot(key, cap);
+  for (unsigned probe = 0; probe < cap; ++probe) {
+    u64 old = atomicCAS(keys + slot, 0ull, key);
+    if (old == 0ull || old == key) {
+      vals[slot] = i + 1;
+      return;
+    }
+    if (++slot == cap) slot = 0;
+  }
+  if (status) atomicOr(status, SPVD_STATUS_HASH_FULL);
+}
+
+__device__ __forceinline__ int find_coord(const u64* __restrict__ keys, const int* __restrict__ vals, unsigned cap,
+                                          int b, int x, int y, int z) {
+  if (!coord_in_range(b, x, y, z)) return 0;
+  return hash_find(keys, vals, cap, pack_key(b, x, y, z));
+}
+
+// offsets: kernel_size 3 -> {-1,0,1}^3 with x fastest; 2 -> {0,1}^3 with z fastest; 1 -> {0}
+__device__ __forceinline__ void kernel_offset(int ks, int k, int& dx, int& dy, int& dz) {
+  if (ks == 3) {
+    dx = k % 3 - 1;
+    dy = (k / 3) % 3 - 1;
+    dz = k / 9 - 1;
+  } else if (ks == 2) {
+    dx = (k >> 2) & 1;
+    dy = (k >> 1) & 1;
+    dz = k & 1;
+  } else {
+    dx = dy = dz = 0;
+  }
+}
+
+__global__ void k_hash_query(const int* __restrict__ query, int m, int order, int ks, int kvol,
+                             const u64* __restrict__ keys, const int* __restrict__ vals, unsigned cap,
+                             int* __restrict__ out) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)m * kvol) return;
+  int i = (int)(t / kvol), k = (int)(t % kvol);
+  int4 c = load_coord(query, i, order);
+  int dx, dy, dz;
+  kernel_offset(ks, k, dx, dy, dz);
+  out[t] = find_coord(keys, vals, cap, c.x, c.y + dx, c.z + dy, c.w + dz);
+}
+
+// K1: one CTA = one 128-row output tile
+__global__ void __launch_bounds__(128) k_kmap_subm3(const int4* __restrict__ coords, int n_cap,
+                                                    const int* __restrict__ n_dev, const u64* __restrict__ keys,
+                                                    const int* __restrict__ vals, unsigned cap,
+                                                    int* __restrict__ map_t, int ld, unsigned* __restrict__ tile_mask) {
+  __shared__ unsigned s_mask;
+  if (threadIdx.x == 0) s_mask = 0;
+  __syncthreads();
+  int n = resolve_n(n_dev, n_cap);
+  int o = blockIdx.x * 128 + threadIdx.x;
+  bool valid = o < n;
+  int4 c = valid ? coords[o] : make_int4(0, 0, 0, 0);
+  unsigned wmask = 0;
+#pragma unroll 1
+  for (int k = 0; k < 27; ++k) {
+    int r = -1;
+    if (valid) {
+      if (k == 13) {
+        r = o;
+      } else {
+        int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
+        r = find_coord(keys, vals, cap, c.x, c.y + dx, c.z + dy, c.w + dz) - 1;
+      }
+    }
+    if (o < ld) map_t[(size_t)k * ld + o] = r;
+    if (__ballot_sync(0xffffffffu, r >= 0)) wmask |= 1u << k;
+  }
+  if ((threadIdx.x & 31) == 0 && wmask) atomicOr(&s_mask, wmask);
+  __syncthreads();
+  if (threadIdx.x == 0 && tile_mask) tile_mask[blockIdx.x] = s_mask;
+}
+
+// K2/K3: fine voxel i has parent floor(c/2) (a row of the coarse table or absent) and parity offset
+// koff = 4*px + 2*py + pz.
+__global__ void k_kmap_down2(const int4* __restrict__ fine, int n_cap, const int* __restrict__ n_dev,
+                             const u64* __restrict__ keys, const int* __restrict__ vals, unsigned cap,
+                             int* __restrict__ map_down_t, int ld_coarse, unsigned* tile_mask_down,
+                             int* __restrict__ map_up_t, int ld_fine, unsigned* tile_mask_up,
+                             int* __restrict__ parent_out, int* __restrict__ koff_out) {
+  int n = resolve_n(n_dev, n_cap);
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ld_fine && i >= n_cap) return;
+  int prow = -1, koff = 0;
+  if (i < n) {
+    int4 c = fine[i];
+    int px = c.y >> 1, py = c.z >> 1, pz = c.w >> 1;
+    koff = ((c.y & 1) << 2) | ((c.z & 1) << 1) | (c.w & 1);
+    prow = find_coord(keys, vals, cap, c.x, px, py, pz) - 1;
+    if (prow >= 0) {
+      if (map_down_t && prow < ld_coarse) {
+        map_down_t[(size_t)koff * ld_coarse + prow] = i;
+        if (tile_mask_down) atomicOr(tile_mask_down + (prow >> 7), 1u << koff);
+      }
+      if (tile_mask_up) atomicOr(tile_mask_up + (i >> 7), 1u << koff);
+    }
+  }
+  if (i < n_cap) {
+    if (parent_out) parent_out[i] = prow;
+    if (koff_out) koff_out[i] = koff;
+  }
+  if (map_up_t && i < ld_fine) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) map_up_t[(size_t)k * ld_fine + i] = (k == koff && prow >= 0) ? prow : -1;
+  }
+}
+
+// V2: voxel of a point at tensor stride s = (int(b), floor(xyz / s))  (models/sparse_utils.py:81-87)
+__global__ void k_point_voxel_query(const float4* __restrict__ pc, int n, float s, const u64* __restrict__ keys,
+                                    const int* __restrict__ vals, unsigned cap, int* __restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pc[i];
+  int x = (int)floorf(__fdiv_rn(p.y, s)), y = (int)floorf(__fdiv_rn(p.z, s)), z = (int)floorf(__fdiv_rn(p.w, s));
+  idx[i] = find_coord(keys, vals, cap, (int)p.x, x, y, z) - 1;
+}
+
+// V3: 8 corner rows (z fastest) + trilinear weights (torchsparse calc_ti_weights, scale=1): zero where
+// the corner is absent, renormalised by (sum + 1e-8)
+__global__ void k_devox_query(const float4* __restrict__ pc, int n, float s, const u64* __restrict__ keys,
+                              const int* __restrict__ vals, unsigned cap, int* __restrict__ idx8,
+                              float* __restrict__ w8) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float4 p = pc[i];
+  float x = __fdiv_rn(p.y, s), y = __fdiv_rn(p.z, s), z = __fdiv_rn(p.w, s);
+  float xf = floorf(x), yf = floorf(y), zf = floorf(z);
+  int b = (int)p.x, ix = (int)xf, iy = (int)yf, iz = (int)zf;
+  float ax[2] = {__fsub_rn(__fadd_rn(xf, 1.f), x), __fsub_rn(x, xf)};
+  float ay[2] = {__fsub_rn(__fadd_rn(yf, 1.f), y), __fsub_rn(y, yf)};
+  float az[2] = {__fsub_rn(__fadd_rn(zf, 1.f), z), __fsub_rn(z, zf)};
+  int id[8];
+  float w[8], sum = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    int dx = (k >> 2) & 1, dy = (k >> 1) & 1, dz = k & 1;
+    id[k] = find_coord(keys, vals, cap, b, ix + dx, iy + dy, iz + dz) - 1;
+    w[k] = id[k] >= 0 ? __fmul_rn(__fmul_rn(ax[dx], ay[dy]), az[dz]) : 0.f;
+    sum = __fadd_rn(sum, w[k]);
+  }
+  float den = __fadd_rn(sum, 1e-8f);
+  int4* io = reinterpret_cast<int4*>(idx8 + (size_t)i * 8);
+  float4* wo = reinterpret_cast<float4*>(w8 + (size_t)i * 8);
+  io[0] = make_int4(id[0], id[1], id[2], id[3]);
+  io[1] = make_int4(id[4], id[5], id[6], id[7]);
+  wo[0] = make_float4(__fdiv_rn(w[0], den), __fdiv_rn(w[1], den), __fdiv_rn(w[2], den), __fdiv_rn(w[3], den));
+  wo[1] = make_float4(__fdiv_rn(w[4], den), __fdiv_rn(w[5], den), __fdiv_rn(w[6], den), __fdiv_rn(w[7], den));
+}
+
+}  // namespace spvd
+
+using namespace spvd;
+
+extern "C" int spvd_hash_build(const int32_t* coords, int n_cap, const int32_t* n_dev, int coord_order,
+                               int64_t* keys, int32_t* vals, int capacity, int32_t* status, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(coords && keys && vals && n_cap >= 0, "spvd_hash_build: bad arguments");
+  SPVD_CHECK_ARG(capacity >= 2 * n_cap && capacity > 0, "spvd_hash_build: capacity %d < 2*%d", capacity, n_cap);
+  cudaStream_t s = (cudaStream_t)stream;
+  SPVD_CUDA(cudaMemsetAsync(keys, 0, (size_t)capacity * 8, s));
+  SPVD_CUDA(cudaMemsetAsync(vals, 0, (size_t)capacity * 4, s));
+  if (n_cap == 0) return SPVD_OK;
+  k_hash_insert<<<cdiv(n_cap, 256), 256, 0, s>>>(coords, n_cap, n_dev, coord_order, (u64*)keys, vals,
+                                                 (unsigned)capacity, status);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_hash_query(const int32_t* query, int m, int coord_order, int kernel_size, const int64_t* keys,
+                               const int32_t* vals, int capacity, int32_t* out, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(query && keys && vals && out && m >= 0 && capacity > 0, "spvd_hash_query: bad arguments");
+  SPVD_CHECK_ARG(kernel_size >= 1 && kernel_size <= 3, "spvd_hash_query: kernel_size %d not in 1..3", kernel_size);
+  if (m == 0) return SPVD_OK;
+  int kvol = kernel_size * kernel_size * kernel_size;
+  long long total = (long long)m * kvol;
+  k_hash_query<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(query, m, coord_order, kernel_size, kvol,
+                                                                   (const u64*)keys, vals, (unsigned)capacity, out);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_kmap_subm3(const int32_t* coords, int n_cap, const int32_t* n_dev, const int64_t* keys,
+                               const int32_t* vals, int capacity, int32_t* map_t, int ld, uint32_t* tile_mask,
+                               spvd_stream_t stream) {
+  SPVD_CHECK_ARG(coords && keys && vals && map_t && capacity > 0, "spvd_kmap_subm3: bad arguments");
+  SPVD_CHECK_ARG(ld >= n_cap && ld % 128 == 0, "spvd_kmap_subm3: ld %d must be a multiple of 128 >= %d", ld, n_cap);
+  if (ld == 0) return SPVD_OK;
+  k_kmap_subm3<<<ld / 128, 128, 0, (cudaStream_t)stream>>>((const int4*)coords, n_cap, n_dev, (const u64*)keys, vals,
+                                                           (unsigned)capacity, map_t, ld, tile_mask);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_kmap_down2(const int32_t* fine_coords, int n_fine_cap, const int32_t* n_fine_dev,
+                               const int64_t* keys, const int32_t* vals, int capacity, int32_t* map_down_t,
+                               int ld_coarse, uint32_t* tile_mask_down, int32_t* map_up_t, int ld_fine,
+                               uint32_t* tile_mask_up, int32_t* parent, int32_t* koff, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(fine_coords && keys && vals && capacity > 0 && n_fine_cap >= 0, "spvd_kmap_down2: bad arguments");
+  SPVD_CHECK_ARG(!map_down_t || (ld_coarse > 0 && ld_coarse % 128 == 0), "spvd_kmap_down2: bad ld_coarse %d", ld_coarse);
+  SPVD_CHECK_ARG(!map_up_t || (ld_fine >= n_fine_cap && ld_fine % 128 == 0), "spvd_kmap_down2: bad ld_fine %d", ld_fine);
+  cudaStream_t s = (cudaStream_t)stream;
+  if (map_down_t) SPVD_CUDA(cudaMemsetAsync(map_down_t, 0xFF, (size_t)8 * ld_coarse * 4, s));
+  if (tile_mask_down) SPVD_CUDA(cudaMemsetAsync(tile_mask_down, 0, (size_t)(ld_coarse / 128) * 4, s));
+  if (tile_mask_up) SPVD_CUDA(cudaMemsetAsync(tile_mask_up, 0, (size_t)(ld_fine / 128) * 4, s));
+  int span = map_up_t ? (ld_fine > n_fine_cap ? ld_fine : n_fine_cap) : n_fine_cap;
+  if (span == 0) return SPVD_OK;
+  k_kmap_down2<<<cdiv(span, 256), 256, 0, s>>>((const int4*)fine_coords, n_fine_cap, n_fine_dev, (const u64*)keys,
+                                               vals, (unsigned)capacity, map_down_t, ld_coarse, tile_mask_down,
+                                               map_up_t, map_up_t ? ld_fine : 0, tile_mask_up, parent, koff);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_point_voxel_query(const float* pc, int n, int stride, const int64_t* keys, const int32_t* vals,
+                                      int capacity, int32_t* idx, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(pc && keys && vals && idx && n >= 0 && stride >= 1 && capacity > 0, "spvd_point_voxel_query: bad arguments");
+  if (n == 0) return SPVD_OK;
+  k_point_voxel_query<<<cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>((const float4*)pc, n, (float)stride,
+                                                                      (const u64*)keys, vals, (unsigned)capacity, idx);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_devox_query(const float* pc, int n, int stride, const int64_t* keys, const int32_t* vals,
+                                int capacity, int32_t* idx8, float* w8, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(pc && keys && vals && idx8 && w8 && n >= 0 && stride >= 1 && capacity > 0, "spvd_devox_query: bad arguments");
+  if (n == 0) return SPVD_OK;
+  k_devox_query<<<cdiv(n, 128), 128, 0, (cudaStream_t)stream>>>((const float4*)pc, n, (float)stride, (const u64*)keys,
+                                                                vals, (unsigned)capacity, idx8, w8);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}

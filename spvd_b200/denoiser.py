@@ -1,0 +1,340 @@
+"""The SPVD point-voxel denoiser on the sm_100a backend.
+
+Same module tree, constructor arguments and parameter names as the reference's ``SPVUnet``
+(models/spvd.py:367-457; building blocks models/spvd.py:16-271, models/ddpm_unet_attn.py:24-65,
+models/modules/graph.py:8-41, models/modules/transformer.py:40-125), so a reference ``state_dict``
+loads with ``strict=True`` -- but the forward is organised differently: the coordinate work of the
+whole U-Net is planned once (spvd_b200.geometry.Geometry, one host sync instead of ~20) and the
+network then runs on plain feature matrices through the CUDA ops of libspvd_b200.so.  The modules
+below only own parameters; ``SPVUnet.forward`` drives them.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as SF
+from . import ops
+from .geometry import Geometry
+from .sparse import SparseTensor
+
+
+# ------------------------------------------------------------------------------ parameter holders
+class Conv3d(nn.Module):
+    """Parameters of torchsparse.nn.Conv3d: ``kernel`` [K,Cin,Cout] ([Cin,Cout] for K=1), optional
+    ``bias``; uniform(+-1/sqrt(K*fan)) init with fan = Cout when transposed else Cin."""
+
+    def __init__(self, in_channels, out_channels, kernel_size=3, stride=1, padding=0, dilation=1, bias=False,
+                 transposed=False):
+        super().__init__()
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.kernel_size, self.stride, self.transposed = int(kernel_size), int(stride), bool(transposed)
+        kvol = self.kernel_size ** 3
+        shape = (kvol, in_channels, out_channels) if kvol > 1 else (in_channels, out_channels)
+        bound = 1.0 / math.sqrt((out_channels if transposed else in_channels) * kvol)
+        self.kernel = nn.Parameter(torch.empty(shape).uniform_(-bound, bound))
+        self.bias = nn.Parameter(torch.empty(out_channels).uniform_(-bound, bound)) if bias else None
+        self._packed = SF.PackedWeight()
+        self.impl = ops.CONV_AUTO
+
+    def forward(self, feats, kmap):
+        return SF.sparse_conv(feats, self.kernel, self.bias, kmap, self._packed, self.impl)
+
+    def extra_repr(self):
+        return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
+                f"transposed={self.transposed}, bias={self.bias is not None}")
+
+
+def _bn_silu_linear(ni, nf, bias=True):
+    return nn.Sequential(nn.BatchNorm1d(ni), nn.SiLU(), nn.Linear(ni, nf, bias=bias))
+
+
+class PointBlock(nn.Module):                      # models/spvd.py:16-28
+    def __init__(self, ni, nf):
+        super().__init__()
+        self.conv = _bn_silu_linear(ni, nf)
+
+
+class StemBlock(nn.Module):                       # models/spvd.py:30-62
+    def __init__(self, ni, nf, ks=3):
+        super().__init__()
+        self.voxel_conv = nn.Sequential(Conv3d(ni, nf, ks), nn.BatchNorm1d(nf), nn.SiLU(), Conv3d(nf, nf, ks))
+        self.point_conv = PointBlock(ni, nf)
+
+
+class TimeEmbeddingBlock(nn.Module):              # models/modules/graph.py:8-41
+    def __init__(self, n_emb, embed_dim):
+        super().__init__()
+        self.proj_mlp = nn.Linear(n_emb, embed_dim * 2)
+
+
+class _AttentionCore(nn.Module):                  # models/modules/transformer.py:40-67
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.num_heads = num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=False)
+        self.proj = nn.Linear(dim, dim)
+
+
+class SparseAttention(nn.Module):                 # models/modules/transformer.py:102-125
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim)
+        self.attn = _AttentionCore(dim, num_heads)
+
+
+def _unet_conv(ni, nf, ks):                       # models/ddpm_unet_attn.py:24-30
+    return nn.Sequential(nn.BatchNorm1d(ni), nn.SiLU(), Conv3d(ni, nf, ks, bias=True))
+
+
+class EmbResBlock(nn.Module):                     # models/ddpm_unet_attn.py:32-65
+    def __init__(self, n_emb, ni, nf=None, ks=3, attn_chans=None):
+        super().__init__()
+        nf = nf or ni
+        self.conv1 = _unet_conv(ni, nf, ks)
+        self.conv2 = _unet_conv(nf, nf, ks)
+        self.t_emb = TimeEmbeddingBlock(n_emb, nf)
+        if ni != nf:
+            self.idconv = nn.Linear(ni, nf)
+        if attn_chans:
+            self.attn = SparseAttention(nf, attn_chans)
+
+
+class DownBlock(nn.Module):                       # models/spvd.py:102-119
+    def __init__(self, n_emb, ni, nf, add_down=True, num_layers=1, attn_chans=None):
+        super().__init__()
+        self.resnets = nn.ModuleList([EmbResBlock(n_emb, ni, ni, attn_chans=attn_chans) for _ in range(num_layers)])
+        self.add_down = add_down
+        self.down = Conv3d(ni, nf, 2, stride=2) if add_down else Conv3d(ni, nf, 1)
+
+
+class SPVDownStage(nn.Module):                    # models/spvd.py:121-159
+    def __init__(self, n_emb, nfs, add_down, num_layers, attn_chans):
+        super().__init__()
+        self.downs = nn.ModuleList([DownBlock(n_emb, nfs[i], nfs[i + 1], add_down[i], num_layers, attn_chans[i])
+                                    for i in range(len(nfs) - 1)])
+        self.point_block = PointBlock(nfs[0], nfs[-1])
+
+
+class UpBlock(nn.Module):                         # models/spvd.py:212-233
+    def __init__(self, n_emb, prev_nf, ni, add_up=True, num_layers=2, attn_chans=None, ks=3):
+        super().__init__()
+        self.resnets = nn.ModuleList([EmbResBlock(n_emb, prev_nf + ni, prev_nf, ks=ks, attn_chans=attn_chans)
+                                      for _ in range(num_layers)])
+        self.add_up = add_up
+        self.up = Conv3d(prev_nf, ni, 2, stride=2, transposed=True) if add_up else Conv3d(prev_nf, ni, 1)
+
+
+class SPVUpStage(nn.Module):                      # models/spvd.py:235-271
+    def __init__(self, n_emb, nfs, add_up, num_layers, attn_chans, ks):
+        super().__init__()
+        self.ups = nn.ModuleList()
+        prev = nfs[0]
+        for i in range(len(nfs) - 1):
+            self.ups.append(UpBlock(n_emb, prev, nfs[i + 1], add_up[i], num_layers, attn_chans[i], ks[i]))
+            prev = nfs[i + 1]
+        self.point_block = PointBlock(nfs[0], nfs[-1])
+
+
+# ------------------------------------------------------------------------------------- the network
+class SPVUnet(nn.Module):
+    """``model((SparseTensor x, LongTensor t)) -> FloatTensor [N_points, point_channels]`` exactly like the
+    reference (models/spvd.py:432-457); ``x.C`` int32 [N,4] = (batch, ix, iy, iz) in units of ``pres``,
+    ``x.F`` the point features.
+
+    Extra knobs that the reference hard-wires inside torchsparse: ``downsample_mode`` ('spconv' =
+    torchsparse 2.1 default boundary rule, 'floor'), ``scale_mode`` ('mul' = what torch-CUDA computes
+    for ``c*pres/voxel_size``, 'div' = torch-CPU), ``conv_impl`` (ops.CONV_AUTO / CONV_SIMT / CONV_UMMA).
+    """
+
+    def __init__(self, point_channels=3, voxel_size=0.1,
+                 down_blocks=[[(64, 128, 192, 256, 384, 384), (True, True, True, True, False), (None, None, None, 8, 8)]],
+                 up_blocks=[[(384, 384, 256), (True, True), (8, 8), (3, 3)],
+                            [(256, 192, 128, 64), (True, True, False), (None, None, None), (3, 3, 3)]],
+                 num_layers=1, pres=1e-5, downsample_mode="spconv", scale_mode="mul"):
+        super().__init__()
+        self.pres, self.voxel_size = pres, voxel_size
+        self.downsample_mode, self.scale_mode = downsample_mode, scale_mode
+        self.point_channels = point_channels
+        self.n_temb = nf0 = down_blocks[0][0][0]
+        n_emb = nf0 * 4
+        self.emb_mlp = nn.Sequential(_bn_silu_linear(self.n_temb, n_emb), nn.Sequential(nn.SiLU(), nn.Linear(n_emb, n_emb)))
+        self.stem_conv = StemBlock(point_channels, nf0)
+        self.down_stages = nn.ModuleList([SPVDownStage(n_emb, nfs, add_down, num_layers, attn)
+                                          for nfs, add_down, attn in down_blocks])
+        self.mid_stages = nn.Identity()
+        self.up_stages = nn.ModuleList([SPVUpStage(n_emb, nfs, add_up, num_layers + 1, attn, ks)
+                                        for nfs, add_up, attn, ks in up_blocks])
+        c_out = up_blocks[-1][0][-1]
+        self.out_conv = _bn_silu_linear(c_out, point_channels, bias=False)
+        self._plan = self._make_plan(down_blocks, up_blocks)
+        self._folded = {}
+
+    # -- static description of which strides need which maps (so Geometry can build all of them up front)
+    @staticmethod
+    def _make_plan(down_blocks, up_blocks):
+        s, strides, p2v, devox = 1, [1], [1], [1]
+        for nfs, add_down, _ in down_blocks:
+            for d in add_down:
+                if d:
+                    s *= 2
+                    strides.append(s)
+            p2v.append(s)
+            devox.append(s)
+        top = s
+        for nfs, add_up, _, _ in up_blocks:
+            for u in add_up:
+                if u:
+                    s //= 2
+            p2v.append(s)
+            devox.append(s)
+        assert s >= 1
+        return dict(strides=tuple(strides), p2v=tuple(sorted(set(p2v))), devox=tuple(sorted(set(devox))), top=top)
+
+    def set_conv_impl(self, impl):
+        for m in self.modules():
+            if isinstance(m, Conv3d):
+                m.impl = impl
+        return self
+
+    def num_params(self):
+        return sum(p.numel() for p in self.parameters())
+
+    # -- helpers -------------------------------------------------------------------------------
+    def _fast(self):
+        return (not self.training) and (not torch.is_grad_enabled())
+
+    def _bn_act(self, bn: nn.BatchNorm1d, x, act=True):
+        """BatchNorm1d (+ SiLU).  Inference: one fused kernel on the folded affine."""
+        if self._fast():
+            key = id(bn)
+            ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version)
+            hit = self._folded.get(key)
+            if hit is None or hit[0] != ver:
+                scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+                shift = bn.bias.detach() - bn.running_mean * scale
+                hit = (ver, scale.contiguous(), shift.contiguous())
+                self._folded[key] = hit
+            return ops.affine_act(x.contiguous(), hit[1], hit[2], 1 if act else 0)
+        y = bn(x)
+        return F.silu(y) if act else y
+
+    def _point_block(self, pb: PointBlock, z1, z):
+        return z1 + pb.conv[2](self._bn_act(pb.conv[0], z))
+
+    def _attention(self, blk: SparseAttention, x, geo: Geometry, s):
+        dense_idx, mask, nb, nmax = geo.dense_layout(s)
+        C = x.shape[1]
+        h = blk.attn.num_heads
+        dense = x.new_zeros((nb * nmax, C)).index_copy_(0, dense_idx, x).view(nb, nmax, C)
+        y = blk.norm1(dense)
+        qkv = blk.attn.qkv(y).view(nb, nmax, 3, h, C // h).permute(2, 0, 3, 1, 4)
+        o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=mask[:, None, None, :])
+        o = blk.attn.proj(o.transpose(1, 2).reshape(nb, nmax, C))
+        return (dense + o).view(nb * nmax, C).index_select(0, dense_idx)
+
+    def _res_block(self, blk: EmbResBlock, x_in, emb_act, geo: Geometry, s):
+        lv = geo.level(s)
+        x = blk.conv1[2](self._bn_act(blk.conv1[0], x_in), lv.kmap3)
+        tt = blk.t_emb.proj_mlp(emb_act)                                    # [B, 2C]
+        if self._fast():
+            x = ops.film(x, tt.contiguous(), lv.coords)
+        else:
+            scale, shift = torch.chunk(tt[geo.batch_index(s)], 2, dim=-1)
+            x = (1 + scale) * x + shift
+        x = blk.conv2[2](self._bn_act(blk.conv2[0], x), lv.kmap3)
+        x = x + (blk.idconv(x_in) if hasattr(blk, "idconv") else x_in)
+        if hasattr(blk, "attn"):
+            x = self._attention(blk.attn, x, geo, s)
+        return x
+
+    # -- forward -------------------------------------------------------------------------------
+    def plan_geometry(self, coords: torch.Tensor, n_batch: int) -> Geometry:
+        p = self._plan
+        return Geometry(coords.float() if coords.dtype != torch.float32 else coords, self.pres, self.voxel_size,
+                        strides=p["strides"], p2v_strides=p["p2v"], devox_strides=p["devox"], n_batch=n_batch,
+                        downsample_mode=self.downsample_mode, scale_mode=self.scale_mode)
+
+    def forward(self, inp, geometry: Geometry = None):
+        x_in, t = inp[0], inp[1]
+        coords, feats = (x_in.C, x_in.F) if isinstance(x_in, SparseTensor) or hasattr(x_in, "C") else x_in
+        if not feats.is_cuda:
+            raise RuntimeError("spvd_b200.SPVUnet runs on CUDA only (no CPU fallback)")
+        geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0])
+        # timestep embedding (models/utils.py:15-19; linspace(0,1,d/2) includes 1.0) + MLP
+        exponent = -math.log(10000) * torch.linspace(0, 1, self.n_temb // 2, device=t.device)
+        e = t[:, None].float() * exponent.exp()[None, :]
+        e = torch.cat([e.sin(), e.cos()], dim=-1)
+        emb = self.emb_mlp[0][2](F.silu(self.emb_mlp[0][0](e)))
+        emb = self.emb_mlp[1][1](F.silu(emb))
+        emb_act = F.silu(emb)                      # every TimeEmbeddingBlock starts with SiLU(emb)
+
+        def v2p(x, s):
+            idx8, w8 = geo.devox[s]
+            return SF.devoxelize(x, idx8, w8)
+
+        def p2v(zf, s):
+            return SF.scatter_mean(zf, geo.p2v[s], geo.level(s).n)
+
+        z = feats.contiguous().float()
+        s = 1
+        x = p2v(z, 1)                                                        # initial_voxelize
+        st = self.stem_conv
+        x = st.voxel_conv[0](x, geo.level(1).kmap3)
+        x = self._bn_act(st.voxel_conv[1], x)
+        x = st.voxel_conv[3](x, geo.level(1).kmap3)
+        z = self._point_block(st.point_conv, v2p(x, 1), z)
+        x = p2v(z, 1)
+        saved = [x]
+        for stage in self.down_stages:
+            for blk in stage.downs:
+                for r in blk.resnets:
+                    x = self._res_block(r, x, emb_act, geo, s)
+                    saved.append(x)
+                if blk.add_down:
+                    x = blk.down(x, geo.level(s).kmap_down)
+                    s *= 2
+                    saved.append(x)
+                else:
+                    x = blk.down(x, None)
+            z = self._point_block(stage.point_block, v2p(x, s), z)
+            x = p2v(z, s)
+        for si, stage in enumerate(self.up_stages):
+            for blk in stage.ups:
+                for r in blk.resnets:
+                    x = self._res_block(r, torch.cat([x, saved.pop()], dim=1), emb_act, geo, s)
+                if blk.add_up:
+                    s //= 2
+                    x = blk.up(x, geo.level(s).kmap_up)
+                else:
+                    x = blk.up(x, None)
+            z = self._point_block(stage.point_block, v2p(x, s), z)
+            if si + 1 < len(self.up_stages):
+                x = p2v(z, s)            # the reference's last point_to_voxel is dead work (models/spvd.py:269)
+        return self.out_conv[2](self._bn_act(self.out_conv[0], z))
+
+
+# models/__init__.py:9-38
+PRESETS = {
+    "SPVD": dict(point_channels=3, voxel_size=0.1, num_layers=1, pres=1e-5,
+                 down_blocks=[[(32, 64, 128, 192, 192, 256), (True, True, True, True, False), (None, None, None, 8, 8)]],
+                 up_blocks=[[(256, 192, 192), (True, True), (8, 8), (3, 3)],
+                            [(192, 128, 64, 32), (True, True, False), (None, None, None), (3, 3, 3)]]),
+    "SPVD_L": dict(point_channels=3, voxel_size=0.1, num_layers=1, pres=1e-5,
+                   down_blocks=[[(64, 128, 192, 256, 384, 384), (True, True, True, True, False), (None, None, None, 8, 8)]],
+                   up_blocks=[[(384, 384, 256), (True, True), (8, 8), (3, 3)],
+                              [(256, 192, 128, 64), (True, True, False), (None, None, None), (3, 3, 3)]]),
+    "SPVD_TINY": dict(point_channels=3, voxel_size=0.1, num_layers=1, pres=1e-5,
+                      down_blocks=[[(32, 32, 64, 64), (True, True, False), (None, 4, 4)]],
+                      up_blocks=[[(64, 64), (True,), (4,), (3,)],
+                                 [(64, 32, 32), (True, False), (None, None), (3, 3)]]),
+}
+
+
+def build_model(preset="SPVD", **overrides) -> SPVUnet:
+    cfg = dict(PRESETS[preset])
+    cfg.update(overrides)
+    return SPVUnet(**cfg)

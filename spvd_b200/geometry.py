@@ -1,0 +1,157 @@
+"""Coordinate-only state of one forward pass: voxel levels, hash tables, kernel maps, point<->voxel
+indices and trilinear weights -- everything the reference caches lazily in ``_caches``
+(models/sparse_utils.py:71,90,122-125 and torchsparse's kmaps/cmaps) -- built up front on the GPU.
+
+None of it depends on features, so the whole pyramid is enqueued back to back with device-side
+sizes (every buffer has the point count as its upper bound) and the host reads the level sizes
+ONCE.  The reference synchronises at every torch.unique / scatter_mean / kernel-map build
+(SURVEY.md section 3.1).
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+
+
+class KernelMap:
+    """Offset-major map [kvol, ld] (+ per-128-row-tile offset mask) of one sparse convolution and the
+    map of its data gradient."""
+
+    __slots__ = ("map_t", "mask", "n_out", "n_in", "kvol", "grad", "flip")
+
+    def __init__(self, map_t, mask, n_out, n_in, kvol, flip):
+        self.map_t, self.mask, self.n_out, self.n_in, self.kvol, self.flip = map_t, mask, n_out, n_in, kvol, flip
+        self.grad = None   # KernelMap that produces d(in) from d(out)
+
+
+class Level:
+    def __init__(self, stride, coords, n_dev):
+        self.stride, self.coords_cap, self.n_dev = stride, coords, n_dev
+        self.n = None
+        self.table = None
+        self._kmap3_raw = None
+        self._down_raw = None
+        self.kmap3 = None          # KernelMap, k=3 submanifold
+        self.kmap_down = None      # KernelMap, this level -> 2*stride (k=2, s=2)
+        self.kmap_up = None        # KernelMap, 2*stride -> this level (transposed)
+        self.batch_counts = None   # int32 [B] (device)
+        self.batch_counts_host = None
+
+    @property
+    def coords(self):
+        return self.coords_cap[: self.n]
+
+
+class Geometry:
+    def __init__(self, pc: torch.Tensor, pres: float, voxel_size: float, strides=(1, 2, 4, 8, 16),
+                 k3_strides=None, p2v_strides=(1,), devox_strides=(1,), n_batch=None,
+                 downsample_mode="spconv", scale_mode="mul"):
+        """pc: float32 [Np,4] = (batch, x, y, z) point coordinates in units of ``pres`` (x.C.float(),
+        models/spvd.py:436)."""
+        if not pc.is_cuda:
+            raise RuntimeError("spvd_b200.Geometry needs CUDA tensors (no CPU fallback)")
+        dev = pc.device
+        np_ = pc.shape[0]
+        self.n_points = np_
+        self.mode = downsample_mode
+        k3_strides = strides if k3_strides is None else k3_strides
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        ws = torch.empty(max(ops.lib.spvd_unique_workspace_bytes(np_), 1), dtype=torch.uint8, device=dev)
+        ld = ops.round128(np_)
+        # V1: coordinates of the points at stride 1, voxel set, point -> voxel index
+        self.fcoords, icoords = ops.point_voxel_coords(pc, pres, voxel_size, scale_mode)
+        coords, cnt = ops.unique_coords(icoords, None, self.status, ws)
+        self.levels = {}
+        lv = Level(1, coords, cnt)
+        lv.table = ops.HashTable(2 * np_, dev).build(coords, cnt, status=self.status)
+        self.levels[1] = lv
+        idx1 = ops.point_voxel_query(self.fcoords, 1, lv.table)      # == sphashquery(new_int_coord, sparse_coord)
+        self.p2v = {1: idx1}
+        # K2: the coarser levels
+        prev = lv
+        for s in strides:
+            if s == 1:
+                continue
+            assert s == 2 * prev.stride, "strides must be consecutive powers of two"
+            c2, n2 = ops.downsample_coords(prev.coords_cap, prev.n_dev, downsample_mode, self.status, ws)
+            cur = Level(s, c2, n2)
+            cur.table = ops.HashTable(2 * np_, dev).build(c2, n2, status=self.status)
+            prev._down_raw = ops.kmap_down2(prev.coords_cap, prev.n_dev, cur.table, ld)
+            self.levels[s] = cur
+            prev = cur
+        # K1
+        for s in k3_strides:
+            l = self.levels[s]
+            l._kmap3_raw = ops.kmap_subm3(l.coords_cap, l.n_dev, l.table, ld)
+        # V2 / V3 queries
+        for s in p2v_strides:
+            if s not in self.p2v:
+                self.p2v[s] = ops.point_voxel_query(self.fcoords, s, self.levels[s].table)
+        self.devox = {s: ops.devox_query(self.fcoords, s, self.levels[s].table) for s in devox_strides}
+        # misses go to row 0 (idx_query.clamp_(0), models/sparse_utils.py:93)
+        for s in self.p2v:
+            self.p2v[s].clamp_(min=0)
+        if n_batch is not None:
+            for l in self.levels.values():
+                l.batch_counts = ops.batch_counts(l.coords_cap, l.n_dev, n_batch)
+        # ---- the one host synchronisation of the forward: level sizes (+ per-cloud counts, status)
+        order = sorted(self.levels)
+        parts = [self.levels[s].n_dev for s in order] + [self.status]
+        if n_batch is not None:
+            parts += [self.levels[s].batch_counts for s in order]
+        host = torch.cat(parts).cpu()
+        sizes = host[: len(order)].tolist()
+        st = int(host[len(order)])
+        if st:
+            raise RuntimeError("spvd_b200: " + ("coordinate outside the packed 16-bit range; " if st & 1 else "") +
+                               ("hash table full" if st & 2 else ""))
+        for i, s in enumerate(order):
+            l = self.levels[s]
+            l.n = int(sizes[i])
+            if l.n == 0:
+                raise RuntimeError(f"empty voxel level at tensor stride {s} (downsample_mode={downsample_mode!r}); "
+                                   "the reference crashes here too (experiments/ConditionalGeneration.ipynb:421)")
+            if n_batch is not None:
+                o = len(order) + 1 + i * n_batch
+                l.batch_counts_host = host[o: o + n_batch].tolist()
+        for s in order:
+            l = self.levels[s]
+            if l._kmap3_raw is not None:
+                m, k = l._kmap3_raw
+                l.kmap3 = KernelMap(m, k, l.n, l.n, 27, flip=True)
+                l.kmap3.grad = l.kmap3
+            if l._down_raw is not None:
+                md, kd, mu, ku, _, _ = l._down_raw
+                c = self.levels[2 * s]
+                l.kmap_down = KernelMap(md, kd, c.n, l.n, 8, flip=False)
+                l.kmap_up = KernelMap(mu, ku, l.n, c.n, 8, flip=False)
+                l.kmap_down.grad, l.kmap_up.grad = l.kmap_up, l.kmap_down
+
+    def level(self, s):
+        return self.levels[s]
+
+    # ---- derived index tensors (geometry only, cached per level) --------------------------------
+    def batch_index(self, s):
+        lv = self.levels[s]
+        if getattr(lv, "_batch_index", None) is None:
+            lv._batch_index = lv.coords[:, 0].long()
+        return lv._batch_index
+
+    def dense_layout(self, s):
+        """Row -> slot map of the padded [B, Nmax] layout that the reference builds with
+        torch_geometric.utils.to_dense_batch (models/modules/transformer.py:12-15,118-125); rows are
+        batch-major so slot = batch * Nmax + (row - first row of the batch).  No host sync: Nmax came
+        with the level sizes."""
+        lv = self.levels[s]
+        if getattr(lv, "_dense", None) is None:
+            if lv.batch_counts is None:
+                raise RuntimeError("Geometry was built without n_batch; attention needs per-cloud counts")
+            counts = lv.batch_counts.long()
+            nb, nmax = counts.shape[0], max(1, max(lv.batch_counts_host))
+            start = torch.cumsum(counts, 0) - counts
+            b = self.batch_index(s)
+            pos = torch.arange(lv.n, device=b.device) - start[b]
+            mask = torch.arange(nmax, device=b.device)[None, :] < counts[:, None]
+            lv._dense = (b * nmax + pos, mask, nb, nmax)
+        return lv._dense

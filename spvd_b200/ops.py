@@ -1,0 +1,242 @@
+"""Thin torch-tensor wrappers over the C ABI (one function per entry point of include/spvd_b200.h).
+
+torch is plumbing here: it owns device memory and the stream; every byte of arithmetic happens in
+libspvd_b200.so.  All wrappers require CUDA tensors -- there is no CPU path in the product.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+
+from ._C import check, lib
+
+SCALE_MUL, SCALE_DIV = 0, 1
+DOWNSAMPLE_SPCONV, DOWNSAMPLE_FLOOR = 0, 1
+ORDER_BXYZ, ORDER_XYZB = 0, 1
+CONV_AUTO, CONV_SIMT, CONV_UMMA = 0, 1, 2
+STATUS_COORD_RANGE, STATUS_HASH_FULL = 1, 2
+
+_DOWNSAMPLE = {"spconv": DOWNSAMPLE_SPCONV, "floor": DOWNSAMPLE_FLOOR}
+_SCALE = {"mul": SCALE_MUL, "div": SCALE_DIV}
+
+
+def _p(t, dtype=None):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("spvd_b200 ops need CUDA tensors (there is no CPU fallback)")
+    if not t.is_contiguous():
+        raise RuntimeError("spvd_b200 ops need contiguous tensors")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"expected {dtype}, got {t.dtype}")
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _s():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def round128(n: int) -> int:
+    return max(128, (n + 127) // 128 * 128)
+
+
+# ------------------------------------------------------------------------------------ coordinates
+def point_voxel_coords(pc, init_res, after_res, scale_mode="mul", want_int=True):
+    n = pc.shape[0]
+    f = torch.empty_like(pc)
+    i = torch.empty((n, 4), dtype=torch.int32, device=pc.device) if want_int else None
+    check(lib.spvd_point_voxel_coords(_p(pc, torch.float32), n, init_res, after_res, _SCALE[scale_mode], _p(f), _p(i), _s()))
+    return f, i
+
+
+def unique_coords(icoords, n_dev=None, status=None, workspace=None):
+    """-> (coords [n_cap,4] sorted, count int32[1]) ; sizes stay on the device"""
+    n_cap = icoords.shape[0]
+    out = torch.empty((n_cap, 4), dtype=torch.int32, device=icoords.device)
+    cnt = torch.empty(1, dtype=torch.int32, device=icoords.device)
+    nbytes = lib.spvd_unique_workspace_bytes(n_cap)
+    ws = workspace if workspace is not None and workspace.numel() >= nbytes else torch.empty(nbytes, dtype=torch.uint8, device=icoords.device)
+    check(lib.spvd_unique_coords(_p(icoords, torch.int32), n_cap, _p(n_dev), _p(out), _p(cnt), _p(status), _p(ws),
+                                 ws.numel(), _s()))
+    return out, cnt
+
+
+def downsample_coords(coords, n_dev=None, mode="spconv", status=None, workspace=None):
+    n_cap = coords.shape[0]
+    out = torch.empty((n_cap, 4), dtype=torch.int32, device=coords.device)
+    cnt = torch.empty(1, dtype=torch.int32, device=coords.device)
+    nbytes = lib.spvd_downsample_workspace_bytes(n_cap)
+    ws = workspace if workspace is not None and workspace.numel() >= nbytes else torch.empty(nbytes, dtype=torch.uint8, device=coords.device)
+    check(lib.spvd_downsample_coords(_p(coords, torch.int32), n_cap, _p(n_dev), _DOWNSAMPLE[mode], _p(out), _p(cnt),
+                                     _p(status), _p(ws), ws.numel(), _s()))
+    return out, cnt
+
+
+class HashTable:
+    """keys int64[capacity] + vals int32[capacity]; values are row+1, 0 = absent."""
+
+    def __init__(self, capacity, device):
+        self.capacity = int(capacity)
+        self.keys = torch.empty(self.capacity, dtype=torch.int64, device=device)
+        self.vals = torch.empty(self.capacity, dtype=torch.int32, device=device)
+
+    def build(self, coords, n_dev=None, order=ORDER_BXYZ, status=None):
+        check(lib.spvd_hash_build(_p(coords, torch.int32), coords.shape[0], _p(n_dev), order, _p(self.keys), _p(self.vals),
+                                  self.capacity, _p(status), _s()))
+        return self
+
+    def query(self, q, kernel_size=1, order=ORDER_BXYZ):
+        """-> int32 [m, kernel_size^3], 1-based rows, 0 = absent"""
+        m = q.shape[0]
+        out = torch.empty((m, kernel_size ** 3), dtype=torch.int32, device=q.device)
+        check(lib.spvd_hash_query(_p(q, torch.int32), m, order, kernel_size, _p(self.keys), _p(self.vals), self.capacity,
+                                  _p(out), _s()))
+        return out
+
+
+def kmap_subm3(coords, n_dev, table: HashTable, ld=None):
+    n_cap = coords.shape[0]
+    ld = ld or round128(n_cap)
+    map_t = torch.empty((27, ld), dtype=torch.int32, device=coords.device)
+    mask = torch.empty(ld // 128, dtype=torch.int32, device=coords.device)
+    check(lib.spvd_kmap_subm3(_p(coords, torch.int32), n_cap, _p(n_dev), _p(table.keys), _p(table.vals), table.capacity,
+                              _p(map_t), ld, _p(mask), _s()))
+    return map_t, mask
+
+
+def kmap_down2(fine_coords, n_fine_dev, coarse_table: HashTable, ld_coarse, want_parent=False):
+    n_cap = fine_coords.shape[0]
+    dev = fine_coords.device
+    ld_fine = round128(n_cap)
+    md = torch.empty((8, ld_coarse), dtype=torch.int32, device=dev)
+    mu = torch.empty((8, ld_fine), dtype=torch.int32, device=dev)
+    kd = torch.empty(ld_coarse // 128, dtype=torch.int32, device=dev)
+    ku = torch.empty(ld_fine // 128, dtype=torch.int32, device=dev)
+    parent = torch.empty(n_cap, dtype=torch.int32, device=dev) if want_parent else None
+    koff = torch.empty(n_cap, dtype=torch.int32, device=dev) if want_parent else None
+    check(lib.spvd_kmap_down2(_p(fine_coords, torch.int32), n_cap, _p(n_fine_dev), _p(coarse_table.keys),
+                              _p(coarse_table.vals), coarse_table.capacity, _p(md), ld_coarse, _p(kd), _p(mu), ld_fine,
+                              _p(ku), _p(parent), _p(koff), _s()))
+    return md, kd, mu, ku, parent, koff
+
+
+def batch_counts(coords, n_dev, nb):
+    out = torch.empty(nb, dtype=torch.int32, device=coords.device)
+    check(lib.spvd_batch_counts(_p(coords, torch.int32), coords.shape[0], _p(n_dev), nb, _p(out), _s()))
+    return out
+
+
+def point_voxel_query(fcoords, stride, table: HashTable):
+    n = fcoords.shape[0]
+    idx = torch.empty(n, dtype=torch.int32, device=fcoords.device)
+    check(lib.spvd_point_voxel_query(_p(fcoords, torch.float32), n, int(stride), _p(table.keys), _p(table.vals),
+                                     table.capacity, _p(idx), _s()))
+    return idx
+
+
+def devox_query(fcoords, stride, table: HashTable):
+    n = fcoords.shape[0]
+    idx8 = torch.empty((n, 8), dtype=torch.int32, device=fcoords.device)
+    w8 = torch.empty((n, 8), dtype=torch.float32, device=fcoords.device)
+    check(lib.spvd_devox_query(_p(fcoords, torch.float32), n, int(stride), _p(table.keys), _p(table.vals), table.capacity,
+                               _p(idx8), _p(w8), _s()))
+    return idx8, w8
+
+
+# --------------------------------------------------------------------------------- point <-> voxel
+def scatter_mean_fwd(src, idx, nv):
+    n, c = src.shape
+    out = torch.empty((nv, c), dtype=torch.float32, device=src.device)
+    counts = torch.empty(nv, dtype=torch.float32, device=src.device)
+    check(lib.spvd_scatter_mean_fwd(_p(src, torch.float32), _p(idx, torch.int32), n, c, _p(out), _p(counts), nv, _s()))
+    return out, counts
+
+
+def scatter_mean_bwd(gout, idx, counts, n):
+    c = gout.shape[1]
+    gsrc = torch.empty((n, c), dtype=torch.float32, device=gout.device)
+    check(lib.spvd_scatter_mean_bwd(_p(gout, torch.float32), _p(idx, torch.int32), _p(counts, torch.float32), n, c,
+                                    _p(gsrc), _s()))
+    return gsrc
+
+
+def devoxelize_fwd(feats, idx8, w8):
+    n, c = idx8.shape[0], feats.shape[1]
+    out = torch.empty((n, c), dtype=torch.float32, device=feats.device)
+    check(lib.spvd_devoxelize_fwd(_p(feats, torch.float32), _p(idx8, torch.int32), _p(w8, torch.float32), n, c, _p(out), _s()))
+    return out
+
+
+def devoxelize_bwd(gout, idx8, w8, nv):
+    n, c = gout.shape
+    g = torch.empty((nv, c), dtype=torch.float32, device=gout.device)
+    check(lib.spvd_devoxelize_bwd(_p(gout, torch.float32), _p(idx8, torch.int32), _p(w8, torch.float32), n, c, _p(g), nv, _s()))
+    return g
+
+
+# --------------------------------------------------------------------------------------- conv
+def umma_supported(kvol, cin, cout):
+    return bool(lib.spvd_conv_umma_supported(kvol, cin, cout))
+
+
+def pack_weights(w3):
+    """w3 [kvol, cin, cout] -> tensor-core tile image (same element count)"""
+    kvol, cin, cout = w3.shape
+    wp = torch.empty(kvol * cin * cout, dtype=torch.float32, device=w3.device)
+    check(lib.spvd_conv_pack_weights(_p(w3, torch.float32), kvol, cin, cout, _p(wp), _s()))
+    return wp
+
+
+def transpose_weights(w3, flip):
+    kvol, cin, cout = w3.shape
+    wt = torch.empty((kvol, cout, cin), dtype=torch.float32, device=w3.device)
+    check(lib.spvd_conv_transpose_weights(_p(w3, torch.float32), kvol, cin, cout, int(flip), _p(wt), _s()))
+    return wt
+
+
+def conv_fwd(x, w3, w_packed, map_t, mask, n_out, bias=None, impl=CONV_AUTO, bn=0):
+    """x [n_in, cin]; w3 [kvol, cin, cout] (may be None when w_packed is given and the UMMA path applies);
+    map_t [kvol, ld] or None (identity)."""
+    if w3 is not None:
+        kvol, cin, cout = w3.shape
+    else:
+        raise RuntimeError("conv_fwd needs the weight tensor for its shape")
+    out = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
+    ld = map_t.shape[1] if map_t is not None else 0
+    if impl == CONV_UMMA or (impl == CONV_AUTO and w_packed is not None and umma_supported(kvol, cin, cout)):
+        check(lib.spvd_conv_fwd_umma(_p(x, torch.float32), _p(w_packed, torch.float32), _p(map_t), ld, _p(mask), n_out, kvol,
+                                     cin, cout, _p(bias), _p(out), int(bn), _s()))
+    else:
+        check(lib.spvd_conv_fwd_simt(_p(x, torch.float32), _p(w3, torch.float32), _p(map_t), ld, _p(mask), n_out, kvol, cin,
+                                     cout, _p(bias), _p(out), _s()))
+    return out
+
+
+def conv_wgrad(x, gout, map_t, n_out, kvol):
+    cin, cout = x.shape[1], gout.shape[1]
+    gw = torch.empty((kvol, cin, cout), dtype=torch.float32, device=x.device)
+    ld = map_t.shape[1] if map_t is not None else 0
+    check(lib.spvd_conv_wgrad(_p(x, torch.float32), _p(gout, torch.float32), _p(map_t), ld, n_out, kvol, cin, cout, _p(gw), _s()))
+    return gw
+
+
+def round_tf32(x):
+    y = torch.empty_like(x)
+    check(lib.spvd_round_tf32(_p(x, torch.float32), _p(y), x.numel(), _s()))
+    return y
+
+
+# ----------------------------------------------------------------------------------- fused glue
+def affine_act(x, scale, shift, act=1):
+    rows, c = x.shape
+    y = torch.empty_like(x)
+    check(lib.spvd_bn_silu_fwd(_p(x, torch.float32), _p(scale, torch.float32), _p(shift, torch.float32), rows, c, act, _p(y), _s()))
+    return y
+
+
+def film(x, tt, coords):
+    rows, c = x.shape
+    y = torch.empty_like(x)
+    check(lib.spvd_film_fwd(_p(x, torch.float32), _p(tt, torch.float32), _p(coords, torch.int32), rows, c, _p(y), _s()))
+    return y

@@ -1,0 +1,314 @@
+"""GPU parity tests, op by op: the CUDA path (through the C ABI, via spvd_b200.ops) against the CPU
+oracle on the same seeded inputs.  Integer results (coordinates, indices, kernel maps) must be
+bit-exact; fp32 features within 1e-5 relative (plain fp32 kernels) or 1e-3 (TF32 tensor-core conv,
+the tolerance BASELINE.json states), and within 2e-5 of the oracle that emulates TF32 rounding."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def sp():
+    import spvd_b200
+    return spvd_b200
+
+
+def dev(a, dtype=None):
+    t = torch.as_tensor(np.ascontiguousarray(a))
+    if dtype is not None:
+        t = t.to(dtype)
+    return t.cuda().contiguous()
+
+
+def random_coords(n, nb, extent, seed, lo=0):
+    rng = np.random.default_rng(seed)
+    c = np.empty((n, 4), dtype=np.int32)
+    c[:, 0] = rng.integers(0, nb, n)
+    c[:, 1:] = rng.integers(lo, lo + extent, (n, 3))
+    return c
+
+
+def cloud_points(B, N, seed):
+    """integer point coordinates (b,x,y,z) at 1e-5 resolution like utils/schedulers.py:249-257"""
+    from oracle import model as om
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.randn(B, N, 3, generator=g).clamp(-3, 3)
+    coords, feats, _ = om.torch2sparse(pts)
+    return coords, feats
+
+
+# ------------------------------------------------------------------------------------------ V1
+@pytest.mark.parametrize("mode", ["mul", "div"])
+def test_point_voxel_coords_rounding(sp, mode):
+    from oracle import ops as oo
+    c = np.concatenate([np.arange(0, 900001, 10000), np.arange(0, 900001, 10000) - 1,
+                        np.random.default_rng(0).integers(0, 900000, 50000)]).clip(0).astype(np.float32)
+    n = len(c) // 3 * 3
+    pc = np.zeros((n // 3, 4), dtype=np.float32)
+    pc[:, 1:] = c[:n].reshape(-1, 3)
+    pc[:, 0] = np.arange(n // 3) % 7
+    f, i = sp.ops.point_voxel_coords(dev(pc), 1e-5, 0.1, mode)
+    want = oo.scale_point_coords(pc[:, 1:], 1e-5, 0.1, mode)
+    assert np.array_equal(f.cpu().numpy()[:, 1:], want)            # bit-exact fp32
+    assert np.array_equal(i.cpu().numpy()[:, 1:], np.floor(want).astype(np.int32))
+    assert np.array_equal(i.cpu().numpy()[:, 0], pc[:, 0].astype(np.int32))
+
+
+# ------------------------------------------------------------------------------- unique / sort
+@pytest.mark.parametrize("n,nb,extent,lo", [(1, 1, 4, 0), (37, 2, 3, -1), (4096, 3, 12, -5), (4097, 4, 40, 0),
+                                            (100000, 32, 61, 0), (300000, 5, 700, -300)])
+def test_unique_coords(sp, n, nb, extent, lo):
+    from oracle import ops as oo
+    c = random_coords(n, nb, extent, n, lo)
+    out, cnt = sp.ops.unique_coords(dev(c))
+    want, inv = oo.unique_voxels(c)
+    k = int(cnt.item())
+    assert k == want.shape[0]
+    assert np.array_equal(out[:k].cpu().numpy(), want)
+
+
+def test_unique_coords_device_count_and_range_flag(sp):
+    from oracle import ops as oo
+    c = random_coords(5000, 2, 9, 1)
+    n_dev = torch.tensor([1234], dtype=torch.int32).cuda()
+    status = torch.zeros(1, dtype=torch.int32).cuda()
+    out, cnt = sp.ops.unique_coords(dev(c), n_dev, status)
+    want, _ = oo.unique_voxels(c[:1234])
+    assert int(cnt.item()) == want.shape[0] and np.array_equal(out[: want.shape[0]].cpu().numpy(), want)
+    assert int(status.item()) == 0
+    c[17, 2] = 40000                                       # does not fit the 16-bit packed key
+    sp.ops.unique_coords(dev(c), None, status)
+    assert int(status.item()) & sp.ops.STATUS_COORD_RANGE
+
+
+# ---------------------------------------------------------------------------------------- hash
+@pytest.mark.parametrize("ks", [1, 2, 3])
+def test_hash_query(sp, ks):
+    from oracle import ops as oo
+    target, _ = oo.unique_voxels(random_coords(20000, 4, 25, 5, -3))
+    query = random_coords(30000, 5, 29, 6, -5)
+    tab = sp.ops.HashTable(2 * target.shape[0], "cuda").build(dev(target))
+    got = tab.query(dev(query), ks).cpu().numpy() - 1
+    assert np.array_equal(got, oo.hash_query(query, target, ks))
+    # (x,y,z,b) column order, the way sphashquery passes coordinates (models/sparse_utils.py:44,51)
+    tab2 = sp.ops.HashTable(2 * target.shape[0], "cuda").build(dev(target[:, [1, 2, 3, 0]]), order=sp.ops.ORDER_XYZB)
+    got2 = tab2.query(dev(query[:, [1, 2, 3, 0]]), ks, order=sp.ops.ORDER_XYZB).cpu().numpy() - 1
+    assert np.array_equal(got2, got)
+
+
+def test_kmap_subm3(sp):
+    from oracle import ops as oo
+    vox, _ = oo.unique_voxels(random_coords(50000, 8, 30, 7))
+    n = vox.shape[0]
+    d = dev(vox)
+    tab = sp.ops.HashTable(2 * n, "cuda").build(d)
+    map_t, mask = sp.ops.kmap_subm3(d, None, tab)
+    want = oo.kmap_subm(vox, 3)                              # [n,27]
+    got = map_t.cpu().numpy()
+    assert np.array_equal(got[:, :n].T, want)
+    assert np.all(got[:, n:] == -1)
+    m = mask.cpu().numpy().astype(np.uint32)
+    ld = got.shape[1]
+    pad = np.full((ld, 27), -1, dtype=np.int32)
+    pad[:n] = want
+    bits = ((pad.reshape(ld // 128, 128, 27) >= 0).any(axis=1) * (1 << np.arange(27, dtype=np.uint64))).sum(axis=1)
+    assert np.array_equal(m.astype(np.uint64), bits.astype(np.uint64))
+
+
+@pytest.mark.parametrize("mode", ["spconv", "floor"])
+def test_downsample_and_strided_maps(sp, mode):
+    from oracle import ops as oo
+    fine, _ = oo.unique_voxels(random_coords(40000, 6, 31, 9))
+    n = fine.shape[0]
+    d = dev(fine)
+    coarse, cnt = sp.ops.downsample_coords(d, None, mode)
+    want_c, want_parent, want_koff = oo.downsample_coords(fine, mode)
+    nc = int(cnt.item())
+    assert nc == want_c.shape[0]
+    assert np.array_equal(coarse[:nc].cpu().numpy(), want_c)
+    if mode == "spconv":
+        assert (want_parent < 0).any()                       # the boundary drop really happens in this case
+    tab = sp.ops.HashTable(2 * n, "cuda").build(coarse, cnt)
+    md, kd, mu, ku, parent, koff = sp.ops.kmap_down2(d, None, tab, sp.ops.round128(n), want_parent=True)
+    assert np.array_equal(parent.cpu().numpy(), want_parent)
+    assert np.array_equal(koff.cpu().numpy(), want_koff)
+    want_md = oo.kmap_down(nc, want_parent, want_koff)
+    got_md = md.cpu().numpy()
+    assert np.array_equal(got_md[:, :nc].T, want_md) and np.all(got_md[:, nc:] == -1)
+    want_mu = np.full((n, 8), -1, dtype=np.int32)
+    rows = np.nonzero(want_parent >= 0)[0]
+    want_mu[rows, want_koff[rows]] = want_parent[rows]
+    got_mu = mu.cpu().numpy()
+    assert np.array_equal(got_mu[:, :n].T, want_mu) and np.all(got_mu[:, n:] == -1)
+
+
+def test_empty_level_is_reported(sp):
+    """spconv rule with max coordinate 0 on an axis drops everything: the count
+    comes back 0 and Geometry raises a clear error instead of crashing inside a kernel."""
+    c = np.zeros((50, 4), dtype=np.int32)
+    c[:, 1] = np.arange(50)
+    out, cnt = sp.ops.downsample_coords(dev(c), None, "spconv")
+    assert int(cnt.item()) == 0
+    out, cnt = sp.ops.downsample_coords(dev(c), None, "floor")
+    assert int(cnt.item()) == 25
+
+
+# ------------------------------------------------------------------------------ geometry pyramid
+@pytest.mark.parametrize("mode", ["spconv", "floor"])
+def test_geometry_matches_oracle(sp, mode):
+    from oracle import model as om
+    coords, feats = cloud_points(4, 2048, 3)
+    og = om.Geometry(coords, 1e-5, 0.1, mode, "mul")
+    geo = sp.Geometry(coords.float().cuda(), 1e-5, 0.1, strides=(1, 2, 4, 8, 16), p2v_strides=(1, 4, 16),
+                      devox_strides=(1, 4, 16), n_batch=4, downsample_mode=mode)
+    assert np.array_equal(geo.fcoords.cpu().numpy()[:, 1:], og.fcoords)
+    for s in (1, 2, 4, 8):
+        og.downsample(s)
+    for s in (1, 2, 4, 8, 16):
+        lv = geo.level(s)
+        assert lv.n == og.level(s).n
+        assert np.array_equal(lv.coords.cpu().numpy(), og.level(s).coords)
+        assert np.array_equal(lv.kmap3.map_t.cpu().numpy()[:, : lv.n].T, og.kmap3(s))
+        assert lv.batch_counts_host == np.bincount(og.level(s).coords[:, 0], minlength=4).tolist()
+    for s in (1, 4, 16):
+        assert np.array_equal(geo.p2v[s].cpu().numpy(), og.point_to_voxel_idx(s))
+        idx, w = og.devox_idx_weights(s)
+        assert np.array_equal(geo.devox[s][0].cpu().numpy(), idx.numpy())
+        assert np.allclose(geo.devox[s][1].cpu().numpy(), w.numpy(), atol=2e-7)
+
+
+# ---------------------------------------------------------------------------- point <-> voxel ops
+@pytest.mark.parametrize("c", [3, 32, 192])
+def test_scatter_mean_and_devoxelize(sp, c):
+    from oracle import model as om, ops as oo
+    coords, _ = cloud_points(2, 1024, 5)
+    og = om.Geometry(coords, 1e-5, 0.1, "floor", "mul")
+    og.downsample(1)
+    og.downsample(2)
+    g = torch.Generator().manual_seed(c)
+    n = coords.shape[0]
+    src = torch.randn(n, c, generator=g)
+    idx = torch.from_numpy(og.point_to_voxel_idx(4))
+    nv = og.level(4).n
+    a = src.clone().requires_grad_(True)
+    want = oo.scatter_mean(a, idx, nv)
+    gout = torch.randn(nv, c, generator=g)
+    want.backward(gout)
+    b = src.cuda().requires_grad_(True)
+    got = sp.functional.scatter_mean(b, idx.int().cuda(), nv)
+    got.backward(gout.cuda())
+    assert rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < 1e-6
+    assert rel_err(b.grad.cpu().numpy(), a.grad.numpy()) < 1e-6
+    # devoxelize
+    idx8, w8 = og.devox_idx_weights(4)
+    vf = torch.randn(nv, c, generator=g)
+    a = vf.clone().requires_grad_(True)
+    want = oo.spdevoxelize(a, idx8, w8)
+    gp = torch.randn(n, c, generator=g)
+    want.backward(gp)
+    b = vf.cuda().requires_grad_(True)
+    got = sp.functional.devoxelize(b, idx8.int().cuda().contiguous(), w8.cuda().contiguous())
+    got.backward(gp.cuda())
+    assert rel_err(got.detach().cpu().numpy(), want.detach().numpy()) < 1e-6
+    assert rel_err(b.grad.cpu().numpy(), a.grad.numpy()) < 1e-5
+
+
+# ------------------------------------------------------------------------------------------ conv
+def _conv_case(sp, kind, cin, cout, seed, B=2, N=1024):
+    from oracle import model as om, ops as oo
+    coords, _ = cloud_points(B, N, seed)
+    og = om.Geometry(coords, 1e-5, 0.1, "spconv", "mul")
+    geo = sp.Geometry(coords.float().cuda(), 1e-5, 0.1, strides=(1, 2, 4), p2v_strides=(1,), devox_strides=(1,),
+                      downsample_mode="spconv")
+    g = torch.Generator().manual_seed(seed)
+    if kind == "k3":
+        s = 2
+        og.downsample(1)
+        m, n_in, n_out, kvol, km = og.kmap3(s), og.level(s).n, og.level(s).n, 27, geo.level(s).kmap3
+    elif kind == "down":
+        _, _, _, md, _ = og.downsample(1)
+        m, n_in, n_out, kvol, km = md, og.level(1).n, og.level(2).n, 8, geo.level(1).kmap_down
+    elif kind == "up":
+        _, _, _, _, mu = og.downsample(1)
+        m, n_in, n_out, kvol, km = mu, og.level(2).n, og.level(1).n, 8, geo.level(1).kmap_up
+    else:
+        n_in = n_out = og.level(1).n
+        m, kvol, km = np.arange(n_in, dtype=np.int32)[:, None], 1, None
+    x = torch.randn(n_in, cin, generator=g)
+    w = torch.randn(kvol, cin, cout, generator=g) / (kvol * cin) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1
+    return x, w, b, m, n_out, km, oo
+
+
+SHAPES = [("k3", 32, 32), ("k3", 64, 96), ("k3", 320, 192), ("down", 32, 64), ("up", 256, 192), ("k1", 192, 256),
+          ("k3", 448, 256)]
+
+
+@pytest.mark.parametrize("kind,cin,cout", SHAPES + [("k3", 3, 32), ("k3", 20, 24)])
+def test_conv_forward_simt(sp, kind, cin, cout):
+    x, w, b, m, n_out, km, oo = _conv_case(sp, kind, cin, cout, 11)
+    want = oo.conv_gather_gemm_scatter(x, w, m, n_out, b)
+    got = sp.functional.sparse_conv(x.cuda(), w.cuda() if kind != "k1" else w[0].cuda(), b.cuda(), km, None, sp.ops.CONV_SIMT)
+    assert rel_err(got.cpu().numpy(), want.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("kind,cin,cout", SHAPES)
+def test_conv_forward_tcgen05(sp, kind, cin, cout):
+    x, w, b, m, n_out, km, oo = _conv_case(sp, kind, cin, cout, 13)
+    want = oo.conv_gather_gemm_scatter(x, w, m, n_out, b)
+    want_tf32 = oo.conv_gather_gemm_scatter(x, w, m, n_out, b, emulate_tf32=True)
+    got = sp.functional.sparse_conv(x.cuda(), w.cuda() if kind != "k1" else w[0].cuda(), b.cuda(), km,
+                                    sp.functional.PackedWeight(), sp.ops.CONV_UMMA).cpu().numpy()
+    assert rel_err(got, want_tf32.numpy()) < 2e-5          # same operand rounding as the oracle's emulation
+    assert rel_err(got, want.numpy()) < 1e-3                # BASELINE.json tolerance vs plain fp32
+
+
+@pytest.mark.parametrize("bn", [32, 64, 96, 128, 192])
+def test_conv_tcgen05_slice_widths(sp, bn):
+    x, w, b, m, n_out, km, oo = _conv_case(sp, "k3", 64, 192, 17)
+    want = oo.conv_gather_gemm_scatter(x, w, m, n_out, b, emulate_tf32=True)
+    wp = sp.ops.pack_weights(w.cuda())
+    got = sp.ops.conv_fwd(x.cuda(), w.cuda(), wp, km.map_t, km.mask, n_out, b.cuda(), sp.ops.CONV_UMMA, bn=bn)
+    assert rel_err(got.cpu().numpy(), want.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("impl", ["simt", "umma"])
+@pytest.mark.parametrize("kind,cin,cout", [("k3", 32, 64), ("down", 64, 128), ("up", 128, 64), ("k1", 64, 32)])
+def test_conv_backward(sp, kind, cin, cout, impl):
+    x, w, b, m, n_out, km, oo = _conv_case(sp, kind, cin, cout, 19)
+    g = torch.Generator().manual_seed(1)
+    gout = torch.randn(n_out, cout, generator=g)
+    xa, wa, ba = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    oo.conv_gather_gemm_scatter(xa, wa, m, n_out, ba).backward(gout)
+    xb = x.cuda().requires_grad_(True)
+    wb = (w.cuda() if kind != "k1" else w[0].cuda()).requires_grad_(True)
+    bb = b.cuda().requires_grad_(True)
+    code = sp.ops.CONV_SIMT if impl == "simt" else sp.ops.CONV_AUTO
+    sp.functional.sparse_conv(xb, wb, bb, km, sp.functional.PackedWeight(), code).backward(gout.cuda())
+    tol = 1e-5 if impl == "simt" else 1e-3
+    assert rel_err(xb.grad.cpu().numpy(), xa.grad.numpy()) < tol
+    assert rel_err(wb.grad.cpu().numpy().reshape(wa.shape), wa.grad.numpy()) < 1e-5     # wgrad is fp32 SIMT
+    assert rel_err(bb.grad.cpu().numpy(), ba.grad.numpy()) < 1e-5
+
+
+def test_fused_glue(sp):
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1000, 64, generator=g).cuda()
+    sc, sh = torch.randn(64, generator=g).cuda(), torch.randn(64, generator=g).cuda()
+    want = torch.nn.functional.silu(x * sc + sh)
+    assert rel_err(sp.ops.affine_act(x, sc, sh, 1).cpu().numpy(), want.cpu().numpy()) < 1e-6
+    coords = torch.zeros(1000, 4, dtype=torch.int32)
+    coords[:, 0] = torch.arange(1000) // 250
+    tt = torch.randn(4, 128, generator=g).cuda()
+    b = coords[:, 0].long().cuda()
+    want = (1 + tt[b, :64]) * x + tt[b, 64:]
+    assert rel_err(sp.ops.film(x, tt, coords.cuda()).cpu().numpy(), want.cpu().numpy()) < 1e-6
+
+
+def test_cpu_tensors_are_refused(sp):
+    with pytest.raises(RuntimeError):
+        sp.ops.point_voxel_coords(torch.zeros(4, 4), 1e-5, 0.1)
