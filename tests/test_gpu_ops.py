@@ -267,9 +267,9 @@ def test_conv_forward_tcgen05(sp, kind, cin, cout):
     assert rel_err(got, want.numpy()) < 1e-3                # BASELINE.json tolerance vs plain fp32
 
 
-@pytest.mark.parametrize("bn", [32, 64, 96, 128, 192])
-def test_conv_tcgen05_slice_widths(sp, bn):
-    x, w, b, m, n_out, km, oo = _conv_case(sp, "k3", 64, 192, 17)
+@pytest.mark.parametrize("bn,cout", [(32, 384), (64, 384), (96, 384), (128, 384), (192, 384), (256, 256)])
+def test_conv_tcgen05_slice_widths(sp, bn, cout):
+    x, w, b, m, n_out, km, oo = _conv_case(sp, "k3", 64, cout, 17)
     want = oo.conv_gather_gemm_scatter(x, w, m, n_out, b, emulate_tf32=True)
     wp = sp.ops.pack_weights(w.cuda())
     got = sp.ops.conv_fwd(x.cuda(), w.cuda(), wp, km.map_t, km.mask, n_out, b.cuda(), sp.ops.CONV_UMMA, bn=bn)
