@@ -1,0 +1,335 @@
+#!/usr/bin/env python
+"""bench.py -- SPVD denoise steps/s at B=32 x 2048 points (BASELINE.json metric, configs[1]).
+
+One "step" = one DDPM denoising step of the sampling loop at batch 32 x 2048 points: SPVD forward
+(voxelize -> kernel maps -> sparse convs -> devoxelize) + DDPM update + re-sparsification
+(utils/schedulers.py:148-170,207-212,249-257).  Open-loop replay:
+step j denoises x_t = sqrt(abar_t) x0 + sqrt(1-abar_t) eps for a timestep t spread over 999..0, x0 =
+points on a sphere of radius sqrt(3); with random-init weights the closed loop diverges, the replay
+keeps the voxel occupancy of a real trajectory.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+N > 1 is launched by torchrun (one rank per GPU); sampling shards clouds across ranks with no
+collective (weak scaling: every rank denoises its own 32 x 2048 batch).
+--impl reference times the CPU oracle (oracle/model.py -- the reference's torchsparse path cannot
+run without CUDA and torchsparse is not installable here) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "SPVD denoise steps/s, B=32x2048 pts"
+UNIT = "steps/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--preset", default="SPVD")
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--points", type=int, default=2048)
+    ap.add_argument("--downsample-mode", default="spconv", choices=["spconv", "floor"])
+    ap.add_argument("--cpu-baseline-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-flush", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------- workload
+def make_workload(n_steps, B, N, seed):
+    """Host tensors: per step the noisy cloud x_t [B,N,3] and its timestep."""
+    from spvd_b200.sampler import DDPM
+    strat = DDPM()
+    g = torch.Generator().manual_seed(seed)
+    x0 = torch.randn(B, N, 3, generator=g)
+    x0 = x0 / x0.norm(dim=-1, keepdim=True) * math.sqrt(3.0)
+    xs, ts = [], []
+    for j in range(n_steps):
+        t = int(round(999 - j * 999 / max(1, n_steps - 1))) if n_steps > 1 else 999
+        ah = float(strat.alpha_hat[t])
+        eps = torch.randn(B, N, 3, generator=g)
+        xs.append((math.sqrt(ah) * x0 + math.sqrt(1 - ah) * eps).contiguous())
+        ts.append(t)
+    return strat, xs, ts
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                       "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        time.sleep(0.15)
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [v.strip() for v in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1]))
+                mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+# ---------------------------------------------------------------------------------- B200 arm
+def run_b200(args):
+    import torch.distributed as dist
+    import spvd_b200
+    from spvd_b200 import ops
+    from spvd_b200.sampler import DDPMSparseSchedulerGPU
+    from oracle import model as om          # deterministic random-init weights (names/shapes of the reference)
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N, K, W = args.batch, args.points, args.steps, args.warmup
+    model = spvd_b200.build_model(args.preset, downsample_mode=args.downsample_mode)
+    model.load_state_dict(om.make_state_dict(args.preset, seed=0))
+    model = model.to(dev).eval()
+    sched = DDPMSparseSchedulerGPU()
+    strat, xs, ts = make_workload(K + W, B, N, seed=1234 + rank)
+    shape = (B, N, 3)
+    flush = None if args.no_flush else torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device(x_pts, t, i):
+        st = sched.torch2sparse(x_pts, shape)
+        tb = torch.full((B,), t, device=dev, dtype=torch.long)
+        eps = model((st, tb))
+        new = strat.update(st.F, eps, t, i, lambda s: torch.randn(s, device=dev))
+        return sched.torch2sparse(new, shape)
+
+    # ---- device-resident leg (value)
+    xs_dev = [x.to(dev) for x in xs]
+    with torch.no_grad():
+        for j in range(W):
+            step_device(xs_dev[j], ts[j], j)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clocks = ClockSampler(local) if rank == 0 else None
+        ops.stats.reset(time_convs=True)
+        ev = []
+        torch_launch_guess = 0
+        for j in range(W, W + K):
+            if flush is not None:
+                flush.fill_(j & 0xFF)                  # L2 flush: 256 MiB write between timed steps
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_device(xs_dev[j], ts[j], j)
+            b.record()
+            ev.append((a, b))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        clk = clocks.stop() if clocks else None
+    total_ms = sum(a.elapsed_time(b) for a, b in ev)
+    launches = ops.stats.launches
+    conv_events = ops.stats.conv_events
+    ops.stats.reset(False)
+    if world > 1:
+        tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_ms = float(tt.item())
+
+    # ---- roofline of the dominant kernel (tcgen05 sparse conv), from the events of the timed region
+    roof = None
+    if rank == 0 and conv_events:
+        pairs_cache, flops, ms, n = {}, 0.0, 0.0, 0
+        for a, b, (kvol, cin, cout, n_out, kind, map_t) in conv_events:
+            if kind != "umma":
+                continue
+            if map_t is None:
+                P = n_out
+            else:
+                key = (map_t.data_ptr(), n_out)
+                if key not in pairs_cache:
+                    pairs_cache[key] = int((map_t[:, :n_out] >= 0).sum().item())
+                P = pairs_cache[key]
+            flops += 2.0 * P * cin * cout
+            ms += a.elapsed_time(b)
+            n += 1
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_umma_traffic.json")))["dram_bytes_per_launch"]
+        except Exception:
+            pass
+        ach = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
+        roof = {"bound": "tensor", "kernel": "k_conv_fwd_umma (tcgen05 kind::tf32)", "achieved": round(ach, 2),
+                "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
+                "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained",
+                "note": "TF32 operands: the tensor pipe runs kind::tf32 at half the bf16 rate, so frac <= 0.5 by construction",
+                "launches": n, "avg_launch_us": round(ms * 1e3 / max(n, 1), 2),
+                "algorithmic_gflop_per_step": round(flops / K / 1e9, 1),
+                "conv_share_of_step": round(ms / total_ms, 3) if total_ms else None}
+    conv_events = None
+
+    # ---- end-to-end leg through the public API with host buffers
+    pin_in = [x.pin_memory() for x in xs]
+    pin_out = torch.empty(shape, dtype=torch.float32).pin_memory()
+    with torch.no_grad():
+        for j in range(min(W, 2)):
+            st = sched.torch2sparse(pin_in[j].to(dev, non_blocking=True), shape)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for j in range(W, W + K):
+            x = pin_in[j].to(dev, non_blocking=True)                      # H2D of this step's input
+            st = sched.torch2sparse(x, shape)
+            tb = torch.full((B,), ts[j], device=dev, dtype=torch.long)
+            eps = model((st, tb))
+            new = strat.update(st.F, eps, ts[j], j, lambda s: torch.randn(s, device=dev))
+            pin_out.copy_(new.view(shape), non_blocking=True)             # D2H of the step's result
+            torch.cuda.current_stream().synchronize()                     # the caller owns x_{t-1} on the host
+        e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+
+    out = None
+    if rank == 0:
+        nbytes = B * N * 3 * 4
+        out = {"metric": METRIC, "value": round(world * K / (total_ms * 1e-3), 3), "unit": UNIT, "n_gpus": world,
+               "steps": K, "warmup": W, "ms_per_step": round(total_ms / K, 4), "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core operands, f32 accumulate)",
+               "data": "synthetic",
+               "config": {"workload": f"{args.preset} DDPM sampling step (forward + update + re-sparsify), open-loop replay over t=999..0, "
+                                      f"B={B}x{N} points per GPU, random-init weights, downsample_mode={args.downsample_mode}",
+                          "preset": args.preset, "batch_per_gpu": B, "points": N, "parallelism": f"dp{world} (clouds sharded, no collective)",
+                          "l2": "256 MiB flush write between timed steps" if flush is not None else "no flush (per-step working set > L2)"},
+               "e2e": {"value": round(world * K / e2e_s, 3), "unit": UNIT, "h2d_bytes_per_step": nbytes,
+                       "d2h_bytes_per_step": nbytes},
+               "gpu_launches": launches, "clocks": clk, "roofline": roof}
+    return out, rank, world
+
+
+# -------------------------------------------------------------------------------- CPU oracle arm
+def cpu_steps(args, n_steps, warmup, seed=1234):
+    """The reference algorithm restated on the CPU (oracle/), timed on the host cores."""
+    from oracle import model as om
+    from spvd_b200.sampler import DDPM  # coefficient tables only (pure python/torch-CPU)
+    B, N = args.batch, args.points
+    strat, xs, ts = make_workload(n_steps + warmup, B, N, seed)
+    sd = om.make_state_dict(args.preset, seed=0)
+    times = []
+    with torch.no_grad():
+        for j in range(n_steps + warmup):
+            t0 = time.perf_counter()
+            coords, feats, _ = om.torch2sparse(xs[j])
+            eps = om.forward(sd, args.preset, coords, feats, torch.full((B,), ts[j], dtype=torch.long),
+                             downsample_mode=args.downsample_mode)
+            new = strat.update(feats, eps, ts[j], j, lambda s: torch.randn(s))
+            if new.shape[0] == B * N:
+                om.torch2sparse(new.view(B, N, 3))
+            dt = time.perf_counter() - t0
+            if j >= warmup:
+                times.append(dt)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if rank != 0:
+        return None, rank, world
+    K, W = args.steps, args.warmup
+    times = cpu_steps(args, K, W)
+    total = sum(times)
+    v = round(K / total, 4)
+    cores = torch.get_num_threads()
+    sample = f"{K} full-size steps ({args.preset}, B={args.batch}x{args.points}) of the same open-loop replay, torch-CPU"
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+           "ms_per_step": round(total / K * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "f32", "data": "synthetic",
+           "config": {"workload": f"{args.preset} DDPM sampling step (forward + update + re-sparsify), open-loop replay over t=999..0, "
+                                  f"B={args.batch}x{args.points} points, random-init weights, downsample_mode={args.downsample_mode}",
+                      "preset": args.preset, "batch_per_gpu": args.batch, "points": args.points,
+                      "note": "reference's torchsparse path cannot run on CPU (GPUHashTable, models/sparse_utils.py:43) "
+                              "and torchsparse is not installed: this arm is the CPU oracle port (oracle/model.py)"},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+           "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    return out, rank, world
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        out, rank, world = run_reference(args)
+    else:
+        out, rank, world = run_b200(args)
+        if rank == 0 and world == 1 and not args.no_cpu_baseline:
+            n = max(1, args.cpu_baseline_steps)
+            times = cpu_steps(args, n, 0)
+            out["cpu_baseline"] = {"value": round(n / sum(times), 4), "unit": UNIT, "cores": torch.get_num_threads(),
+                                   "kind": "port",
+                                   "sample": f"{n} full-size steps (t spread over 999..0) of the same workload on the "
+                                             f"CPU oracle (oracle/model.py), os.cpu_count()={os.cpu_count()}"}
+        elif rank == 0:
+            out["cpu_baseline"] = None
+    if rank == 0 and out is not None:
+        print(json.dumps(out), flush=True)
+    if world > 1 and args.impl != "reference":
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -37,12 +37,38 @@ def _s():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+class _Stats:
+    """Kernel-launch accounting (bench.py's ``gpu_launches``) and optional CUDA-event timing of the
+    convolution launches (bench.py's live roofline measurement)."""
+
+    def __init__(self):
+        self.launches = 0
+        self.conv_events = None      # list of (start, end, tag) when enabled
+
+    def reset(self, time_convs=False):
+        self.launches = 0
+        self.conv_events = [] if time_convs else None
+
+
+stats = _Stats()
+# kernels launched by one call of each entry point (memsets are not kernels)
+_K = {"point_voxel_coords": 1, "unique_coords": 22, "downsample_coords": 23, "hash_build": 1, "hash_query": 1,
+      "kmap_subm3": 1, "kmap_down2": 1, "batch_counts": 1, "point_voxel_query": 1, "devox_query": 1,
+      "scatter_mean_fwd": 2, "scatter_mean_bwd": 1, "devoxelize_fwd": 1, "devoxelize_bwd": 1, "pack_weights": 1,
+      "transpose_weights": 1, "conv_fwd": 1, "conv_wgrad": 1, "round_tf32": 1, "affine_act": 1, "film": 1}
+
+
+def _count(name):
+    stats.launches += _K[name]
+
+
 def round128(n: int) -> int:
     return max(128, (n + 127) // 128 * 128)
 
 
 # ------------------------------------------------------------------------------------ coordinates
 def point_voxel_coords(pc, init_res, after_res, scale_mode="mul", want_int=True):
+    _count("point_voxel_coords")
     n = pc.shape[0]
     f = torch.empty_like(pc)
     i = torch.empty((n, 4), dtype=torch.int32, device=pc.device) if want_int else None
@@ -52,6 +78,7 @@ def point_voxel_coords(pc, init_res, after_res, scale_mode="mul", want_int=True)
 
 def unique_coords(icoords, n_dev=None, status=None, workspace=None):
     """-> (coords [n_cap,4] sorted, count int32[1]) ; sizes stay on the device"""
+    _count("unique_coords")
     n_cap = icoords.shape[0]
     out = torch.empty((n_cap, 4), dtype=torch.int32, device=icoords.device)
     cnt = torch.empty(1, dtype=torch.int32, device=icoords.device)
@@ -63,6 +90,7 @@ def unique_coords(icoords, n_dev=None, status=None, workspace=None):
 
 
 def downsample_coords(coords, n_dev=None, mode="spconv", status=None, workspace=None):
+    _count("downsample_coords")
     n_cap = coords.shape[0]
     out = torch.empty((n_cap, 4), dtype=torch.int32, device=coords.device)
     cnt = torch.empty(1, dtype=torch.int32, device=coords.device)
@@ -82,12 +110,14 @@ class HashTable:
         self.vals = torch.empty(self.capacity, dtype=torch.int32, device=device)
 
     def build(self, coords, n_dev=None, order=ORDER_BXYZ, status=None):
+        _count("hash_build")
         check(lib.spvd_hash_build(_p(coords, torch.int32), coords.shape[0], _p(n_dev), order, _p(self.keys), _p(self.vals),
                                   self.capacity, _p(status), _s()))
         return self
 
     def query(self, q, kernel_size=1, order=ORDER_BXYZ):
         """-> int32 [m, kernel_size^3], 1-based rows, 0 = absent"""
+        _count("hash_query")
         m = q.shape[0]
         out = torch.empty((m, kernel_size ** 3), dtype=torch.int32, device=q.device)
         check(lib.spvd_hash_query(_p(q, torch.int32), m, order, kernel_size, _p(self.keys), _p(self.vals), self.capacity,
@@ -96,6 +126,7 @@ class HashTable:
 
 
 def kmap_subm3(coords, n_dev, table: HashTable, ld=None):
+    _count("kmap_subm3")
     n_cap = coords.shape[0]
     ld = ld or round128(n_cap)
     map_t = torch.empty((27, ld), dtype=torch.int32, device=coords.device)
@@ -106,6 +137,7 @@ def kmap_subm3(coords, n_dev, table: HashTable, ld=None):
 
 
 def kmap_down2(fine_coords, n_fine_dev, coarse_table: HashTable, ld_coarse, want_parent=False):
+    _count("kmap_down2")
     n_cap = fine_coords.shape[0]
     dev = fine_coords.device
     ld_fine = round128(n_cap)
@@ -122,12 +154,14 @@ def kmap_down2(fine_coords, n_fine_dev, coarse_table: HashTable, ld_coarse, want
 
 
 def batch_counts(coords, n_dev, nb):
+    _count("batch_counts")
     out = torch.empty(nb, dtype=torch.int32, device=coords.device)
     check(lib.spvd_batch_counts(_p(coords, torch.int32), coords.shape[0], _p(n_dev), nb, _p(out), _s()))
     return out
 
 
 def point_voxel_query(fcoords, stride, table: HashTable):
+    _count("point_voxel_query")
     n = fcoords.shape[0]
     idx = torch.empty(n, dtype=torch.int32, device=fcoords.device)
     check(lib.spvd_point_voxel_query(_p(fcoords, torch.float32), n, int(stride), _p(table.keys), _p(table.vals),
@@ -136,6 +170,7 @@ def point_voxel_query(fcoords, stride, table: HashTable):
 
 
 def devox_query(fcoords, stride, table: HashTable):
+    _count("devox_query")
     n = fcoords.shape[0]
     idx8 = torch.empty((n, 8), dtype=torch.int32, device=fcoords.device)
     w8 = torch.empty((n, 8), dtype=torch.float32, device=fcoords.device)
@@ -146,6 +181,7 @@ def devox_query(fcoords, stride, table: HashTable):
 
 # --------------------------------------------------------------------------------- point <-> voxel
 def scatter_mean_fwd(src, idx, nv):
+    _count("scatter_mean_fwd")
     n, c = src.shape
     out = torch.empty((nv, c), dtype=torch.float32, device=src.device)
     counts = torch.empty(nv, dtype=torch.float32, device=src.device)
@@ -154,6 +190,7 @@ def scatter_mean_fwd(src, idx, nv):
 
 
 def scatter_mean_bwd(gout, idx, counts, n):
+    _count("scatter_mean_bwd")
     c = gout.shape[1]
     gsrc = torch.empty((n, c), dtype=torch.float32, device=gout.device)
     check(lib.spvd_scatter_mean_bwd(_p(gout, torch.float32), _p(idx, torch.int32), _p(counts, torch.float32), n, c,
@@ -162,6 +199,7 @@ def scatter_mean_bwd(gout, idx, counts, n):
 
 
 def devoxelize_fwd(feats, idx8, w8):
+    _count("devoxelize_fwd")
     n, c = idx8.shape[0], feats.shape[1]
     out = torch.empty((n, c), dtype=torch.float32, device=feats.device)
     check(lib.spvd_devoxelize_fwd(_p(feats, torch.float32), _p(idx8, torch.int32), _p(w8, torch.float32), n, c, _p(out), _s()))
@@ -169,6 +207,7 @@ def devoxelize_fwd(feats, idx8, w8):
 
 
 def devoxelize_bwd(gout, idx8, w8, nv):
+    _count("devoxelize_bwd")
     n, c = gout.shape
     g = torch.empty((nv, c), dtype=torch.float32, device=gout.device)
     check(lib.spvd_devoxelize_bwd(_p(gout, torch.float32), _p(idx8, torch.int32), _p(w8, torch.float32), n, c, _p(g), nv, _s()))
@@ -182,6 +221,7 @@ def umma_supported(kvol, cin, cout):
 
 def pack_weights(w3):
     """w3 [kvol, cin, cout] -> tensor-core tile image (same element count)"""
+    _count("pack_weights")
     kvol, cin, cout = w3.shape
     wp = torch.empty(kvol * cin * cout, dtype=torch.float32, device=w3.device)
     check(lib.spvd_conv_pack_weights(_p(w3, torch.float32), kvol, cin, cout, _p(wp), _s()))
@@ -189,6 +229,7 @@ def pack_weights(w3):
 
 
 def transpose_weights(w3, flip):
+    _count("transpose_weights")
     kvol, cin, cout = w3.shape
     wt = torch.empty((kvol, cout, cin), dtype=torch.float32, device=w3.device)
     check(lib.spvd_conv_transpose_weights(_p(w3, torch.float32), kvol, cin, cout, int(flip), _p(wt), _s()))
@@ -202,18 +243,28 @@ def conv_fwd(x, w3, w_packed, map_t, mask, n_out, bias=None, impl=CONV_AUTO, bn=
         kvol, cin, cout = w3.shape
     else:
         raise RuntimeError("conv_fwd needs the weight tensor for its shape")
+    _count("conv_fwd")
     out = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
     ld = map_t.shape[1] if map_t is not None else 0
+    ev = None
+    if stats.conv_events is not None:
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
     if impl == CONV_UMMA or (impl == CONV_AUTO and w_packed is not None and umma_supported(kvol, cin, cout)):
         check(lib.spvd_conv_fwd_umma(_p(x, torch.float32), _p(w_packed, torch.float32), _p(map_t), ld, _p(mask), n_out, kvol,
                                      cin, cout, _p(bias), _p(out), int(bn), _s()))
     else:
         check(lib.spvd_conv_fwd_simt(_p(x, torch.float32), _p(w3, torch.float32), _p(map_t), ld, _p(mask), n_out, kvol, cin,
                                      cout, _p(bias), _p(out), _s()))
+    if ev is not None:
+        ev[1].record()
+        umma = impl == CONV_UMMA or (impl == CONV_AUTO and w_packed is not None and umma_supported(kvol, cin, cout))
+        stats.conv_events.append((ev[0], ev[1], (kvol, cin, cout, n_out, "umma" if umma else "simt", map_t)))
     return out
 
 
 def conv_wgrad(x, gout, map_t, n_out, kvol):
+    _count("conv_wgrad")
     cin, cout = x.shape[1], gout.shape[1]
     gw = torch.empty((kvol, cin, cout), dtype=torch.float32, device=x.device)
     ld = map_t.shape[1] if map_t is not None else 0
@@ -222,6 +273,7 @@ def conv_wgrad(x, gout, map_t, n_out, kvol):
 
 
 def round_tf32(x):
+    _count("round_tf32")
     y = torch.empty_like(x)
     check(lib.spvd_round_tf32(_p(x, torch.float32), _p(y), x.numel(), _s()))
     return y
@@ -229,6 +281,7 @@ def round_tf32(x):
 
 # ----------------------------------------------------------------------------------- fused glue
 def affine_act(x, scale, shift, act=1):
+    _count("affine_act")
     rows, c = x.shape
     y = torch.empty_like(x)
     check(lib.spvd_bn_silu_fwd(_p(x, torch.float32), _p(scale, torch.float32), _p(shift, torch.float32), rows, c, act, _p(y), _s()))
@@ -236,6 +289,7 @@ def affine_act(x, scale, shift, act=1):
 
 
 def film(x, tt, coords):
+    _count("film")
     rows, c = x.shape
     y = torch.empty_like(x)
     check(lib.spvd_film_fwd(_p(x, torch.float32), _p(tt, torch.float32), _p(coords, torch.int32), rows, c, _p(y), _s()))

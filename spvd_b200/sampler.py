@@ -1,0 +1,149 @@
+"""Diffusion sampling loop around the denoiser (the caller of the hot path for BASELINE config 2).
+
+Mirrors the public surface of the reference's schedulers (utils/schedulers.py:64-145,172-278:
+``DDPMSparseSchedulerGPU(...).sample(model, bs, n_points)``, ``sample_step``, ``torch2sparse``,
+``create_noise``, ``update_rule``) with the per-step host work removed: the DDPM coefficients are
+plain floats computed once, the noise is drawn on the device (``rng='cpu'`` reproduces the
+reference's CPU draw + H2D copy, utils/schedulers.py:81), and re-sparsification is a handful of
+sync-free device ops (``order='keep'``; ``order='reference'`` reproduces the reference's
+(batch, ravel-hash) row order and first-occurrence de-duplication, models/sparse_utils.py:217-258,
+at the price of one torch.unique sync).
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+
+from .sparse import SparseTensor
+
+
+class DDPM:
+    """utils/schedulers.py:38-89 (linear / 'warm0.1' beta schedules, sigma = sqrt(beta) or the posterior std)."""
+
+    def __init__(self, beta_min=0.0001, beta_max=0.02, n_steps=1000, mode="linear", sigma="bt"):
+        self.n_steps = n_steps
+        if mode == "linear":
+            beta = torch.linspace(beta_min, beta_max, n_steps)
+        elif mode == "warm0.1":
+            beta = beta_max * torch.ones(n_steps)
+            w = int(0.1 * n_steps)
+            beta[:w] = torch.linspace(beta_min, beta_max, w)
+        else:
+            raise NotImplementedError(mode)
+        alpha = 1.0 - beta
+        alpha_hat = torch.cumprod(alpha, dim=0)
+        if sigma == "bt":
+            sig = beta.sqrt()
+        elif sigma == "coef_bt":
+            prev = torch.ones_like(alpha_hat)
+            prev[1:] = alpha_hat[:-1]
+            sig = torch.sqrt(beta * (1 - prev) / (1 - alpha_hat))
+        else:
+            raise ValueError(sigma)
+        self.beta, self.alpha, self.alpha_hat, self.sigma = beta, alpha, alpha_hat, sig
+        self.steps = list(range(n_steps - 1, -1, -1))
+        # x_{t-1} = c1[t] * (x_t - c2[t] * eps) + sigma[t] * z
+        self.c1 = [1.0 / math.sqrt(float(a)) for a in alpha]
+        self.c2 = [float((1 - a) / math.sqrt(1 - ah)) for a, ah in zip(alpha, alpha_hat)]
+        self.sig = [float(s) for s in sig]
+
+    def update(self, x_t, eps, t, i, noise_fn):
+        z = noise_fn(x_t.shape) if t > 0 else None          # no noise on the last step
+        out = (x_t - self.c2[t] * eps) * self.c1[t]
+        return out if z is None else out.add_(z, alpha=self.sig[t])
+
+
+class DDIM(DDPM):
+    """utils/schedulers.py:91-112."""
+
+    def __init__(self, beta_min=0.0001, beta_max=0.02, n_steps=1000, mode="linear", s_steps=100, s_mode="linear"):
+        super().__init__(beta_min, beta_max, n_steps, mode)
+        if s_mode != "linear":
+            raise NotImplementedError(s_mode)
+        inds = torch.floor(torch.linspace(0, n_steps - 1, s_steps + 1)).long()
+        self.prev = list(reversed(inds[:-1].tolist()))
+        self.steps = list(reversed(inds[1:].tolist()))
+
+    def update(self, x_t, eps, t, i, noise_fn):
+        ah, ah1 = float(self.alpha_hat[t]), float(self.alpha_hat[self.prev[i]])
+        return math.sqrt(ah1) * ((x_t - math.sqrt(1 - ah) * eps) / math.sqrt(ah)) + math.sqrt(1 - ah1) * eps
+
+
+def torch2sparse(pts: torch.Tensor, pres: float = 1e-5, order: str = "keep") -> SparseTensor:
+    """[B,N,F] points (xyz first) -> SparseTensor(coords int32 [M,4] = (b, floor((p - min_cloud p)/pres)), feats).
+    Reference: SparseSchedulerGPU.torch2sparse, utils/schedulers.py:249-257."""
+    B, N, Fd = pts.shape
+    c = pts[..., :3]
+    c = c - c.amin(dim=1, keepdim=True)
+    vs = torch.full((3,), pres, device=pts.device, dtype=pts.dtype)
+    ci = torch.floor(c / vs).int()
+    b = torch.arange(B, device=pts.device, dtype=torch.int32).repeat_interleave(N)
+    coords = torch.cat([b.view(-1, 1), ci.view(-1, 3)], dim=1)
+    feats = pts.reshape(-1, Fd)
+    if order == "keep":
+        return SparseTensor(feats.contiguous(), coords.contiguous())
+    if order != "reference":
+        raise ValueError(order)
+    x = (ci - ci.amin(dim=1, keepdim=True)).long()                       # batched_ravel_hash_torch
+    xmax = x.amax(dim=1, keepdim=True) + 1
+    h = (x[..., 0] * xmax[..., 1] + x[..., 1]) * xmax[..., 2] + x[..., 2]
+    key = torch.stack([b.long(), h.reshape(-1)], dim=1)
+    _, inv = torch.unique(key, dim=0, sorted=True, return_inverse=True)
+    perm = torch.arange(inv.shape[0], device=pts.device)
+    first = inv.new_full((int(inv.max()) + 1,), inv.shape[0]).scatter_reduce_(0, inv, perm, "amin")
+    return SparseTensor(feats[first].contiguous(), coords[first].contiguous())
+
+
+class SparseScheduler:
+    def __init__(self, strategy, pres=1e-5, save_process=False, rng="cuda", order="keep"):
+        self.strategy, self.pres, self.save_process, self.rng, self.order = strategy, pres, save_process, rng, order
+
+    def _noise(self, device):
+        if self.rng == "cpu":
+            return lambda shape: torch.randn(shape).to(device)
+        return lambda shape: torch.randn(shape, device=device)
+
+    def torch2sparse(self, pts, shape):
+        return torch2sparse(pts.reshape(shape), self.pres, self.order)
+
+    def create_noise(self, shape, device):
+        noise = self._noise(device)(shape).clamp_(-3, 3)                  # utils/schedulers.py:197-201
+        return self.torch2sparse(noise, shape)
+
+    def get_pc(self, x_t, shape):
+        return x_t.F.detach().cpu().reshape(shape)
+
+    def update_rule(self, x_t, noise_pred, t, i, shape, device):
+        new = self.strategy.update(x_t.F, noise_pred, t, i, self._noise(device))
+        return self.torch2sparse(new, shape)
+
+    def sample_step(self, model, x_t, t, i, emb, shape, device):
+        t_batch = torch.full((shape[0],), t, device=device, dtype=torch.long)
+        noise_pred = model((x_t, t_batch)) if emb is None else model((x_t, t_batch, emb))
+        return self.update_rule(x_t, noise_pred, t, i, shape, device)
+
+    @torch.no_grad()
+    def sample(self, model, bs, n_points=2048, nf=3, emb=None, save_process=False):
+        device = next(model.parameters()).device
+        shape = (bs, n_points, nf)
+        emb = torch.full((bs,), emb, dtype=torch.long, device=device) if emb is not None else None
+        x_t = self.create_noise(shape, device)
+        preds = [self.get_pc(x_t, shape)] if save_process else None
+        for i, t in enumerate(self.strategy.steps):
+            x_t = self.sample_step(model, x_t, t, i, emb, shape, device)
+            if save_process:
+                preds.append(self.get_pc(x_t, shape))
+        return preds if save_process else self.get_pc(x_t, shape)
+
+
+class DDPMSparseSchedulerGPU(SparseScheduler):
+    def __init__(self, beta_min=0.0001, beta_max=0.02, n_steps=1000, mode="linear", sigma="bt", pres=1e-5,
+                 save_process=False, rng="cuda", order="keep"):
+        super().__init__(DDPM(beta_min, beta_max, n_steps, mode, sigma), pres, save_process, rng, order)
+
+
+class DDIMSparseSchedulerGPU(SparseScheduler):
+    def __init__(self, beta_min=0.0001, beta_max=0.02, n_steps=1000, s_steps=100, s_mode="linear", mode="linear",
+                 pres=1e-5, save_process=False, rng="cuda", order="keep"):
+        super().__init__(DDIM(beta_min, beta_max, n_steps, mode, s_steps, s_mode), pres, save_process, rng, order)
