@@ -185,7 +185,20 @@ def run_b200(args):
     roof = None
     if rank == 0 and conv_events:
         pairs_cache, flops, ms, n = {}, 0.0, 0.0, 0
+        table = {}
         for a, b, (kvol, cin, cout, n_out, kind, map_t) in conv_events:
+            if os.environ.get("SPVD_BENCH_VERBOSE"):
+                if map_t is None:
+                    Pv = n_out
+                else:
+                    kk = (map_t.data_ptr(), n_out)
+                    if kk not in pairs_cache:
+                        pairs_cache[kk] = int((map_t[:, :n_out] >= 0).sum().item())
+                    Pv = pairs_cache[kk]
+                e = table.setdefault((kind, kvol, cin, cout, n_out // 2000 * 2000), [0, 0.0, 0.0])
+                e[0] += 1
+                e[1] += a.elapsed_time(b)
+                e[2] += 2.0 * Pv * cin * cout
             if kind != "umma":
                 continue
             if map_t is None:
@@ -198,6 +211,10 @@ def run_b200(args):
             flops += 2.0 * P * cin * cout
             ms += a.elapsed_time(b)
             n += 1
+        for key in sorted(table, key=lambda k: -table[k][1]):
+            c, t_ms, fl = table[key]
+            print(f"[conv] {key} launches={c} total_ms={t_ms:.3f} avg_us={t_ms / c * 1e3:.1f} alg_TFLOPs={fl / (t_ms * 1e-3) / 1e12:.1f}",
+                  file=sys.stderr)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))

@@ -176,10 +176,16 @@ int spvd_conv_fwd(const float* in, const float* w, const float* w_packed, const 
 int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, int ld,
                        const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
                        const float* bias, float* out, spvd_stream_t stream);
-/* bn = output-channel slice width per CTA (32,64,96,128,192,256 dividing cout; 0 = choose) */
+/* bn = output-channel slice width per CTA (32,64,96,128,192,256 dividing cout; 0 = widest);
+ * nsplit = number of CTAs sharing one tile's (offset, 32-channel slab) iterations, partial sums
+ * accumulated with vector RED into the zero-filled output (0 = choose from the grid size);
+ * a_is_tf32 != 0 promises that `in` is already TF32-representable (spvd_round_tf32, or a producer
+ * that rounds, e.g. spvd_bn_silu_fwd with act & 2): the gather then runs as cp.async with kStages
+ * slabs in flight instead of through registers with cvt.rna. */
 int spvd_conv_fwd_umma(const float* in, const float* w_packed, const int32_t* map_t, int ld,
                        const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
-                       const float* bias, float* out, int bn, spvd_stream_t stream);
+                       const float* bias, float* out, int bn, int nsplit, int a_is_tf32,
+                       spvd_stream_t stream);
 /* gw[k] = sum over pairs (i,o) of offset k of in[i]^T gout[o];  gw [kvol,cin,cout] zero-filled inside */
 int spvd_conv_wgrad(const float* in, const float* gout, const int32_t* map_t, int ld, int n_out,
                     int kvol, int cin, int cout, float* gw, spvd_stream_t stream);
@@ -187,7 +193,8 @@ int spvd_conv_wgrad(const float* in, const float* gout, const int32_t* map_t, in
 /* ------------------------------------------------------------------------------------------------
  * C5/M1  inference-time glue fused into single passes
  * spvd_bn_silu_fwd: y = act(x*scale[c] + shift[c]) -- spnn.BatchNorm (eval: scale = w/sqrt(var+eps),
- *     shift = b - mean*scale) followed by spnn.SiLU (act = 1) or nothing (act = 0);
+ *     shift = b - mean*scale) followed by spnn.SiLU (act & 1) or nothing; act & 2 additionally rounds
+ *     y to TF32 (round-to-nearest) so that the following convolution can gather it with cp.async;
  *     reference: models/ddpm_unet_attn.py:24-28, models/spvd.py:36-37.
  * spvd_film_fwd: y[i] = (1 + tt[b_i, c]) * x[i, c] + tt[b_i, C + c], b_i = coords[i].batch, tt [B, 2C];
  *     reference: TimeEmbeddingBlock.message, models/modules/graph.py:35-41.

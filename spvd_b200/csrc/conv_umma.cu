@@ -102,7 +102,23 @@ struct UmmaCfg {
                                      ((uint32_t)(BM >> 4) << 24);
 };
 
-template <int BN>
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+// kAsyncA: the input rows are already TF32-representable (the producing kernel rounded them), so the
+// gather is a zero-register cp.async (LDGSTS) with up to kStages slabs in flight per CTA.  Otherwise the
+// rows go through registers (cvt.rna.tf32) with the next slab's loads issued before the current stores.
+// gridDim.z > 1 = split over the (offset, slab) iterations; partial tiles are accumulated with vector RED
+// into a zero-initialised output (bias added by split 0).
+template <int BN, bool kAsyncA>
 __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __restrict__ in,
                                                                const float* __restrict__ w_packed,
                                                                const int* __restrict__ map_t, int ld,
@@ -125,8 +141,13 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
 
   unsigned mask = kvol >= 32 ? 0xffffffffu : ((1u << kvol) - 1u);
   if (tile_mask) mask &= tile_mask[blockIdx.x];
-  const int n_active = __popc(mask);
-  const int num_iters = n_active * nchunks;
+  const int total_iters = __popc(mask) * nchunks;
+  const int per_split = (total_iters + (int)gridDim.z - 1) / (int)gridDim.z;
+  const int it_begin = min(total_iters, (int)blockIdx.z * per_split);
+  const int it_end = min(total_iters, it_begin + per_split);
+  const int num_iters = it_end - it_begin;
+  const bool split = gridDim.z > 1;
+  if (split && num_iters == 0) return;  // nothing to add (uniform across the CTA, before any barrier/alloc)
 
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -155,40 +176,82 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
     const int chunk16 = tid & 7;  // which 16-byte piece of the 128-byte row
     const int r0 = tid >> 3;      // rows r0 + 16*i
     int rows[8];
-    for (int it = 0; it < num_iters; ++it) {
-      const int stage = it % kStages;
-      const uint32_t parity = (uint32_t)(it / kStages) & 1u;
-      const int ka = it / nchunks, c = it - ka * nchunks;
-      const int k = active_k[ka];
-      if (c == 0) {
+    auto load_rows = [&](int k) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) rows[i] = map_t ? __ldg(map_t + (size_t)k * ld + m0 + r0 + 16 * i)
-                                                    : (m0 + r0 + 16 * i < n_out ? m0 + r0 + 16 * i : -1);
+      for (int i = 0; i < 8; ++i)
+        rows[i] = map_t ? __ldg(map_t + (size_t)k * ld + m0 + r0 + 16 * i)
+                        : (m0 + r0 + 16 * i < n_out ? m0 + r0 + 16 * i : -1);
+    };
+    if constexpr (kAsyncA) {
+      for (int it = it_begin; it < it_end; ++it) {
+        const int li = it - it_begin;
+        const int stage = li % kStages;
+        const uint32_t parity = (uint32_t)(li / kStages) & 1u;
+        const int ka = it / nchunks, c = it - ka * nchunks;
+        const int k = active_k[ka];
+        if (c == 0 || li == 0) load_rows(k);
+        mbar_wait(bar_base + 8 * (kStages + stage), parity ^ 1u);
+        const uint32_t a_s = base + stage * Cfg::kStageBytes;
+        if (tid == 0) {
+          mbar_arrive_expect_tx(bar_base + 8 * stage, Cfg::kBTileBytes);
+          bulk_g2s(a_s + kATileBytes, w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK, Cfg::kBTileBytes,
+                   bar_base + 8 * stage);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 16 * i;
+          const uint32_t dst = a_s + r * 128 + ((chunk16 ^ (r & 7)) << 4);
+          const bool ok = rows[i] >= 0;
+          const float* src = ok ? in + (size_t)rows[i] * cin + c * BK + chunk16 * 4 : in;
+          cp_async16(dst, src, ok ? 16u : 0u);
+        }
+        cp_async_mbar_arrive_noinc(bar_base + 8 * stage);
       }
-      mbar_wait(bar_base + 8 * (kStages + stage), parity ^ 1u);
-      const uint32_t a_s = base + stage * Cfg::kStageBytes;
-      if (tid == 0) {
-        mbar_arrive_expect_tx(bar_base + 8 * stage, Cfg::kBTileBytes);
-        const float* src = w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK;
-        bulk_g2s(a_s + kATileBytes, src, Cfg::kBTileBytes, bar_base + 8 * stage);
-      }
+    } else {
       float4 v[8];
+      auto issue_loads = [&](int it) {
+        const int ka = it / nchunks, c = it - ka * nchunks;
+        if (c == 0 || it == it_begin) load_rows(active_k[ka]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (rows[i] >= 0)
-          v[i] = __ldg(reinterpret_cast<const float4*>(in + (size_t)rows[i] * cin + c * BK) + chunk16);
-      }
+        for (int i = 0; i < 8; ++i) {
+          v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (rows[i] >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(in + (size_t)rows[i] * cin + c * BK) + chunk16);
+        }
+      };
+      if (num_iters > 0) issue_loads(it_begin);
+      for (int it = it_begin; it < it_end; ++it) {
+        const int li = it - it_begin;
+        const int stage = li % kStages;
+        const uint32_t parity = (uint32_t)(li / kStages) & 1u;
+        const int ka = it / nchunks, c = it - ka * nchunks;
+        const int k = active_k[ka];
+        uint32_t t[8][4];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r0 + 16 * i;
-        const uint32_t dst = a_s + r * 128 + ((chunk16 ^ (r & 7)) << 4);
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(to_tf32(v[i].x)),
-                     "r"(to_tf32(v[i].y)), "r"(to_tf32(v[i].z)), "r"(to_tf32(v[i].w))
-                     : "memory");
+        for (int i = 0; i < 8; ++i) {
+          t[i][0] = to_tf32(v[i].x);
+          t[i][1] = to_tf32(v[i].y);
+          t[i][2] = to_tf32(v[i].z);
+          t[i][3] = to_tf32(v[i].w);
+        }
+        if (it + 1 < it_end) issue_loads(it + 1);   // next slab's loads fly while this one is stored
+        mbar_wait(bar_base + 8 * (kStages + stage), parity ^ 1u);
+        const uint32_t a_s = base + stage * Cfg::kStageBytes;
+        if (tid == 0) {
+          mbar_arrive_expect_tx(bar_base + 8 * stage, Cfg::kBTileBytes);
+          bulk_g2s(a_s + kATileBytes, w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK, Cfg::kBTileBytes,
+                   bar_base + 8 * stage);
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int r = r0 + 16 * i;
+          const uint32_t dst = a_s + r * 128 + ((chunk16 ^ (r & 7)) << 4);
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst), "r"(t[i][0]), "r"(t[i][1]), "r"(t[i][2]),
+                       "r"(t[i][3])
+                       : "memory");
+        }
+        fence_proxy_async();
+        mbar_arrive(bar_base + 8 * stage);
       }
-      fence_proxy_async();
-      mbar_arrive(bar_base + 8 * stage);
     }
     // ------------------------------------------------------------------ epilogue
     const int row = m0 + warp * 32 + lane;
@@ -196,6 +259,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
       mbar_wait(bar_base + 8 * (2 * kStages), 0);
       tc_fence_after();
     }
+    const bool add_bias = bias != nullptr && blockIdx.z == 0;
 #pragma unroll 1
     for (int cb = 0; cb < BN / 32; ++cb) {
       uint32_t r[32];
@@ -217,8 +281,8 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
         for (int j = 0; j < 32; ++j) r[j] = 0u;
       }
       if (row < n_out) {
-        float4* dst = reinterpret_cast<float4*>(out + (size_t)row * cout + n0 + cb * 32);
-        const float4* bp = bias ? reinterpret_cast<const float4*>(bias + n0 + cb * 32) : nullptr;
+        float* dstf = out + (size_t)row * cout + n0 + cb * 32;
+        const float4* bp = add_bias ? reinterpret_cast<const float4*>(bias + n0 + cb * 32) : nullptr;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
@@ -227,16 +291,18 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
             float4 b = __ldg(bp + j);
             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
-          dst[j] = o;
+          if (split) red_add_v4(dstf + 4 * j, o);
+          else reinterpret_cast<float4*>(dstf)[j] = o;
         }
       }
     }
   } else {
     // ------------------------------------------------------------------ MMA issuer (warp 4)
-    for (int it = 0; it < num_iters; ++it) {
-      const int stage = it % kStages;
-      const uint32_t parity = (uint32_t)(it / kStages) & 1u;
+    for (int li = 0; li < num_iters; ++li) {
+      const int stage = li % kStages;
+      const uint32_t parity = (uint32_t)(li / kStages) & 1u;
       mbar_wait(bar_base + 8 * stage, parity);
+      if constexpr (kAsyncA) fence_proxy_async();   // cp.async wrote the A tile through the generic proxy
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_s = base + stage * Cfg::kStageBytes;
@@ -245,9 +311,9 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
 #pragma unroll
         for (int kk = 0; kk < BK / 8; ++kk)
           umma_tf32(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), Cfg::kIdesc,
-                    (it > 0 || kk > 0) ? 1u : 0u);
+                    (li > 0 || kk > 0) ? 1u : 0u);
         umma_commit(bar_base + 8 * (kStages + stage));
-        if (it == num_iters - 1) umma_commit(bar_base + 8 * (2 * kStages));
+        if (li == num_iters - 1) umma_commit(bar_base + 8 * (2 * kStages));
       }
       __syncwarp();
     }
@@ -275,35 +341,49 @@ __global__ void k_pack_weights(const float* __restrict__ w, int kvol, int cin, i
   wp[dst] = __uint_as_float(to_tf32(w[t]));
 }
 
-template <int BN>
+template <int BN, bool kAsyncA>
 static int launch_umma(const float* in, const float* wp, const int32_t* map_t, int ld, const uint32_t* tile_mask,
-                       int n_out, int kvol, int cin, int cout, const float* bias, float* out, cudaStream_t s) {
+                       int n_out, int kvol, int cin, int cout, const float* bias, float* out, int nsplit,
+                       cudaStream_t s) {
   using Cfg = UmmaCfg<BN>;
   static bool configured = false;
   if (!configured) {
-    SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN, kAsyncA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
     configured = true;
   }
-  dim3 grid(cdiv(n_out, BM), cout / BN);
-  k_conv_fwd_umma<BN><<<grid, kUmmaThreads, Cfg::kSmemBytes, s>>>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout,
-                                                                 bias, out);
+  if (nsplit > 1) SPVD_CUDA(cudaMemsetAsync(out, 0, (size_t)n_out * cout * 4, s));
+  dim3 grid(cdiv(n_out, BM), cout / BN, nsplit);
+  k_conv_fwd_umma<BN, kAsyncA><<<grid, kUmmaThreads, Cfg::kSmemBytes, s>>>(in, wp, map_t, ld, tile_mask, n_out, kvol,
+                                                                          cin, cout, bias, out);
   SPVD_LAUNCH_CHECK();
   return SPVD_OK;
 }
 
-static int pick_bn(int n_tiles, int cout) {
-  // largest slice width that still gives every SM a CTA, among the instantiated widths
+template <int BN>
+static int launch_umma_bn(bool async_a, const float* in, const float* wp, const int32_t* map_t, int ld,
+                          const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
+                          float* out, int nsplit, cudaStream_t s) {
+  return async_a ? launch_umma<BN, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s)
+                 : launch_umma<BN, false>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
+}
+
+// widest instantiated slice that divides cout: the A tile is gathered once per slice, so fewer is better
+static int pick_bn(int cout) {
   const int widths[] = {256, 192, 128, 96, 64, 32};
-  int best = 0;
-  for (int w : widths) {
-    if (cout % w) continue;
-    if (!best) best = w;
-    if ((long long)n_tiles * (cout / w) >= 148) return w;
-  }
-  // not enough tiles at any width: take the narrowest that divides cout (most CTAs)
-  for (int i = 5; i >= 0; --i)
-    if (cout % widths[i] == 0) return widths[i];
-  return best;
+  for (int w : widths)
+    if (cout % w == 0) return w;
+  return 32;
+}
+
+// split the (offset, slab) iterations over gridDim.z when the tiles alone cannot fill the GPU
+static int pick_split(int n_ctas, int max_iters) {
+  const int target = 2 * 148;
+  if (n_ctas >= 148) return 1;
+  int s = (target + n_ctas - 1) / n_ctas;
+  int cap = max_iters / 6;  // keep >= 6 pipeline iterations per CTA
+  if (s > cap) s = cap;
+  return s < 1 ? 1 : s;
 }
 
 }  // namespace spvd
@@ -328,7 +408,8 @@ extern "C" int spvd_conv_pack_weights(const float* w, int kvol, int cin, int cou
 
 extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const int32_t* map_t, int ld,
                                   const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
-                                  const float* bias, float* out, int bn, spvd_stream_t stream) {
+                                  const float* bias, float* out, int bn, int nsplit, int a_is_tf32,
+                                  spvd_stream_t stream) {
   SPVD_CHECK_ARG(in && w_packed && out && n_out >= 0, "spvd_conv_fwd_umma: bad arguments");
   SPVD_CHECK_ARG(spvd_conv_umma_supported(kvol, cin, cout), "spvd_conv_fwd_umma: unsupported shape %dx%dx%d", kvol, cin, cout);
   SPVD_CHECK_ARG(map_t || kvol == 1, "spvd_conv_fwd_umma: a NULL map needs kvol == 1");
@@ -338,15 +419,19 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
                  "spvd_conv_fwd_umma: pointers must be 16-byte aligned");
   if (n_out == 0) return SPVD_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (bn <= 0) bn = pick_bn(cdiv(n_out, BM), cout);
+  if (bn <= 0) bn = pick_bn(cout);
   SPVD_CHECK_ARG(cout % bn == 0, "spvd_conv_fwd_umma: slice width %d does not divide cout %d", bn, cout);
+  const int max_iters = kvol * (cin / 32);
+  if (nsplit <= 0) nsplit = pick_split(cdiv(n_out, BM) * (cout / bn), max_iters);
+  if (nsplit > max_iters) nsplit = max_iters;
+  const bool aa = a_is_tf32 != 0;
   switch (bn) {
-    case 32: return launch_umma<32>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
-    case 64: return launch_umma<64>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
-    case 96: return launch_umma<96>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
-    case 128: return launch_umma<128>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
-    case 192: return launch_umma<192>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
-    case 256: return launch_umma<256>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, s);
+    case 32: return launch_umma_bn<32>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
+    case 64: return launch_umma_bn<64>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
+    case 96: return launch_umma_bn<96>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
+    case 128: return launch_umma_bn<128>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
+    case 192: return launch_umma_bn<192>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
+    case 256: return launch_umma_bn<256>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
   }
   set_error("spvd_conv_fwd_umma: slice width %d is not instantiated", bn);
   return SPVD_ERR_INVALID;
@@ -362,7 +447,7 @@ extern "C" int spvd_conv_fwd(const float* in, const float* w, const float* w_pac
   bool umma_ok = w_packed && spvd_conv_umma_supported(kvol, cin, cout) && (!map_t || ld % 128 == 0);
   if (impl == SPVD_CONV_UMMA || (impl == SPVD_CONV_AUTO && umma_ok)) {
     SPVD_CHECK_ARG(umma_ok, "spvd_conv_fwd: the tcgen05 path needs packed weights, cin %% 32 == 0 and cout %% 32 == 0");
-    return spvd_conv_fwd_umma(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, 0, stream);
+    return spvd_conv_fwd_umma(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, 0, 0, 0, stream);
   }
   SPVD_CHECK_ARG(w, "spvd_conv_fwd: the SIMT path needs the unpacked weights");
   return spvd_conv_fwd_simt(in, w, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, stream);

@@ -7,8 +7,13 @@
 namespace spvd {
 
 __device__ __forceinline__ float silu(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float rna_tf32(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
 
-// y = act(x * scale[c] + shift[c]);  act: 0 none, 1 SiLU
+// y = act(x * scale[c] + shift[c]);  act bit 0: SiLU, bit 1: round the result to TF32 (rna)
 __global__ void k_affine_act4(const float4* __restrict__ x, const float4* __restrict__ scale,
                               const float4* __restrict__ shift, long long total4, int c4, int act,
                               float4* __restrict__ y) {
@@ -20,11 +25,17 @@ __global__ void k_affine_act4(const float4* __restrict__ x, const float4* __rest
   v.y = fmaf(v.y, s.y, b.y);
   v.z = fmaf(v.z, s.z, b.z);
   v.w = fmaf(v.w, s.w, b.w);
-  if (act == 1) {
+  if (act & 1) {
     v.x = silu(v.x);
     v.y = silu(v.y);
     v.z = silu(v.z);
     v.w = silu(v.w);
+  }
+  if (act & 2) {
+    v.x = rna_tf32(v.x);
+    v.y = rna_tf32(v.y);
+    v.z = rna_tf32(v.z);
+    v.w = rna_tf32(v.w);
   }
   y[t] = v;
 }
@@ -36,7 +47,9 @@ __global__ void k_affine_act1(const float* __restrict__ x, const float* __restri
   if (t >= total) return;
   int q = (int)(t % c);
   float v = fmaf(x[t], scale[q], shift[q]);
-  y[t] = act == 1 ? silu(v) : v;
+  if (act & 1) v = silu(v);
+  if (act & 2) v = rna_tf32(v);
+  y[t] = v;
 }
 
 // y[i] = (1 + tt[b_i, c]) * x[i, c] + tt[b_i, C + c],  b_i = coords[i].batch

@@ -40,8 +40,8 @@ class Conv3d(nn.Module):
         self._packed = SF.PackedWeight()
         self.impl = ops.CONV_AUTO
 
-    def forward(self, feats, kmap):
-        return SF.sparse_conv(feats, self.kernel, self.bias, kmap, self._packed, self.impl)
+    def forward(self, feats, kmap, a_tf32=False):
+        return SF.sparse_conv(feats, self.kernel, self.bias, kmap, self._packed, self.impl, a_tf32)
 
     def extra_repr(self):
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
@@ -207,8 +207,9 @@ class SPVUnet(nn.Module):
     def _fast(self):
         return (not self.training) and (not torch.is_grad_enabled())
 
-    def _bn_act(self, bn: nn.BatchNorm1d, x, act=True):
-        """BatchNorm1d (+ SiLU).  Inference: one fused kernel on the folded affine."""
+    def _bn_act(self, bn: nn.BatchNorm1d, x, act=True, tf32=False):
+        """BatchNorm1d (+ SiLU).  Inference: one fused kernel on the folded affine; ``tf32`` also rounds the
+        result to TF32 there, so that the convolution consuming it can gather with cp.async."""
         if self._fast():
             key = id(bn)
             ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version)
@@ -218,7 +219,7 @@ class SPVUnet(nn.Module):
                 shift = bn.bias.detach() - bn.running_mean * scale
                 hit = (ver, scale.contiguous(), shift.contiguous())
                 self._folded[key] = hit
-            return ops.affine_act(x.contiguous(), hit[1], hit[2], 1 if act else 0)
+            return ops.affine_act(x.contiguous(), hit[1], hit[2], (1 if act else 0) | (2 if tf32 else 0))
         y = bn(x)
         return F.silu(y) if act else y
 
@@ -238,14 +239,15 @@ class SPVUnet(nn.Module):
 
     def _res_block(self, blk: EmbResBlock, x_in, emb_act, geo: Geometry, s):
         lv = geo.level(s)
-        x = blk.conv1[2](self._bn_act(blk.conv1[0], x_in), lv.kmap3)
+        fast = self._fast()
+        x = blk.conv1[2](self._bn_act(blk.conv1[0], x_in, tf32=fast), lv.kmap3, fast)
         tt = blk.t_emb.proj_mlp(emb_act)                                    # [B, 2C]
-        if self._fast():
+        if fast:
             x = ops.film(x, tt.contiguous(), lv.coords)
         else:
             scale, shift = torch.chunk(tt[geo.batch_index(s)], 2, dim=-1)
             x = (1 + scale) * x + shift
-        x = blk.conv2[2](self._bn_act(blk.conv2[0], x), lv.kmap3)
+        x = blk.conv2[2](self._bn_act(blk.conv2[0], x, tf32=fast), lv.kmap3, fast)
         x = x + (blk.idconv(x_in) if hasattr(blk, "idconv") else x_in)
         if hasattr(blk, "attn"):
             x = self._attention(blk.attn, x, geo, s)
@@ -284,8 +286,8 @@ class SPVUnet(nn.Module):
         x = p2v(z, 1)                                                        # initial_voxelize
         st = self.stem_conv
         x = st.voxel_conv[0](x, geo.level(1).kmap3)
-        x = self._bn_act(st.voxel_conv[1], x)
-        x = st.voxel_conv[3](x, geo.level(1).kmap3)
+        x = self._bn_act(st.voxel_conv[1], x, tf32=self._fast())
+        x = st.voxel_conv[3](x, geo.level(1).kmap3, self._fast())
         z = self._point_block(st.point_conv, v2p(x, 1), z)
         x = p2v(z, 1)
         saved = [x]

@@ -23,7 +23,7 @@ class PackedWeight:
 
 class _SparseConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, kmap, cache, impl):
+    def forward(ctx, x, weight, bias, kmap, cache, impl, a_tf32=False):
         w3 = weight if weight.dim() == 3 else weight.unsqueeze(0)
         w3 = w3.contiguous()
         wp = cache.get(w3) if (cache is not None and impl != ops.CONV_SIMT) else None
@@ -32,7 +32,7 @@ class _SparseConv(torch.autograd.Function):
         n_out = kmap.n_out if kmap is not None else x.shape[0]
         x = x.contiguous()
         out = ops.conv_fwd(x, w3, wp, kmap.map_t if kmap is not None else None,
-                           kmap.mask if kmap is not None else None, n_out, bias, impl)
+                           kmap.mask if kmap is not None else None, n_out, bias, impl, a_tf32=a_tf32)
         ctx.save_for_backward(x, weight)
         ctx.kmap, ctx.impl, ctx.has_bias = kmap, impl, bias is not None
         return out
@@ -59,12 +59,13 @@ class _SparseConv(torch.autograd.Function):
             gw = ops.conv_wgrad(x, g, kmap.map_t if kmap is not None else None, n_out, kvol).view_as(weight)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g.sum(0)
-        return gx, gw, gb, None, None, None
+        return gx, gw, gb, None, None, None, None
 
 
-def sparse_conv(x, weight, bias, kmap, cache=None, impl=ops.CONV_AUTO):
-    """out[o] = sum_k x[kmap[k][o]] @ weight[k] (+ bias); kmap None = kernel size 1."""
-    return _SparseConv.apply(x, weight, bias, kmap, cache, impl)
+def sparse_conv(x, weight, bias, kmap, cache=None, impl=ops.CONV_AUTO, a_tf32=False):
+    """out[o] = sum_k x[kmap[k][o]] @ weight[k] (+ bias); kmap None = kernel size 1.  ``a_tf32``: the caller
+    guarantees x is already TF32-representable (enables the cp.async gather of the tcgen05 path)."""
+    return _SparseConv.apply(x, weight, bias, kmap, cache, impl, a_tf32)
 
 
 class _ScatterMean(torch.autograd.Function):

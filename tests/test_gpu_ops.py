@@ -295,12 +295,31 @@ def test_conv_backward(sp, kind, cin, cout, impl):
     assert rel_err(bb.grad.cpu().numpy(), ba.grad.numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("nsplit", [1, 3, 16])
+@pytest.mark.parametrize("a_tf32", [False, True])
+def test_conv_tcgen05_split_and_async_gather(sp, nsplit, a_tf32):
+    """split-K accumulation (vector RED into a zeroed output) and the cp.async gather of pre-rounded rows"""
+    x, w, b, m, n_out, km, oo = _conv_case(sp, "k3", 96, 128, 23)
+    want = oo.conv_gather_gemm_scatter(x, w, m, n_out, b, emulate_tf32=True)
+    xd = x.cuda()
+    if a_tf32:
+        xd = sp.ops.round_tf32(xd)
+        assert torch.equal(xd.cpu(), oo.round_tf32(x))          # cvt.rna.tf32 == the oracle's rounding
+    wp = sp.ops.pack_weights(w.cuda())
+    got = sp.ops.conv_fwd(xd, w.cuda(), wp, km.map_t, km.mask, n_out, b.cuda(), sp.ops.CONV_UMMA, nsplit=nsplit,
+                          a_tf32=a_tf32)
+    assert rel_err(got.cpu().numpy(), want.numpy()) < 2e-5
+
+
 def test_fused_glue(sp):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(1000, 64, generator=g).cuda()
     sc, sh = torch.randn(64, generator=g).cuda(), torch.randn(64, generator=g).cuda()
     want = torch.nn.functional.silu(x * sc + sh)
     assert rel_err(sp.ops.affine_act(x, sc, sh, 1).cpu().numpy(), want.cpu().numpy()) < 1e-6
+    from oracle import ops as oo
+    r = sp.ops.affine_act(x, sc, sh, 3).cpu()
+    assert torch.equal(r, oo.round_tf32(r)) and rel_err(r.numpy(), want.cpu().numpy()) < 5e-4
     coords = torch.zeros(1000, 4, dtype=torch.int32)
     coords[:, 0] = torch.arange(1000) // 250
     tt = torch.randn(4, 128, generator=g).cuda()
