@@ -156,9 +156,8 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
         clocks = ClockSampler(local) if rank == 0 else None
-        ops.stats.reset(time_convs=True)
+        ops.stats.reset(False)
         ev = []
-        torch_launch_guess = 0
         for j in range(W, W + K):
             if flush is not None:
                 flush.fill_(j & 0xFF)                  # L2 flush: 256 MiB write between timed steps
@@ -174,47 +173,55 @@ def run_b200(args):
         clk = clocks.stop() if clocks else None
     total_ms = sum(a.elapsed_time(b) for a, b in ev)
     launches = ops.stats.launches
-    conv_events = ops.stats.conv_events
     ops.stats.reset(False)
     if world > 1:
         tt = torch.tensor([total_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         total_ms = float(tt.item())
 
-    # ---- roofline of the dominant kernel (tcgen05 sparse conv), from the events of the timed region
+    # ---- roofline of the dominant kernel (tcgen05 sparse conv): an instrumented replay of the timed steps,
+    #      CUDA events recorded around every convolution launch on the launching stream (inside the C executor)
     roof = None
-    if rank == 0 and conv_events:
-        pairs_cache, flops, ms, n = {}, 0.0, 0.0, 0
+    if rank == 0:
+        sink = []
+        model.profile_sink = sink
+        with torch.no_grad():
+            for j in range(W, W + K):
+                if flush is not None:
+                    flush.fill_(j & 0xFF)
+                step_device(xs_dev[j], ts[j], j)
+        torch.cuda.synchronize()
+        model.profile_sink = None
+        flops = ms = 0.0
+        n = 0
         table = {}
-        for a, b, (kvol, cin, cout, n_out, kind, map_t) in conv_events:
-            if os.environ.get("SPVD_BENCH_VERBOSE"):
-                if map_t is None:
-                    Pv = n_out
+        for evs, meta, geo, strides in sink:
+            pairs = {}
+            for ci, (kvol, cin, cout, rows_out, level, map_kind, kind) in enumerate(meta):
+                dt = evs[2 * ci].elapsed_time(evs[2 * ci + 1])
+                if map_kind == 0:
+                    n_out = geo.n_points if rows_out == -1 else (len(ts) and (args.batch if rows_out == -2 else geo.level(strides[rows_out]).n))
+                    P = n_out
                 else:
-                    kk = (map_t.data_ptr(), n_out)
-                    if kk not in pairs_cache:
-                        pairs_cache[kk] = int((map_t[:, :n_out] >= 0).sum().item())
-                    Pv = pairs_cache[kk]
-                e = table.setdefault((kind, kvol, cin, cout, n_out // 2000 * 2000), [0, 0.0, 0.0])
+                    lv = geo.level(strides[level])
+                    km = {1: lv.kmap3, 2: lv.kmap_down, 3: lv.kmap_up}[map_kind]
+                    if (level, map_kind) not in pairs:
+                        pairs[(level, map_kind)] = int((km.map_t[:, :km.n_out] >= 0).sum().item())
+                    P, n_out = pairs[(level, map_kind)], km.n_out
+                fl = 2.0 * P * cin * cout
+                e = table.setdefault((kind, kvol, cin, cout, strides[level] if level >= 0 else rows_out), [0, 0.0, 0.0])
                 e[0] += 1
-                e[1] += a.elapsed_time(b)
-                e[2] += 2.0 * Pv * cin * cout
-            if kind != "umma":
-                continue
-            if map_t is None:
-                P = n_out
-            else:
-                key = (map_t.data_ptr(), n_out)
-                if key not in pairs_cache:
-                    pairs_cache[key] = int((map_t[:, :n_out] >= 0).sum().item())
-                P = pairs_cache[key]
-            flops += 2.0 * P * cin * cout
-            ms += a.elapsed_time(b)
-            n += 1
-        for key in sorted(table, key=lambda k: -table[k][1]):
-            c, t_ms, fl = table[key]
-            print(f"[conv] {key} launches={c} total_ms={t_ms:.3f} avg_us={t_ms / c * 1e3:.1f} alg_TFLOPs={fl / (t_ms * 1e-3) / 1e12:.1f}",
-                  file=sys.stderr)
+                e[1] += dt
+                e[2] += fl
+                if kind == "umma":
+                    flops += fl
+                    ms += dt
+                    n += 1
+        if os.environ.get("SPVD_BENCH_VERBOSE"):
+            for key in sorted(table, key=lambda k: -table[k][1]):
+                c, t_ms, fl = table[key]
+                print(f"[conv] {key} launches={c} total_ms={t_ms:.3f} avg_us={t_ms / c * 1e3:.1f} "
+                      f"alg_TFLOPs={fl / (t_ms * 1e-3) / 1e12:.1f}", file=sys.stderr)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -230,11 +237,11 @@ def run_b200(args):
         roof = {"bound": "tensor", "kernel": "k_conv_fwd_umma (tcgen05 kind::tf32)", "achieved": round(ach, 2),
                 "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained",
-                "note": "TF32 operands: the tensor pipe runs kind::tf32 at half the bf16 rate, so frac <= 0.5 by construction",
+                "note": "TF32 operands (kind::tf32 runs at half the bf16 rate, so frac <= 0.5 by construction); durations from "
+                        "CUDA events around each launch in an instrumented replay of the timed steps",
                 "launches": n, "avg_launch_us": round(ms * 1e3 / max(n, 1), 2),
                 "algorithmic_gflop_per_step": round(flops / K / 1e9, 1),
                 "conv_share_of_step": round(ms / total_ms, 3) if total_ms else None}
-    conv_events = None
 
     # ---- end-to-end leg through the public API with host buffers
     pin_in = [x.pin_memory() for x in xs]

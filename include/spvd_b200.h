@@ -173,9 +173,11 @@ int spvd_conv_umma_supported(int kvol, int cin, int cout);
 int spvd_conv_fwd(const float* in, const float* w, const float* w_packed, const int32_t* map_t, int ld,
                   const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
                   const float* bias, float* out, int impl, spvd_stream_t stream);
+/* residual (optional, [n_out,cout], must not alias out): out = conv + bias + residual in the epilogue
+ * (the skip connection of EmbResBlock, models/ddpm_unet_attn.py:60, and of PointBlock, models/spvd.py:27) */
 int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, int ld,
                        const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
-                       const float* bias, float* out, spvd_stream_t stream);
+                       const float* bias, const float* residual, float* out, spvd_stream_t stream);
 /* bn = output-channel slice width per CTA (32,64,96,128,192,256 dividing cout; 0 = widest);
  * nsplit = number of CTAs sharing one tile's (offset, 32-channel slab) iterations, partial sums
  * accumulated with vector RED into the zero-filled output (0 = choose from the grid size);
@@ -184,8 +186,8 @@ int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, in
  * slabs in flight instead of through registers with cvt.rna. */
 int spvd_conv_fwd_umma(const float* in, const float* w_packed, const int32_t* map_t, int ld,
                        const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
-                       const float* bias, float* out, int bn, int nsplit, int a_is_tf32,
-                       spvd_stream_t stream);
+                       const float* bias, const float* residual, float* out, int bn, int nsplit,
+                       int a_is_tf32, spvd_stream_t stream);
 /* gw[k] = sum over pairs (i,o) of offset k of in[i]^T gout[o];  gw [kvol,cin,cout] zero-filled inside */
 int spvd_conv_wgrad(const float* in, const float* gout, const int32_t* map_t, int ld, int n_out,
                     int kvol, int cin, int cout, float* gw, spvd_stream_t stream);
@@ -206,6 +208,81 @@ int spvd_film_fwd(const float* x, const float* tt, const int32_t* coords, long l
                   float* y, spvd_stream_t stream);
 int spvd_batch_counts(const int32_t* coords, int n_cap, const int32_t* n_dev, int nb, int32_t* counts,
                       spvd_stream_t stream);
+
+/* FiLM + the BatchNorm/SiLU that follows it in EmbResBlock (models/ddpm_unet_attn.py:54-57) in one
+ * pass: y = act(((1 + tt[b,c]) * x + tt[b,C+c]) * scale[c] + shift[c]); tt rows are ldt floats apart. */
+int spvd_film_affine_fwd(const float* x, const float* tt, int ldt, const int32_t* coords,
+                         const float* scale, const float* shift, long long rows, int c, int act,
+                         float* y, spvd_stream_t stream);
+/* torchsparse.cat (models/spvd.py:232): y = [a | b] along channels */
+int spvd_cat_fwd(const float* a, const float* b, long long rows, int ca, int cb, float* y,
+                 spvd_stream_t stream);
+/* SparseAttention (models/modules/transformer.py:102-125): LayerNorm, then per-cloud multi-head
+ * attention over batch-major rows (batch_offsets [n_batch+1] = first row of each cloud); qkv is
+ * [rows, 3c] laid out which*c + head*d + d_i.  act & 2 rounds the output to TF32. */
+int spvd_layernorm_fwd(const float* x, const float* gamma, const float* beta, int rows, int c,
+                       float eps, int act, float* y, spvd_stream_t stream);
+int spvd_attention_fwd(const float* qkv, const int32_t* batch_offsets, int n_batch, int max_len, int c,
+                       int heads, int act, float* out, spvd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * M2  native inference executor: SPVUnet.forward (models/spvd.py:432-457, eval mode) as one call.
+ * The host compiles the module tree once into spvd_op_t records whose operands are byte offsets
+ * into one activation arena; row counts are resolved per call from the planned geometry. */
+#define SPVD_OP_SCATTER_MEAN 0 /* src0 [points,c0] -> dst [level rows,c0]; aux = counts scratch   */
+#define SPVD_OP_DEVOX 1        /* src0 [level rows,c0] -> dst [points,c0]                          */
+#define SPVD_OP_CONV 2         /* src0 [rows_in,c0] -> dst [rows_out,c1] (+bias, +src1 residual)   */
+#define SPVD_OP_AFFINE 3       /* dst = act(src0 * p0[c] + p1[c])                                  */
+#define SPVD_OP_FILM_AFFINE 4  /* src1 = tt table (row stride i0 floats, column offset i1)         */
+#define SPVD_OP_CAT 5          /* dst = [src0 (c0) | src1 (c1)]                                    */
+#define SPVD_OP_LAYERNORM 6    /* p0 = gamma, p1 = beta                                            */
+#define SPVD_OP_ATTENTION 7    /* src0 = qkv [rows,3*c1] -> dst [rows,c1]; i0 = heads              */
+
+#define SPVD_MAP_NONE 0 /* kernel size 1 / nn.Linear */
+#define SPVD_MAP_K3 1
+#define SPVD_MAP_DOWN 2 /* level -> level+1 */
+#define SPVD_MAP_UP 3   /* level+1 -> level */
+
+#define SPVD_ROWS_POINTS (-1)
+#define SPVD_ROWS_BATCH (-2)
+
+#define SPVD_FLAG_SILU 1   /* AFFINE / FILM_AFFINE: apply SiLU                                     */
+#define SPVD_FLAG_ROUND 2  /* producer rounds its output to TF32                                    */
+#define SPVD_FLAG_A_TF32 4 /* CONV: src0 is TF32-representable (cp.async gather)                   */
+#define SPVD_FLAG_SIMT 8   /* CONV: force the fp32 SIMT kernel                                     */
+
+typedef struct spvd_level_geom {
+  const int32_t* coords; /* [n,4] */
+  const int32_t* kmap3;
+  const uint32_t* mask3;
+  const int32_t* kmap_down;
+  const uint32_t* mask_down;
+  const int32_t* kmap_up;
+  const uint32_t* mask_up;
+  const int32_t* p2v;       /* [n_points] or NULL */
+  const int32_t* devox_idx; /* [n_points,8] or NULL */
+  const float* devox_w;
+  const int32_t* batch_offsets; /* [n_batch+1] or NULL */
+  int32_t n, ld3, ld_down, ld_up, max_per_batch, pad;
+} spvd_level_geom_t;
+
+typedef struct spvd_op {
+  int32_t op, flags, level, map_kind;
+  int32_t rows_in, rows_out; /* level index, SPVD_ROWS_POINTS or SPVD_ROWS_BATCH */
+  int32_t c0, c1, kvol, i0, i1, pad;
+  int64_t src0, src1, dst, aux; /* byte offsets into the arena, -1 = none */
+  const float* w;
+  const float* w_packed;
+  const float* bias;
+  const float* p0;
+  const float* p1;
+} spvd_op_t;
+
+/* conv_events: NULL, or 2 CUDA events (cudaEvent_t) per SPVD_OP_CONV in program order, recorded
+ * around each convolution launch (bench.py's live roofline measurement). */
+int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_level_geom_t* levels, int n_levels,
+                     int n_points, int n_batch, void* arena, size_t arena_bytes,
+                     void* const* conv_events, spvd_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -38,11 +38,16 @@ SIGNATURES = {
     "spvd_conv_pack_weights": (_i, [_p, _i, _i, _i, _p, _p]),
     "spvd_conv_umma_supported": (_i, [_i, _i, _i]),
     "spvd_conv_fwd": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _p]),
-    "spvd_conv_fwd_simt": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p]),
-    "spvd_conv_fwd_umma": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
+    "spvd_conv_fwd_simt": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
+    "spvd_conv_fwd_umma": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _p]),
     "spvd_conv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "spvd_bn_silu_fwd": (_i, [_p, _p, _p, _ll, _i, _i, _p, _p]),
     "spvd_film_fwd": (_i, [_p, _p, _p, _ll, _i, _p, _p]),
+    "spvd_film_affine_fwd": (_i, [_p, _p, _i, _p, _p, _p, _ll, _i, _i, _p, _p]),
+    "spvd_cat_fwd": (_i, [_p, _p, _ll, _i, _i, _p, _p]),
+    "spvd_layernorm_fwd": (_i, [_p, _p, _p, _i, _i, _f, _i, _p, _p]),
+    "spvd_attention_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
+    "spvd_program_run": (_i, [_p, _i, _p, _i, _i, _i, _p, _sz, _p, _p]),
 }
 
 

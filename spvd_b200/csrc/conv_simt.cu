@@ -12,6 +12,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd_simt(const float* __restrict__
                                                        const int* __restrict__ map_t, int ld,
                                                        const unsigned* __restrict__ tile_mask, int n_out, int kvol,
                                                        int cin, int cout, const float* __restrict__ bias,
+                                                       const float* __restrict__ residual,
                                                        float* __restrict__ out) {
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN];
@@ -74,7 +75,9 @@ __global__ void __launch_bounds__(256) k_conv_fwd_simt(const float* __restrict__
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int n = n0 + tx * 4 + j;
-      if (n < cout) out[(size_t)o * cout + n] = acc[i][j] + (bias ? bias[n] : 0.f);
+      if (n < cout)
+        out[(size_t)o * cout + n] =
+            acc[i][j] + (bias ? bias[n] : 0.f) + (residual ? residual[(size_t)o * cout + n] : 0.f);
     }
   }
 }
@@ -165,13 +168,13 @@ using namespace spvd;
 
 extern "C" int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, int ld,
                                   const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
-                                  float* out, spvd_stream_t stream) {
+                                  const float* residual, float* out, spvd_stream_t stream) {
   SPVD_CHECK_ARG(in && w && out && n_out >= 0 && kvol >= 1 && cin >= 1 && cout >= 1, "spvd_conv_fwd: bad arguments");
   SPVD_CHECK_ARG(map_t || kvol == 1, "spvd_conv_fwd: a NULL map needs kvol == 1");
   SPVD_CHECK_ARG(!map_t || ld >= n_out, "spvd_conv_fwd: ld %d < n_out %d", ld, n_out);
   if (n_out == 0) return SPVD_OK;
   dim3 grid(cdiv(n_out, TM), cdiv(cout, TN));
-  k_conv_fwd_simt<<<grid, 256, 0, (cudaStream_t)stream>>>(in, w, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out);
+  k_conv_fwd_simt<<<grid, 256, 0, (cudaStream_t)stream>>>(in, w, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out);
   SPVD_LAUNCH_CHECK();
   return SPVD_OK;
 }

@@ -125,6 +125,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
                                                                const unsigned* __restrict__ tile_mask, int n_out,
                                                                int kvol, int cin, int cout,
                                                                const float* __restrict__ bias,
+                                                               const float* __restrict__ residual,
                                                                float* __restrict__ out) {
   using Cfg = UmmaCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
@@ -260,6 +261,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
       tc_fence_after();
     }
     const bool add_bias = bias != nullptr && blockIdx.z == 0;
+    const bool add_res = residual != nullptr && blockIdx.z == 0;
 #pragma unroll 1
     for (int cb = 0; cb < BN / 32; ++cb) {
       uint32_t r[32];
@@ -289,6 +291,10 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
                                  __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
           if (bp) {
             float4 b = __ldg(bp + j);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (add_res) {
+            float4 b = *reinterpret_cast<const float4*>(residual + (size_t)row * cout + n0 + cb * 32 + 4 * j);
             o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
           }
           if (split) red_add_v4(dstf + 4 * j, o);
@@ -343,8 +349,8 @@ __global__ void k_pack_weights(const float* __restrict__ w, int kvol, int cin, i
 
 template <int BN, bool kAsyncA>
 static int launch_umma(const float* in, const float* wp, const int32_t* map_t, int ld, const uint32_t* tile_mask,
-                       int n_out, int kvol, int cin, int cout, const float* bias, float* out, int nsplit,
-                       cudaStream_t s) {
+                       int n_out, int kvol, int cin, int cout, const float* bias, const float* residual, float* out,
+                       int nsplit, cudaStream_t s) {
   using Cfg = UmmaCfg<BN>;
   static bool configured = false;
   if (!configured) {
@@ -355,7 +361,7 @@ static int launch_umma(const float* in, const float* wp, const int32_t* map_t, i
   if (nsplit > 1) SPVD_CUDA(cudaMemsetAsync(out, 0, (size_t)n_out * cout * 4, s));
   dim3 grid(cdiv(n_out, BM), cout / BN, nsplit);
   k_conv_fwd_umma<BN, kAsyncA><<<grid, kUmmaThreads, Cfg::kSmemBytes, s>>>(in, wp, map_t, ld, tile_mask, n_out, kvol,
-                                                                          cin, cout, bias, out);
+                                                                          cin, cout, bias, residual, out);
   SPVD_LAUNCH_CHECK();
   return SPVD_OK;
 }
@@ -363,9 +369,9 @@ static int launch_umma(const float* in, const float* wp, const int32_t* map_t, i
 template <int BN>
 static int launch_umma_bn(bool async_a, const float* in, const float* wp, const int32_t* map_t, int ld,
                           const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
-                          float* out, int nsplit, cudaStream_t s) {
-  return async_a ? launch_umma<BN, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s)
-                 : launch_umma<BN, false>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
+                          const float* residual, float* out, int nsplit, cudaStream_t s) {
+  return async_a ? launch_umma<BN, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s)
+                 : launch_umma<BN, false>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
 }
 
 // widest instantiated slice that divides cout: the A tile is gathered once per slice, so fewer is better
@@ -408,9 +414,10 @@ extern "C" int spvd_conv_pack_weights(const float* w, int kvol, int cin, int cou
 
 extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const int32_t* map_t, int ld,
                                   const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
-                                  const float* bias, float* out, int bn, int nsplit, int a_is_tf32,
-                                  spvd_stream_t stream) {
+                                  const float* bias, const float* residual, float* out, int bn, int nsplit,
+                                  int a_is_tf32, spvd_stream_t stream) {
   SPVD_CHECK_ARG(in && w_packed && out && n_out >= 0, "spvd_conv_fwd_umma: bad arguments");
+  SPVD_CHECK_ARG(residual != out || residual == nullptr, "spvd_conv_fwd_umma: residual must not alias out");
   SPVD_CHECK_ARG(spvd_conv_umma_supported(kvol, cin, cout), "spvd_conv_fwd_umma: unsupported shape %dx%dx%d", kvol, cin, cout);
   SPVD_CHECK_ARG(map_t || kvol == 1, "spvd_conv_fwd_umma: a NULL map needs kvol == 1");
   SPVD_CHECK_ARG(!map_t || (ld % 128 == 0 && ld >= n_out), "spvd_conv_fwd_umma: ld %d must be a multiple of 128 >= n_out", ld);
@@ -426,12 +433,12 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
   if (nsplit > max_iters) nsplit = max_iters;
   const bool aa = a_is_tf32 != 0;
   switch (bn) {
-    case 32: return launch_umma_bn<32>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
-    case 64: return launch_umma_bn<64>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
-    case 96: return launch_umma_bn<96>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
-    case 128: return launch_umma_bn<128>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
-    case 192: return launch_umma_bn<192>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
-    case 256: return launch_umma_bn<256>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, nsplit, s);
+    case 32: return launch_umma_bn<32>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 64: return launch_umma_bn<64>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 96: return launch_umma_bn<96>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 128: return launch_umma_bn<128>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 192: return launch_umma_bn<192>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 256: return launch_umma_bn<256>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
   }
   set_error("spvd_conv_fwd_umma: slice width %d is not instantiated", bn);
   return SPVD_ERR_INVALID;
@@ -439,7 +446,7 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
 
 extern "C" int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, int ld,
                                   const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
-                                  float* out, spvd_stream_t stream);
+                                  const float* residual, float* out, spvd_stream_t stream);
 
 extern "C" int spvd_conv_fwd(const float* in, const float* w, const float* w_packed, const int32_t* map_t, int ld,
                              const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
@@ -447,8 +454,8 @@ extern "C" int spvd_conv_fwd(const float* in, const float* w, const float* w_pac
   bool umma_ok = w_packed && spvd_conv_umma_supported(kvol, cin, cout) && (!map_t || ld % 128 == 0);
   if (impl == SPVD_CONV_UMMA || (impl == SPVD_CONV_AUTO && umma_ok)) {
     SPVD_CHECK_ARG(umma_ok, "spvd_conv_fwd: the tcgen05 path needs packed weights, cin %% 32 == 0 and cout %% 32 == 0");
-    return spvd_conv_fwd_umma(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, 0, 0, 0, stream);
+    return spvd_conv_fwd_umma(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, nullptr, out, 0, 0, 0, stream);
   }
   SPVD_CHECK_ARG(w, "spvd_conv_fwd: the SIMT path needs the unpacked weights");
-  return spvd_conv_fwd_simt(in, w, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, out, stream);
+  return spvd_conv_fwd_simt(in, w, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, nullptr, out, stream);
 }

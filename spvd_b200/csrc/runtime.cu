@@ -1,0 +1,341 @@
+// Native inference executor: runs a whole SPVD denoiser forward (models/spvd.py:432-457 in eval
+// mode) from ONE C call.  The host side (spvd_b200/runtime.py) compiles the module tree once into a
+// flat program of spvd_op_t records over a single activation arena; per step the interpreter below
+// resolves row counts from the planned geometry and enqueues ~180 kernels back to back, instead
+// of ~480 Python-dispatched launches.  Also holds the kernels only the executor needs: LayerNorm,
+// per-cloud attention (models/modules/transformer.py:40-67,118-125), FiLM fused with the following
+// BatchNorm+SiLU (models/modules/graph.py:35-41 + models/ddpm_unet_attn.py:57), channel concat.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace spvd {
+
+__device__ __forceinline__ float silu_f(float v) { return v / (1.f + __expf(-v)); }
+__device__ __forceinline__ float rna_tf32_f(float x) {
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// y = act(((1 + tt[b,c]) * x + tt[b,C+c]) * scale[c] + shift[c]);  tt rows are ldt floats apart
+__global__ void k_film_affine4(const float4* __restrict__ x, const float* __restrict__ tt, int ldt,
+                               const int4* __restrict__ coords, const float4* __restrict__ scale,
+                               const float4* __restrict__ shift, long long total4, int c4, int act,
+                               float4* __restrict__ y) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= total4) return;
+  int row = (int)(t / c4), q = (int)(t % c4);
+  int b = coords[row].x;
+  const float4* tb = reinterpret_cast<const float4*>(tt + (size_t)b * ldt);
+  float4 v = x[t], sc = __ldg(tb + q), sh = __ldg(tb + c4 + q);
+  float4 s = __ldg(scale + q), o = __ldg(shift + q);
+  v.x = fmaf(fmaf(1.f + sc.x, v.x, sh.x), s.x, o.x);
+  v.y = fmaf(fmaf(1.f + sc.y, v.y, sh.y), s.y, o.y);
+  v.z = fmaf(fmaf(1.f + sc.z, v.z, sh.z), s.z, o.z);
+  v.w = fmaf(fmaf(1.f + sc.w, v.w, sh.w), s.w, o.w);
+  if (act & 1) {
+    v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+  }
+  if (act & 2) {
+    v.x = rna_tf32_f(v.x); v.y = rna_tf32_f(v.y); v.z = rna_tf32_f(v.z); v.w = rna_tf32_f(v.w);
+  }
+  y[t] = v;
+}
+
+__global__ void k_cat4(const float4* __restrict__ a, const float4* __restrict__ b, long long rows, int ca4, int cb4,
+                       float4* __restrict__ y) {
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int c4 = ca4 + cb4;
+  if (t >= rows * c4) return;
+  long long row = t / c4;
+  int q = (int)(t % c4);
+  y[t] = q < ca4 ? a[row * ca4 + q] : b[row * cb4 + (q - ca4)];
+}
+
+// one warp per row
+__global__ void k_layernorm(const float* __restrict__ x, const float* __restrict__ gamma,
+                            const float* __restrict__ beta, int rows, int c, float eps, int act,
+                            float* __restrict__ y) {
+  int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * c;
+  float s = 0.f;
+  for (int i = lane; i < c; i += 32) s += xr[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / c;
+  float v = 0.f;
+  for (int i = lane; i < c; i += 32) {
+    float d = xr[i] - mean;
+    v = fmaf(d, d, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  float rstd = rsqrtf(v / c + eps);
+  for (int i = lane; i < c; i += 32) {
+    float r = (xr[i] - mean) * rstd * gamma[i] + beta[i];
+    y[(size_t)row * c + i] = (act & 2) ? rna_tf32_f(r) : r;
+  }
+}
+
+// Per-cloud multi-head attention over the voxels of one level.  qkv [rows, 3C] with channel layout
+// which*C + head*D + d (the reference's reshape(B,N,3,H,D)); rows of a cloud are contiguous
+// (batch-major voxel order).  One query per thread, keys/values staged in shared memory 128 at a
+// time, online softmax (the reference's exp(x)*mask/sum is the same function).
+template <int D>
+__global__ void __launch_bounds__(128) k_attention(const float* __restrict__ qkv, const int* __restrict__ offsets,
+                                                   int C, float scale, int act, float* __restrict__ out) {
+  constexpr int KB = D <= 32 ? 128 : 64;   // static shared memory stays under 48 KB
+  __shared__ float4 Ks[KB][D / 4];
+  __shared__ float4 Vs[KB][D / 4];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int r0 = offsets[b], L = offsets[b + 1] - r0;
+  if ((int)blockIdx.x * 128 >= L) return;
+  const int qi = blockIdx.x * 128 + threadIdx.x;
+  const bool valid = qi < L;
+  float q[D], acc[D];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(qkv + (size_t)(r0 + (valid ? qi : 0)) * 3 * C + h * D);
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+      float4 t = qp[i];
+      q[4 * i] = t.x * scale; q[4 * i + 1] = t.y * scale; q[4 * i + 2] = t.z * scale; q[4 * i + 3] = t.w * scale;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < L; k0 += KB) {
+    __syncthreads();
+    const int nk = min(KB, L - k0);
+    for (int e = threadIdx.x; e < nk * (D / 4); e += 128) {
+      int j = e / (D / 4), i = e % (D / 4);
+      const float4* kp = reinterpret_cast<const float4*>(qkv + (size_t)(r0 + k0 + j) * 3 * C + C + h * D);
+      Ks[j][i] = kp[i];
+      Vs[j][i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(kp) + C)[i];
+    }
+    __syncthreads();
+    for (int j0 = 0; j0 < nk; j0 += 8) {
+      float s[8], mc = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        float d = -INFINITY;
+        if (j0 + jj < nk) {
+          d = 0.f;
+#pragma unroll
+          for (int i = 0; i < D / 4; ++i) {
+            float4 k4 = Ks[j0 + jj][i];
+            d = fmaf(q[4 * i], k4.x, d);
+            d = fmaf(q[4 * i + 1], k4.y, d);
+            d = fmaf(q[4 * i + 2], k4.z, d);
+            d = fmaf(q[4 * i + 3], k4.w, d);
+          }
+        }
+        s[jj] = d;
+        mc = fmaxf(mc, d);
+      }
+      float mn = fmaxf(m, mc);
+      float alpha = __expf(m - mn);
+      m = mn;
+      l *= alpha;
+#pragma unroll
+      for (int i = 0; i < D; ++i) acc[i] *= alpha;
+#pragma unroll
+      for (int jj = 0; jj < 8; ++jj) {
+        if (j0 + jj < nk) {
+          float p = __expf(s[jj] - mn);
+          l += p;
+#pragma unroll
+          for (int i = 0; i < D / 4; ++i) {
+            float4 v4 = Vs[j0 + jj][i];
+            acc[4 * i] = fmaf(p, v4.x, acc[4 * i]);
+            acc[4 * i + 1] = fmaf(p, v4.y, acc[4 * i + 1]);
+            acc[4 * i + 2] = fmaf(p, v4.z, acc[4 * i + 2]);
+            acc[4 * i + 3] = fmaf(p, v4.w, acc[4 * i + 3]);
+          }
+        }
+      }
+    }
+  }
+  if (valid) {
+    float inv = 1.f / l;
+    float4* op = reinterpret_cast<float4*>(out + (size_t)(r0 + qi) * C + h * D);
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+      float4 o = make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
+      if (act & 2) {
+        o.x = rna_tf32_f(o.x); o.y = rna_tf32_f(o.y); o.z = rna_tf32_f(o.z); o.w = rna_tf32_f(o.w);
+      }
+      op[i] = o;
+    }
+  }
+}
+
+template <int D>
+static void launch_attention(const float* qkv, const int* offsets, int C, int heads, int nb, int max_len, int act,
+                             float* out, cudaStream_t s) {
+  dim3 grid(cdiv(max_len, 128), heads, nb);
+  k_attention<D><<<grid, 128, 0, s>>>(qkv, offsets, C, 1.0f / sqrtf((float)D), act, out);
+}
+
+}  // namespace spvd
+
+using namespace spvd;
+
+extern "C" {
+int spvd_scatter_mean_fwd(const float*, const int32_t*, int, int, float*, float*, int, spvd_stream_t);
+int spvd_devoxelize_fwd(const float*, const int32_t*, const float*, int, int, float*, spvd_stream_t);
+int spvd_conv_fwd_simt(const float*, const float*, const int32_t*, int, const uint32_t*, int, int, int, int,
+                       const float*, const float*, float*, spvd_stream_t);
+int spvd_conv_fwd_umma(const float*, const float*, const int32_t*, int, const uint32_t*, int, int, int, int,
+                       const float*, const float*, float*, int, int, int, spvd_stream_t);
+int spvd_bn_silu_fwd(const float*, const float*, const float*, long long, int, int, float*, spvd_stream_t);
+}
+
+extern "C" int spvd_film_affine_fwd(const float* x, const float* tt, int ldt, const int32_t* coords,
+                                    const float* scale, const float* shift, long long rows, int c, int act, float* y,
+                                    spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && tt && coords && scale && shift && y && rows >= 0 && c > 0 && c % 4 == 0 && ldt % 4 == 0,
+                 "spvd_film_affine_fwd: bad arguments (c, ldt multiples of 4)");
+  SPVD_CHECK_ARG((((size_t)x | (size_t)y | (size_t)tt | (size_t)scale | (size_t)shift) & 15) == 0,
+                 "spvd_film_affine_fwd: pointers must be 16-byte aligned");
+  if (rows == 0) return SPVD_OK;
+  k_film_affine4<<<cdiv(rows * (c / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+      (const float4*)x, tt, ldt, (const int4*)coords, (const float4*)scale, (const float4*)shift, rows * (c / 4),
+      c / 4, act, (float4*)y);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_cat_fwd(const float* a, const float* b, long long rows, int ca, int cb, float* y,
+                            spvd_stream_t stream) {
+  SPVD_CHECK_ARG(a && b && y && rows >= 0 && ca > 0 && cb > 0 && ca % 4 == 0 && cb % 4 == 0,
+                 "spvd_cat_fwd: bad arguments (channel counts multiples of 4)");
+  if (rows == 0) return SPVD_OK;
+  k_cat4<<<cdiv(rows * ((ca + cb) / 4), 256), 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, rows,
+                                                                            ca / 4, cb / 4, (float4*)y);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_layernorm_fwd(const float* x, const float* gamma, const float* beta, int rows, int c, float eps,
+                                  int act, float* y, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && gamma && beta && y && rows >= 0 && c > 0, "spvd_layernorm_fwd: bad arguments");
+  if (rows == 0) return SPVD_OK;
+  k_layernorm<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, rows, c, eps, act, y);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_attention_fwd(const float* qkv, const int32_t* batch_offsets, int n_batch, int max_len, int c,
+                                  int heads, int act, float* out, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(qkv && batch_offsets && out && n_batch > 0 && heads > 0 && c % heads == 0,
+                 "spvd_attention_fwd: bad arguments");
+  if (max_len <= 0) return SPVD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  int d = c / heads;
+  switch (d) {
+    case 8: launch_attention<8>(qkv, batch_offsets, c, heads, n_batch, max_len, act, out, s); break;
+    case 16: launch_attention<16>(qkv, batch_offsets, c, heads, n_batch, max_len, act, out, s); break;
+    case 24: launch_attention<24>(qkv, batch_offsets, c, heads, n_batch, max_len, act, out, s); break;
+    case 32: launch_attention<32>(qkv, batch_offsets, c, heads, n_batch, max_len, act, out, s); break;
+    case 48: launch_attention<48>(qkv, batch_offsets, c, heads, n_batch, max_len, act, out, s); break;
+    case 64: launch_attention<64>(qkv, batch_offsets, c, heads, n_batch, max_len, act, out, s); break;
+    default:
+      set_error("spvd_attention_fwd: head dim %d is not instantiated (8,16,24,32,48,64)", d);
+      return SPVD_ERR_INVALID;
+  }
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// program interpreter
+// ------------------------------------------------------------------------------------------------
+static inline long long rows_of(int kind, const spvd_level_geom_t* lv, int n_levels, int n_points, int n_batch) {
+  if (kind == SPVD_ROWS_POINTS) return n_points;
+  if (kind == SPVD_ROWS_BATCH) return n_batch;
+  if (kind >= 0 && kind < n_levels) return lv[kind].n;
+  return -1;
+}
+
+extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_level_geom_t* levels, int n_levels,
+                                int n_points, int n_batch, void* arena, size_t arena_bytes, void* const* conv_events,
+                                spvd_stream_t stream) {
+  SPVD_CHECK_ARG(ops && levels && arena && n_ops >= 0 && n_levels > 0, "spvd_program_run: bad arguments");
+  char* base = (char*)arena;
+  int conv_index = 0;
+  auto at = [&](long long off) -> float* { return off < 0 ? nullptr : (float*)(base + off); };
+  for (int i = 0; i < n_ops; ++i) {
+    const spvd_op_t& o = ops[i];
+    const long long rin = rows_of(o.rows_in, levels, n_levels, n_points, n_batch);
+    const long long rout = rows_of(o.rows_out, levels, n_levels, n_points, n_batch);
+    if (rin < 0 || rout < 0) {
+      set_error("spvd_program_run: op %d has a bad row space", i);
+      return SPVD_ERR_INVALID;
+    }
+    const long long need = o.dst + rout * (long long)(o.op == SPVD_OP_CAT ? o.c0 + o.c1 : o.c1) * 4;  // c1 = output channels
+    if (o.dst < 0 || (size_t)need > arena_bytes) {
+      set_error("spvd_program_run: op %d writes past the arena (%lld > %zu)", i, need, arena_bytes);
+      return SPVD_ERR_WORKSPACE;
+    }
+    const spvd_level_geom_t* lv = (o.level >= 0 && o.level < n_levels) ? &levels[o.level] : nullptr;
+    int rc = SPVD_OK;
+    switch (o.op) {
+      case SPVD_OP_SCATTER_MEAN:
+        SPVD_CHECK_ARG(lv && lv->p2v, "op %d: level %d has no point->voxel index", i, o.level);
+        rc = spvd_scatter_mean_fwd(at(o.src0), lv->p2v, n_points, o.c0, at(o.dst), at(o.aux), lv->n, stream);
+        break;
+      case SPVD_OP_DEVOX:
+        SPVD_CHECK_ARG(lv && lv->devox_idx && lv->devox_w, "op %d: level %d has no devoxelize query", i, o.level);
+        rc = spvd_devoxelize_fwd(at(o.src0), lv->devox_idx, lv->devox_w, n_points, o.c0, at(o.dst), stream);
+        break;
+      case SPVD_OP_CONV: {
+        const int32_t* map = nullptr;
+        const uint32_t* mask = nullptr;
+        int ld = 0;
+        if (o.map_kind != SPVD_MAP_NONE) {
+          SPVD_CHECK_ARG(lv, "op %d: conv without a level", i);
+          if (o.map_kind == SPVD_MAP_K3) { map = lv->kmap3; mask = lv->mask3; ld = lv->ld3; }
+          else if (o.map_kind == SPVD_MAP_DOWN) { map = lv->kmap_down; mask = lv->mask_down; ld = lv->ld_down; }
+          else { map = lv->kmap_up; mask = lv->mask_up; ld = lv->ld_up; }
+          SPVD_CHECK_ARG(map, "op %d: level %d lacks kernel map kind %d", i, o.level, o.map_kind);
+        }
+        if (conv_events) SPVD_CUDA(cudaEventRecord((cudaEvent_t)conv_events[2 * conv_index], (cudaStream_t)stream));
+        if (o.w_packed && !(o.flags & SPVD_FLAG_SIMT))
+          rc = spvd_conv_fwd_umma(at(o.src0), o.w_packed, map, ld, mask, (int)rout, o.kvol, o.c0, o.c1, o.bias,
+                                  at(o.src1), at(o.dst), 0, 0, (o.flags & SPVD_FLAG_A_TF32) ? 1 : 0, stream);
+        else
+          rc = spvd_conv_fwd_simt(at(o.src0), o.w, map, ld, mask, (int)rout, o.kvol, o.c0, o.c1, o.bias, at(o.src1),
+                                  at(o.dst), stream);
+        if (conv_events) SPVD_CUDA(cudaEventRecord((cudaEvent_t)conv_events[2 * conv_index + 1], (cudaStream_t)stream));
+        ++conv_index;
+        break;
+      }
+      case SPVD_OP_AFFINE:
+        rc = spvd_bn_silu_fwd(at(o.src0), o.p0, o.p1, rin, o.c0, o.flags & 3, at(o.dst), stream);
+        break;
+      case SPVD_OP_FILM_AFFINE:
+        SPVD_CHECK_ARG(lv, "op %d: FiLM without a level", i);
+        rc = spvd_film_affine_fwd(at(o.src0), at(o.src1) + o.i1, o.i0, lv->coords, o.p0, o.p1, rin, o.c0, o.flags & 3,
+                                  at(o.dst), stream);
+        break;
+      case SPVD_OP_CAT:
+        rc = spvd_cat_fwd(at(o.src0), at(o.src1), rin, o.c0, o.c1, at(o.dst), stream);
+        break;
+      case SPVD_OP_LAYERNORM:
+        rc = spvd_layernorm_fwd(at(o.src0), o.p0, o.p1, (int)rin, o.c0, 1e-5f, o.flags & 3, at(o.dst), stream);
+        break;
+      case SPVD_OP_ATTENTION:
+        SPVD_CHECK_ARG(lv && lv->batch_offsets, "op %d: level %d has no per-cloud offsets", i, o.level);
+        rc = spvd_attention_fwd(at(o.src0), lv->batch_offsets, n_batch, lv->max_per_batch, o.c1, o.i0, o.flags & 3,
+                                at(o.dst), stream);
+        break;
+      default:
+        set_error("spvd_program_run: op %d has unknown opcode %d", i, o.op);
+        return SPVD_ERR_INVALID;
+    }
+    if (rc != SPVD_OK) return rc;
+  }
+  return SPVD_OK;
+}

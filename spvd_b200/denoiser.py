@@ -172,6 +172,8 @@ class SPVUnet(nn.Module):
         self.out_conv = _bn_silu_linear(c_out, point_channels, bias=False)
         self._plan = self._make_plan(down_blocks, up_blocks)
         self._folded = {}
+        self._programs = {}          # (n_points, n_batch) -> runtime.Program (native inference executor)
+        self.use_executor = True
 
     # -- static description of which strides need which maps (so Geometry can build all of them up front)
     @staticmethod
@@ -194,7 +196,27 @@ class SPVUnet(nn.Module):
         assert s >= 1
         return dict(strides=tuple(strides), p2v=tuple(sorted(set(p2v))), devox=tuple(sorted(set(devox))), top=top)
 
+    # -- compiled inference programs hold raw pointers to prepared weights: drop them whenever the
+    #    parameters can have changed (mode switch, device move, state-dict load)
+    def invalidate_programs(self):
+        self._programs.clear()
+        self._folded.clear()
+
+    def train(self, mode=True):
+        self.invalidate_programs()
+        return super().train(mode)
+
+    def _apply(self, fn, *args, **kwargs):
+        self.invalidate_programs()
+        return super()._apply(fn, *args, **kwargs)
+
+    def load_state_dict(self, *args, **kwargs):
+        self.invalidate_programs()
+        return super().load_state_dict(*args, **kwargs)
+
     def set_conv_impl(self, impl):
+        self.invalidate_programs()
+        self.use_executor = impl == ops.CONV_AUTO
         for m in self.modules():
             if isinstance(m, Conv3d):
                 m.impl = impl
@@ -266,6 +288,21 @@ class SPVUnet(nn.Module):
         if not feats.is_cuda:
             raise RuntimeError("spvd_b200.SPVUnet runs on CUDA only (no CPU fallback)")
         geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0])
+        if self.use_executor and self._fast() and len(inp) == 2:
+            from .runtime import Program
+            key = (feats.shape[0], t.shape[0])
+            prog = self._programs.get(key)
+            if prog is None:
+                prog = self._programs[key] = Program(self, *key)
+            sink = getattr(self, "profile_sink", None)
+            if sink is None:
+                return prog.run(geo, feats.contiguous().float(), t)
+            evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(prog.conv_meta))]
+            for e in evs:
+                e.record()                      # materialises the cudaEvent_t handles
+            out = prog.run(geo, feats.contiguous().float(), t, conv_events=[e.cuda_event for e in evs])
+            sink.append((evs, prog.conv_meta, geo, prog.strides))
+            return out
         # timestep embedding (models/utils.py:15-19; linspace(0,1,d/2) includes 1.0) + MLP
         exponent = -math.log(10000) * torch.linspace(0, 1, self.n_temb // 2, device=t.device)
         e = t[:, None].float() * exponent.exp()[None, :]

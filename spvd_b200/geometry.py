@@ -155,3 +155,14 @@ class Geometry:
             mask = torch.arange(nmax, device=b.device)[None, :] < counts[:, None]
             lv._dense = (b * nmax + pos, mask, nb, nmax)
         return lv._dense
+
+    def batch_offsets(self, s):
+        """int32 [B+1]: first row of every cloud at tensor stride s (rows are batch-major)."""
+        lv = self.levels[s]
+        if getattr(lv, "_offsets", None) is None:
+            if lv.batch_counts is None:
+                raise RuntimeError("Geometry was built without n_batch; attention needs per-cloud counts")
+            off = torch.zeros(lv.batch_counts.shape[0] + 1, dtype=torch.int32, device=lv.batch_counts.device)
+            off[1:] = torch.cumsum(lv.batch_counts, 0)
+            lv._offsets = off
+        return lv._offsets

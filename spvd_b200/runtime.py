@@ -1,0 +1,344 @@
+"""Host side of the native inference executor (include/spvd_b200.h, section M2).
+
+``compile_model`` walks an ``SPVUnet`` once and emits a flat program of ``spvd_op_t`` records --
+the eval-mode forward of the reference (models/spvd.py:432-457) with BatchNorm folded into affines,
+FiLM fused with the following BatchNorm+SiLU, residual adds fused into the convolution epilogues
+and every nn.Linear expressed as a kernel-size-1 sparse convolution -- over one activation arena
+whose slots are assigned by liveness.  ``Program.run`` then executes a whole forward with a single
+C call (spvd_program_run); row counts come from the planned Geometry.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn.functional as F
+
+from . import ops
+from ._C import check, lib
+from .geometry import Geometry
+
+OP_SCATTER_MEAN, OP_DEVOX, OP_CONV, OP_AFFINE, OP_FILM_AFFINE, OP_CAT, OP_LAYERNORM, OP_ATTENTION = range(8)
+MAP_NONE, MAP_K3, MAP_DOWN, MAP_UP = range(4)
+ROWS_POINTS, ROWS_BATCH = -1, -2
+FLAG_SILU, FLAG_ROUND, FLAG_A_TF32, FLAG_SIMT = 1, 2, 4, 8
+KERNELS_PER_OP = {OP_SCATTER_MEAN: 2, OP_DEVOX: 1, OP_CONV: 1, OP_AFFINE: 1, OP_FILM_AFFINE: 1, OP_CAT: 1,
+                  OP_LAYERNORM: 1, OP_ATTENTION: 1}
+
+
+class LevelGeom(C.Structure):
+    _fields_ = [("coords", C.c_void_p), ("kmap3", C.c_void_p), ("mask3", C.c_void_p), ("kmap_down", C.c_void_p),
+                ("mask_down", C.c_void_p), ("kmap_up", C.c_void_p), ("mask_up", C.c_void_p), ("p2v", C.c_void_p),
+                ("devox_idx", C.c_void_p), ("devox_w", C.c_void_p), ("batch_offsets", C.c_void_p),
+                ("n", C.c_int32), ("ld3", C.c_int32), ("ld_down", C.c_int32), ("ld_up", C.c_int32),
+                ("max_per_batch", C.c_int32), ("pad", C.c_int32)]
+
+
+class Op(C.Structure):
+    _fields_ = [("op", C.c_int32), ("flags", C.c_int32), ("level", C.c_int32), ("map_kind", C.c_int32),
+                ("rows_in", C.c_int32), ("rows_out", C.c_int32),
+                ("c0", C.c_int32), ("c1", C.c_int32), ("kvol", C.c_int32), ("i0", C.c_int32), ("i1", C.c_int32),
+                ("pad", C.c_int32),
+                ("src0", C.c_int64), ("src1", C.c_int64), ("dst", C.c_int64), ("aux", C.c_int64),
+                ("w", C.c_void_p), ("w_packed", C.c_void_p), ("bias", C.c_void_p), ("p0", C.c_void_p), ("p1", C.c_void_p)]
+
+
+class _Reg:
+    __slots__ = ("rows", "ch", "offset", "last", "name")
+
+    def __init__(self, rows, ch, name=""):
+        self.rows, self.ch, self.offset, self.last, self.name = rows, ch, -1, -1, name
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+class Program:
+    def __init__(self, model, n_points, n_batch):
+        self.model, self.n_points, self.n_batch = model, n_points, n_batch
+        self.dev = next(model.parameters()).device
+        self.keep = []            # prepared parameter tensors (kept alive; the ops hold raw pointers)
+        self.recs = []            # dicts before register allocation
+        self.regs = []
+        self.strides = list(model._plan["strides"])
+        self._emit()
+        self._allocate()
+        self._finalize()
+        self.key = self.param_key(model)
+
+    # ------------------------------------------------------------------------------ parameters
+    @staticmethod
+    def param_key(model):
+        return tuple((p.data_ptr(), p._version) for p in list(model.parameters()) + list(model.buffers()))
+
+    def _hold(self, t):
+        t = t.detach().contiguous().float()
+        self.keep.append(t)
+        return t
+
+    def _conv_params(self, w3, bias, force_simt=False):
+        w3 = self._hold(w3)
+        wp = None
+        if not force_simt and ops.umma_supported(*w3.shape):
+            wp = ops.pack_weights(w3)
+            self.keep.append(wp)
+        return w3, wp, (self._hold(bias) if bias is not None else None)
+
+    def _linear_params(self, lin):
+        return self._conv_params(lin.weight.detach().t().unsqueeze(0), lin.bias)
+
+    def _bn(self, bn):
+        scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
+        shift = bn.bias.detach() - bn.running_mean * scale
+        return self._hold(scale), self._hold(shift)
+
+    # ------------------------------------------------------------------------------ emission
+    def reg(self, rows, ch, name=""):
+        r = _Reg(rows, ch, name)
+        self.regs.append(r)
+        return r
+
+    def op(self, op, dst, src0, src1=None, aux=None, **kw):
+        self.recs.append(dict(op=op, dst=dst, src0=src0, src1=src1, aux=aux, **kw))
+        return dst
+
+    def conv(self, x, params, kvol, map_kind, level, rows_out, cout, residual=None, a_tf32=False):
+        w3, wp, bias = params
+        flags = (FLAG_A_TF32 if (a_tf32 and wp is not None) else 0) | (FLAG_SIMT if wp is None else 0)
+        return self.op(OP_CONV, self.reg(rows_out, cout), x, residual, flags=flags, level=level, map_kind=map_kind,
+                       rows_in=x.rows, rows_out=rows_out, c0=x.ch, c1=cout, kvol=kvol, w=w3, w_packed=wp, bias=bias)
+
+    def linear(self, x, lin, residual=None, a_tf32=False):
+        return self.conv(x, self._linear_params(lin), 1, MAP_NONE, -1, x.rows, lin.out_features, residual, a_tf32)
+
+    def affine(self, x, bn, silu=True, rnd=False):
+        s, b = self._bn(bn)
+        return self.op(OP_AFFINE, self.reg(x.rows, x.ch), x, flags=(FLAG_SILU if silu else 0) | (FLAG_ROUND if rnd else 0),
+                       level=-1, rows_in=x.rows, rows_out=x.rows, c0=x.ch, c1=x.ch, p0=s, p1=b)
+
+    def _umma_ok(self, lin_or_conv_in, cout):
+        return lin_or_conv_in % 32 == 0 and cout % 32 == 0
+
+    def point_block(self, pb, z1, z):
+        lin = pb.conv[2]
+        rnd = self._umma_ok(lin.in_features, lin.out_features)
+        a = self.affine(z, pb.conv[0], True, rnd)
+        return self.linear(a, lin, residual=z1, a_tf32=rnd)
+
+    def res_block(self, blk, x, lvl):
+        c1, c2 = blk.conv1[2], blk.conv2[2]
+        nf = c1.out_channels
+        a1 = self.affine(x, blk.conv1[0], True, True)
+        h1 = self.conv(a1, self._conv_params(c1.kernel, c1.bias), 27, MAP_K3, lvl, lvl, nf, a_tf32=True)
+        s2, b2 = self._bn(blk.conv2[0])
+        off = self.tt_offsets[id(blk)]
+        a2 = self.op(OP_FILM_AFFINE, self.reg(lvl, nf), h1, self.tt, flags=FLAG_SILU | FLAG_ROUND, level=lvl, rows_in=lvl,
+                     rows_out=lvl, c0=nf, c1=nf, i0=self.tt_width, i1=off, p0=s2, p1=b2)
+        res = self.linear(x, blk.idconv) if hasattr(blk, "idconv") else x
+        h2 = self.conv(a2, self._conv_params(c2.kernel, c2.bias), 27, MAP_K3, lvl, lvl, nf, residual=res, a_tf32=True)
+        if hasattr(blk, "attn"):
+            at = blk.attn
+            ln = self.op(OP_LAYERNORM, self.reg(lvl, nf), h2, flags=FLAG_ROUND, level=-1, rows_in=lvl, rows_out=lvl,
+                         c0=nf, c1=nf, p0=self._hold(at.norm1.weight), p1=self._hold(at.norm1.bias))
+            qkv = self.linear(ln, at.attn.qkv, a_tf32=True)
+            ao = self.op(OP_ATTENTION, self.reg(lvl, nf), qkv, flags=FLAG_ROUND, level=lvl, rows_in=lvl, rows_out=lvl,
+                         c0=3 * nf, c1=nf, i0=at.attn.num_heads)
+            h2 = self.linear(ao, at.attn.proj, residual=h2, a_tf32=True)
+            self.attn_levels.add(lvl)
+        return h2
+
+    def _emit(self):
+        m = self.model
+        P = ROWS_POINTS
+        pc = m.point_channels
+        n_emb = m.emb_mlp[1][1].out_features
+        # one GEMM for all FiLM projections: tt = Linear_cat(silu(emb))  [B, sum 2C]
+        blocks = [mod for mod in m.modules() if mod.__class__.__name__ == "EmbResBlock"]
+        ws, bs, self.tt_offsets, col = [], [], {}, 0
+        for b in blocks:
+            self.tt_offsets[id(b)] = col
+            ws.append(b.t_emb.proj_mlp.weight.detach())
+            bs.append(b.t_emb.proj_mlp.bias.detach())
+            col += b.t_emb.proj_mlp.out_features
+        self.tt_width = col
+        self.attn_levels = set()
+        self.in_feats = self.reg(P, pc, "feats")
+        self.in_emb = self.reg(ROWS_BATCH, n_emb, "emb_act")
+        wcat = torch.cat(ws, 0).t().unsqueeze(0)          # [1, n_emb, sum 2C]
+        self.tt = self.conv(self.in_emb, self._conv_params(wcat, torch.cat(bs, 0), force_simt=True), 1, MAP_NONE, -1,
+                            ROWS_BATCH, col)
+
+        def scatter(z, lvl):
+            return self.op(OP_SCATTER_MEAN, self.reg(lvl, z.ch), z, aux=self.reg(lvl, 1, "counts"), flags=0, level=lvl,
+                           rows_in=P, rows_out=lvl, c0=z.ch, c1=z.ch)
+
+        def devox(x, lvl):
+            return self.op(OP_DEVOX, self.reg(P, x.ch), x, flags=0, level=lvl, rows_in=lvl, rows_out=P, c0=x.ch, c1=x.ch)
+
+        z = self.in_feats
+        lvl = 0
+        x = scatter(z, 0)
+        st = m.stem_conv
+        c0, c3 = st.voxel_conv[0], st.voxel_conv[3]
+        x = self.conv(x, self._conv_params(c0.kernel, c0.bias), 27, MAP_K3, 0, 0, c0.out_channels)
+        x = self.affine(x, st.voxel_conv[1], True, True)
+        x = self.conv(x, self._conv_params(c3.kernel, c3.bias), 27, MAP_K3, 0, 0, c3.out_channels, a_tf32=True)
+        z = self.point_block(st.point_conv, devox(x, 0), z)
+        x = scatter(z, 0)
+        saved = [x]
+        for stage in m.down_stages:
+            for blk in stage.downs:
+                for r in blk.resnets:
+                    x = self.res_block(r, x, lvl)
+                    saved.append(x)
+                d = blk.down
+                if blk.add_down:
+                    x = self.conv(x, self._conv_params(d.kernel, d.bias), 8, MAP_DOWN, lvl, lvl + 1, d.out_channels)
+                    lvl += 1
+                    saved.append(x)
+                else:
+                    x = self.conv(x, self._conv_params(d.kernel.unsqueeze(0), d.bias), 1, MAP_NONE, -1, lvl, d.out_channels)
+            z = self.point_block(stage.point_block, devox(x, lvl), z)
+            x = scatter(z, lvl)
+        for si, stage in enumerate(m.up_stages):
+            for blk in stage.ups:
+                for r in blk.resnets:
+                    skip = saved.pop()
+                    xc = self.op(OP_CAT, self.reg(lvl, x.ch + skip.ch), x, skip, flags=0, level=-1, rows_in=lvl,
+                                 rows_out=lvl, c0=x.ch, c1=skip.ch)
+                    x = self.res_block(r, xc, lvl)
+                u = blk.up
+                if blk.add_up:
+                    lvl -= 1
+                    x = self.conv(x, self._conv_params(u.kernel, u.bias), 8, MAP_UP, lvl, lvl, u.out_channels)
+                    self.recs[-1]["rows_in"] = lvl + 1
+                else:
+                    x = self.conv(x, self._conv_params(u.kernel.unsqueeze(0), u.bias), 1, MAP_NONE, -1, lvl, u.out_channels)
+            z = self.point_block(stage.point_block, devox(x, lvl), z)
+            if si + 1 < len(m.up_stages):
+                x = scatter(z, lvl)
+        assert not saved
+        a = self.affine(z, m.out_conv[0], True, False)
+        self.out = self.linear(a, m.out_conv[2])
+
+    # ------------------------------------------------------------------------------ arena
+    def _bytes(self, r):
+        rows = self.n_batch if r.rows == ROWS_BATCH else self.n_points
+        return (rows * r.ch * 4 + 255) // 256 * 256
+
+    def _allocate(self):
+        for i, rec in enumerate(self.recs):
+            for k in ("src0", "src1", "aux", "dst"):
+                if rec[k] is not None:
+                    rec[k].last = i
+        self.in_feats.last = max(self.in_feats.last, 0)
+        self.out.last = len(self.recs) + 1
+        free, top = [], 0                       # free: list of (offset, size)
+
+        def alloc(r):
+            nonlocal top
+            need = self._bytes(r)
+            for j, (off, size) in enumerate(free):
+                if size >= need:
+                    if size == need:
+                        free.pop(j)
+                    else:
+                        free[j] = (off + need, size - need)
+                    r.offset = off
+                    return
+            r.offset = top
+            top += need
+
+        def release(r):
+            free.append((r.offset, self._bytes(r)))
+            free.sort()
+            merged = []
+            for off, size in free:
+                if merged and merged[-1][0] + merged[-1][1] == off:
+                    merged[-1] = (merged[-1][0], merged[-1][1] + size)
+                else:
+                    merged.append((off, size))
+            free[:] = merged
+
+        alloc(self.in_feats)
+        alloc(self.in_emb)
+        for i, rec in enumerate(self.recs):
+            for k in ("dst", "aux"):
+                r = rec[k]
+                if r is not None and r.offset < 0:
+                    alloc(r)
+            for r in {id(rec[k]): rec[k] for k in ("src0", "src1", "aux", "dst") if rec[k] is not None}.values():
+                if r.last == i and r is not self.out:
+                    release(r)
+        self.arena_bytes = top + 256
+
+    def _finalize(self):
+        n = len(self.recs)
+        self.c_ops = (Op * n)()
+        self.n_kernels = 0
+        self.conv_meta = []
+        for i, rec in enumerate(self.recs):
+            o = self.c_ops[i]
+            o.op, o.flags, o.level, o.map_kind = rec["op"], rec.get("flags", 0), rec.get("level", -1), rec.get("map_kind", 0)
+            o.rows_in, o.rows_out = rec["rows_in"], rec["rows_out"]
+            o.c0, o.c1, o.kvol, o.i0, o.i1 = rec["c0"], rec["c1"], rec.get("kvol", 0), rec.get("i0", 0), rec.get("i1", 0)
+            o.src0 = rec["src0"].offset
+            o.src1 = rec["src1"].offset if rec["src1"] is not None else -1
+            o.dst = rec["dst"].offset
+            o.aux = rec["aux"].offset if rec["aux"] is not None else -1
+            for k in ("w", "w_packed", "bias", "p0", "p1"):
+                t = rec.get(k)
+                setattr(o, k, t.data_ptr() if t is not None else None)
+            self.n_kernels += KERNELS_PER_OP[rec["op"]]
+            if rec["op"] == OP_CONV:
+                self.conv_meta.append((rec["kvol"], rec["c0"], rec["c1"], rec["rows_out"], rec["level"], rec["map_kind"],
+                                       "umma" if (rec.get("w_packed") is not None) else "simt"))
+        self.arena = torch.empty(self.arena_bytes, dtype=torch.uint8, device=self.dev)
+        self.arena_f = self.arena.view(torch.float32)
+        self.c_levels = (LevelGeom * len(self.strides))()
+
+    # ------------------------------------------------------------------------------ execution
+    def _view(self, r, rows):
+        o = r.offset // 4
+        return self.arena_f[o: o + rows * r.ch].view(rows, r.ch)
+
+    def fill_levels(self, geo: Geometry):
+        for i, s in enumerate(self.strides):
+            lv, g = geo.level(s), self.c_levels[i]
+            g.coords, g.n = lv.coords_cap.data_ptr(), lv.n
+            if lv.kmap3 is not None:
+                g.kmap3, g.mask3, g.ld3 = lv.kmap3.map_t.data_ptr(), lv.kmap3.mask.data_ptr(), lv.kmap3.map_t.shape[1]
+            if lv.kmap_down is not None:
+                g.kmap_down, g.mask_down, g.ld_down = (lv.kmap_down.map_t.data_ptr(), lv.kmap_down.mask.data_ptr(),
+                                                       lv.kmap_down.map_t.shape[1])
+                g.kmap_up, g.mask_up, g.ld_up = lv.kmap_up.map_t.data_ptr(), lv.kmap_up.mask.data_ptr(), lv.kmap_up.map_t.shape[1]
+            g.p2v = geo.p2v[s].data_ptr() if s in geo.p2v else None
+            if s in geo.devox:
+                g.devox_idx, g.devox_w = geo.devox[s][0].data_ptr(), geo.devox[s][1].data_ptr()
+            if i in self.attn_levels:
+                g.batch_offsets = geo.batch_offsets(s).data_ptr()
+                g.max_per_batch = max(lv.batch_counts_host)
+
+    def run(self, geo: Geometry, feats: torch.Tensor, t: torch.Tensor, conv_events=None):
+        m = self.model
+        if feats.shape[0] != self.n_points or t.shape[0] != self.n_batch:
+            raise RuntimeError("Program was compiled for a different number of points / clouds")
+        # timestep embedding + MLP on [B, n_temb] (models/utils.py:15-19; models/spvd.py:391-392)
+        exponent = -math.log(10000) * torch.linspace(0, 1, m.n_temb // 2, device=t.device)
+        e = t[:, None].float() * exponent.exp()[None, :]
+        e = torch.cat([e.sin(), e.cos()], dim=-1)
+        emb = m.emb_mlp[0][2](F.silu(m.emb_mlp[0][0](e)))
+        emb = m.emb_mlp[1][1](F.silu(emb))
+        self._view(self.in_emb, self.n_batch).copy_(F.silu(emb))
+        self._view(self.in_feats, self.n_points).copy_(feats)
+        self.fill_levels(geo)
+        ev = None
+        if conv_events is not None:
+            ev = (C.c_void_p * len(conv_events))(*conv_events)
+        check(lib.spvd_program_run(self.c_ops, len(self.recs), self.c_levels, len(self.strides), self.n_points,
+                                   self.n_batch, C.c_void_p(self.arena.data_ptr()), self.arena_bytes, ev,
+                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ops.stats.launches += self.n_kernels
+        return self._view(self.out, self.n_points).clone()

@@ -75,9 +75,37 @@ def test_config1_b4x2048_vs_oracle(sp, mode):
     with torch.no_grad():
         want = om.forward(sd, "SPVD", coords, feats, t, downsample_mode=mode, scale_mode="mul")
         want_tf32 = om.forward(sd, "SPVD", coords, feats, t, downsample_mode=mode, scale_mode="mul", emulate_tf32=True)
-        y = m((sp.SparseTensor(feats.cuda(), coords.cuda()), t.cuda())).cpu().numpy()
+        y_exec = m((sp.SparseTensor(feats.cuda(), coords.cuda()), t.cuda())).cpu().numpy()   # native executor
+        m.use_executor = False
+        y = m((sp.SparseTensor(feats.cuda(), coords.cuda()), t.cuda())).cpu().numpy()        # op-by-op python path
         m.set_conv_impl(sp.ops.CONV_SIMT)
         y32 = m((sp.SparseTensor(feats.cuda(), coords.cuda()), t.cuda())).cpu().numpy()
     assert rel_err(y32, want.numpy()) < 2e-5                 # fp32 kernels vs fp32 oracle
     assert rel_err(y, want_tf32.numpy()) < 1e-4              # tensor-core path vs TF32-emulating oracle
     assert rel_err(y, want.numpy()) < 1e-3                   # and within the stated tolerance of plain fp32
+    assert rel_err(y_exec, want.numpy()) < 1e-3              # executor: nn.Linear layers also run as TF32 k=1 convs
+
+
+def test_native_executor_matches_python_path_and_oracle(sp):
+    """The one-call C executor (spvd_program_run) against the op-by-op Python path on the same weights and
+    geometry, and against the TF32-emulating oracle."""
+    from oracle import model as om
+    g = torch.Generator().manual_seed(5)
+    pts = torch.randn(3, 1024, 3, generator=g).clamp(-3, 3)
+    coords, feats, _ = om.torch2sparse(pts)
+    t = torch.tensor([999, 500, 3])
+    for preset in ("SPVD_TINY", "SPVD"):
+        m, sd = make_model(sp, preset, 1, "spconv", "mul", sp.ops.CONV_AUTO)
+        m.eval()
+        x = sp.SparseTensor(feats.cuda(), coords.cuda())
+        with torch.no_grad():
+            assert m.use_executor
+            y_exec = m((x, t.cuda())).cpu().numpy()
+            assert len(m._programs) == 1
+            m.use_executor = False
+            y_py = m((x, t.cuda())).cpu().numpy()
+            want = om.forward(sd, preset, coords, feats, t, emulate_tf32=True).numpy()
+            want32 = om.forward(sd, preset, coords, feats, t).numpy()
+        assert rel_err(y_exec, y_py) < 3e-4        # Linear layers run as TF32 k=1 convs in the executor
+        assert rel_err(y_exec, want32) < 1e-3
+        assert rel_err(y_py, want) < 1e-4

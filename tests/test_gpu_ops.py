@@ -328,6 +328,44 @@ def test_fused_glue(sp):
     assert rel_err(sp.ops.film(x, tt, coords.cuda()).cpu().numpy(), want.cpu().numpy()) < 1e-6
 
 
+def test_layernorm_attention_cat_kernels(sp):
+    import ctypes
+    from spvd_b200._C import lib, check
+    g = torch.Generator().manual_seed(3)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    S = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for C_, heads in ((192, 8), (256, 8), (64, 4), (384, 8)):
+        counts = torch.tensor([37, 0, 300, 129, 1], dtype=torch.int32)
+        n = int(counts.sum())
+        off = torch.zeros(6, dtype=torch.int32)
+        off[1:] = torch.cumsum(counts, 0)
+        x = torch.randn(n, C_, generator=g).cuda()
+        gam, bet = torch.randn(C_, generator=g).cuda(), torch.randn(C_, generator=g).cuda()
+        y = torch.empty_like(x)
+        check(lib.spvd_layernorm_fwd(P(x), P(gam), P(bet), n, C_, 1e-5, 0, P(y), S))
+        want = torch.nn.functional.layer_norm(x, (C_,), gam, bet, 1e-5)
+        assert rel_err(y.cpu().numpy(), want.cpu().numpy()) < 1e-5
+        qkv = torch.randn(n, 3 * C_, generator=g).cuda()
+        out = torch.zeros(n, C_).cuda()
+        offd = off.cuda()
+        check(lib.spvd_attention_fwd(P(qkv), P(offd), 5, int(counts.max()), C_, heads, 0, P(out), S))
+        d = C_ // heads
+        ref = torch.zeros(n, C_)
+        q4 = qkv.cpu().view(n, 3, heads, d)
+        for b in range(5):
+            lo, hi = int(off[b]), int(off[b + 1])
+            if hi == lo:
+                continue
+            q, k, v = (q4[lo:hi, j].transpose(0, 1) for j in range(3))       # [H, L, d]
+            a = torch.softmax(q @ k.transpose(-2, -1) * d ** -0.5, dim=-1)
+            ref[lo:hi] = (a @ v).transpose(0, 1).reshape(hi - lo, C_)
+        assert rel_err(out.cpu().numpy(), ref.numpy()) < 1e-5
+    a, b = torch.randn(100, 64, generator=g).cuda(), torch.randn(100, 32, generator=g).cuda()
+    y = torch.empty(100, 96).cuda()
+    check(lib.spvd_cat_fwd(P(a), P(b), 100, 64, 32, P(y), S))
+    assert torch.equal(y, torch.cat([a, b], 1))
+
+
 def test_cpu_tensors_are_refused(sp):
     with pytest.raises(RuntimeError):
         sp.ops.point_voxel_coords(torch.zeros(4, 4), 1e-5, 0.1)
