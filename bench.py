@@ -195,19 +195,14 @@ def run_b200(args):
         flops = ms = 0.0
         n = 0
         table = {}
-        for evs, meta, geo, strides in sink:
-            pairs = {}
+        strides = model._plan["strides"]
+        for evs, meta, pairs, sizes in sink:
             for ci, (kvol, cin, cout, rows_out, level, map_kind, kind) in enumerate(meta):
                 dt = evs[2 * ci].elapsed_time(evs[2 * ci + 1])
                 if map_kind == 0:
-                    n_out = geo.n_points if rows_out == -1 else (len(ts) and (args.batch if rows_out == -2 else geo.level(strides[rows_out]).n))
-                    P = n_out
+                    P = B * N if rows_out == -1 else (B if rows_out == -2 else sizes[rows_out])
                 else:
-                    lv = geo.level(strides[level])
-                    km = {1: lv.kmap3, 2: lv.kmap_down, 3: lv.kmap_up}[map_kind]
-                    if (level, map_kind) not in pairs:
-                        pairs[(level, map_kind)] = int((km.map_t[:, :km.n_out] >= 0).sum().item())
-                    P, n_out = pairs[(level, map_kind)], km.n_out
+                    P = pairs[(level, map_kind)]
                 fl = 2.0 * P * cin * cout
                 e = table.setdefault((kind, kvol, cin, cout, strides[level] if level >= 0 else rows_out), [0, 0.0, 0.0])
                 e[0] += 1

@@ -226,6 +226,40 @@ int spvd_attention_fwd(const float* qkv, const int32_t* batch_offsets, int n_bat
                        int heads, int act, float* out, spvd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Geometry planner: V1 + K1 + K2/K3 + V2/V3 for every tensor stride of the U-Net in one call, into
+ * caller-owned buffers (level i has tensor stride 2^i; NULL pointers = not needed at that level).
+ * Everything the reference caches lazily in _caches (models/sparse_utils.py:71,90,122-125 and the
+ * torchsparse kmaps/cmaps).  All buffers have n_points rows of capacity; maps have leading
+ * dimension ld.  When summary_host is non-NULL the call ends with ONE device->host copy of
+ * summary_count int32 from summary_dev (the caller lays the level counts, the status word and the
+ * per-cloud counts out contiguously there) followed by a stream synchronise -- the only host sync
+ * of a forward pass. */
+typedef struct spvd_plan_level {
+  int32_t* coords;  /* [n_points,4] */
+  int32_t* count;   /* [1] */
+  int64_t* keys;    /* hash table, capacity >= 2*n_points */
+  int32_t* vals;
+  int32_t* kmap3;   /* [27,ld] */
+  uint32_t* mask3;  /* [ld/128] */
+  int32_t* kmap_down; /* [8,ld]: next coarser level <- this level */
+  uint32_t* mask_down;
+  int32_t* kmap_up;   /* [8,ld]: this level <- next coarser level */
+  uint32_t* mask_up;
+  int32_t* p2v;       /* [n_points], misses clamped to row 0 (models/sparse_utils.py:93) */
+  int32_t* devox_idx; /* [n_points,8] */
+  float* devox_w;     /* [n_points,8] */
+  int32_t* batch_counts;  /* [n_batch] */
+  int32_t* batch_offsets; /* [n_batch+1] */
+  int32_t capacity, pad;
+} spvd_plan_level_t;
+
+int spvd_plan_build(const float* pc, int n_points, int n_batch, float init_res, float after_res,
+                    int scale_mode, int downsample_mode, const spvd_plan_level_t* levels, int n_levels,
+                    int ld, float* fcoords, int32_t* icoords, int32_t* status, const int32_t* summary_dev,
+                    int32_t* summary_host, int summary_count, void* workspace, size_t workspace_bytes,
+                    spvd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * M2  native inference executor: SPVUnet.forward (models/spvd.py:432-457, eval mode) as one call.
  * The host compiles the module tree once into spvd_op_t records whose operands are byte offsets
  * into one activation arena; row counts are resolved per call from the planned geometry. */

@@ -1,0 +1,103 @@
+// Geometry planner: every coordinate-only structure of one forward (voxel pyramid, hash tables,
+// kernel maps, point<->voxel indices, trilinear weights, per-cloud counts) from ONE C call into
+// caller-owned buffers, ending with the single device->host read of the level sizes.  Replaces the
+// ~20 synchronising steps of the reference (torch.unique / scatter_mean sizes / kernel-map builds,
+// SURVEY.md section 3.1) with ~150 back-to-back launches and one 1 KB copy.
+#include "common.cuh"
+
+namespace spvd {
+
+__global__ void k_batch_offsets(const int* __restrict__ counts, int nb, int* __restrict__ offsets) {
+  // nb is small (clouds per batch): one thread
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    int run = 0;
+    offsets[0] = 0;
+    for (int b = 0; b < nb; ++b) {
+      run += counts[b];
+      offsets[b + 1] = run;
+    }
+  }
+}
+
+__global__ void k_clamp_min0(int* __restrict__ idx, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && idx[i] < 0) idx[i] = 0;
+}
+
+}  // namespace spvd
+
+using namespace spvd;
+
+extern "C" {
+int spvd_point_voxel_coords(const float*, int, float, float, int, float*, int32_t*, spvd_stream_t);
+size_t spvd_unique_workspace_bytes(int);
+int spvd_unique_coords(const int32_t*, int, const int32_t*, int32_t*, int32_t*, int32_t*, void*, size_t, spvd_stream_t);
+int spvd_downsample_coords(const int32_t*, int, const int32_t*, int, int32_t*, int32_t*, int32_t*, void*, size_t,
+                           spvd_stream_t);
+int spvd_hash_build(const int32_t*, int, const int32_t*, int, int64_t*, int32_t*, int, int32_t*, spvd_stream_t);
+int spvd_kmap_subm3(const int32_t*, int, const int32_t*, const int64_t*, const int32_t*, int, int32_t*, int, uint32_t*,
+                    spvd_stream_t);
+int spvd_kmap_down2(const int32_t*, int, const int32_t*, const int64_t*, const int32_t*, int, int32_t*, int, uint32_t*,
+                    int32_t*, int, uint32_t*, int32_t*, int32_t*, spvd_stream_t);
+int spvd_point_voxel_query(const float*, int, int, const int64_t*, const int32_t*, int, int32_t*, spvd_stream_t);
+int spvd_devox_query(const float*, int, int, const int64_t*, const int32_t*, int, int32_t*, float*, spvd_stream_t);
+int spvd_batch_counts(const int32_t*, int, const int32_t*, int, int32_t*, spvd_stream_t);
+}
+
+#define SPVD_TRY(call)            \
+  do {                            \
+    int rc_ = (call);             \
+    if (rc_ != SPVD_OK) return rc_; \
+  } while (0)
+
+extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, float init_res, float after_res,
+                               int scale_mode, int downsample_mode, const spvd_plan_level_t* levels, int n_levels,
+                               int ld, float* fcoords, int32_t* icoords, int32_t* status, const int32_t* summary_dev,
+                               int32_t* summary_host, int summary_count, void* workspace, size_t workspace_bytes,
+                               spvd_stream_t stream) {
+  SPVD_CHECK_ARG(pc && levels && fcoords && icoords && status && workspace && n_points > 0 && n_levels > 0,
+                 "spvd_plan_build: bad arguments");
+  SPVD_CHECK_ARG(ld % 128 == 0 && ld >= n_points, "spvd_plan_build: ld %d must be a multiple of 128 >= n_points", ld);
+  cudaStream_t s = (cudaStream_t)stream;
+  SPVD_CUDA(cudaMemsetAsync(status, 0, 4, s));
+  SPVD_TRY(spvd_point_voxel_coords(pc, n_points, init_res, after_res, scale_mode, fcoords, icoords, stream));
+  for (int i = 0; i < n_levels; ++i) {
+    const spvd_plan_level_t& L = levels[i];
+    SPVD_CHECK_ARG(L.coords && L.count && L.keys && L.vals && L.capacity >= 2 * n_points,
+                   "spvd_plan_build: level %d lacks coords / count / hash buffers", i);
+    if (i == 0)
+      SPVD_TRY(spvd_unique_coords(icoords, n_points, nullptr, L.coords, L.count, status, workspace, workspace_bytes, stream));
+    else
+      SPVD_TRY(spvd_downsample_coords(levels[i - 1].coords, n_points, levels[i - 1].count, downsample_mode, L.coords,
+                                      L.count, status, workspace, workspace_bytes, stream));
+    SPVD_TRY(spvd_hash_build(L.coords, n_points, L.count, SPVD_ORDER_BXYZ, L.keys, L.vals, L.capacity, status, stream));
+    if (i > 0) {
+      const spvd_plan_level_t& F = levels[i - 1];
+      if (F.kmap_down || F.kmap_up)
+        SPVD_TRY(spvd_kmap_down2(F.coords, n_points, F.count, L.keys, L.vals, L.capacity, F.kmap_down, ld, F.mask_down,
+                                 F.kmap_up, ld, F.mask_up, nullptr, nullptr, stream));
+    }
+  }
+  for (int i = 0; i < n_levels; ++i) {
+    const spvd_plan_level_t& L = levels[i];
+    const int stride = 1 << i;
+    if (L.kmap3) SPVD_TRY(spvd_kmap_subm3(L.coords, n_points, L.count, L.keys, L.vals, L.capacity, L.kmap3, ld, L.mask3, stream));
+    if (L.p2v) {
+      SPVD_TRY(spvd_point_voxel_query(fcoords, n_points, stride, L.keys, L.vals, L.capacity, L.p2v, stream));
+      // misses go to row 0: idx_query.clamp_(0), models/sparse_utils.py:93
+      k_clamp_min0<<<cdiv(n_points, 256), 256, 0, s>>>(L.p2v, n_points);
+    }
+    if (L.devox_idx && L.devox_w)
+      SPVD_TRY(spvd_devox_query(fcoords, n_points, stride, L.keys, L.vals, L.capacity, L.devox_idx, L.devox_w, stream));
+    if (L.batch_counts) {
+      SPVD_TRY(spvd_batch_counts(L.coords, n_points, L.count, n_batch, L.batch_counts, stream));
+      if (L.batch_offsets) k_batch_offsets<<<1, 32, 0, s>>>(L.batch_counts, n_batch, L.batch_offsets);
+    }
+  }
+  SPVD_LAUNCH_CHECK();
+  if (summary_dev && summary_host && summary_count > 0) {
+    SPVD_CUDA(cudaMemcpyAsync(summary_host, summary_dev, (size_t)summary_count * 4, cudaMemcpyDeviceToHost, s));
+    SPVD_CUDA(cudaStreamSynchronize(s));
+  }
+  return SPVD_OK;
+}

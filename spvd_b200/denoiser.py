@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 from . import functional as SF
 from . import ops
-from .geometry import Geometry
+from .geometry import Geometry, PlanWorkspace
 from .sparse import SparseTensor
 
 
@@ -174,6 +174,8 @@ class SPVUnet(nn.Module):
         self._folded = {}
         self._programs = {}          # (n_points, n_batch) -> runtime.Program (native inference executor)
         self.use_executor = True
+        self._plan_ws = {}           # (n_points, n_batch, device) -> [PlanWorkspace pool, cursor]
+        self.geometry_pool = 2
 
     # -- static description of which strides need which maps (so Geometry can build all of them up front)
     @staticmethod
@@ -277,10 +279,22 @@ class SPVUnet(nn.Module):
 
     # -- forward -------------------------------------------------------------------------------
     def plan_geometry(self, coords: torch.Tensor, n_batch: int) -> Geometry:
+        """Plan every coordinate structure of the forward with one C call into persistent buffers.  Two
+        buffer sets alternate, so the geometry of the previous call stays valid while the next one is
+        planned (``geometry_pool`` > 2 keeps more alive, e.g. when several forwards precede one backward)."""
         p = self._plan
-        return Geometry(coords.float() if coords.dtype != torch.float32 else coords, self.pres, self.voxel_size,
-                        strides=p["strides"], p2v_strides=p["p2v"], devox_strides=p["devox"], n_batch=n_batch,
-                        downsample_mode=self.downsample_mode, scale_mode=self.scale_mode)
+        pc = (coords.float() if coords.dtype != torch.float32 else coords).contiguous()
+        key = (pc.shape[0], n_batch, pc.device)
+        pool = self._plan_ws.get(key)
+        if pool is None:
+            pool = self._plan_ws[key] = [[], 0]
+        if len(pool[0]) < self.geometry_pool:
+            pool[0].append(PlanWorkspace(pc.shape[0], n_batch, p["strides"], p["strides"], p["p2v"], p["devox"], pc.device))
+            ws = pool[0][-1]
+        else:
+            pool[1] = (pool[1] + 1) % len(pool[0])
+            ws = pool[0][pool[1]]
+        return ws.build(pc, self.pres, self.voxel_size, self.scale_mode, self.downsample_mode)
 
     def forward(self, inp, geometry: Geometry = None):
         x_in, t = inp[0], inp[1]
@@ -301,7 +315,14 @@ class SPVUnet(nn.Module):
             for e in evs:
                 e.record()                      # materialises the cudaEvent_t handles
             out = prog.run(geo, feats.contiguous().float(), t, conv_events=[e.cuda_event for e in evs])
-            sink.append((evs, prog.conv_meta, geo, prog.strides))
+            pairs = {}
+            for (kvol, cin, cout, rows_out, level, map_kind, kind) in prog.conv_meta:
+                if map_kind and (level, map_kind) not in pairs:
+                    lv = geo.level(prog.strides[level])
+                    km = {1: lv.kmap3, 2: lv.kmap_down, 3: lv.kmap_up}[map_kind]
+                    pairs[(level, map_kind)] = (km.map_t[:, :km.n_out] >= 0).sum()
+            sizes = {i: geo.level(s).n for i, s in enumerate(prog.strides)}
+            sink.append((evs, prog.conv_meta, {k: int(v.item()) for k, v in pairs.items()}, sizes))
             return out
         # timestep embedding (models/utils.py:15-19; linspace(0,1,d/2) includes 1.0) + MLP
         exponent = -math.log(10000) * torch.linspace(0, 1, self.n_temb // 2, device=t.device)

@@ -166,3 +166,116 @@ class Geometry:
             off[1:] = torch.cumsum(lv.batch_counts, 0)
             lv._offsets = off
         return lv._offsets
+
+
+# --------------------------------------------------------------------------------------------------
+# One-call planner (spvd_plan_build): persistent buffers + a single C call per forward
+# --------------------------------------------------------------------------------------------------
+import ctypes as _C
+
+from ._C import check as _check, lib as _lib
+
+
+class _PlanLevel(_C.Structure):
+    _fields_ = [(n, _C.c_void_p) for n in ("coords", "count", "keys", "vals", "kmap3", "mask3", "kmap_down", "mask_down",
+                                           "kmap_up", "mask_up", "p2v", "devox_idx", "devox_w", "batch_counts",
+                                           "batch_offsets")] + [("capacity", _C.c_int32), ("pad", _C.c_int32)]
+
+
+class _Table:
+    """view of a workspace hash table with the ops.HashTable attribute surface"""
+
+    def __init__(self, keys, vals):
+        self.keys, self.vals, self.capacity = keys, vals, keys.shape[0]
+
+    query = ops.HashTable.query
+
+
+class PlanWorkspace:
+    """All buffers of one Geometry for a fixed (n_points, n_batch, plan), allocated once; ``build`` fills them
+    with one C call and returns a Geometry that VIEWS them (valid until the workspace is built again)."""
+
+    def __init__(self, n_points, n_batch, strides, k3_strides, p2v_strides, devox_strides, device):
+        self.n_points, self.n_batch, self.strides = n_points, n_batch, tuple(strides)
+        assert all(s == 1 << i for i, s in enumerate(self.strides)), "strides must be 1,2,4,..."
+        i32 = dict(dtype=torch.int32, device=device)
+        nl, ld = len(self.strides), ops.round128(n_points)
+        self.ld = ld
+        self.fcoords = torch.empty((n_points, 4), dtype=torch.float32, device=device)
+        self.icoords = torch.empty((n_points, 4), **i32)
+        self.n_summary = nl + 1 + nl * n_batch
+        self.summary = torch.zeros(self.n_summary, **i32)
+        self.summary_host = torch.zeros(self.n_summary, dtype=torch.int32).pin_memory()
+        self.ws = torch.empty(max(_lib.spvd_unique_workspace_bytes(n_points), 256), dtype=torch.uint8, device=device)
+        self.c_levels = (_PlanLevel * nl)()
+        self.bufs = []
+        for i, s in enumerate(self.strides):
+            b = dict(coords=torch.empty((n_points, 4), **i32), keys=torch.empty(2 * n_points, dtype=torch.int64, device=device),
+                     vals=torch.empty(2 * n_points, **i32), count=self.summary[i: i + 1],
+                     batch_counts=self.summary[nl + 1 + i * n_batch: nl + 1 + (i + 1) * n_batch],
+                     batch_offsets=torch.zeros(n_batch + 1, **i32))
+            if s in k3_strides:
+                b["kmap3"], b["mask3"] = torch.empty((27, ld), **i32), torch.empty(ld // 128, **i32)
+            if i + 1 < nl:
+                b["kmap_down"], b["mask_down"] = torch.empty((8, ld), **i32), torch.empty(ld // 128, **i32)
+                b["kmap_up"], b["mask_up"] = torch.empty((8, ld), **i32), torch.empty(ld // 128, **i32)
+            if s in p2v_strides:
+                b["p2v"] = torch.empty(n_points, **i32)
+            if s in devox_strides:
+                b["devox_idx"] = torch.empty((n_points, 8), **i32)
+                b["devox_w"] = torch.empty((n_points, 8), dtype=torch.float32, device=device)
+            self.bufs.append(b)
+            L = self.c_levels[i]
+            for name, t in b.items():
+                setattr(L, name, t.data_ptr())
+            L.capacity = 2 * n_points
+        self.status = self.summary[nl: nl + 1]
+        # kernels launched by one build (ops.stats accounting)
+        self.n_kernels = 1 + 22 + 23 * (nl - 1) + nl + (nl - 1) + len(k3_strides) + 2 * len(p2v_strides) + len(devox_strides) + 2 * nl
+
+    def build(self, pc, pres, voxel_size, scale_mode="mul", downsample_mode="spconv"):
+        if not pc.is_cuda or pc.dtype != torch.float32 or not pc.is_contiguous() or pc.shape != (self.n_points, 4):
+            raise RuntimeError("PlanWorkspace.build needs a contiguous CUDA float32 [n_points,4] tensor")
+        _check(_lib.spvd_plan_build(
+            _C.c_void_p(pc.data_ptr()), self.n_points, self.n_batch, pres, voxel_size, ops._SCALE[scale_mode],
+            ops._DOWNSAMPLE[downsample_mode], self.c_levels, len(self.strides), self.ld,
+            _C.c_void_p(self.fcoords.data_ptr()), _C.c_void_p(self.icoords.data_ptr()), _C.c_void_p(self.status.data_ptr()),
+            _C.c_void_p(self.summary.data_ptr()), _C.c_void_p(self.summary_host.data_ptr()), self.n_summary,
+            _C.c_void_p(self.ws.data_ptr()), self.ws.numel(), _C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        ops.stats.launches += self.n_kernels
+        host = self.summary_host.tolist()
+        nl, nb = len(self.strides), self.n_batch
+        st = host[nl]
+        if st:
+            raise RuntimeError("spvd_b200: " + ("coordinate outside the packed 16-bit range; " if st & 1 else "") +
+                               ("hash table full" if st & 2 else ""))
+        geo = Geometry.__new__(Geometry)
+        geo.n_points, geo.mode, geo.status = self.n_points, downsample_mode, self.status
+        geo.fcoords, geo.levels, geo.p2v, geo.devox = self.fcoords, {}, {}, {}
+        for i, s in enumerate(self.strides):
+            b = self.bufs[i]
+            lv = Level(s, b["coords"], b["count"])
+            lv.n = host[i]
+            if lv.n == 0:
+                raise RuntimeError(f"empty voxel level at tensor stride {s} (downsample_mode={downsample_mode!r}); "
+                                   "the reference crashes here too (experiments/ConditionalGeneration.ipynb:421)")
+            lv.table = _Table(b["keys"], b["vals"])
+            lv.batch_counts = b["batch_counts"]
+            lv.batch_counts_host = host[nl + 1 + i * nb: nl + 1 + (i + 1) * nb]
+            lv._offsets = b["batch_offsets"]
+            geo.levels[s] = lv
+            if "p2v" in b:
+                geo.p2v[s] = b["p2v"]
+            if "devox_idx" in b:
+                geo.devox[s] = (b["devox_idx"], b["devox_w"])
+        for i, s in enumerate(self.strides):
+            b, lv = self.bufs[i], geo.levels[s]
+            if "kmap3" in b:
+                lv.kmap3 = KernelMap(b["kmap3"], b["mask3"], lv.n, lv.n, 27, flip=True)
+                lv.kmap3.grad = lv.kmap3
+            if "kmap_down" in b:
+                c = geo.levels[2 * s]
+                lv.kmap_down = KernelMap(b["kmap_down"], b["mask_down"], c.n, lv.n, 8, flip=False)
+                lv.kmap_up = KernelMap(b["kmap_up"], b["mask_up"], lv.n, c.n, 8, flip=False)
+                lv.kmap_down.grad, lv.kmap_up.grad = lv.kmap_up, lv.kmap_down
+        return geo

@@ -181,6 +181,31 @@ def test_geometry_matches_oracle(sp, mode):
         assert np.allclose(geo.devox[s][1].cpu().numpy(), w.numpy(), atol=2e-7)
 
 
+def test_one_call_planner_matches_op_by_op_geometry(sp):
+    """spvd_plan_build (one C call, persistent buffers) against the Geometry assembled from individual ops."""
+    coords, _ = cloud_points(4, 2048, 8)
+    pc = coords.float().cuda()
+    kw = dict(strides=(1, 2, 4, 8, 16), p2v_strides=(1, 4, 16), devox_strides=(1, 4, 16))
+    for mode in ("spconv", "floor"):
+        ref = sp.Geometry(pc, 1e-5, 0.1, n_batch=4, downsample_mode=mode, **kw)
+        ws = sp.geometry.PlanWorkspace(pc.shape[0], 4, kw["strides"], kw["strides"], kw["p2v_strides"], kw["devox_strides"], pc.device)
+        for _ in range(2):                                   # buffers are reused: build twice
+            geo = ws.build(pc, 1e-5, 0.1, "mul", mode)
+        assert torch.equal(geo.fcoords, ref.fcoords)
+        for s in kw["strides"]:
+            a, b = geo.level(s), ref.level(s)
+            assert a.n == b.n and torch.equal(a.coords, b.coords)
+            assert torch.equal(a.kmap3.map_t, b.kmap3.map_t) and torch.equal(a.kmap3.mask, b.kmap3.mask)
+            assert a.batch_counts_host == b.batch_counts_host
+            assert torch.equal(geo.batch_offsets(s), ref.batch_offsets(s))
+            if s < 16:
+                assert torch.equal(a.kmap_down.map_t, b.kmap_down.map_t) and torch.equal(a.kmap_up.map_t, b.kmap_up.map_t)
+                assert torch.equal(a.kmap_down.mask, b.kmap_down.mask) and torch.equal(a.kmap_up.mask, b.kmap_up.mask)
+        for s in (1, 4, 16):
+            assert torch.equal(geo.p2v[s], ref.p2v[s])
+            assert torch.equal(geo.devox[s][0], ref.devox[s][0]) and torch.equal(geo.devox[s][1], ref.devox[s][1])
+
+
 # ---------------------------------------------------------------------------- point <-> voxel ops
 @pytest.mark.parametrize("c", [3, 32, 192])
 def test_scatter_mean_and_devoxelize(sp, c):
