@@ -183,11 +183,12 @@ int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, in
  * accumulated with vector RED into the zero-filled output (0 = choose from the grid size);
  * a_is_tf32 != 0 promises that `in` is already TF32-representable (spvd_round_tf32, or a producer
  * that rounds, e.g. spvd_bn_silu_fwd with act & 2): the gather then runs as cp.async with kStages
- * slabs in flight instead of through registers with cvt.rna. */
+ * slabs in flight instead of through registers with cvt.rna;
+ * mt = 128-row output tiles per CTA sharing each weight tile (1 or 2; 0 = choose; 2 needs a_is_tf32). */
 int spvd_conv_fwd_umma(const float* in, const float* w_packed, const int32_t* map_t, int ld,
                        const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
                        const float* bias, const float* residual, float* out, int bn, int nsplit,
-                       int a_is_tf32, spvd_stream_t stream);
+                       int a_is_tf32, int mt, spvd_stream_t stream);
 /* gw[k] = sum over pairs (i,o) of offset k of in[i]^T gout[o];  gw [kvol,cin,cout] zero-filled inside */
 int spvd_conv_wgrad(const float* in, const float* gout, const int32_t* map_t, int ld, int n_out,
                     int kvol, int cin, int cout, float* gw, spvd_stream_t stream);

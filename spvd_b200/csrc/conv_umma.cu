@@ -91,15 +91,19 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return r;
 }
 
-template <int BN>
+template <int BN, int MT>
 struct UmmaCfg {
-  static constexpr int kTmemCols = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;
+  static constexpr int kCols = BN * MT;
+  static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
   static constexpr int kBTileBytes = BN * BK * 4;
-  static constexpr int kStageBytes = kATileBytes + kBTileBytes;
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kStageBytes = MT * kATileBytes + kBTileBytes;
+  static constexpr int kStages = (4 * kStageBytes <= 200 * 1024) ? 4 : (3 * kStageBytes <= 200 * 1024) ? 3 : 2;
+  static constexpr int kRowsBytes = MT * 27 * BM * 4;  // row indices of every offset of the tile, staged once
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kRowsBytes;
   // idesc: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
   static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                      ((uint32_t)(BM >> 4) << 24);
+  static_assert(kCols <= 512, "accumulators exceed TMEM");
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
@@ -113,12 +117,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
                : "memory");
 }
 
+// One CTA owns MT consecutive 128-row output tiles x BN output channels: every weight tile fetched from
+// L2 feeds MT tensor-core tiles (the weight stream, not the gathered rows, dominates L2 traffic).
 // kAsyncA: the input rows are already TF32-representable (the producing kernel rounded them), so the
 // gather is a zero-register cp.async (LDGSTS) with up to kStages slabs in flight per CTA.  Otherwise the
-// rows go through registers (cvt.rna.tf32) with the next slab's loads issued before the current stores.
-// gridDim.z > 1 = split over the (offset, slab) iterations; partial tiles are accumulated with vector RED
-// into a zero-initialised output (bias added by split 0).
-template <int BN, bool kAsyncA>
+// rows go through registers (cvt.rna.tf32) with the next slab's loads issued before the current stores
+// (MT = 1 only).  gridDim.z > 1 = split over the (offset, slab) iterations; partial tiles are accumulated
+// with vector RED into a zero-initialised output (bias / residual added by split 0).
+template <int BN, int MT, bool kAsyncA>
 __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __restrict__ in,
                                                                const float* __restrict__ w_packed,
                                                                const int* __restrict__ map_t, int ld,
@@ -127,7 +133,9 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
                                                                const float* __restrict__ bias,
                                                                const float* __restrict__ residual,
                                                                float* __restrict__ out) {
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, MT>;
+  constexpr int kStages = Cfg::kStages;
+  static_assert(kAsyncA || MT == 1, "the register gather path is instantiated for MT = 1 only");
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -135,13 +143,21 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   const uint32_t bar_base = base + kStages * Cfg::kStageBytes;  // full[kStages], empty[kStages], accum, tmem slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 1));
   int* active_k = reinterpret_cast<int*>(smem + kStages * Cfg::kStageBytes + 8 * (2 * kStages + 1) + 16);
+  int* s_rows = reinterpret_cast<int*>(smem + kStages * Cfg::kStageBytes + 256);   // [offset slot][MT*128]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * BM, n0 = blockIdx.y * BN;
+  const int m0 = blockIdx.x * (BM * MT), n0 = blockIdx.y * BN;
   const int nchunks = cin / BK;
+  const int n_tiles = (n_out + BM - 1) / BM;
 
   unsigned mask = kvol >= 32 ? 0xffffffffu : ((1u << kvol) - 1u);
-  if (tile_mask) mask &= tile_mask[blockIdx.x];
+  if (tile_mask) {
+    unsigned u = 0;
+#pragma unroll
+    for (int t = 0; t < MT; ++t)
+      if ((int)blockIdx.x * MT + t < n_tiles) u |= tile_mask[blockIdx.x * MT + t];
+    mask &= u;
+  }
   const int total_iters = __popc(mask) * nchunks;
   const int per_split = (total_iters + (int)gridDim.z - 1) / (int)gridDim.z;
   const int it_begin = min(total_iters, (int)blockIdx.z * per_split);
@@ -172,16 +188,32 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
+  // stage the input-row indices of every offset this CTA will visit (one coalesced pass; the per-iteration
+  // critical path then has no dependent global load in front of the gather)
+  const int ka_begin = num_iters > 0 ? it_begin / nchunks : 0;
+  const int ka_end = num_iters > 0 ? (it_end - 1) / nchunks + 1 : 0;
+  for (int e = tid; e < (ka_end - ka_begin) * (MT * BM); e += kUmmaThreads) {
+    const int slot = e / (MT * BM), r = e - slot * (MT * BM);
+    const int o = m0 + r;
+    int v = -1;
+    if (map_t) {
+      if (o < ld) v = __ldg(map_t + (size_t)active_k[ka_begin + slot] * ld + o);
+    } else if (o < n_out) {
+      v = o;
+    }
+    s_rows[e] = v;
+  }
+  __syncthreads();
+
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
     const int chunk16 = tid & 7;  // which 16-byte piece of the 128-byte row
-    const int r0 = tid >> 3;      // rows r0 + 16*i
-    int rows[8];
-    auto load_rows = [&](int k) {
+    const int r0 = tid >> 3;      // rows r0 + 16*i of each 128-row tile
+    int rows[MT * 8];
+    auto load_rows = [&](int ka) {
+      const int* sr = s_rows + (ka - ka_begin) * (MT * BM);
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        rows[i] = map_t ? __ldg(map_t + (size_t)k * ld + m0 + r0 + 16 * i)
-                        : (m0 + r0 + 16 * i < n_out ? m0 + r0 + 16 * i : -1);
+      for (int i = 0; i < MT * 8; ++i) rows[i] = sr[(i >> 3) * BM + r0 + 16 * (i & 7)];
     };
     if constexpr (kAsyncA) {
       for (int it = it_begin; it < it_end; ++it) {
@@ -190,18 +222,18 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
         const uint32_t parity = (uint32_t)(li / kStages) & 1u;
         const int ka = it / nchunks, c = it - ka * nchunks;
         const int k = active_k[ka];
-        if (c == 0 || li == 0) load_rows(k);
+        if (c == 0 || li == 0) load_rows(ka);
         mbar_wait(bar_base + 8 * (kStages + stage), parity ^ 1u);
         const uint32_t a_s = base + stage * Cfg::kStageBytes;
         if (tid == 0) {
           mbar_arrive_expect_tx(bar_base + 8 * stage, Cfg::kBTileBytes);
-          bulk_g2s(a_s + kATileBytes, w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK, Cfg::kBTileBytes,
+          bulk_g2s(a_s + MT * kATileBytes, w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK, Cfg::kBTileBytes,
                    bar_base + 8 * stage);
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int r = r0 + 16 * i;
-          const uint32_t dst = a_s + r * 128 + ((chunk16 ^ (r & 7)) << 4);
+        for (int i = 0; i < MT * 8; ++i) {
+          const int r = r0 + 16 * (i & 7);
+          const uint32_t dst = a_s + (i >> 3) * kATileBytes + r * 128 + ((chunk16 ^ (r & 7)) << 4);
           const bool ok = rows[i] >= 0;
           const float* src = ok ? in + (size_t)rows[i] * cin + c * BK + chunk16 * 4 : in;
           cp_async16(dst, src, ok ? 16u : 0u);
@@ -212,7 +244,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
       float4 v[8];
       auto issue_loads = [&](int it) {
         const int ka = it / nchunks, c = it - ka * nchunks;
-        if (c == 0 || it == it_begin) load_rows(active_k[ka]);
+        if (c == 0 || it == it_begin) load_rows(ka);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -239,7 +271,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
         const uint32_t a_s = base + stage * Cfg::kStageBytes;
         if (tid == 0) {
           mbar_arrive_expect_tx(bar_base + 8 * stage, Cfg::kBTileBytes);
-          bulk_g2s(a_s + kATileBytes, w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK, Cfg::kBTileBytes,
+          bulk_g2s(a_s + MT * kATileBytes, w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK, Cfg::kBTileBytes,
                    bar_base + 8 * stage);
         }
 #pragma unroll
@@ -255,7 +287,6 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
       }
     }
     // ------------------------------------------------------------------ epilogue
-    const int row = m0 + warp * 32 + lane;
     if (num_iters > 0) {
       mbar_wait(bar_base + 8 * (2 * kStages), 0);
       tc_fence_after();
@@ -263,42 +294,47 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
     const bool add_bias = bias != nullptr && blockIdx.z == 0;
     const bool add_res = residual != nullptr && blockIdx.z == 0;
 #pragma unroll 1
-    for (int cb = 0; cb < BN / 32; ++cb) {
-      uint32_t r[32];
-      if (num_iters > 0) {
-        const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(cb * 32);
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-            "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-            "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-            : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-              "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-              "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-              "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-            : "r"(taddr)
-            : "memory");
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      } else {
+    for (int mt = 0; mt < MT; ++mt) {
+      const int row = m0 + mt * BM + warp * 32 + lane;
+#pragma unroll 1
+      for (int cb = 0; cb < BN / 32; ++cb) {
+        uint32_t r[32];
+        if (num_iters > 0) {
+          const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(mt * BN + cb * 32);
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+              "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+              "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+              : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+                "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]),
+                "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+                "=r"(r[30]), "=r"(r[31])
+              : "r"(taddr)
+              : "memory");
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) r[j] = 0u;
-      }
-      if (row < n_out) {
-        float* dstf = out + (size_t)row * cout + n0 + cb * 32;
-        const float4* bp = add_bias ? reinterpret_cast<const float4*>(bias + n0 + cb * 32) : nullptr;
+          for (int j = 0; j < 32; ++j) r[j] = 0u;
+        }
+        if (row < n_out) {
+          float* dstf = out + (size_t)row * cout + n0 + cb * 32;
+          const float4* bp = add_bias ? reinterpret_cast<const float4*>(bias + n0 + cb * 32) : nullptr;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                 __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-          if (bp) {
-            float4 b = __ldg(bp + j);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          for (int j = 0; j < 8; ++j) {
+            float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+            if (bp) {
+              float4 b = __ldg(bp + j);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (add_res) {
+              float4 b = *reinterpret_cast<const float4*>(residual + (size_t)row * cout + n0 + cb * 32 + 4 * j);
+              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+            }
+            if (split) red_add_v4(dstf + 4 * j, o);
+            else reinterpret_cast<float4*>(dstf)[j] = o;
           }
-          if (add_res) {
-            float4 b = *reinterpret_cast<const float4*>(residual + (size_t)row * cout + n0 + cb * 32 + 4 * j);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (split) red_add_v4(dstf + 4 * j, o);
-          else reinterpret_cast<float4*>(dstf)[j] = o;
         }
       }
     }
@@ -308,16 +344,19 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
       const int stage = li % kStages;
       const uint32_t parity = (uint32_t)(li / kStages) & 1u;
       mbar_wait(bar_base + 8 * stage, parity);
-      if constexpr (kAsyncA) fence_proxy_async();   // cp.async wrote the A tile through the generic proxy
+      if constexpr (kAsyncA) fence_proxy_async();   // cp.async wrote the A tiles through the generic proxy
       tc_fence_after();
       if (lane == 0) {
         const uint32_t a_s = base + stage * Cfg::kStageBytes;
-        const uint64_t adesc = make_desc(a_s);
-        const uint64_t bdesc = make_desc(a_s + kATileBytes);
+        const uint64_t bdesc = make_desc(a_s + MT * kATileBytes);
 #pragma unroll
-        for (int kk = 0; kk < BK / 8; ++kk)
-          umma_tf32(tmem_d, adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), Cfg::kIdesc,
-                    (li > 0 || kk > 0) ? 1u : 0u);
+        for (int mt = 0; mt < MT; ++mt) {
+          const uint64_t adesc = make_desc(a_s + mt * kATileBytes);
+#pragma unroll
+          for (int kk = 0; kk < BK / 8; ++kk)
+            umma_tf32(tmem_d + (uint32_t)(mt * BN), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), Cfg::kIdesc,
+                      (li > 0 || kk > 0) ? 1u : 0u);
+        }
         umma_commit(bar_base + 8 * (kStages + stage));
         if (li == num_iters - 1) umma_commit(bar_base + 8 * (2 * kStages));
       }
@@ -347,31 +386,34 @@ __global__ void k_pack_weights(const float* __restrict__ w, int kvol, int cin, i
   wp[dst] = __uint_as_float(to_tf32(w[t]));
 }
 
-template <int BN, bool kAsyncA>
+template <int BN, int MT, bool kAsyncA>
 static int launch_umma(const float* in, const float* wp, const int32_t* map_t, int ld, const uint32_t* tile_mask,
                        int n_out, int kvol, int cin, int cout, const float* bias, const float* residual, float* out,
                        int nsplit, cudaStream_t s) {
-  using Cfg = UmmaCfg<BN>;
+  using Cfg = UmmaCfg<BN, MT>;
   static bool configured = false;
   if (!configured) {
-    SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN, kAsyncA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN, MT, kAsyncA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     configured = true;
   }
   if (nsplit > 1) SPVD_CUDA(cudaMemsetAsync(out, 0, (size_t)n_out * cout * 4, s));
-  dim3 grid(cdiv(n_out, BM), cout / BN, nsplit);
-  k_conv_fwd_umma<BN, kAsyncA><<<grid, kUmmaThreads, Cfg::kSmemBytes, s>>>(in, wp, map_t, ld, tile_mask, n_out, kvol,
-                                                                          cin, cout, bias, residual, out);
+  dim3 grid(cdiv(n_out, BM * MT), cout / BN, nsplit);
+  k_conv_fwd_umma<BN, MT, kAsyncA><<<grid, kUmmaThreads, Cfg::kSmemBytes, s>>>(in, wp, map_t, ld, tile_mask, n_out,
+                                                                              kvol, cin, cout, bias, residual, out);
   SPVD_LAUNCH_CHECK();
   return SPVD_OK;
 }
 
 template <int BN>
-static int launch_umma_bn(bool async_a, const float* in, const float* wp, const int32_t* map_t, int ld,
+static int launch_umma_bn(bool async_a, int mt, const float* in, const float* wp, const int32_t* map_t, int ld,
                           const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
                           const float* residual, float* out, int nsplit, cudaStream_t s) {
-  return async_a ? launch_umma<BN, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s)
-                 : launch_umma<BN, false>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+  if (!async_a)
+    return launch_umma<BN, 1, false>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+  if (mt >= 2)
+    return launch_umma<BN, 2, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+  return launch_umma<BN, 1, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
 }
 
 // widest instantiated slice that divides cout: the A tile is gathered once per slice, so fewer is better
@@ -415,7 +457,7 @@ extern "C" int spvd_conv_pack_weights(const float* w, int kvol, int cin, int cou
 extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const int32_t* map_t, int ld,
                                   const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
                                   const float* bias, const float* residual, float* out, int bn, int nsplit,
-                                  int a_is_tf32, spvd_stream_t stream) {
+                                  int a_is_tf32, int mt, spvd_stream_t stream) {
   SPVD_CHECK_ARG(in && w_packed && out && n_out >= 0, "spvd_conv_fwd_umma: bad arguments");
   SPVD_CHECK_ARG(residual != out || residual == nullptr, "spvd_conv_fwd_umma: residual must not alias out");
   SPVD_CHECK_ARG(spvd_conv_umma_supported(kvol, cin, cout), "spvd_conv_fwd_umma: unsupported shape %dx%dx%d", kvol, cin, cout);
@@ -429,16 +471,18 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
   if (bn <= 0) bn = pick_bn(cout);
   SPVD_CHECK_ARG(cout % bn == 0, "spvd_conv_fwd_umma: slice width %d does not divide cout %d", bn, cout);
   const int max_iters = kvol * (cin / 32);
-  if (nsplit <= 0) nsplit = pick_split(cdiv(n_out, BM) * (cout / bn), max_iters);
-  if (nsplit > max_iters) nsplit = max_iters;
   const bool aa = a_is_tf32 != 0;
+  if (mt <= 0) mt = (aa && n_out > BM && bn >= 128) ? 2 : 1;   // sharing the weight tile pays when it is large
+  if (!aa) mt = 1;
+  if (nsplit <= 0) nsplit = pick_split(cdiv(n_out, BM * mt) * (cout / bn), max_iters);
+  if (nsplit > max_iters) nsplit = max_iters;
   switch (bn) {
-    case 32: return launch_umma_bn<32>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 64: return launch_umma_bn<64>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 96: return launch_umma_bn<96>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 128: return launch_umma_bn<128>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 192: return launch_umma_bn<192>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 256: return launch_umma_bn<256>(aa, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 32: return launch_umma_bn<32>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 64: return launch_umma_bn<64>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 96: return launch_umma_bn<96>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 128: return launch_umma_bn<128>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 192: return launch_umma_bn<192>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 256: return launch_umma_bn<256>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
   }
   set_error("spvd_conv_fwd_umma: slice width %d is not instantiated", bn);
   return SPVD_ERR_INVALID;
@@ -454,7 +498,7 @@ extern "C" int spvd_conv_fwd(const float* in, const float* w, const float* w_pac
   bool umma_ok = w_packed && spvd_conv_umma_supported(kvol, cin, cout) && (!map_t || ld % 128 == 0);
   if (impl == SPVD_CONV_UMMA || (impl == SPVD_CONV_AUTO && umma_ok)) {
     SPVD_CHECK_ARG(umma_ok, "spvd_conv_fwd: the tcgen05 path needs packed weights, cin %% 32 == 0 and cout %% 32 == 0");
-    return spvd_conv_fwd_umma(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, nullptr, out, 0, 0, 0, stream);
+    return spvd_conv_fwd_umma(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, nullptr, out, 0, 0, 0, 0, stream);
   }
   SPVD_CHECK_ARG(w, "spvd_conv_fwd: the SIMT path needs the unpacked weights");
   return spvd_conv_fwd_simt(in, w, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, nullptr, out, stream);

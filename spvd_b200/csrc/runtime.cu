@@ -188,7 +188,7 @@ int spvd_devoxelize_fwd(const float*, const int32_t*, const float*, int, int, fl
 int spvd_conv_fwd_simt(const float*, const float*, const int32_t*, int, const uint32_t*, int, int, int, int,
                        const float*, const float*, float*, spvd_stream_t);
 int spvd_conv_fwd_umma(const float*, const float*, const int32_t*, int, const uint32_t*, int, int, int, int,
-                       const float*, const float*, float*, int, int, int, spvd_stream_t);
+                       const float*, const float*, float*, int, int, int, int, spvd_stream_t);
 int spvd_bn_silu_fwd(const float*, const float*, const float*, long long, int, int, float*, spvd_stream_t);
 }
 
@@ -304,7 +304,7 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
         if (conv_events) SPVD_CUDA(cudaEventRecord((cudaEvent_t)conv_events[2 * conv_index], (cudaStream_t)stream));
         if (o.w_packed && !(o.flags & SPVD_FLAG_SIMT))
           rc = spvd_conv_fwd_umma(at(o.src0), o.w_packed, map, ld, mask, (int)rout, o.kvol, o.c0, o.c1, o.bias,
-                                  at(o.src1), at(o.dst), 0, 0, (o.flags & SPVD_FLAG_A_TF32) ? 1 : 0, stream);
+                                  at(o.src1), at(o.dst), 0, 0, (o.flags & SPVD_FLAG_A_TF32) ? 1 : 0, 0, stream);
         else
           rc = spvd_conv_fwd_simt(at(o.src0), o.w, map, ld, mask, (int)rout, o.kvol, o.c0, o.c1, o.bias, at(o.src1),
                                   at(o.dst), stream);

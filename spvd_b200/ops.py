@@ -236,7 +236,7 @@ def transpose_weights(w3, flip):
     return wt
 
 
-def conv_fwd(x, w3, w_packed, map_t, mask, n_out, bias=None, impl=CONV_AUTO, bn=0, nsplit=0, a_tf32=False, residual=None):
+def conv_fwd(x, w3, w_packed, map_t, mask, n_out, bias=None, impl=CONV_AUTO, bn=0, nsplit=0, a_tf32=False, residual=None, mt=0):
     """x [n_in, cin]; w3 [kvol, cin, cout] (may be None when w_packed is given and the UMMA path applies);
     map_t [kvol, ld] or None (identity)."""
     if w3 is not None:
@@ -252,7 +252,7 @@ def conv_fwd(x, w3, w_packed, map_t, mask, n_out, bias=None, impl=CONV_AUTO, bn=
         ev[0].record()
     if impl == CONV_UMMA or (impl == CONV_AUTO and w_packed is not None and umma_supported(kvol, cin, cout)):
         check(lib.spvd_conv_fwd_umma(_p(x, torch.float32), _p(w_packed, torch.float32), _p(map_t), ld, _p(mask), n_out, kvol,
-                                     cin, cout, _p(bias), _p(residual), _p(out), int(bn), int(nsplit), int(bool(a_tf32)), _s()))
+                                     cin, cout, _p(bias), _p(residual), _p(out), int(bn), int(nsplit), int(bool(a_tf32)), int(mt), _s()))
     else:
         check(lib.spvd_conv_fwd_simt(_p(x, torch.float32), _p(w3, torch.float32), _p(map_t), ld, _p(mask), n_out, kvol, cin,
                                      cout, _p(bias), _p(residual), _p(out), _s()))

@@ -320,6 +320,19 @@ def test_conv_backward(sp, kind, cin, cout, impl):
     assert rel_err(bb.grad.cpu().numpy(), ba.grad.numpy()) < 1e-5
 
 
+@pytest.mark.parametrize("mt", [1, 2])
+@pytest.mark.parametrize("cout", [32, 128, 192, 256])
+def test_conv_tcgen05_two_tiles_per_cta(sp, mt, cout):
+    x, w, b, m, n_out, km, oo = _conv_case(sp, "k3", 64, cout, 29)
+    want = oo.conv_gather_gemm_scatter(x, w, m, n_out, b, emulate_tf32=True)
+    xd = sp.ops.round_tf32(x.cuda())
+    res = torch.randn(n_out, cout, generator=torch.Generator().manual_seed(2))
+    wp = sp.ops.pack_weights(w.cuda())
+    got = sp.ops.conv_fwd(xd, w.cuda(), wp, km.map_t, km.mask, n_out, b.cuda(), sp.ops.CONV_UMMA, a_tf32=True, mt=mt,
+                          residual=res.cuda())
+    assert rel_err(got.cpu().numpy(), (want + res).numpy()) < 2e-5
+
+
 @pytest.mark.parametrize("nsplit", [1, 3, 16])
 @pytest.mark.parametrize("a_tf32", [False, True])
 def test_conv_tcgen05_split_and_async_gather(sp, nsplit, a_tf32):
