@@ -1,0 +1,86 @@
+"""GPU: the plugin surface (spvd_b200.compat: torchsparse / torch_scatter names backed by libspvd_b200.so) driven
+the way the reference drives it -- the call sequences below restate models/sparse_utils.py:36-134 and a small
+spnn.Conv3d stack against those names -- compared with the CPU oracle."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ts():
+    import spvd_b200.compat as c
+    c.install()
+    import torchsparse
+    return torchsparse
+
+
+def sphashquery(ts, query, target, kernel_size=1):
+    # models/sparse_utils.py:36-55
+    keys = torch.zeros(2 * target.shape[0], dtype=torch.int64, device=target.device)
+    vals = torch.zeros(2 * target.shape[0], dtype=torch.int32, device=target.device)
+    table = ts.backend.GPUHashTable(keys, vals)
+    table.insert_coords(target[:, [1, 2, 3, 0]])
+    ks = ts.utils.make_tensor(ts.utils.make_ntuple(kernel_size, 3), device=target.device, dtype=torch.int32)
+    st = ts.utils.make_tensor((1, 1, 1), device=target.device, dtype=torch.int32)
+    return (table.lookup_coords(query[:, [1, 2, 3, 0]], ks, st, kernel_size ** 3) - 1)[: query.shape[0]]
+
+
+def test_reference_call_sequences(ts):
+    import torch_scatter
+    import torchsparse.nn as spnn
+    import torchsparse.nn.functional as spf
+    from torchsparse.nn.functional.devoxelize import calc_ti_weights
+    from oracle import model as om, ops as oo
+    g = torch.Generator().manual_seed(4)
+    pts = torch.randn(2, 1024, 3, generator=g).clamp(-3, 3)
+    coords, feats, _ = om.torch2sparse(pts)
+    og = om.Geometry(coords, 1e-5, 0.1, "spconv", "mul")
+    zc, zf = coords.float().cuda(), feats.cuda()
+    # initial_voxelize, models/sparse_utils.py:60-73
+    new_float = torch.cat([zc[:, 0].view(-1, 1), (zc[:, 1:] * 1e-5) / 0.1], 1)
+    new_int = torch.floor(new_float).int()
+    sparse_coord = torch.unique(new_int, dim=0)
+    idx = sphashquery(ts, new_int, sparse_coord).reshape(-1)
+    x0 = ts.SparseTensor(torch_scatter.scatter_mean(zf, idx.long(), dim=0), sparse_coord, 1)
+    assert np.array_equal(sparse_coord.cpu().numpy(), og.level(1).coords)
+    assert np.array_equal(idx.cpu().numpy(), og.p2v[1])
+    want0 = oo.scatter_mean(feats, torch.from_numpy(og.p2v[1]))
+    assert rel_err(x0.F.cpu().numpy(), want0.numpy()) < 1e-6
+    # a small voxel branch: k3 conv -> BN -> SiLU -> k2s2 down -> k2s2 transposed up
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(spnn.Conv3d(3, 32, 3), spnn.BatchNorm(32), spnn.SiLU(), spnn.Conv3d(32, 64, 2, stride=2)).cuda().eval()
+    up = spnn.Conv3d(64, 32, 2, stride=2, transposed=True).cuda()
+    with torch.no_grad():
+        x2 = net(x0)
+        x1 = up(x2)
+    assert x2.s == (2, 2, 2) and x1.s == (1, 1, 1) and x1.C.shape == x0.C.shape
+    coarse, parent, koff, md, mu = None, *og.downsample(1)[1:]
+    assert np.array_equal(x2.C.cpu().numpy(), og.level(2).coords)
+    sd = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+    h = oo.conv_gather_gemm_scatter(want0, sd["0.kernel"], og.kmap3(1), og.level(1).n)
+    h = torch.nn.functional.silu(torch.nn.functional.batch_norm(h, sd["1.running_mean"], sd["1.running_var"], sd["1.weight"], sd["1.bias"]))
+    h2 = oo.conv_gather_gemm_scatter(h, sd["3.kernel"], md, og.level(2).n)
+    h1 = oo.conv_gather_gemm_scatter(h2, up.kernel.detach().cpu(), mu, og.level(1).n)
+    assert rel_err(x2.F.cpu().numpy(), h2.numpy()) < 1e-3
+    assert rel_err(x1.F.cpu().numpy(), h1.numpy()) < 1e-3
+    # voxel_to_point at stride 2, models/sparse_utils.py:103-134
+    pf = torch.cat([new_float[:, 0].int().view(-1, 1), new_float[:, 1:] / 2], 1)
+    idx8 = sphashquery(ts, torch.floor(pf).int(), x2.C, kernel_size=2)
+    w8 = calc_ti_weights(pf[:, 1:], idx8, scale=1)
+    zf2 = spf.spdevoxelize(x2.F, idx8, w8)
+    oi, ow = og.devox_idx_weights(2)
+    assert np.array_equal(idx8.cpu().numpy(), oi.numpy())
+    assert np.allclose(w8.cpu().numpy(), ow.numpy(), atol=2e-6)
+    assert rel_err(zf2.cpu().numpy(), oo.spdevoxelize(h2, oi, ow).numpy()) < 1e-3
+    # point_to_voxel at stride 2 with the clamp, models/sparse_utils.py:78-98
+    q = torch.cat([new_float[:, 0].int().view(-1, 1), torch.floor(new_float[:, 1:] / 2).int()], 1)
+    idq = sphashquery(ts, q, x2.C).clamp_(0)
+    v = torch_scatter.scatter_mean(zf2, idq.long(), dim=0)
+    assert np.array_equal(idq.reshape(-1).cpu().numpy(), og.point_to_voxel_idx(2))
+    assert v.shape[0] == x2.C.shape[0]
+    cat = ts.cat([x2, x2])
+    assert cat.F.shape[1] == 128 and cat._caches is x2._caches
