@@ -37,6 +37,34 @@ void set_error(const char* fmt, ...);
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch.  The feature-path kernels (convolutions and the elementwise glue)
+// are launched with programmaticStreamSerialization: each one lets its successor start early
+// (pdl_trigger at the top) and itself waits for its predecessor's memory (pdl_wait) only right
+// before it touches activations, so launch latency and prologues (barrier init, TMEM allocation,
+// staging of geometry, which is complete long before: spvd_plan_build ends with a stream sync, and
+// the op-by-op geometry kernels never trigger early) overlap the previous kernel's tail.
+// Launched without the attribute, both instructions are no-ops.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
+                                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // coordinate keys: (b,x,y,z) -> 64 bit, 16 bits per field, xyz biased so that unsigned key order is
 // the lexicographic order of (b,x,y,z) and a valid key is never 0 (0 = empty hash slot, the
 // reference zero-initialises its tables: models/sparse_utils.py:37-42).

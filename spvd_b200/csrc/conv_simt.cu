@@ -17,6 +17,8 @@ __global__ void __launch_bounds__(256) k_conv_fwd_simt(const float* __restrict__
   __shared__ float As[TK][TM + 4];
   __shared__ float Bs[TK][TN];
   __shared__ int rows[TM];
+  pdl_trigger();
+  pdl_wait();
   const int tid = threadIdx.x, ty = tid >> 4, tx = tid & 15;
   const int m0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
   unsigned mask = 0xffffffffu;
@@ -174,8 +176,8 @@ extern "C" int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t
   SPVD_CHECK_ARG(!map_t || ld >= n_out, "spvd_conv_fwd: ld %d < n_out %d", ld, n_out);
   if (n_out == 0) return SPVD_OK;
   dim3 grid(cdiv(n_out, TM), cdiv(cout, TN));
-  k_conv_fwd_simt<<<grid, 256, 0, (cudaStream_t)stream>>>(in, w, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out);
-  SPVD_LAUNCH_CHECK();
+  SPVD_CUDA(launch_pdl(k_conv_fwd_simt, grid, dim3(256), 0, (cudaStream_t)stream, in, w, map_t, ld, tile_mask, n_out, kvol,
+                       cin, cout, bias, residual, out));
   return SPVD_OK;
 }
 

@@ -136,6 +136,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   using Cfg = UmmaCfg<BN, MT>;
   constexpr int kStages = Cfg::kStages;
   static_assert(kAsyncA || MT == 1, "the register gather path is instantiated for MT = 1 only");
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -203,6 +204,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
     }
     s_rows[e] = v;
   }
+  pdl_wait();   // everything above read geometry and weights only; activations follow
   __syncthreads();
 
   if (warp < 4) {
@@ -399,9 +401,8 @@ static int launch_umma(const float* in, const float* wp, const int32_t* map_t, i
   }
   if (nsplit > 1) SPVD_CUDA(cudaMemsetAsync(out, 0, (size_t)n_out * cout * 4, s));
   dim3 grid(cdiv(n_out, BM * MT), cout / BN, nsplit);
-  k_conv_fwd_umma<BN, MT, kAsyncA><<<grid, kUmmaThreads, Cfg::kSmemBytes, s>>>(in, wp, map_t, ld, tile_mask, n_out,
-                                                                              kvol, cin, cout, bias, residual, out);
-  SPVD_LAUNCH_CHECK();
+  SPVD_CUDA(launch_pdl(k_conv_fwd_umma<BN, MT, kAsyncA>, grid, dim3(kUmmaThreads), (size_t)Cfg::kSmemBytes, s, in, wp,
+                       map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out));
   return SPVD_OK;
 }
 

@@ -17,6 +17,8 @@ __device__ __forceinline__ float rna_tf32(float x) {
 __global__ void k_affine_act4(const float4* __restrict__ x, const float4* __restrict__ scale,
                               const float4* __restrict__ shift, long long total4, int c4, int act,
                               float4* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total4) return;
   int q = (int)(t % c4);
@@ -43,6 +45,8 @@ __global__ void k_affine_act4(const float4* __restrict__ x, const float4* __rest
 __global__ void k_affine_act1(const float* __restrict__ x, const float* __restrict__ scale,
                               const float* __restrict__ shift, long long total, int c, int act,
                               float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total) return;
   int q = (int)(t % c);
@@ -55,6 +59,8 @@ __global__ void k_affine_act1(const float* __restrict__ x, const float* __restri
 // y[i] = (1 + tt[b_i, c]) * x[i, c] + tt[b_i, C + c],  b_i = coords[i].batch
 __global__ void k_film4(const float4* __restrict__ x, const float* __restrict__ tt, const int4* __restrict__ coords,
                         long long total4, int c4, float4* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total4) return;
   int row = (int)(t / c4), q = (int)(t % c4);
@@ -88,11 +94,10 @@ extern "C" int spvd_bn_silu_fwd(const float* x, const float* scale, const float*
   cudaStream_t s = (cudaStream_t)stream;
   bool v4 = c % 4 == 0 && (((size_t)x | (size_t)y | (size_t)scale | (size_t)shift) & 15) == 0;
   if (v4)
-    k_affine_act4<<<cdiv(rows * (c / 4), 256), 256, 0, s>>>((const float4*)x, (const float4*)scale, (const float4*)shift,
-                                                          rows * (c / 4), c / 4, act, (float4*)y);
+    SPVD_CUDA(launch_pdl(k_affine_act4, dim3(cdiv(rows * (c / 4), 256)), dim3(256), 0, s, (const float4*)x,
+                         (const float4*)scale, (const float4*)shift, rows * (c / 4), c / 4, act, (float4*)y));
   else
-    k_affine_act1<<<cdiv(rows * c, 256), 256, 0, s>>>(x, scale, shift, rows * c, c, act, y);
-  SPVD_LAUNCH_CHECK();
+    SPVD_CUDA(launch_pdl(k_affine_act1, dim3(cdiv(rows * c, 256)), dim3(256), 0, s, x, scale, shift, rows * c, c, act, y));
   return SPVD_OK;
 }
 
@@ -101,9 +106,8 @@ extern "C" int spvd_film_fwd(const float* x, const float* tt, const int32_t* coo
   SPVD_CHECK_ARG(x && tt && coords && y && rows >= 0 && c > 0 && c % 4 == 0, "spvd_film_fwd: bad arguments (c %% 4 == 0)");
   SPVD_CHECK_ARG((((size_t)x | (size_t)y | (size_t)tt) & 15) == 0, "spvd_film_fwd: pointers must be 16-byte aligned");
   if (rows == 0) return SPVD_OK;
-  k_film4<<<cdiv(rows * (c / 4), 256), 256, 0, (cudaStream_t)stream>>>((const float4*)x, tt, (const int4*)coords,
-                                                                      rows * (c / 4), c / 4, (float4*)y);
-  SPVD_LAUNCH_CHECK();
+  SPVD_CUDA(launch_pdl(k_film4, dim3(cdiv(rows * (c / 4), 256)), dim3(256), 0, (cudaStream_t)stream, (const float4*)x, tt,
+                       (const int4*)coords, rows * (c / 4), c / 4, (float4*)y));
   return SPVD_OK;
 }
 

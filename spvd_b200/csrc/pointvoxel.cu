@@ -16,6 +16,8 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
 // ---- scatter_mean ---------------------------------------------------------------------------
 __global__ void k_scatter_add4(const float4* __restrict__ src, const int* __restrict__ idx, int n, int c4,
                                float* __restrict__ out, float* __restrict__ counts) {
+  pdl_trigger();
+  pdl_wait();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * c4) return;
   int p = (int)(t / c4), q = (int)(t % c4);
@@ -27,6 +29,8 @@ __global__ void k_scatter_add4(const float4* __restrict__ src, const int* __rest
 
 __global__ void k_scatter_add1(const float* __restrict__ src, const int* __restrict__ idx, int n, int c,
                                float* __restrict__ out, float* __restrict__ counts) {
+  pdl_trigger();
+  pdl_wait();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * c) return;
   int p = (int)(t / c), q = (int)(t % c);
@@ -37,6 +41,8 @@ __global__ void k_scatter_add1(const float* __restrict__ src, const int* __restr
 }
 
 __global__ void k_divide_rows(float* __restrict__ out, const float* __restrict__ counts, int nv, int c) {
+  pdl_trigger();
+  pdl_wait();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)nv * c) return;
   float cnt = fmaxf(counts[t / c], 1.0f);
@@ -55,6 +61,8 @@ __global__ void k_scatter_mean_bwd(const float* __restrict__ gout, const int* __
 // ---- devoxelize -----------------------------------------------------------------------------
 __global__ void k_devox_fwd4(const float4* __restrict__ feats, const int* __restrict__ idx8,
                              const float* __restrict__ w8, int n, int c4, float4* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * c4) return;
   int p = (int)(t / c4), q = (int)(t % c4);
@@ -80,6 +88,8 @@ __global__ void k_devox_fwd4(const float4* __restrict__ feats, const int* __rest
 
 __global__ void k_devox_fwd1(const float* __restrict__ feats, const int* __restrict__ idx8,
                              const float* __restrict__ w8, int n, int c, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= (long long)n * c) return;
   int p = (int)(t / c), q = (int)(t % c);
@@ -140,8 +150,7 @@ extern "C" int spvd_scatter_mean_fwd(const float* src, const int32_t* idx, int n
     else
       k_scatter_add1<<<cdiv((long long)n * c, 256), 256, 0, s>>>(src, idx, n, c, out, counts);
   }
-  k_divide_rows<<<cdiv((long long)nv * c, 256), 256, 0, s>>>(out, counts, nv, c);
-  SPVD_LAUNCH_CHECK();
+  SPVD_CUDA(launch_pdl(k_divide_rows, dim3(cdiv((long long)nv * c, 256)), dim3(256), 0, s, out, counts, nv, c));
   return SPVD_OK;
 }
 
@@ -160,10 +169,10 @@ extern "C" int spvd_devoxelize_fwd(const float* feats, const int32_t* idx8, cons
   if (n == 0) return SPVD_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (c % 4 == 0 && aligned16(feats) && aligned16(out))
-    k_devox_fwd4<<<cdiv((long long)n * (c / 4), 256), 256, 0, s>>>((const float4*)feats, idx8, w8, n, c / 4, (float4*)out);
+    SPVD_CUDA(launch_pdl(k_devox_fwd4, dim3(cdiv((long long)n * (c / 4), 256)), dim3(256), 0, s, (const float4*)feats, idx8,
+                         w8, n, c / 4, (float4*)out));
   else
-    k_devox_fwd1<<<cdiv((long long)n * c, 256), 256, 0, s>>>(feats, idx8, w8, n, c, out);
-  SPVD_LAUNCH_CHECK();
+    SPVD_CUDA(launch_pdl(k_devox_fwd1, dim3(cdiv((long long)n * c, 256)), dim3(256), 0, s, feats, idx8, w8, n, c, out));
   return SPVD_OK;
 }
 

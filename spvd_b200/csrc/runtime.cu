@@ -23,6 +23,8 @@ __global__ void k_film_affine4(const float4* __restrict__ x, const float* __rest
                                const int4* __restrict__ coords, const float4* __restrict__ scale,
                                const float4* __restrict__ shift, long long total4, int c4, int act,
                                float4* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= total4) return;
   int row = (int)(t / c4), q = (int)(t % c4);
@@ -45,6 +47,8 @@ __global__ void k_film_affine4(const float4* __restrict__ x, const float* __rest
 
 __global__ void k_cat4(const float4* __restrict__ a, const float4* __restrict__ b, long long rows, int ca4, int cb4,
                        float4* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int c4 = ca4 + cb4;
   if (t >= rows * c4) return;
@@ -57,6 +61,8 @@ __global__ void k_cat4(const float4* __restrict__ a, const float4* __restrict__ 
 __global__ void k_layernorm(const float* __restrict__ x, const float* __restrict__ gamma,
                             const float* __restrict__ beta, int rows, int c, float eps, int act,
                             float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   int lane = threadIdx.x & 31;
   if (row >= rows) return;
@@ -88,6 +94,8 @@ __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ qkv
   constexpr int KB = D <= 32 ? 128 : 64;   // static shared memory stays under 48 KB
   __shared__ float4 Ks[KB][D / 4];
   __shared__ float4 Vs[KB][D / 4];
+  pdl_trigger();
+  pdl_wait();
   const int b = blockIdx.z, h = blockIdx.y;
   const int r0 = offsets[b], L = offsets[b + 1] - r0;
   if ((int)blockIdx.x * 128 >= L) return;
@@ -175,7 +183,7 @@ template <int D>
 static void launch_attention(const float* qkv, const int* offsets, int C, int heads, int nb, int max_len, int act,
                              float* out, cudaStream_t s) {
   dim3 grid(cdiv(max_len, 128), heads, nb);
-  k_attention<D><<<grid, 128, 0, s>>>(qkv, offsets, C, 1.0f / sqrtf((float)D), act, out);
+  launch_pdl(k_attention<D>, grid, dim3(128), 0, s, qkv, offsets, C, 1.0f / sqrtf((float)D), act, out);
 }
 
 }  // namespace spvd
@@ -200,10 +208,9 @@ extern "C" int spvd_film_affine_fwd(const float* x, const float* tt, int ldt, co
   SPVD_CHECK_ARG((((size_t)x | (size_t)y | (size_t)tt | (size_t)scale | (size_t)shift) & 15) == 0,
                  "spvd_film_affine_fwd: pointers must be 16-byte aligned");
   if (rows == 0) return SPVD_OK;
-  k_film_affine4<<<cdiv(rows * (c / 4), 256), 256, 0, (cudaStream_t)stream>>>(
-      (const float4*)x, tt, ldt, (const int4*)coords, (const float4*)scale, (const float4*)shift, rows * (c / 4),
-      c / 4, act, (float4*)y);
-  SPVD_LAUNCH_CHECK();
+  SPVD_CUDA(launch_pdl(k_film_affine4, dim3(cdiv(rows * (c / 4), 256)), dim3(256), 0, (cudaStream_t)stream,
+                       (const float4*)x, tt, ldt, (const int4*)coords, (const float4*)scale, (const float4*)shift,
+                       rows * (c / 4), c / 4, act, (float4*)y));
   return SPVD_OK;
 }
 
@@ -212,9 +219,8 @@ extern "C" int spvd_cat_fwd(const float* a, const float* b, long long rows, int 
   SPVD_CHECK_ARG(a && b && y && rows >= 0 && ca > 0 && cb > 0 && ca % 4 == 0 && cb % 4 == 0,
                  "spvd_cat_fwd: bad arguments (channel counts multiples of 4)");
   if (rows == 0) return SPVD_OK;
-  k_cat4<<<cdiv(rows * ((ca + cb) / 4), 256), 256, 0, (cudaStream_t)stream>>>((const float4*)a, (const float4*)b, rows,
-                                                                            ca / 4, cb / 4, (float4*)y);
-  SPVD_LAUNCH_CHECK();
+  SPVD_CUDA(launch_pdl(k_cat4, dim3(cdiv(rows * ((ca + cb) / 4), 256)), dim3(256), 0, (cudaStream_t)stream,
+                       (const float4*)a, (const float4*)b, rows, ca / 4, cb / 4, (float4*)y));
   return SPVD_OK;
 }
 
@@ -222,8 +228,8 @@ extern "C" int spvd_layernorm_fwd(const float* x, const float* gamma, const floa
                                   int act, float* y, spvd_stream_t stream) {
   SPVD_CHECK_ARG(x && gamma && beta && y && rows >= 0 && c > 0, "spvd_layernorm_fwd: bad arguments");
   if (rows == 0) return SPVD_OK;
-  k_layernorm<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, rows, c, eps, act, y);
-  SPVD_LAUNCH_CHECK();
+  SPVD_CUDA(launch_pdl(k_layernorm, dim3(cdiv(rows, 8)), dim3(256), 0, (cudaStream_t)stream, x, gamma, beta, rows, c, eps,
+                       act, y));
   return SPVD_OK;
 }
 
