@@ -189,6 +189,20 @@ int spvd_conv_fwd_umma(const float* in, const float* w_packed, const int32_t* ma
                        const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
                        const float* bias, const float* residual, float* out, int bn, int nsplit,
                        int a_is_tf32, int mt, spvd_stream_t stream);
+/* Pair-major view of a kernel map, for sparse levels (few active offsets per voxel): per offset the valid
+ * (input row, output row) pairs compacted into tiles of 128 pairs, ordered by offset then output row.
+ * pair_in / pair_out [tile_cap*128] (-1 = padding), tile_k [tile_cap] = offset of each tile,
+ * *n_tiles / *n_pairs device counts, scratch >= 32 + kvol * ceil(n_cap / 4096) int32. */
+int spvd_kmap_pairs(const int32_t* map_t, int ld, int n_cap, const int32_t* n_dev, int kvol, int tile_cap,
+                    int32_t* pair_in, int32_t* pair_out, int32_t* tile_k, int32_t* n_tiles, int32_t* n_pairs,
+                    int32_t* scratch, spvd_stream_t stream);
+/* Same convolution, pair-major: one CTA per pair tile, K loop over the channel slabs only, product rows
+ * scattered into the zero-filled output with vector RED; bias / residual are added by the tiles of the
+ * centre offset (center_k), so the map must be submanifold.  `in` must be TF32-representable. */
+int spvd_conv_fwd_pairs(const float* in, const float* w_packed, const int32_t* pair_in,
+                        const int32_t* pair_out, const int32_t* tile_k, int n_pair_tiles, int center_k,
+                        int n_out, int kvol, int cin, int cout, const float* bias, const float* residual,
+                        float* out, spvd_stream_t stream);
 /* gw[k] = sum over pairs (i,o) of offset k of in[i]^T gout[o];  gw [kvol,cin,cout] zero-filled inside */
 int spvd_conv_wgrad(const float* in, const float* gout, const int32_t* map_t, int ld, int n_out,
                     int kvol, int cin, int cout, float* gw, spvd_stream_t stream);
@@ -251,7 +265,12 @@ typedef struct spvd_plan_level {
   float* devox_w;     /* [n_points,8] */
   int32_t* batch_counts;  /* [n_batch] */
   int32_t* batch_offsets; /* [n_batch+1] */
-  int32_t capacity, pad;
+  int32_t* pair_in;       /* pair-major view of kmap3 (spvd_kmap_pairs), [pair_tile_cap*128] */
+  int32_t* pair_out;
+  int32_t* pair_tile_k;   /* [pair_tile_cap] */
+  int32_t* pair_counts;   /* [2] = (tiles, pairs) */
+  int32_t* pair_scratch;  /* >= 32 + 27*ceil(n_points/4096) int32 */
+  int32_t capacity, pair_tile_cap;
 } spvd_plan_level_t;
 
 int spvd_plan_build(const float* pc, int n_points, int n_batch, float init_res, float after_res,
@@ -298,7 +317,10 @@ typedef struct spvd_level_geom {
   const int32_t* devox_idx; /* [n_points,8] or NULL */
   const float* devox_w;
   const int32_t* batch_offsets; /* [n_batch+1] or NULL */
-  int32_t n, ld3, ld_down, ld_up, max_per_batch, pad;
+  const int32_t* pair_in;       /* pair-major view of kmap3 or NULL */
+  const int32_t* pair_out;
+  const int32_t* pair_tile_k;
+  int32_t n, ld3, ld_down, ld_up, max_per_batch, n_pair_tiles; /* n_pair_tiles > 0: 3^3 convs run pair-major */
 } spvd_level_geom_t;
 
 typedef struct spvd_op {

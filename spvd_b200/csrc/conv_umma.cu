@@ -91,14 +91,16 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return r;
 }
 
-template <int BN, int MT>
+template <int BN, int MT, bool kPairs = false>
 struct UmmaCfg {
   static constexpr int kCols = BN * MT;
   static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
   static constexpr int kBTileBytes = BN * BK * 4;
   static constexpr int kStageBytes = MT * kATileBytes + kBTileBytes;
-  static constexpr int kStages = (4 * kStageBytes <= 200 * 1024) ? 4 : (3 * kStageBytes <= 200 * 1024) ? 3 : 2;
-  static constexpr int kRowsBytes = MT * 27 * BM * 4;  // row indices of every offset of the tile, staged once
+  // pair-major tiles run only cin/32 iterations: keep the footprint small so that several CTAs share an SM and
+  // one CTA's prologue / RED epilogue overlaps another's main loop
+  static constexpr int kStages = kPairs ? 2 : (4 * kStageBytes <= 200 * 1024) ? 4 : (3 * kStageBytes <= 200 * 1024) ? 3 : 2;
+  static constexpr int kRowsBytes = kPairs ? 2 * BM * 4 : MT * 27 * BM * 4;  // staged row indices
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kRowsBytes;
   // idesc: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
   static constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) |
@@ -124,7 +126,13 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
 // rows go through registers (cvt.rna.tf32) with the next slab's loads issued before the current stores
 // (MT = 1 only).  gridDim.z > 1 = split over the (offset, slab) iterations; partial tiles are accumulated
 // with vector RED into a zero-initialised output (bias / residual added by split 0).
-template <int BN, int MT, bool kAsyncA>
+//
+// kPairs (pair-major, for sparse levels): a CTA owns one tile of 128 (input row, output row) pairs of ONE
+// kernel offset (spvd_kmap_pairs): map_t = pair_in, tile_mask = tile_k (offset of each tile), pair_out =
+// output rows; the K loop runs over the channel slabs only and the epilogue scatters the 128 product rows with
+// vector RED into the zero-initialised output (bias / residual added by the centre-offset tiles, which cover
+// every output row exactly once).  Issued tensor-core rows = real pairs, instead of 128 x (active offsets).
+template <int BN, int MT, bool kAsyncA, bool kPairs = false>
 __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __restrict__ in,
                                                                const float* __restrict__ w_packed,
                                                                const int* __restrict__ map_t, int ld,
@@ -132,10 +140,12 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
                                                                int kvol, int cin, int cout,
                                                                const float* __restrict__ bias,
                                                                const float* __restrict__ residual,
-                                                               float* __restrict__ out) {
-  using Cfg = UmmaCfg<BN, MT>;
+                                                               float* __restrict__ out,
+                                                               const int* __restrict__ pair_out, int center_k) {
+  using Cfg = UmmaCfg<BN, MT, kPairs>;
   constexpr int kStages = Cfg::kStages;
   static_assert(kAsyncA || MT == 1, "the register gather path is instantiated for MT = 1 only");
+  static_assert(!kPairs || (MT == 1 && kAsyncA), "pair-major tiles: MT = 1, cp.async gather");
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -152,7 +162,9 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   const int n_tiles = (n_out + BM - 1) / BM;
 
   unsigned mask = kvol >= 32 ? 0xffffffffu : ((1u << kvol) - 1u);
-  if (tile_mask) {
+  if constexpr (kPairs) {
+    mask = 1u << (reinterpret_cast<const int*>(tile_mask)[blockIdx.x] & 31);   // the tile's single offset
+  } else if (tile_mask) {
     unsigned u = 0;
 #pragma unroll
     for (int t = 0; t < MT; ++t)
@@ -164,7 +176,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   const int it_begin = min(total_iters, (int)blockIdx.z * per_split);
   const int it_end = min(total_iters, it_begin + per_split);
   const int num_iters = it_end - it_begin;
-  const bool split = gridDim.z > 1;
+  const bool split = kPairs || gridDim.z > 1;
   if (split && num_iters == 0) return;  // nothing to add (uniform across the CTA, before any barrier/alloc)
 
   if (tid == 0) {
@@ -193,16 +205,23 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   // critical path then has no dependent global load in front of the gather)
   const int ka_begin = num_iters > 0 ? it_begin / nchunks : 0;
   const int ka_end = num_iters > 0 ? (it_end - 1) / nchunks + 1 : 0;
-  for (int e = tid; e < (ka_end - ka_begin) * (MT * BM); e += kUmmaThreads) {
-    const int slot = e / (MT * BM), r = e - slot * (MT * BM);
-    const int o = m0 + r;
-    int v = -1;
-    if (map_t) {
-      if (o < ld) v = __ldg(map_t + (size_t)active_k[ka_begin + slot] * ld + o);
-    } else if (o < n_out) {
-      v = o;
+  if constexpr (kPairs) {
+    if (tid < BM) {
+      s_rows[tid] = __ldg(map_t + (size_t)blockIdx.x * BM + tid);            // input rows of the pair tile
+      s_rows[BM + tid] = __ldg(pair_out + (size_t)blockIdx.x * BM + tid);    // output rows
     }
-    s_rows[e] = v;
+  } else {
+    for (int e = tid; e < (ka_end - ka_begin) * (MT * BM); e += kUmmaThreads) {
+      const int slot = e / (MT * BM), r = e - slot * (MT * BM);
+      const int o = m0 + r;
+      int v = -1;
+      if (map_t) {
+        if (o < ld) v = __ldg(map_t + (size_t)active_k[ka_begin + slot] * ld + o);
+      } else if (o < n_out) {
+        v = o;
+      }
+      s_rows[e] = v;
+    }
   }
   pdl_wait();   // everything above read geometry and weights only; activations follow
   __syncthreads();
@@ -293,11 +312,16 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
       mbar_wait(bar_base + 8 * (2 * kStages), 0);
       tc_fence_after();
     }
-    const bool add_bias = bias != nullptr && blockIdx.z == 0;
-    const bool add_res = residual != nullptr && blockIdx.z == 0;
+    const bool first = kPairs ? (active_k[0] == center_k) : (blockIdx.z == 0);
+    const bool add_bias = bias != nullptr && first;
+    const bool add_res = residual != nullptr && first;
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
-      const int row = m0 + mt * BM + warp * 32 + lane;
+      int row = m0 + mt * BM + warp * 32 + lane;
+      if constexpr (kPairs) {
+        row = s_rows[BM + warp * 32 + lane];
+        if (row < 0) row = n_out;   // padding pair: nothing to write
+      }
 #pragma unroll 1
       for (int cb = 0; cb < BN / 32; ++cb) {
         uint32_t r[32];
@@ -402,7 +426,26 @@ static int launch_umma(const float* in, const float* wp, const int32_t* map_t, i
   if (nsplit > 1) SPVD_CUDA(cudaMemsetAsync(out, 0, (size_t)n_out * cout * 4, s));
   dim3 grid(cdiv(n_out, BM * MT), cout / BN, nsplit);
   SPVD_CUDA(launch_pdl(k_conv_fwd_umma<BN, MT, kAsyncA>, grid, dim3(kUmmaThreads), (size_t)Cfg::kSmemBytes, s, in, wp,
-                       map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out));
+                       map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, (const int*)nullptr, 0));
+  return SPVD_OK;
+}
+
+template <int BN>
+static int launch_umma_pairs(const float* in, const float* wp, const int32_t* pair_in, const int32_t* pair_out,
+                             const int32_t* tile_k, int n_pair_tiles, int center_k, int n_out, int kvol, int cin, int cout,
+                             const float* bias, const float* residual, float* out, cudaStream_t s) {
+  using Cfg = UmmaCfg<BN, 1, true>;
+  static bool configured = false;
+  if (!configured) {
+    SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                   Cfg::kSmemBytes));
+    configured = true;
+  }
+  SPVD_CUDA(cudaMemsetAsync(out, 0, (size_t)n_out * cout * 4, s));
+  dim3 grid(n_pair_tiles, cout / BN, 1);
+  SPVD_CUDA(launch_pdl(k_conv_fwd_umma<BN, 1, true, true>, grid, dim3(kUmmaThreads), (size_t)Cfg::kSmemBytes, s, in, wp,
+                       pair_in, 0, (const unsigned*)tile_k, n_out, kvol, cin, cout, bias, residual, out, pair_out,
+                       center_k));
   return SPVD_OK;
 }
 
@@ -486,6 +529,29 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
     case 256: return launch_umma_bn<256>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
   }
   set_error("spvd_conv_fwd_umma: slice width %d is not instantiated", bn);
+  return SPVD_ERR_INVALID;
+}
+
+extern "C" int spvd_conv_fwd_pairs(const float* in, const float* w_packed, const int32_t* pair_in,
+                                   const int32_t* pair_out, const int32_t* tile_k, int n_pair_tiles, int center_k,
+                                   int n_out, int kvol, int cin, int cout, const float* bias, const float* residual,
+                                   float* out, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(in && w_packed && pair_in && pair_out && tile_k && out && n_out >= 0 && n_pair_tiles >= 0,
+                 "spvd_conv_fwd_pairs: bad arguments");
+  SPVD_CHECK_ARG(spvd_conv_umma_supported(kvol, cin, cout), "spvd_conv_fwd_pairs: unsupported shape %dx%dx%d", kvol, cin, cout);
+  SPVD_CHECK_ARG(center_k >= 0 && center_k < kvol, "spvd_conv_fwd_pairs: the map needs a centre offset (submanifold)");
+  SPVD_CHECK_ARG(residual != out || residual == nullptr, "spvd_conv_fwd_pairs: residual must not alias out");
+  if (n_out == 0) return SPVD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int bn = pick_bn(cout);
+  switch (bn) {
+    case 32: return launch_umma_pairs<32>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+    case 64: return launch_umma_pairs<64>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+    case 96: return launch_umma_pairs<96>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+    case 128: return launch_umma_pairs<128>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+    case 192: return launch_umma_pairs<192>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+    case 256: return launch_umma_pairs<256>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+  }
   return SPVD_ERR_INVALID;
 }
 

@@ -182,9 +182,138 @@ __global__ void k_devox_query(const float4* __restrict__ pc, int n, float s, con
   wo[1] = make_float4(__fdiv_rn(w[4], den), __fdiv_rn(w[5], den), __fdiv_rn(w[6], den), __fdiv_rn(w[7], den));
 }
 
+// ---- pair-major view of a kernel map ------------------------------------------------------------
+// For sparse levels (few active offsets per voxel) the convolution runs pair-major: per offset k the
+// valid (input row, output row) pairs are compacted into tiles of 128 pairs.  counts -> tile prefix ->
+// ordered compaction (deterministic: pairs of an offset stay sorted by output row).
+constexpr int kPairSeg = 4096;   // map entries per CTA
+
+__global__ void __launch_bounds__(1024) k_pairs_count(const int* __restrict__ map_t, int ld, int n_cap,
+                                                      const int* __restrict__ n_dev, int nseg,
+                                                      int* __restrict__ counts /* [kvol][nseg] */) {
+  __shared__ int s_sum[32];
+  const int k = blockIdx.y, seg = blockIdx.x, n = resolve_n(n_dev, n_cap);
+  const int* row = map_t + (size_t)k * ld;
+  int c = 0;
+  const int end = min(n, (seg + 1) * kPairSeg);
+  for (int o = seg * kPairSeg + threadIdx.x; o < end; o += 1024) c += row[o] >= 0;
+  for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+  if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = c;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    c = s_sum[threadIdx.x];
+    for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+    if (threadIdx.x == 0) counts[k * nseg + seg] = c;
+  }
+}
+
+// per offset: exclusive prefix of its segment counts (in place) and its first tile; then the tile -> offset table
+__global__ void k_pairs_plan(int* __restrict__ counts, int kvol, int nseg, int tile_cap, int* __restrict__ tile_base,
+                             int* __restrict__ tile_k, int* __restrict__ n_tiles, int* __restrict__ n_pairs) {
+  __shared__ int total[32];
+  __shared__ int base[33];
+  if ((int)threadIdx.x < kvol) {
+    int run = 0;
+    int* c = counts + threadIdx.x * nseg;
+    for (int sgm = 0; sgm < nseg; ++sgm) {
+      int v = c[sgm];
+      c[sgm] = run;
+      run += v;
+    }
+    total[threadIdx.x] = run;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0, pairs = 0;
+    for (int k = 0; k < kvol; ++k) {
+      base[k] = run;
+      tile_base[k] = run;
+      run += (total[k] + 127) >> 7;
+      pairs += total[k];
+    }
+    base[kvol] = run;
+    *n_tiles = run < tile_cap ? run : tile_cap;
+    *n_pairs = pairs;
+  }
+  __syncthreads();
+  for (int k = 0; k < kvol; ++k)
+    for (int t = base[k] + threadIdx.x; t < base[k + 1] && t < tile_cap; t += blockDim.x) tile_k[t] = k;
+}
+
+__global__ void __launch_bounds__(1024) k_pairs_fill(const int* __restrict__ map_t, int ld, int n_cap,
+                                                     const int* __restrict__ n_dev, int nseg,
+                                                     const int* __restrict__ seg_base, const int* __restrict__ tile_base,
+                                                     int tile_cap, int* __restrict__ pair_in, int* __restrict__ pair_out) {
+  __shared__ int s_warp[32];
+  __shared__ int s_run;
+  const int k = blockIdx.y, seg = blockIdx.x, n = resolve_n(n_dev, n_cap);
+  const int* row = map_t + (size_t)k * ld;
+  const long long cap = (long long)tile_cap * 128;
+  const long long start = (long long)tile_base[k] * 128 + seg_base[k * nseg + seg];
+  if (threadIdx.x == 0) s_run = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int end = min(n, (seg + 1) * kPairSeg);
+  for (int o0 = seg * kPairSeg; o0 < end; o0 += 1024) {
+    const int o = o0 + threadIdx.x;
+    const int v = o < end ? row[o] : -1;
+    const unsigned bal = __ballot_sync(0xffffffffu, v >= 0);
+    if (lane == 0) s_warp[warp] = __popc(bal);
+    __syncthreads();
+    int wbase = 0, total = 0;
+    for (int w = 0; w < 32; ++w) {
+      const int c = s_warp[w];
+      if (w < warp) wbase += c;
+      total += c;
+    }
+    const int run = s_run;
+    if (v >= 0) {
+      const long long pos = start + run + wbase + __popc(bal & ((1u << lane) - 1u));
+      if (pos < cap) {
+        pair_in[pos] = v;
+        pair_out[pos] = o;
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) s_run = run + total;
+    __syncthreads();
+  }
+  // the CTA of the last segment that holds rows pads the tail of the offset's last tile
+  if (seg == (n > 0 ? (n - 1) / kPairSeg : 0)) {
+    const int cnt = seg_base[k * nseg + seg] + s_run;   // pairs of this offset in total
+    const int padded = (cnt + 127) & ~127;
+    for (int j = cnt + threadIdx.x; j < padded; j += 1024) {
+      const long long pos = (long long)tile_base[k] * 128 + j;
+      if (pos < cap) {
+        pair_in[pos] = -1;
+        pair_out[pos] = -1;
+      }
+    }
+  }
+}
+
 }  // namespace spvd
 
 using namespace spvd;
+
+extern "C" int spvd_kmap_pairs(const int32_t* map_t, int ld, int n_cap, const int32_t* n_dev, int kvol, int tile_cap,
+                               int32_t* pair_in, int32_t* pair_out, int32_t* tile_k, int32_t* n_tiles, int32_t* n_pairs,
+                               int32_t* scratch, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(map_t && pair_in && pair_out && tile_k && n_tiles && n_pairs && scratch && kvol >= 1 && kvol <= 32 &&
+                     tile_cap > 0,
+                 "spvd_kmap_pairs: bad arguments");
+  // scratch: 32 + kvol * ceil(n_cap / 4096) int32
+  cudaStream_t s = (cudaStream_t)stream;
+  const int nseg = cdiv(n_cap > 0 ? n_cap : 1, kPairSeg);
+  int* tile_base = scratch;        // [32]
+  int* counts = scratch + 32;      // [kvol][nseg]
+  k_pairs_count<<<dim3(nseg, kvol), 1024, 0, s>>>(map_t, ld, n_cap, n_dev, nseg, counts);
+  k_pairs_plan<<<1, 256, 0, s>>>(counts, kvol, nseg, tile_cap, tile_base, tile_k, n_tiles, n_pairs);
+  k_pairs_fill<<<dim3(nseg, kvol), 1024, 0, s>>>(map_t, ld, n_cap, n_dev, nseg, counts, tile_base, tile_cap, pair_in,
+                                                 pair_out);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
 
 extern "C" int spvd_hash_build(const int32_t* coords, int n_cap, const int32_t* n_dev, int coord_order,
                                int64_t* keys, int32_t* vals, int capacity, int32_t* status, spvd_stream_t stream) {

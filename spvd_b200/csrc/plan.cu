@@ -42,6 +42,8 @@ int spvd_kmap_down2(const int32_t*, int, const int32_t*, const int64_t*, const i
 int spvd_point_voxel_query(const float*, int, int, const int64_t*, const int32_t*, int, int32_t*, spvd_stream_t);
 int spvd_devox_query(const float*, int, int, const int64_t*, const int32_t*, int, int32_t*, float*, spvd_stream_t);
 int spvd_batch_counts(const int32_t*, int, const int32_t*, int, int32_t*, spvd_stream_t);
+int spvd_kmap_pairs(const int32_t*, int, int, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*,
+                    int32_t*, spvd_stream_t);
 }
 
 #define SPVD_TRY(call)            \
@@ -82,6 +84,9 @@ extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, float
     const spvd_plan_level_t& L = levels[i];
     const int stride = 1 << i;
     if (L.kmap3) SPVD_TRY(spvd_kmap_subm3(L.coords, n_points, L.count, L.keys, L.vals, L.capacity, L.kmap3, ld, L.mask3, stream));
+    if (L.kmap3 && L.pair_in && L.pair_out && L.pair_tile_k && L.pair_counts && L.pair_scratch)
+      SPVD_TRY(spvd_kmap_pairs(L.kmap3, ld, n_points, L.count, 27, L.pair_tile_cap, L.pair_in, L.pair_out, L.pair_tile_k,
+                               L.pair_counts, L.pair_counts + 1, L.pair_scratch, stream));
     if (L.p2v) {
       SPVD_TRY(spvd_point_voxel_query(fcoords, n_points, stride, L.keys, L.vals, L.capacity, L.p2v, stream));
       // misses go to row 0: idx_query.clamp_(0), models/sparse_utils.py:93

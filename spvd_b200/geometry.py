@@ -179,7 +179,8 @@ from ._C import check as _check, lib as _lib
 class _PlanLevel(_C.Structure):
     _fields_ = [(n, _C.c_void_p) for n in ("coords", "count", "keys", "vals", "kmap3", "mask3", "kmap_down", "mask_down",
                                            "kmap_up", "mask_up", "p2v", "devox_idx", "devox_w", "batch_counts",
-                                           "batch_offsets")] + [("capacity", _C.c_int32), ("pad", _C.c_int32)]
+                                           "batch_offsets", "pair_in", "pair_out", "pair_tile_k", "pair_counts",
+                                           "pair_scratch")] + [("capacity", _C.c_int32), ("pair_tile_cap", _C.c_int32)]
 
 
 class _Table:
@@ -195,15 +196,16 @@ class PlanWorkspace:
     """All buffers of one Geometry for a fixed (n_points, n_batch, plan), allocated once; ``build`` fills them
     with one C call and returns a Geometry that VIEWS them (valid until the workspace is built again)."""
 
-    def __init__(self, n_points, n_batch, strides, k3_strides, p2v_strides, devox_strides, device):
+    def __init__(self, n_points, n_batch, strides, k3_strides, p2v_strides, devox_strides, device, pair_strides=(1, 2)):
         self.n_points, self.n_batch, self.strides = n_points, n_batch, tuple(strides)
+        self.pair_strides = tuple(s for s in pair_strides if s in k3_strides)
         assert all(s == 1 << i for i, s in enumerate(self.strides)), "strides must be 1,2,4,..."
         i32 = dict(dtype=torch.int32, device=device)
         nl, ld = len(self.strides), ops.round128(n_points)
         self.ld = ld
         self.fcoords = torch.empty((n_points, 4), dtype=torch.float32, device=device)
         self.icoords = torch.empty((n_points, 4), **i32)
-        self.n_summary = nl + 1 + nl * n_batch
+        self.n_summary = nl + 1 + nl * n_batch + 2 * nl      # level counts | status | per-cloud counts | (pair tiles, pairs)
         self.summary = torch.zeros(self.n_summary, **i32)
         self.summary_host = torch.zeros(self.n_summary, dtype=torch.int32).pin_memory()
         self.ws = torch.empty(max(_lib.spvd_unique_workspace_bytes(n_points), 256), dtype=torch.uint8, device=device)
@@ -224,14 +226,24 @@ class PlanWorkspace:
             if s in devox_strides:
                 b["devox_idx"] = torch.empty((n_points, 8), **i32)
                 b["devox_w"] = torch.empty((n_points, 8), dtype=torch.float32, device=device)
+            tile_cap = 0
+            if s in self.pair_strides:
+                tile_cap = 27 * ld // 128
+                b["pair_in"], b["pair_out"] = torch.empty(tile_cap * 128, **i32), torch.empty(tile_cap * 128, **i32)
+                b["pair_tile_k"] = torch.empty(tile_cap, **i32)
+                o = nl + 1 + nl * n_batch + 2 * i
+                b["pair_counts"] = self.summary[o: o + 2]
+                b["pair_scratch"] = torch.empty(32 + 27 * ((n_points + 4095) // 4096 + 1), **i32)
             self.bufs.append(b)
             L = self.c_levels[i]
             for name, t in b.items():
                 setattr(L, name, t.data_ptr())
             L.capacity = 2 * n_points
+            L.pair_tile_cap = tile_cap
         self.status = self.summary[nl: nl + 1]
         # kernels launched by one build (ops.stats accounting)
-        self.n_kernels = 1 + 22 + 23 * (nl - 1) + nl + (nl - 1) + len(k3_strides) + 2 * len(p2v_strides) + len(devox_strides) + 2 * nl
+        self.n_kernels = (1 + 22 + 23 * (nl - 1) + nl + (nl - 1) + len(k3_strides) + 2 * len(p2v_strides) + len(devox_strides) +
+                          2 * nl + 3 * len(self.pair_strides))
 
     def build(self, pc, pres, voxel_size, scale_mode="mul", downsample_mode="spconv"):
         if not pc.is_cuda or pc.dtype != torch.float32 or not pc.is_contiguous() or pc.shape != (self.n_points, 4):
@@ -263,6 +275,9 @@ class PlanWorkspace:
             lv.batch_counts = b["batch_counts"]
             lv.batch_counts_host = host[nl + 1 + i * nb: nl + 1 + (i + 1) * nb]
             lv._offsets = b["batch_offsets"]
+            if "pair_in" in b:
+                o = nl + 1 + nl * nb + 2 * i
+                lv.pairs = (b["pair_in"], b["pair_out"], b["pair_tile_k"], host[o], host[o + 1])   # (.., tiles, pairs)
             geo.levels[s] = lv
             if "p2v" in b:
                 geo.p2v[s] = b["p2v"]

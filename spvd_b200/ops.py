@@ -53,7 +53,7 @@ class _Stats:
 stats = _Stats()
 # kernels launched by one call of each entry point (memsets are not kernels)
 _K = {"point_voxel_coords": 1, "unique_coords": 22, "downsample_coords": 23, "hash_build": 1, "hash_query": 1,
-      "kmap_subm3": 1, "kmap_down2": 1, "batch_counts": 1, "point_voxel_query": 1, "devox_query": 1,
+      "kmap_subm3": 1, "kmap_down2": 1, "kmap_pairs": 3, "batch_counts": 1, "point_voxel_query": 1, "devox_query": 1,
       "scatter_mean_fwd": 2, "scatter_mean_bwd": 1, "devoxelize_fwd": 1, "devoxelize_bwd": 1, "pack_weights": 1,
       "transpose_weights": 1, "conv_fwd": 1, "conv_wgrad": 1, "round_tf32": 1, "affine_act": 1, "film": 1}
 
@@ -260,6 +260,31 @@ def conv_fwd(x, w3, w_packed, map_t, mask, n_out, bias=None, impl=CONV_AUTO, bn=
         ev[1].record()
         umma = impl == CONV_UMMA or (impl == CONV_AUTO and w_packed is not None and umma_supported(kvol, cin, cout))
         stats.conv_events.append((ev[0], ev[1], (kvol, cin, cout, n_out, "umma" if umma else "simt", map_t)))
+    return out
+
+
+def kmap_pairs(map_t, n, kvol=27, tile_cap=None):
+    """-> (pair_in, pair_out, tile_k, n_tiles int32[1], n_pairs int32[1])"""
+    _count("kmap_pairs")
+    ld = map_t.shape[1]
+    tile_cap = tile_cap or (kvol * ld // 128)
+    dev = map_t.device
+    pin = torch.empty(tile_cap * 128, dtype=torch.int32, device=dev)
+    pout = torch.empty(tile_cap * 128, dtype=torch.int32, device=dev)
+    tk = torch.empty(tile_cap, dtype=torch.int32, device=dev)
+    cnt = torch.empty(2, dtype=torch.int32, device=dev)
+    scratch = torch.empty(32 + kvol * ((int(n) + 4095) // 4096 + 1), dtype=torch.int32, device=dev)
+    check(lib.spvd_kmap_pairs(_p(map_t, torch.int32), ld, int(n), None, kvol, tile_cap, _p(pin), _p(pout), _p(tk),
+                              _p(cnt[0:1]), _p(cnt[1:2]), _p(scratch), _s()))
+    return pin, pout, tk, cnt[0:1], cnt[1:2]
+
+
+def conv_fwd_pairs(x, w3, w_packed, pair_in, pair_out, tile_k, n_tiles, n_out, bias=None, residual=None):
+    _count("conv_fwd")
+    kvol, cin, cout = w3.shape
+    out = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
+    check(lib.spvd_conv_fwd_pairs(_p(x, torch.float32), _p(w_packed, torch.float32), _p(pair_in), _p(pair_out), _p(tile_k),
+                                  int(n_tiles), kvol // 2, n_out, kvol, cin, cout, _p(bias), _p(residual), _p(out), _s()))
     return out
 
 

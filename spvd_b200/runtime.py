@@ -31,8 +31,9 @@ class LevelGeom(C.Structure):
     _fields_ = [("coords", C.c_void_p), ("kmap3", C.c_void_p), ("mask3", C.c_void_p), ("kmap_down", C.c_void_p),
                 ("mask_down", C.c_void_p), ("kmap_up", C.c_void_p), ("mask_up", C.c_void_p), ("p2v", C.c_void_p),
                 ("devox_idx", C.c_void_p), ("devox_w", C.c_void_p), ("batch_offsets", C.c_void_p),
+                ("pair_in", C.c_void_p), ("pair_out", C.c_void_p), ("pair_tile_k", C.c_void_p),
                 ("n", C.c_int32), ("ld3", C.c_int32), ("ld_down", C.c_int32), ("ld_up", C.c_int32),
-                ("max_per_batch", C.c_int32), ("pad", C.c_int32)]
+                ("max_per_batch", C.c_int32), ("n_pair_tiles", C.c_int32)]
 
 
 class Op(C.Structure):
@@ -59,6 +60,7 @@ class Program:
     def __init__(self, model, n_points, n_batch):
         self.model, self.n_points, self.n_batch = model, n_points, n_batch
         self.dev = next(model.parameters()).device
+        self.pair_density = 10.0  # use pair-major convs where a voxel has fewer active offsets than this on average
         self.keep = []            # prepared parameter tensors (kept alive; the ops hold raw pointers)
         self.recs = []            # dicts before register allocation
         self.regs = []
@@ -317,6 +319,11 @@ class Program:
             g.p2v = geo.p2v[s].data_ptr() if s in geo.p2v else None
             if s in geo.devox:
                 g.devox_idx, g.devox_w = geo.devox[s][0].data_ptr(), geo.devox[s][1].data_ptr()
+            pr = getattr(lv, "pairs", None)
+            if pr is not None and pr[4] < self.pair_density * lv.n:      # sparse level: run the 3^3 convs pair-major
+                g.pair_in, g.pair_out, g.pair_tile_k, g.n_pair_tiles = pr[0].data_ptr(), pr[1].data_ptr(), pr[2].data_ptr(), pr[3]
+            else:
+                g.pair_in, g.n_pair_tiles = None, 0
             if i in self.attn_levels:
                 g.batch_offsets = geo.batch_offsets(s).data_ptr()
                 g.max_per_batch = max(lv.batch_counts_host)

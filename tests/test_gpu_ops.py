@@ -333,6 +333,40 @@ def test_conv_tcgen05_two_tiles_per_cta(sp, mt, cout):
     assert rel_err(got.cpu().numpy(), (want + res).numpy()) < 2e-5
 
 
+@pytest.mark.parametrize("stride,cin,cout", [(1, 32, 32), (1, 96, 64), (2, 64, 128), (2, 192, 192)])
+def test_conv_pair_major(sp, stride, cin, cout):
+    """pair lists (spvd_kmap_pairs) are exactly the valid entries of the map, and the pair-major tcgen05
+    convolution (vector-RED scatter epilogue) equals the output-stationary result"""
+    from oracle import model as om, ops as oo
+    coords, _ = cloud_points(4, 2048, 31)
+    og = om.Geometry(coords, 1e-5, 0.1, "spconv", "mul")
+    geo = sp.Geometry(coords.float().cuda(), 1e-5, 0.1, strides=(1, 2), p2v_strides=(1,), devox_strides=(1,))
+    if stride == 2:
+        og.downsample(1)
+    km = geo.level(stride).kmap3
+    n = km.n_out
+    pin, pout, tk, nt, npairs = sp.ops.kmap_pairs(km.map_t, n)
+    m = og.kmap3(stride)                                      # [n,27]
+    T, P = int(nt.item()), int(npairs.item())
+    assert P == int((m >= 0).sum())
+    got = set()
+    pin_h, pout_h, tk_h = pin.cpu().numpy(), pout.cpu().numpy(), tk.cpu().numpy()
+    for t in range(T):
+        sl = slice(t * 128, (t + 1) * 128)
+        v = pout_h[sl] >= 0
+        assert np.all((pin_h[sl] >= 0) == v)
+        got.update(zip([int(tk_h[t])] * int(v.sum()), pin_h[sl][v].tolist(), pout_h[sl][v].tolist()))
+    o_idx, k_idx = np.nonzero(m >= 0)
+    assert got == set(zip(k_idx.tolist(), m[o_idx, k_idx].tolist(), o_idx.tolist())) and len(got) == P
+    g = torch.Generator().manual_seed(5)
+    x = oo.round_tf32(torch.randn(n, cin, generator=g))
+    w = torch.randn(27, cin, cout, generator=g) / (27 * cin) ** 0.5
+    b, res = torch.randn(cout, generator=g), torch.randn(n, cout, generator=g)
+    want = oo.conv_gather_gemm_scatter(x, w, m, n, b, emulate_tf32=True) + res
+    y = sp.ops.conv_fwd_pairs(x.cuda(), w.cuda(), sp.ops.pack_weights(w.cuda()), pin, pout, tk, T, n, b.cuda(), res.cuda())
+    assert rel_err(y.cpu().numpy(), want.numpy()) < 2e-5
+
+
 @pytest.mark.parametrize("nsplit", [1, 3, 16])
 @pytest.mark.parametrize("a_tf32", [False, True])
 def test_conv_tcgen05_split_and_async_gather(sp, nsplit, a_tf32):
