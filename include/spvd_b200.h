@@ -43,6 +43,7 @@ extern "C" {
 
 #define SPVD_STATUS_COORD_RANGE 1 /* a coordinate did not fit the 16-bit packed key */
 #define SPVD_STATUS_HASH_FULL 2   /* insertion found no free slot */
+#define SPVD_STATUS_SEGMENT_OVERFLOW 4 /* a cloud has more rows than the max_cloud_rows hint */
 
 #define SPVD_SCALE_MUL 0 /* fl(fl(c*init_res) * fl(1/after_res)): torch-CUDA's division by a scalar */
 #define SPVD_SCALE_DIV 1 /* fl(fl(c*init_res) / after_res):       torch-CPU's                        */
@@ -81,6 +82,16 @@ size_t spvd_unique_workspace_bytes(int n_cap);
 int spvd_unique_coords(const int32_t* icoords, int n_cap, const int32_t* n_dev, int32_t* out_coords,
                        int32_t* out_count, int32_t* status, void* workspace, size_t workspace_bytes,
                        spvd_stream_t stream);
+
+/* Segmented variants of spvd_unique_coords (parent = 0) / spvd_downsample_coords (parent = 1) for
+ * batch-major rows with at most max_cloud_rows (<= 16384) rows per cloud: every cloud is sorted and
+ * de-duplicated by one CTA in shared memory (3 launches instead of ~20).  Also writes the new level's
+ * per-cloud counts [n_batch] and offsets [n_batch+1].  A cloud larger than the hint sets
+ * SPVD_STATUS_SEGMENT_OVERFLOW.  Workspace: spvd_unique_workspace_bytes(n_cap). */
+int spvd_segmented_unique(const int32_t* coords, int n_cap, const int32_t* n_dev, int n_batch,
+                          int max_cloud_rows, int parent, int downsample_mode, int32_t* out_coords,
+                          int32_t* out_count, int32_t* batch_counts, int32_t* batch_offsets, int32_t* status,
+                          void* workspace, size_t workspace_bytes, spvd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * H1  coordinate hash table                      reference: models/sparse_utils.py:36-55
@@ -215,7 +226,8 @@ int spvd_conv_wgrad(const float* in, const float* gout, const int32_t* map_t, in
  *     reference: models/ddpm_unet_attn.py:24-28, models/spvd.py:36-37.
  * spvd_film_fwd: y[i] = (1 + tt[b_i, c]) * x[i, c] + tt[b_i, C + c], b_i = coords[i].batch, tt [B, 2C];
  *     reference: TimeEmbeddingBlock.message, models/modules/graph.py:35-41.
- * spvd_batch_counts: counts[b] = number of rows of batch b (what to_dense_batch derives,
+ * spvd_batch_counts: counts[b] = number of rows of batch b; rows must be batch-major (every voxel level
+ *     of this library is; what to_dense_batch derives,
  *     models/modules/transformer.py:12-15). */
 int spvd_bn_silu_fwd(const float* x, const float* scale, const float* shift, long long rows, int c,
                      int act, float* y, spvd_stream_t stream);
@@ -273,7 +285,9 @@ typedef struct spvd_plan_level {
   int32_t capacity, pair_tile_cap;
 } spvd_plan_level_t;
 
-int spvd_plan_build(const float* pc, int n_points, int n_batch, float init_res, float after_res,
+/* max_cloud_rows > 0: the caller promises batch-major points with at most that many per cloud (the
+ * layout torch2sparse produces) -> the segmented sort path; 0 = no assumption (global radix sort). */
+int spvd_plan_build(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res, float after_res,
                     int scale_mode, int downsample_mode, const spvd_plan_level_t* levels, int n_levels,
                     int ld, float* fcoords, int32_t* icoords, int32_t* status, const int32_t* summary_dev,
                     int32_t* summary_host, int summary_count, void* workspace, size_t workspace_bytes,

@@ -84,6 +84,32 @@ __global__ void __launch_bounds__(256) k_conv_fwd_simt(const float* __restrict__
   }
 }
 
+// Tiny-Cin direct convolution (the network input has 3 channels: 3^3 x 3 -> 32 at stride 1): one thread per
+// (output row, output channel), weights in shared memory, map and input reads are warp broadcasts.
+__global__ void __launch_bounds__(256) k_conv_fwd_small_cin(const float* __restrict__ in, const float* __restrict__ w,
+                                                            const int* __restrict__ map_t, int ld, int n_out, int kvol,
+                                                            int cin, int cout, const float* __restrict__ bias,
+                                                            const float* __restrict__ residual, float* __restrict__ out) {
+  extern __shared__ float s_w[];   // [kvol][cin][cout]
+  pdl_trigger();
+  for (int i = threadIdx.x; i < kvol * cin * cout; i += blockDim.x) s_w[i] = w[i];
+  pdl_wait();
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_out * cout) return;
+  const int o = (int)(t / cout), c = (int)(t % cout);
+  float acc = bias ? bias[c] : 0.f;
+  if (residual) acc += residual[t];
+  for (int k = 0; k < kvol; ++k) {
+    const int r = map_t ? __ldg(map_t + (size_t)k * ld + o) : o;
+    if (r < 0) continue;
+    const float* x = in + (size_t)r * cin;
+    const float* wk = s_w + (k * cin) * cout + c;
+    for (int ci = 0; ci < cin; ++ci) acc = fmaf(__ldg(x + ci), wk[ci * cout], acc);
+  }
+  out[t] = acc;
+}
+
 // gw[k][ci][co] += sum over a chunk of output rows of in[map[k][o]][ci] * gout[o][co]
 constexpr int WI = 32, WO = 64, WR = 16;
 
@@ -175,6 +201,12 @@ extern "C" int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t
   SPVD_CHECK_ARG(map_t || kvol == 1, "spvd_conv_fwd: a NULL map needs kvol == 1");
   SPVD_CHECK_ARG(!map_t || ld >= n_out, "spvd_conv_fwd: ld %d < n_out %d", ld, n_out);
   if (n_out == 0) return SPVD_OK;
+  if (cin <= 4 && (size_t)kvol * cin * cout * 4 <= 40 * 1024) {
+    SPVD_CUDA(launch_pdl(k_conv_fwd_small_cin, dim3(cdiv((long long)n_out * cout, 256)), dim3(256),
+                         (size_t)kvol * cin * cout * 4, (cudaStream_t)stream, in, w, map_t, ld, n_out, kvol, cin, cout, bias,
+                         residual, out));
+    return SPVD_OK;
+  }
   dim3 grid(cdiv(n_out, TM), cdiv(cout, TN));
   SPVD_CUDA(launch_pdl(k_conv_fwd_simt, grid, dim3(256), 0, (cudaStream_t)stream, in, w, map_t, ld, tile_mask, n_out, kvol,
                        cin, cout, bias, residual, out));

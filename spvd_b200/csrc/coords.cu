@@ -376,9 +376,219 @@ static int sorted_unique(const SortWs& w, int n_cap, int4* out_coords, int* out_
   return SPVD_OK;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Segmented path: when the rows are batch-major and no cloud has more than `cap` rows (the caller's
+// hint), each cloud is sorted and de-duplicated by ONE CTA entirely in shared memory (bitonic sort of
+// the packed keys) -- 3 launches per level instead of ~20 for the global radix sort.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int lower_bound_batch(const int4* __restrict__ coords, int n, int b) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (coords[mid].x < b) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__global__ void k_coord_max2(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev,
+                             int* __restrict__ cmax) {
+  int n = resolve_n(n_dev, n_cap);
+  int mx = INT_MIN, my = INT_MIN, mz = INT_MIN;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    int4 c = coords[i];
+    mx = max(mx, c.y);
+    my = max(my, c.z);
+    mz = max(mz, c.w);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    my = max(my, __shfl_xor_sync(0xffffffffu, my, o));
+    mz = max(mz, __shfl_xor_sync(0xffffffffu, mz, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(&cmax[0], mx);
+    atomicMax(&cmax[1], my);
+    atomicMax(&cmax[2], mz);
+  }
+}
+
+// parent_mode: 0 = keys of the rows themselves (stride-1 voxels of the points), 1 = floor(c/2), 2 = floor(c/2)
+// with the spconv bound (cmax = batch-wide maxima of the fine level)
+__global__ void __launch_bounds__(1024) k_seg_sort(const int4* __restrict__ coords, int n_cap,
+                                                   const int* __restrict__ n_dev, int cap, int parent_mode,
+                                                   const int* __restrict__ cmax, u64* __restrict__ temp,
+                                                   int* __restrict__ cloud_count, int* status) {
+  extern __shared__ u64 s_keys[];
+  __shared__ int s_wsum[32];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = resolve_n(n_dev, n_cap);
+  const int lo = lower_bound_batch(coords, n, b), hi = lower_bound_batch(coords, n, b + 1);
+  int cnt = hi - lo;
+  if (cnt > cap) {
+    if (tid == 0 && status) atomicOr(status, SPVD_STATUS_SEGMENT_OVERFLOW);
+    cnt = cap;
+  }
+  int bx = 0, by = 0, bz = 0;
+  if (parent_mode == 2) {
+    bx = (cmax[0] - 1) >> 1;
+    by = (cmax[1] - 1) >> 1;
+    bz = (cmax[2] - 1) >> 1;
+  }
+  for (int i = tid; i < cap; i += 1024) {
+    u64 key = kKeySentinel;
+    if (i < cnt) {
+      int4 c = coords[lo + i];
+      int x = c.y, y = c.z, z = c.w;
+      bool keep = true;
+      if (parent_mode) {
+        x >>= 1; y >>= 1; z >>= 1;
+        if (parent_mode == 2) keep = x <= bx && y <= by && z <= bz;
+      }
+      if (!coord_in_range(c.x, x, y, z)) {
+        keep = false;
+        if (status) atomicOr(status, SPVD_STATUS_COORD_RANGE);
+      }
+      if (keep) key = pack_key(c.x, x, y, z);
+    }
+    s_keys[i] = key;
+  }
+  __syncthreads();
+  for (int k = 2; k <= cap; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (cap >> 1); t += 1024) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // lower index of the pair
+        const int l = i | j;
+        const bool up = (i & k) == 0;
+        const u64 a = s_keys[i], c2 = s_keys[l];
+        if ((a > c2) == up) {
+          s_keys[i] = c2;
+          s_keys[l] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // unique: each thread owns a contiguous run of cap/1024 (>= 1) elements
+  const int per = (cap + 1023) >> 10;
+  const int first = tid * per;
+  int heads = 0;
+  for (int j = 0; j < per; ++j) {
+    const int i = first + j;
+    if (i < cap) {
+      const u64 k = s_keys[i];
+      heads += (k != kKeySentinel && (i == 0 || k != s_keys[i - 1])) ? 1 : 0;
+    }
+  }
+  int incl = heads;
+  const int lane = tid & 31, warp = tid >> 5;
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  int wbase = 0, total = 0;
+  for (int w = 0; w < 32; ++w) {
+    const int v = s_wsum[w];
+    if (w < warp) wbase += v;
+    total += v;
+  }
+  int pos = lo + wbase + incl - heads;
+  for (int j = 0; j < per; ++j) {
+    const int i = first + j;
+    if (i < cap) {
+      const u64 k = s_keys[i];
+      if (k != kKeySentinel && (i == 0 || k != s_keys[i - 1])) temp[pos++] = k;
+    }
+  }
+  if (tid == 0) cloud_count[b] = total;
+}
+
+// gather the per-cloud unique runs into the level's coordinate array; also yields the level's per-cloud
+// counts (= cloud_count) and offsets
+__global__ void __launch_bounds__(256) k_seg_compact(const int4* __restrict__ src_coords, int n_cap,
+                                                     const int* __restrict__ n_dev, const u64* __restrict__ temp,
+                                                     const int* __restrict__ cloud_count, int nb,
+                                                     int4* __restrict__ out_coords, int* __restrict__ out_count,
+                                                     int* __restrict__ batch_offsets) {
+  __shared__ int s_base;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  if (tid < 32) {
+    int sum = 0;
+    for (int i = tid; i < b; i += 32) sum += cloud_count[i];
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (tid == 0) s_base = sum;
+  }
+  __syncthreads();
+  const int base = s_base, cnt = cloud_count[b];
+  const int n = resolve_n(n_dev, n_cap);
+  const int lo = lower_bound_batch(src_coords, n, b);
+  for (int i = tid; i < cnt; i += 256) out_coords[base + i] = unpack_key(temp[lo + i]);
+  if (tid == 0) {
+    if (batch_offsets) batch_offsets[b] = base;
+    if (b == nb - 1) {
+      *out_count = base + cnt;
+      if (batch_offsets) batch_offsets[nb] = base + cnt;
+    }
+  }
+}
+
+static int next_pow2(int v) {
+  int p = 32;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+// sorted-unique of batch-major rows, one CTA per cloud.  temp: n_cap u64; cloud_count: nb int32 (doubles as
+// the new level's per-cloud counts); cmax: 3 int32 scratch (spconv bound)
+static int seg_sorted_unique(const int4* coords, int n_cap, const int* n_dev, int nb, int max_cloud_rows, int parent_mode,
+                             int* cmax, u64* temp, int* cloud_count, int4* out_coords, int* out_count,
+                             int* batch_offsets, int* status, cudaStream_t s) {
+  const int cap = next_pow2(max_cloud_rows);
+  const size_t smem = (size_t)cap * 8;
+  static bool configured = false;
+  if (!configured) {
+    SPVD_CUDA(cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+    configured = true;
+  }
+  if (parent_mode == 2) {
+    SPVD_CUDA(cudaMemsetAsync(cmax, 0x80, 12, s));   // 0x80808080 = very negative
+    int grid = cdiv(n_cap, 1024);
+    if (grid > 148) grid = 148;
+    k_coord_max2<<<grid, 256, 0, s>>>(coords, n_cap, n_dev, cmax);
+  }
+  k_seg_sort<<<nb, 1024, smem, s>>>(coords, n_cap, n_dev, cap, parent_mode, cmax, temp, cloud_count, status);
+  k_seg_compact<<<nb, 256, 0, s>>>(coords, n_cap, n_dev, temp, cloud_count, nb, out_coords, out_count, batch_offsets);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
 }  // namespace spvd
 
 using namespace spvd;
+
+// Segmented variants of spvd_unique_coords / spvd_downsample_coords for batch-major rows with at most
+// max_cloud_rows (<= 16384) rows per cloud.  parent = 0: unique of the rows themselves; 1: stride-2 parents.
+// Also writes the new level's per-cloud counts [n_batch] and offsets [n_batch+1].  workspace as for
+// spvd_unique_workspace_bytes(n_cap).
+extern "C" int spvd_segmented_unique(const int32_t* coords, int n_cap, const int32_t* n_dev, int n_batch,
+                                     int max_cloud_rows, int parent, int downsample_mode, int32_t* out_coords,
+                                     int32_t* out_count, int32_t* batch_counts, int32_t* batch_offsets, int32_t* status,
+                                     void* workspace, size_t workspace_bytes, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(coords && out_coords && out_count && batch_counts && workspace && n_cap > 0 && n_batch > 0,
+                 "spvd_segmented_unique: bad arguments");
+  SPVD_CHECK_ARG(max_cloud_rows > 0 && max_cloud_rows <= 16384, "spvd_segmented_unique: max_cloud_rows %d not in 1..16384",
+                 max_cloud_rows);
+  if (workspace_bytes < sort_ws_bytes(n_cap)) {
+    set_error("spvd_segmented_unique: workspace %zu < %zu", workspace_bytes, sort_ws_bytes(n_cap));
+    return SPVD_ERR_WORKSPACE;
+  }
+  SortWs w = carve_ws(workspace, n_cap);
+  int mode = !parent ? 0 : (downsample_mode == SPVD_DOWNSAMPLE_SPCONV ? 2 : 1);
+  return seg_sorted_unique((const int4*)coords, n_cap, n_dev, n_batch, max_cloud_rows, mode, &w.st->cmax[0], w.buf[0],
+                           batch_counts, (int4*)out_coords, out_count, batch_offsets, status, (cudaStream_t)stream);
+}
 
 extern "C" int spvd_point_voxel_coords(const float* pc, int n, float init_res, float after_res, int scale_mode,
                                        float* fcoords, int32_t* icoords, spvd_stream_t stream) {

@@ -74,13 +74,23 @@ __global__ void k_film4(const float4* __restrict__ x, const float* __restrict__ 
   y[t] = v;
 }
 
+// rows are sorted by (batch, x, y, z): counts[b] = lower_bound(b+1) - lower_bound(b), one thread per cloud
+__device__ __forceinline__ int batch_lower_bound(const int4* __restrict__ coords, int n, int b) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    if (coords[mid].x < b) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
 __global__ void k_batch_counts(const int4* __restrict__ coords, int n_cap, const int* __restrict__ n_dev, int nb,
                                int* __restrict__ counts) {
   int n = resolve_n(n_dev, n_cap);
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int b = coords[i].x;
-  if (b >= 0 && b < nb) atomicAdd(counts + b, 1);
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= nb) return;
+  counts[b] = batch_lower_bound(coords, n, b + 1) - batch_lower_bound(coords, n, b);
 }
 
 }  // namespace spvd
@@ -115,9 +125,7 @@ extern "C" int spvd_batch_counts(const int32_t* coords, int n_cap, const int32_t
                                  spvd_stream_t stream) {
   SPVD_CHECK_ARG(coords && counts && n_cap >= 0 && nb > 0, "spvd_batch_counts: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-  SPVD_CUDA(cudaMemsetAsync(counts, 0, (size_t)nb * 4, s));
-  if (n_cap == 0) return SPVD_OK;
-  k_batch_counts<<<cdiv(n_cap, 256), 256, 0, s>>>((const int4*)coords, n_cap, n_dev, nb, counts);
+  k_batch_counts<<<cdiv(nb, 128), 128, 0, s>>>((const int4*)coords, n_cap, n_dev, nb, counts);
   SPVD_LAUNCH_CHECK();
   return SPVD_OK;
 }

@@ -88,18 +88,26 @@ __global__ void __launch_bounds__(128) k_kmap_subm3(const int4* __restrict__ coo
   int4 c = valid ? coords[o] : make_int4(0, 0, 0, 0);
   unsigned wmask = 0;
 #pragma unroll 1
-  for (int k = 0; k < 27; ++k) {
-    int r = -1;
-    if (valid) {
-      if (k == 13) {
-        r = o;
-      } else {
-        int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
-        r = find_coord(keys, vals, cap, c.x, c.y + dx, c.z + dy, c.w + dz) - 1;
+  for (int k0 = 0; k0 < 27; k0 += 9) {   // 9 independent probes in flight per thread
+    int r[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      const int k = k0 + j;
+      r[j] = -1;
+      if (valid) {
+        if (k == 13) {
+          r[j] = o;
+        } else {
+          int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
+          r[j] = find_coord(keys, vals, cap, c.x, c.y + dx, c.z + dy, c.w + dz) - 1;
+        }
       }
     }
-    if (o < ld) map_t[(size_t)k * ld + o] = r;
-    if (__ballot_sync(0xffffffffu, r >= 0)) wmask |= 1u << k;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      if (o < ld) map_t[(size_t)(k0 + j) * ld + o] = r[j];
+      if (__ballot_sync(0xffffffffu, r[j] >= 0)) wmask |= 1u << (k0 + j);
+    }
   }
   if ((threadIdx.x & 31) == 0 && wmask) atomicOr(&s_mask, wmask);
   __syncthreads();

@@ -44,6 +44,8 @@ int spvd_devox_query(const float*, int, int, const int64_t*, const int32_t*, int
 int spvd_batch_counts(const int32_t*, int, const int32_t*, int, int32_t*, spvd_stream_t);
 int spvd_kmap_pairs(const int32_t*, int, int, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*,
                     int32_t*, spvd_stream_t);
+int spvd_segmented_unique(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, int32_t*, int32_t*, int32_t*,
+                          int32_t*, void*, size_t, spvd_stream_t);
 }
 
 #define SPVD_TRY(call)            \
@@ -52,7 +54,7 @@ int spvd_kmap_pairs(const int32_t*, int, int, const int32_t*, int, int, int32_t*
     if (rc_ != SPVD_OK) return rc_; \
   } while (0)
 
-extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, float init_res, float after_res,
+extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res, float after_res,
                                int scale_mode, int downsample_mode, const spvd_plan_level_t* levels, int n_levels,
                                int ld, float* fcoords, int32_t* icoords, int32_t* status, const int32_t* summary_dev,
                                int32_t* summary_host, int summary_count, void* workspace, size_t workspace_bytes,
@@ -67,11 +69,18 @@ extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, float
     const spvd_plan_level_t& L = levels[i];
     SPVD_CHECK_ARG(L.coords && L.count && L.keys && L.vals && L.capacity >= 2 * n_points,
                    "spvd_plan_build: level %d lacks coords / count / hash buffers", i);
-    if (i == 0)
+    const bool seg = max_cloud_rows > 0 && max_cloud_rows <= 16384 && n_batch > 0 && L.batch_counts;
+    if (seg) {
+      // one CTA per cloud sorts in shared memory; per-cloud counts / offsets of the level come for free
+      SPVD_TRY(spvd_segmented_unique(i == 0 ? icoords : levels[i - 1].coords, n_points, i == 0 ? nullptr : levels[i - 1].count,
+                                     n_batch, max_cloud_rows, i > 0, downsample_mode, L.coords, L.count, L.batch_counts,
+                                     L.batch_offsets, status, workspace, workspace_bytes, stream));
+    } else if (i == 0) {
       SPVD_TRY(spvd_unique_coords(icoords, n_points, nullptr, L.coords, L.count, status, workspace, workspace_bytes, stream));
-    else
+    } else {
       SPVD_TRY(spvd_downsample_coords(levels[i - 1].coords, n_points, levels[i - 1].count, downsample_mode, L.coords,
                                       L.count, status, workspace, workspace_bytes, stream));
+    }
     SPVD_TRY(spvd_hash_build(L.coords, n_points, L.count, SPVD_ORDER_BXYZ, L.keys, L.vals, L.capacity, status, stream));
     if (i > 0) {
       const spvd_plan_level_t& F = levels[i - 1];
@@ -94,7 +103,8 @@ extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, float
     }
     if (L.devox_idx && L.devox_w)
       SPVD_TRY(spvd_devox_query(fcoords, n_points, stride, L.keys, L.vals, L.capacity, L.devox_idx, L.devox_w, stream));
-    if (L.batch_counts) {
+    const bool seg = max_cloud_rows > 0 && max_cloud_rows <= 16384 && n_batch > 0 && L.batch_counts;
+    if (L.batch_counts && !seg) {
       SPVD_TRY(spvd_batch_counts(L.coords, n_points, L.count, n_batch, L.batch_counts, stream));
       if (L.batch_offsets) k_batch_offsets<<<1, 32, 0, s>>>(L.batch_counts, n_batch, L.batch_offsets);
     }

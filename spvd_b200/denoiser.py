@@ -278,7 +278,7 @@ class SPVUnet(nn.Module):
         return x
 
     # -- forward -------------------------------------------------------------------------------
-    def plan_geometry(self, coords: torch.Tensor, n_batch: int) -> Geometry:
+    def plan_geometry(self, coords: torch.Tensor, n_batch: int, max_cloud_rows: int = 0) -> Geometry:
         """Plan every coordinate structure of the forward with one C call into persistent buffers.  Two
         buffer sets alternate, so the geometry of the previous call stays valid while the next one is
         planned (``geometry_pool`` > 2 keeps more alive, e.g. when several forwards precede one backward)."""
@@ -294,14 +294,15 @@ class SPVUnet(nn.Module):
         else:
             pool[1] = (pool[1] + 1) % len(pool[0])
             ws = pool[0][pool[1]]
-        return ws.build(pc, self.pres, self.voxel_size, self.scale_mode, self.downsample_mode)
+        return ws.build(pc, self.pres, self.voxel_size, self.scale_mode, self.downsample_mode, max_cloud_rows)
 
     def forward(self, inp, geometry: Geometry = None):
         x_in, t = inp[0], inp[1]
         coords, feats = (x_in.C, x_in.F) if isinstance(x_in, SparseTensor) or hasattr(x_in, "C") else x_in
         if not feats.is_cuda:
             raise RuntimeError("spvd_b200.SPVUnet runs on CUDA only (no CPU fallback)")
-        geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0])
+        geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0],
+                                                                       int(getattr(x_in, "points_per_cloud", 0) or 0))
         if self.use_executor and self._fast() and len(inp) == 2:
             from .runtime import Program
             key = (feats.shape[0], t.shape[0])

@@ -245,22 +245,26 @@ class PlanWorkspace:
         self.n_kernels = (1 + 22 + 23 * (nl - 1) + nl + (nl - 1) + len(k3_strides) + 2 * len(p2v_strides) + len(devox_strides) +
                           2 * nl + 3 * len(self.pair_strides))
 
-    def build(self, pc, pres, voxel_size, scale_mode="mul", downsample_mode="spconv"):
+    def build(self, pc, pres, voxel_size, scale_mode="mul", downsample_mode="spconv", max_cloud_rows=0):
+        """max_cloud_rows > 0: the points are batch-major with at most that many per cloud (what torch2sparse
+        produces) -> per-cloud shared-memory sorts; 0: no assumption (global radix sort)."""
         if not pc.is_cuda or pc.dtype != torch.float32 or not pc.is_contiguous() or pc.shape != (self.n_points, 4):
             raise RuntimeError("PlanWorkspace.build needs a contiguous CUDA float32 [n_points,4] tensor")
         _check(_lib.spvd_plan_build(
-            _C.c_void_p(pc.data_ptr()), self.n_points, self.n_batch, pres, voxel_size, ops._SCALE[scale_mode],
+            _C.c_void_p(pc.data_ptr()), self.n_points, self.n_batch, int(max_cloud_rows), pres, voxel_size, ops._SCALE[scale_mode],
             ops._DOWNSAMPLE[downsample_mode], self.c_levels, len(self.strides), self.ld,
             _C.c_void_p(self.fcoords.data_ptr()), _C.c_void_p(self.icoords.data_ptr()), _C.c_void_p(self.status.data_ptr()),
             _C.c_void_p(self.summary.data_ptr()), _C.c_void_p(self.summary_host.data_ptr()), self.n_summary,
             _C.c_void_p(self.ws.data_ptr()), self.ws.numel(), _C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        ops.stats.launches += self.n_kernels
+        ops.stats.launches += self.n_kernels if not max_cloud_rows else self.n_kernels - 20 * len(self.strides)
         host = self.summary_host.tolist()
         nl, nb = len(self.strides), self.n_batch
         st = host[nl]
         if st:
             raise RuntimeError("spvd_b200: " + ("coordinate outside the packed 16-bit range; " if st & 1 else "") +
-                               ("hash table full" if st & 2 else ""))
+                               ("hash table full; " if st & 2 else "") +
+                               ("a cloud has more points than the max_cloud_rows hint (or the points are not batch-major)"
+                                if st & 4 else ""))
         geo = Geometry.__new__(Geometry)
         geo.n_points, geo.mode, geo.status = self.n_points, downsample_mode, self.status
         geo.fcoords, geo.levels, geo.p2v, geo.devox = self.fcoords, {}, {}, {}

@@ -53,7 +53,7 @@ class _Stats:
 stats = _Stats()
 # kernels launched by one call of each entry point (memsets are not kernels)
 _K = {"point_voxel_coords": 1, "unique_coords": 22, "downsample_coords": 23, "hash_build": 1, "hash_query": 1,
-      "kmap_subm3": 1, "kmap_down2": 1, "kmap_pairs": 3, "batch_counts": 1, "point_voxel_query": 1, "devox_query": 1,
+      "kmap_subm3": 1, "kmap_down2": 1, "kmap_pairs": 3, "segmented_unique": 3, "batch_counts": 1, "point_voxel_query": 1, "devox_query": 1,
       "scatter_mean_fwd": 2, "scatter_mean_bwd": 1, "devoxelize_fwd": 1, "devoxelize_bwd": 1, "pack_weights": 1,
       "transpose_weights": 1, "conv_fwd": 1, "conv_wgrad": 1, "round_tf32": 1, "affine_act": 1, "film": 1}
 
@@ -99,6 +99,22 @@ def downsample_coords(coords, n_dev=None, mode="spconv", status=None, workspace=
     check(lib.spvd_downsample_coords(_p(coords, torch.int32), n_cap, _p(n_dev), _DOWNSAMPLE[mode], _p(out), _p(cnt),
                                      _p(status), _p(ws), ws.numel(), _s()))
     return out, cnt
+
+
+def segmented_unique(coords, n_batch, max_cloud_rows, parent=False, mode="spconv", n_dev=None, status=None):
+    """sorted-unique (parent=False) or stride-2 parents (parent=True) of batch-major rows, one CTA per cloud.
+    -> (coords [n_cap,4], count int32[1], batch_counts int32[n_batch], batch_offsets int32[n_batch+1])"""
+    _count("segmented_unique")
+    n_cap = coords.shape[0]
+    dev = coords.device
+    out = torch.empty((n_cap, 4), dtype=torch.int32, device=dev)
+    cnt = torch.empty(1, dtype=torch.int32, device=dev)
+    bc = torch.empty(n_batch, dtype=torch.int32, device=dev)
+    bo = torch.empty(n_batch + 1, dtype=torch.int32, device=dev)
+    ws = torch.empty(lib.spvd_unique_workspace_bytes(n_cap), dtype=torch.uint8, device=dev)
+    check(lib.spvd_segmented_unique(_p(coords, torch.int32), n_cap, _p(n_dev), n_batch, int(max_cloud_rows), int(parent),
+                                    _DOWNSAMPLE[mode], _p(out), _p(cnt), _p(bc), _p(bo), _p(status), _p(ws), ws.numel(), _s()))
+    return out, cnt, bc, bo
 
 
 class HashTable:

@@ -82,7 +82,9 @@ def torch2sparse(pts: torch.Tensor, pres: float = 1e-5, order: str = "keep") -> 
     coords = torch.cat([b.view(-1, 1), ci.view(-1, 3)], dim=1)
     feats = pts.reshape(-1, Fd)
     if order == "keep":
-        return SparseTensor(feats.contiguous(), coords.contiguous())
+        st = SparseTensor(feats.contiguous(), coords.contiguous())
+        st.points_per_cloud = N          # batch-major, exactly N rows per cloud: lets the planner sort per cloud
+        return st
     if order != "reference":
         raise ValueError(order)
     x = (ci - ci.amin(dim=1, keepdim=True)).long()                       # batched_ravel_hash_torch
@@ -92,7 +94,9 @@ def torch2sparse(pts: torch.Tensor, pres: float = 1e-5, order: str = "keep") -> 
     _, inv = torch.unique(key, dim=0, sorted=True, return_inverse=True)
     perm = torch.arange(inv.shape[0], device=pts.device)
     first = inv.new_full((int(inv.max()) + 1,), inv.shape[0]).scatter_reduce_(0, inv, perm, "amin")
-    return SparseTensor(feats[first].contiguous(), coords[first].contiguous())
+    st = SparseTensor(feats[first].contiguous(), coords[first].contiguous())
+    st.points_per_cloud = N              # rows are (batch, hash)-sorted, at most N per cloud
+    return st
 
 
 class SparseScheduler:

@@ -24,6 +24,7 @@ class SparseTensor:
         self.feats, self.coords = feats, coords
         self.stride = make_ntuple(stride, 3)
         self.spatial_range = spatial_range
+        self.points_per_cloud = 0   # optional hint: rows are batch-major with at most this many per cloud (0 = unknown)
         self._caches = TensorCache()
 
     F = property(lambda self: self.feats, lambda self, v: setattr(self, "feats", v))

@@ -146,6 +146,33 @@ def test_downsample_and_strided_maps(sp, mode):
     assert np.array_equal(got_mu[:, :n].T, want_mu) and np.all(got_mu[:, n:] == -1)
 
 
+@pytest.mark.parametrize("parent,mode", [(False, "spconv"), (True, "spconv"), (True, "floor")])
+def test_segmented_unique_ragged_clouds(sp, parent, mode):
+    """per-cloud shared-memory sort: ragged clouds incl. an empty one and one that fills the capacity exactly"""
+    from oracle import ops as oo
+    rng = np.random.default_rng(3)
+    sizes = [700, 0, 2048, 1, 1500, 33]
+    rows = []
+    for b, n in enumerate(sizes):
+        c = np.empty((n, 4), dtype=np.int32)
+        c[:, 0] = b
+        c[:, 1:] = rng.integers(-6, 14, (n, 3))
+        rows.append(c)
+    c = np.concatenate(rows)
+    if parent:
+        c, _ = oo.unique_voxels(c)                       # a real (sorted, unique) fine level
+    out, cnt, bc, bo = sp.ops.segmented_unique(dev(c), len(sizes), 2048, parent, mode)
+    want = oo.downsample_coords(c, mode)[0] if parent else oo.unique_voxels(c)[0]
+    k = int(cnt.item())
+    assert k == want.shape[0] and np.array_equal(out[:k].cpu().numpy(), want)
+    assert bc.cpu().tolist() == np.bincount(want[:, 0], minlength=len(sizes)).tolist()
+    assert bo.cpu().tolist() == [0] + np.cumsum(bc.cpu().numpy()).tolist()
+    status = torch.zeros(1, dtype=torch.int32).cuda()
+    sp.ops.segmented_unique(dev(c), len(sizes), 512, parent, mode, status=status)      # hint too small -> flagged
+    if max(np.bincount(c[:, 0])) > 512:
+        assert int(status.item()) & 4
+
+
 def test_empty_level_is_reported(sp):
     """spconv rule with max coordinate 0 on an axis drops everything: the count
     comes back 0 and Geometry raises a clear error instead of crashing inside a kernel."""
@@ -189,8 +216,8 @@ def test_one_call_planner_matches_op_by_op_geometry(sp):
     for mode in ("spconv", "floor"):
         ref = sp.Geometry(pc, 1e-5, 0.1, n_batch=4, downsample_mode=mode, **kw)
         ws = sp.geometry.PlanWorkspace(pc.shape[0], 4, kw["strides"], kw["strides"], kw["p2v_strides"], kw["devox_strides"], pc.device)
-        for _ in range(2):                                   # buffers are reused: build twice
-            geo = ws.build(pc, 1e-5, 0.1, "mul", mode)
+        for hint in (0, 0, 2048):                            # buffers are reused; last: per-cloud smem sort path
+            geo = ws.build(pc, 1e-5, 0.1, "mul", mode, max_cloud_rows=hint)
         assert torch.equal(geo.fcoords, ref.fcoords)
         for s in kw["strides"]:
             a, b = geo.level(s), ref.level(s)

@@ -24,7 +24,7 @@ with torch.no_grad():
         st = sched.torch2sparse(xs[j], shape)
         tb = torch.full((32,), ts[j], device=dev, dtype=torch.long)
         e1.record()
-        geo = model.plan_geometry(st.C, 32)
+        geo = model.plan_geometry(st.C, 32, st.points_per_cloud)
         c1 = time.perf_counter(); e2.record()
         eps = model((st, tb), geometry=geo)
         new = strat.update(st.F, eps, ts[j], j, lambda s: torch.randn(s, device=dev))
