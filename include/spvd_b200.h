@@ -209,11 +209,12 @@ int spvd_kmap_pairs(const int32_t* map_t, int ld, int n_cap, const int32_t* n_de
                     int32_t* scratch, spvd_stream_t stream);
 /* Same convolution, pair-major: one CTA per pair tile, K loop over the channel slabs only, product rows
  * scattered into the zero-filled output with vector RED; bias / residual are added by the tiles of the
- * centre offset (center_k), so the map must be submanifold.  `in` must be TF32-representable. */
+ * centre offset (center_k; pass -1 for maps without one -- the stride-2 maps -- which then take neither).
+ * Swapping pair_in and pair_out gives the transposed convolution on the same lists. */
 int spvd_conv_fwd_pairs(const float* in, const float* w_packed, const int32_t* pair_in,
                         const int32_t* pair_out, const int32_t* tile_k, int n_pair_tiles, int center_k,
                         int n_out, int kvol, int cin, int cout, const float* bias, const float* residual,
-                        float* out, spvd_stream_t stream);
+                        float* out, int a_is_tf32, spvd_stream_t stream);
 /* gw[k] = sum over pairs (i,o) of offset k of in[i]^T gout[o];  gw [kvol,cin,cout] zero-filled inside */
 int spvd_conv_wgrad(const float* in, const float* gout, const int32_t* map_t, int ld, int n_out,
                     int kvol, int cin, int cout, float* gw, spvd_stream_t stream);
@@ -282,7 +283,11 @@ typedef struct spvd_plan_level {
   int32_t* pair_tile_k;   /* [pair_tile_cap] */
   int32_t* pair_counts;   /* [2] = (tiles, pairs) */
   int32_t* pair_scratch;  /* >= 32 + 27*ceil(n_points/4096) int32 */
-  int32_t capacity, pair_tile_cap;
+  int32_t* dpair_in;      /* pair-major view of kmap_down: fine rows */
+  int32_t* dpair_out;     /*                               coarse rows */
+  int32_t* dpair_tile_k;
+  int32_t* dpair_counts;  /* [2] */
+  int32_t capacity, pair_tile_cap, dpair_tile_cap, pad;
 } spvd_plan_level_t;
 
 /* max_cloud_rows > 0: the caller promises batch-major points with at most that many per cloud (the
@@ -334,7 +339,11 @@ typedef struct spvd_level_geom {
   const int32_t* pair_in;       /* pair-major view of kmap3 or NULL */
   const int32_t* pair_out;
   const int32_t* pair_tile_k;
+  const int32_t* dpair_in;      /* pair-major view of kmap_down (fine rows) or NULL */
+  const int32_t* dpair_out;     /* coarse rows */
+  const int32_t* dpair_tile_k;
   int32_t n, ld3, ld_down, ld_up, max_per_batch, n_pair_tiles; /* n_pair_tiles > 0: 3^3 convs run pair-major */
+  int32_t n_dpair_tiles, pad;   /* > 0: the stride-2 / transposed convs of this level run pair-major */
 } spvd_level_geom_t;
 
 typedef struct spvd_op {

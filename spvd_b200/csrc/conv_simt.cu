@@ -100,12 +100,17 @@ __global__ void __launch_bounds__(256) k_conv_fwd_small_cin(const float* __restr
   const int o = (int)(t / cout), c = (int)(t % cout);
   float acc = bias ? bias[c] : 0.f;
   if (residual) acc += residual[t];
-  for (int k = 0; k < kvol; ++k) {
-    const int r = map_t ? __ldg(map_t + (size_t)k * ld + o) : o;
-    if (r < 0) continue;
-    const float* x = in + (size_t)r * cin;
-    const float* wk = s_w + (k * cin) * cout + c;
-    for (int ci = 0; ci < cin; ++ci) acc = fmaf(__ldg(x + ci), wk[ci * cout], acc);
+  for (int k0 = 0; k0 < kvol; k0 += 9) {   // 9 independent map reads in flight
+    int r[9];
+#pragma unroll
+    for (int j = 0; j < 9; ++j) r[j] = (k0 + j < kvol) ? (map_t ? __ldg(map_t + (size_t)(k0 + j) * ld + o) : o) : -1;
+#pragma unroll
+    for (int j = 0; j < 9; ++j) {
+      if (r[j] < 0) continue;
+      const float* x = in + (size_t)r[j] * cin;
+      const float* wk = s_w + ((k0 + j) * cin) * cout + c;
+      for (int ci = 0; ci < cin; ++ci) acc = fmaf(__ldg(x + ci), wk[ci * cout], acc);
+    }
   }
   out[t] = acc;
 }

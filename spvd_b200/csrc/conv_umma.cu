@@ -91,7 +91,7 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return r;
 }
 
-template <int BN, int MT, bool kPairs = false>
+template <int BN, int MT, bool kPairs = false, bool kLite = false>
 struct UmmaCfg {
   static constexpr int kCols = BN * MT;
   static constexpr int kTmemCols = kCols <= 32 ? 32 : kCols <= 64 ? 64 : kCols <= 128 ? 128 : kCols <= 256 ? 256 : 512;
@@ -99,7 +99,7 @@ struct UmmaCfg {
   static constexpr int kStageBytes = MT * kATileBytes + kBTileBytes;
   // pair-major tiles run only cin/32 iterations: keep the footprint small so that several CTAs share an SM and
   // one CTA's prologue / RED epilogue overlaps another's main loop
-  static constexpr int kStages = kPairs ? 2 : (4 * kStageBytes <= 200 * 1024) ? 4 : (3 * kStageBytes <= 200 * 1024) ? 3 : 2;
+  static constexpr int kStages = (kPairs || kLite) ? 2 : (4 * kStageBytes <= 200 * 1024) ? 4 : (3 * kStageBytes <= 200 * 1024) ? 3 : 2;
   static constexpr int kRowsBytes = kPairs ? 2 * BM * 4 : MT * 27 * BM * 4;  // staged row indices
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kRowsBytes;
   // idesc: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
@@ -132,7 +132,7 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
 // output rows; the K loop runs over the channel slabs only and the epilogue scatters the 128 product rows with
 // vector RED into the zero-initialised output (bias / residual added by the centre-offset tiles, which cover
 // every output row exactly once).  Issued tensor-core rows = real pairs, instead of 128 x (active offsets).
-template <int BN, int MT, bool kAsyncA, bool kPairs = false>
+template <int BN, int MT, bool kAsyncA, bool kPairs = false, bool kLite = false>
 __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __restrict__ in,
                                                                const float* __restrict__ w_packed,
                                                                const int* __restrict__ map_t, int ld,
@@ -142,10 +142,10 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
                                                                const float* __restrict__ residual,
                                                                float* __restrict__ out,
                                                                const int* __restrict__ pair_out, int center_k) {
-  using Cfg = UmmaCfg<BN, MT, kPairs>;
+  using Cfg = UmmaCfg<BN, MT, kPairs, kLite>;
   constexpr int kStages = Cfg::kStages;
   static_assert(kAsyncA || MT == 1, "the register gather path is instantiated for MT = 1 only");
-  static_assert(!kPairs || (MT == 1 && kAsyncA), "pair-major tiles: MT = 1, cp.async gather");
+  static_assert(!kPairs || MT == 1, "pair-major tiles: MT = 1");
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -412,57 +412,82 @@ __global__ void k_pack_weights(const float* __restrict__ w, int kvol, int cin, i
   wp[dst] = __uint_as_float(to_tf32(w[t]));
 }
 
-template <int BN, int MT, bool kAsyncA>
+template <int BN, int MT, bool kAsyncA, bool kLite = false>
 static int launch_umma(const float* in, const float* wp, const int32_t* map_t, int ld, const uint32_t* tile_mask,
                        int n_out, int kvol, int cin, int cout, const float* bias, const float* residual, float* out,
                        int nsplit, cudaStream_t s) {
-  using Cfg = UmmaCfg<BN, MT>;
+  using Cfg = UmmaCfg<BN, MT, false, kLite>;
   static bool configured = false;
   if (!configured) {
-    SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN, MT, kAsyncA>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN, MT, kAsyncA, false, kLite>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     configured = true;
   }
   if (nsplit > 1) SPVD_CUDA(cudaMemsetAsync(out, 0, (size_t)n_out * cout * 4, s));
   dim3 grid(cdiv(n_out, BM * MT), cout / BN, nsplit);
-  SPVD_CUDA(launch_pdl(k_conv_fwd_umma<BN, MT, kAsyncA>, grid, dim3(kUmmaThreads), (size_t)Cfg::kSmemBytes, s, in, wp,
-                       map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, (const int*)nullptr, 0));
+  SPVD_CUDA(launch_pdl(k_conv_fwd_umma<BN, MT, kAsyncA, false, kLite>, grid, dim3(kUmmaThreads), (size_t)Cfg::kSmemBytes,
+                       s, in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, (const int*)nullptr, 0));
   return SPVD_OK;
 }
 
-template <int BN>
-static int launch_umma_pairs(const float* in, const float* wp, const int32_t* pair_in, const int32_t* pair_out,
-                             const int32_t* tile_k, int n_pair_tiles, int center_k, int n_out, int kvol, int cin, int cout,
-                             const float* bias, const float* residual, float* out, cudaStream_t s) {
+template <int BN, bool kAsyncA>
+static int launch_umma_pairs_a(const float* in, const float* wp, const int32_t* pair_in, const int32_t* pair_out,
+                               const int32_t* tile_k, int n_pair_tiles, int center_k, int n_out, int kvol, int cin, int cout,
+                               const float* bias, const float* residual, float* out, cudaStream_t s) {
   using Cfg = UmmaCfg<BN, 1, true>;
   static bool configured = false;
   if (!configured) {
-    SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN, 1, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN, 1, kAsyncA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                    Cfg::kSmemBytes));
     configured = true;
   }
   SPVD_CUDA(cudaMemsetAsync(out, 0, (size_t)n_out * cout * 4, s));
+  if (n_pair_tiles == 0) return SPVD_OK;
   dim3 grid(n_pair_tiles, cout / BN, 1);
-  SPVD_CUDA(launch_pdl(k_conv_fwd_umma<BN, 1, true, true>, grid, dim3(kUmmaThreads), (size_t)Cfg::kSmemBytes, s, in, wp,
+  SPVD_CUDA(launch_pdl(k_conv_fwd_umma<BN, 1, kAsyncA, true>, grid, dim3(kUmmaThreads), (size_t)Cfg::kSmemBytes, s, in, wp,
                        pair_in, 0, (const unsigned*)tile_k, n_out, kvol, cin, cout, bias, residual, out, pair_out,
                        center_k));
   return SPVD_OK;
 }
 
 template <int BN>
+static int launch_umma_pairs(bool async_a, const float* in, const float* wp, const int32_t* pair_in,
+                             const int32_t* pair_out, const int32_t* tile_k, int n_pair_tiles, int center_k, int n_out,
+                             int kvol, int cin, int cout, const float* bias, const float* residual, float* out,
+                             cudaStream_t s) {
+  return async_a ? launch_umma_pairs_a<BN, true>(in, wp, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol,
+                                                 cin, cout, bias, residual, out, s)
+                 : launch_umma_pairs_a<BN, false>(in, wp, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol,
+                                                  cin, cout, bias, residual, out, s);
+}
+
+template <int BN>
 static int launch_umma_bn(bool async_a, int mt, const float* in, const float* wp, const int32_t* map_t, int ld,
                           const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
                           const float* residual, float* out, int nsplit, cudaStream_t s) {
-  if (!async_a)
+  if (!async_a) {
+    if (mt == 3)
+      return launch_umma<BN, 1, false, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
     return launch_umma<BN, 1, false>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+  }
+  if (mt == 3)   // one tile per CTA, two stages: small enough for two CTAs per SM
+    return launch_umma<BN, 1, true, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
   if (mt >= 2)
     return launch_umma<BN, 2, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
   return launch_umma<BN, 1, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
 }
 
 // widest instantiated slice that divides cout: the A tile is gathered once per slice, so fewer is better
-static int pick_bn(int cout) {
+static int pick_bn(int cout, int n_tiles = 1 << 30, int kvol = 27) {
   const int widths[] = {256, 192, 128, 96, 64, 32};
+  if (kvol == 1) {
+    // dense layer (nn.Linear): only cin/32 iterations per tile, nothing to split -> narrow the slices until the
+    // grid covers the GPU (the A tile of a dense layer is cheap to re-read)
+    for (int w : widths)
+      if (cout % w == 0 && (long long)n_tiles * (cout / w) >= 148) return w;
+    for (int i = 5; i >= 0; --i)
+      if (cout % widths[i] == 0 && widths[i] >= 64) return widths[i];
+  }
   for (int w : widths)
     if (cout % w == 0) return w;
   return 32;
@@ -512,13 +537,16 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
                  "spvd_conv_fwd_umma: pointers must be 16-byte aligned");
   if (n_out == 0) return SPVD_OK;
   cudaStream_t s = (cudaStream_t)stream;
-  if (bn <= 0) bn = pick_bn(cout);
+  if (bn <= 0) bn = pick_bn(cout, cdiv(n_out, BM), kvol);
   SPVD_CHECK_ARG(cout % bn == 0, "spvd_conv_fwd_umma: slice width %d does not divide cout %d", bn, cout);
   const int max_iters = kvol * (cin / 32);
   const bool aa = a_is_tf32 != 0;
-  if (mt <= 0) mt = (aa && n_out > BM && bn >= 128) ? 2 : 1;   // sharing the weight tile pays when it is large
-  if (!aa) mt = 1;
-  if (nsplit <= 0) nsplit = pick_split(cdiv(n_out, BM * mt) * (cout / bn), max_iters);
+  // default: one tile per CTA with a two-stage ring (<= 111 KB of shared memory), so two CTAs share an SM and one's
+  // prologue / epilogue overlaps the other's main loop -- measured 10-25% faster than two tiles per CTA sharing the
+  // weight tile (tools/conv_bench.py)
+  if (mt <= 0) mt = 3;
+  if (!aa && mt == 2) mt = 1;
+  if (nsplit <= 0) nsplit = pick_split(cdiv(n_out, BM * (mt == 2 ? 2 : 1)) * (cout / bn), max_iters);
   if (nsplit > max_iters) nsplit = max_iters;
   switch (bn) {
     case 32: return launch_umma_bn<32>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
@@ -535,22 +563,24 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
 extern "C" int spvd_conv_fwd_pairs(const float* in, const float* w_packed, const int32_t* pair_in,
                                    const int32_t* pair_out, const int32_t* tile_k, int n_pair_tiles, int center_k,
                                    int n_out, int kvol, int cin, int cout, const float* bias, const float* residual,
-                                   float* out, spvd_stream_t stream) {
+                                   float* out, int a_is_tf32, spvd_stream_t stream) {
   SPVD_CHECK_ARG(in && w_packed && pair_in && pair_out && tile_k && out && n_out >= 0 && n_pair_tiles >= 0,
                  "spvd_conv_fwd_pairs: bad arguments");
   SPVD_CHECK_ARG(spvd_conv_umma_supported(kvol, cin, cout), "spvd_conv_fwd_pairs: unsupported shape %dx%dx%d", kvol, cin, cout);
-  SPVD_CHECK_ARG(center_k >= 0 && center_k < kvol, "spvd_conv_fwd_pairs: the map needs a centre offset (submanifold)");
+  SPVD_CHECK_ARG((center_k >= 0 && center_k < kvol) || (!bias && !residual),
+                 "spvd_conv_fwd_pairs: bias / residual need a centre offset (submanifold map)");
+  const bool aa = a_is_tf32 != 0;
   SPVD_CHECK_ARG(residual != out || residual == nullptr, "spvd_conv_fwd_pairs: residual must not alias out");
   if (n_out == 0) return SPVD_OK;
   cudaStream_t s = (cudaStream_t)stream;
   const int bn = pick_bn(cout);
   switch (bn) {
-    case 32: return launch_umma_pairs<32>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
-    case 64: return launch_umma_pairs<64>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
-    case 96: return launch_umma_pairs<96>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
-    case 128: return launch_umma_pairs<128>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
-    case 192: return launch_umma_pairs<192>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
-    case 256: return launch_umma_pairs<256>(in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+    case 32: return launch_umma_pairs<32>(aa, in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+    case 64: return launch_umma_pairs<64>(aa, in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+    case 96: return launch_umma_pairs<96>(aa, in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+    case 128: return launch_umma_pairs<128>(aa, in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+    case 192: return launch_umma_pairs<192>(aa, in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
+    case 256: return launch_umma_pairs<256>(aa, in, w_packed, pair_in, pair_out, tile_k, n_pair_tiles, center_k, n_out, kvol, cin, cout, bias, residual, out, s);
   }
   return SPVD_ERR_INVALID;
 }

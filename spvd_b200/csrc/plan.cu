@@ -87,6 +87,9 @@ extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, int m
       if (F.kmap_down || F.kmap_up)
         SPVD_TRY(spvd_kmap_down2(F.coords, n_points, F.count, L.keys, L.vals, L.capacity, F.kmap_down, ld, F.mask_down,
                                  F.kmap_up, ld, F.mask_up, nullptr, nullptr, stream));
+      if (F.kmap_down && F.dpair_in && F.dpair_out && F.dpair_tile_k && F.dpair_counts && F.pair_scratch)
+        SPVD_TRY(spvd_kmap_pairs(F.kmap_down, ld, n_points, L.count, 8, F.dpair_tile_cap, F.dpair_in, F.dpair_out,
+                                 F.dpair_tile_k, F.dpair_counts, F.dpair_counts + 1, F.pair_scratch, stream));
     }
   }
   for (int i = 0; i < n_levels; ++i) {

@@ -199,7 +199,7 @@ int spvd_conv_fwd_umma(const float*, const float*, const int32_t*, int, const ui
                        const float*, const float*, float*, int, int, int, int, spvd_stream_t);
 int spvd_bn_silu_fwd(const float*, const float*, const float*, long long, int, int, float*, spvd_stream_t);
 int spvd_conv_fwd_pairs(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int,
-                        int, const float*, const float*, float*, spvd_stream_t);
+                        int, const float*, const float*, float*, int, spvd_stream_t);
 }
 
 extern "C" int spvd_film_affine_fwd(const float* x, const float* tt, int ldt, const int32_t* coords,
@@ -313,7 +313,14 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
         if (o.w_packed && o.map_kind == SPVD_MAP_K3 && (o.flags & SPVD_FLAG_A_TF32) && !(o.flags & SPVD_FLAG_SIMT) &&
             lv->n_pair_tiles > 0 && lv->pair_in)
           rc = spvd_conv_fwd_pairs(at(o.src0), o.w_packed, lv->pair_in, lv->pair_out, lv->pair_tile_k, lv->n_pair_tiles,
-                                   o.kvol / 2, (int)rout, o.kvol, o.c0, o.c1, o.bias, at(o.src1), at(o.dst), stream);
+                                   o.kvol / 2, (int)rout, o.kvol, o.c0, o.c1, o.bias, at(o.src1), at(o.dst), 1, stream);
+        else if (o.w_packed && (o.map_kind == SPVD_MAP_DOWN || o.map_kind == SPVD_MAP_UP) && !(o.flags & SPVD_FLAG_SIMT) &&
+                 lv->n_dpair_tiles > 0 && lv->dpair_in && !o.bias && o.src1 < 0)
+          // stride-2 conv: (fine -> coarse) pairs; its transpose runs on the same lists with the roles swapped
+          rc = spvd_conv_fwd_pairs(at(o.src0), o.w_packed, o.map_kind == SPVD_MAP_DOWN ? lv->dpair_in : lv->dpair_out,
+                                   o.map_kind == SPVD_MAP_DOWN ? lv->dpair_out : lv->dpair_in, lv->dpair_tile_k,
+                                   lv->n_dpair_tiles, -1, (int)rout, o.kvol, o.c0, o.c1, nullptr, nullptr, at(o.dst),
+                                   (o.flags & SPVD_FLAG_A_TF32) ? 1 : 0, stream);
         else if (o.w_packed && !(o.flags & SPVD_FLAG_SIMT))
           rc = spvd_conv_fwd_umma(at(o.src0), o.w_packed, map, ld, mask, (int)rout, o.kvol, o.c0, o.c1, o.bias,
                                   at(o.src1), at(o.dst), 0, 0, (o.flags & SPVD_FLAG_A_TF32) ? 1 : 0, 0, stream);

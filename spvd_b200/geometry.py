@@ -180,7 +180,8 @@ class _PlanLevel(_C.Structure):
     _fields_ = [(n, _C.c_void_p) for n in ("coords", "count", "keys", "vals", "kmap3", "mask3", "kmap_down", "mask_down",
                                            "kmap_up", "mask_up", "p2v", "devox_idx", "devox_w", "batch_counts",
                                            "batch_offsets", "pair_in", "pair_out", "pair_tile_k", "pair_counts",
-                                           "pair_scratch")] + [("capacity", _C.c_int32), ("pair_tile_cap", _C.c_int32)]
+                                           "pair_scratch", "dpair_in", "dpair_out", "dpair_tile_k", "dpair_counts")] + \
+               [("capacity", _C.c_int32), ("pair_tile_cap", _C.c_int32), ("dpair_tile_cap", _C.c_int32), ("pad", _C.c_int32)]
 
 
 class _Table:
@@ -205,7 +206,7 @@ class PlanWorkspace:
         self.ld = ld
         self.fcoords = torch.empty((n_points, 4), dtype=torch.float32, device=device)
         self.icoords = torch.empty((n_points, 4), **i32)
-        self.n_summary = nl + 1 + nl * n_batch + 2 * nl      # level counts | status | per-cloud counts | (pair tiles, pairs)
+        self.n_summary = nl + 1 + nl * n_batch + 4 * nl      # level counts | status | per-cloud counts | (pair tiles, pairs) x2
         self.summary = torch.zeros(self.n_summary, **i32)
         self.summary_host = torch.zeros(self.n_summary, dtype=torch.int32).pin_memory()
         self.ws = torch.empty(max(_lib.spvd_unique_workspace_bytes(n_points), 256), dtype=torch.uint8, device=device)
@@ -233,6 +234,14 @@ class PlanWorkspace:
                 b["pair_tile_k"] = torch.empty(tile_cap, **i32)
                 o = nl + 1 + nl * n_batch + 2 * i
                 b["pair_counts"] = self.summary[o: o + 2]
+            dcap = 0
+            if i + 1 < nl:                                   # pair-major view of the stride-2 map (down and transposed convs)
+                dcap = 8 * ld // 128
+                b["dpair_in"], b["dpair_out"] = torch.empty(dcap * 128, **i32), torch.empty(dcap * 128, **i32)
+                b["dpair_tile_k"] = torch.empty(dcap, **i32)
+                o = nl + 1 + nl * n_batch + 2 * nl + 2 * i
+                b["dpair_counts"] = self.summary[o: o + 2]
+            if tile_cap or dcap:
                 b["pair_scratch"] = torch.empty(32 + 27 * ((n_points + 4095) // 4096 + 1), **i32)
             self.bufs.append(b)
             L = self.c_levels[i]
@@ -240,10 +249,11 @@ class PlanWorkspace:
                 setattr(L, name, t.data_ptr())
             L.capacity = 2 * n_points
             L.pair_tile_cap = tile_cap
+            L.dpair_tile_cap = dcap
         self.status = self.summary[nl: nl + 1]
         # kernels launched by one build (ops.stats accounting)
         self.n_kernels = (1 + 22 + 23 * (nl - 1) + nl + (nl - 1) + len(k3_strides) + 2 * len(p2v_strides) + len(devox_strides) +
-                          2 * nl + 3 * len(self.pair_strides))
+                          2 * nl + 3 * len(self.pair_strides) + 3 * (nl - 1))
 
     def build(self, pc, pres, voxel_size, scale_mode="mul", downsample_mode="spconv", max_cloud_rows=0):
         """max_cloud_rows > 0: the points are batch-major with at most that many per cloud (what torch2sparse
@@ -282,6 +292,9 @@ class PlanWorkspace:
             if "pair_in" in b:
                 o = nl + 1 + nl * nb + 2 * i
                 lv.pairs = (b["pair_in"], b["pair_out"], b["pair_tile_k"], host[o], host[o + 1])   # (.., tiles, pairs)
+            if "dpair_in" in b:
+                o = nl + 1 + nl * nb + 2 * nl + 2 * i
+                lv.dpairs = (b["dpair_in"], b["dpair_out"], b["dpair_tile_k"], host[o], host[o + 1])
             geo.levels[s] = lv
             if "p2v" in b:
                 geo.p2v[s] = b["p2v"]

@@ -295,12 +295,15 @@ def kmap_pairs(map_t, n, kvol=27, tile_cap=None):
     return pin, pout, tk, cnt[0:1], cnt[1:2]
 
 
-def conv_fwd_pairs(x, w3, w_packed, pair_in, pair_out, tile_k, n_tiles, n_out, bias=None, residual=None):
+def conv_fwd_pairs(x, w3, w_packed, pair_in, pair_out, tile_k, n_tiles, n_out, bias=None, residual=None, a_tf32=True,
+                   center=None):
     _count("conv_fwd")
     kvol, cin, cout = w3.shape
     out = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
+    center = (kvol // 2 if kvol % 2 else -1) if center is None else center
     check(lib.spvd_conv_fwd_pairs(_p(x, torch.float32), _p(w_packed, torch.float32), _p(pair_in), _p(pair_out), _p(tile_k),
-                                  int(n_tiles), kvol // 2, n_out, kvol, cin, cout, _p(bias), _p(residual), _p(out), _s()))
+                                  int(n_tiles), center, n_out, kvol, cin, cout, _p(bias), _p(residual), _p(out),
+                                  int(bool(a_tf32)), _s()))
     return out
 
 

@@ -32,8 +32,9 @@ class LevelGeom(C.Structure):
                 ("mask_down", C.c_void_p), ("kmap_up", C.c_void_p), ("mask_up", C.c_void_p), ("p2v", C.c_void_p),
                 ("devox_idx", C.c_void_p), ("devox_w", C.c_void_p), ("batch_offsets", C.c_void_p),
                 ("pair_in", C.c_void_p), ("pair_out", C.c_void_p), ("pair_tile_k", C.c_void_p),
+                ("dpair_in", C.c_void_p), ("dpair_out", C.c_void_p), ("dpair_tile_k", C.c_void_p),
                 ("n", C.c_int32), ("ld3", C.c_int32), ("ld_down", C.c_int32), ("ld_up", C.c_int32),
-                ("max_per_batch", C.c_int32), ("n_pair_tiles", C.c_int32)]
+                ("max_per_batch", C.c_int32), ("n_pair_tiles", C.c_int32), ("n_dpair_tiles", C.c_int32), ("pad", C.c_int32)]
 
 
 class Op(C.Structure):
@@ -324,6 +325,11 @@ class Program:
                 g.pair_in, g.pair_out, g.pair_tile_k, g.n_pair_tiles = pr[0].data_ptr(), pr[1].data_ptr(), pr[2].data_ptr(), pr[3]
             else:
                 g.pair_in, g.n_pair_tiles = None, 0
+            dp = getattr(lv, "dpairs", None)
+            if dp is not None:
+                g.dpair_in, g.dpair_out, g.dpair_tile_k, g.n_dpair_tiles = dp[0].data_ptr(), dp[1].data_ptr(), dp[2].data_ptr(), dp[3]
+            else:
+                g.dpair_in, g.n_dpair_tiles = None, 0
             if i in self.attn_levels:
                 g.batch_offsets = geo.batch_offsets(s).data_ptr()
                 g.max_per_batch = max(lv.batch_counts_host)

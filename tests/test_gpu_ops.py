@@ -394,6 +394,34 @@ def test_conv_pair_major(sp, stride, cin, cout):
     assert rel_err(y.cpu().numpy(), want.numpy()) < 2e-5
 
 
+@pytest.mark.parametrize("a_tf32", [True, False])
+def test_conv_pair_major_strided_and_transposed(sp, a_tf32):
+    """the stride-2 conv and its transpose on ONE pair list (roles of the two row arrays swapped)"""
+    from oracle import model as om, ops as oo
+    coords, _ = cloud_points(4, 2048, 37)
+    og = om.Geometry(coords, 1e-5, 0.1, "spconv", "mul")
+    geo = sp.Geometry(coords.float().cuda(), 1e-5, 0.1, strides=(1, 2), p2v_strides=(1,), devox_strides=(1,))
+    _, _, _, md, mu = og.downsample(1)
+    nf, nc = og.level(1).n, og.level(2).n
+    km = geo.level(1).kmap_down
+    pin, pout, tk, nt, npairs = sp.ops.kmap_pairs(km.map_t, nc, kvol=8)
+    T = int(nt.item())
+    assert int(npairs.item()) == int((md >= 0).sum())
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(nf, 64, generator=g)
+    w = torch.randn(8, 64, 96, generator=g) / (8 * 64) ** 0.5
+    xr = oo.round_tf32(x) if a_tf32 else x
+    want = oo.conv_gather_gemm_scatter(xr, w, md, nc, None, emulate_tf32=True)
+    y = sp.ops.conv_fwd_pairs(xr.cuda(), w.cuda(), sp.ops.pack_weights(w.cuda()), pin, pout, tk, T, nc, a_tf32=a_tf32)
+    assert rel_err(y.cpu().numpy(), want.numpy()) < 2e-5
+    xc = torch.randn(nc, 96, generator=g)
+    wt = torch.randn(8, 96, 32, generator=g) / 96 ** 0.5
+    xcr = oo.round_tf32(xc) if a_tf32 else xc
+    want_up = oo.conv_gather_gemm_scatter(xcr, wt, mu, nf, None, emulate_tf32=True)
+    yu = sp.ops.conv_fwd_pairs(xcr.cuda(), wt.cuda(), sp.ops.pack_weights(wt.cuda()), pout, pin, tk, T, nf, a_tf32=a_tf32)
+    assert rel_err(yu.cpu().numpy(), want_up.numpy()) < 2e-5
+
+
 @pytest.mark.parametrize("nsplit", [1, 3, 16])
 @pytest.mark.parametrize("a_tf32", [False, True])
 def test_conv_tcgen05_split_and_async_gather(sp, nsplit, a_tf32):

@@ -41,8 +41,8 @@ for s, cin, cout in layers:
     bias = torch.randn(cout, device=dev)
     res = []
     bns = [b for b in (32, 64, 96, 128, 192, 256) if cout % b == 0]
-    for bn, mt, ns in itertools.product(bns, (1, 2), (0, 1, 2, 4)):
-        if bn * mt > 512: continue
+    for bn, mt, ns in itertools.product(bns, (1, 2, 3), (0, 1, 2, 4, 8)):
+        if bn * min(mt, 2) > 512: continue
         try:
             us = timeit(lambda: ops.conv_fwd(xin, w, wp, km.map_t, km.mask, lv.n, bias, ops.CONV_UMMA, bn=bn, nsplit=ns, a_tf32=True, mt=mt))
         except RuntimeError as e:
