@@ -33,6 +33,20 @@ PRESETS = {
                    down_blocks=[[(64, 128, 192, 256, 384, 384), (True, True, True, True, False), (None, None, None, 8, 8)]],
                    up_blocks=[[(384, 384, 256), (True, True), (8, 8), (3, 3)],
                               [(256, 192, 128, 64), (True, True, False), (None, None, None), (3, 3, 3)]]),
+    # experiments/ConditionalGeneration.ipynb cell 4: SPVD-L topology + nn.Embedding(55, n_emb) added to the time embedding
+    "COND_SPVD_L": dict(point_channels=3, voxel_size=0.1, pres=1e-5, num_layers=1, n_classes=55,
+                        down_blocks=[[(64, 128, 192, 256, 384, 384), (True, True, True, True, False), (None, None, None, 8, 8)]],
+                        up_blocks=[[(384, 384, 256), (True, True), (8, 8), (3, 3)],
+                                   [(256, 192, 128, 64), (True, True, False), (None, None, None), (3, 3, 3)]]),
+    # experiments/SuperResolution.ipynb cell 12: 4-channel points (xyz + mask), three strided levels, no attention
+    "SUPERRES": dict(point_channels=4, voxel_size=0.1, pres=1e-5, num_layers=1,
+                     down_blocks=[[(64, 128, 192, 256, 256), (True, True, True, False), (None, None, None, None)]],
+                     up_blocks=[[(256, 256, 192), (True, True), (None, None), (3, 3)],
+                                [(192, 128, 64), (True, False), (None, None), (3, 3)]]),
+    "COND_TINY": dict(point_channels=3, voxel_size=0.1, pres=1e-5, num_layers=1, n_classes=7,
+                      down_blocks=[[(32, 32, 64, 64), (True, True, False), (None, 4, 4)]],
+                      up_blocks=[[(64, 64), (True,), (4,), (3,)],
+                                 [(64, 32, 32), (True, False), (None, None), (3, 3)]]),
     # a narrow topology with the same structure (strided + k1 convs, attention, three point branches)
     # used by fast CPU tests and the committed golden vectors
     "SPVD_TINY": dict(point_channels=3, voxel_size=0.1, pres=1e-5, num_layers=1,
@@ -98,6 +112,8 @@ def param_spec(cfg) -> "OrderedDict[str, tuple]":
     _bn(spec, "emb_mlp.0.0.", nf0)
     _linear(spec, "emb_mlp.0.2.", nf0, n_emb)
     _linear(spec, "emb_mlp.1.1.", n_emb, n_emb)
+    if cfg.get("n_classes"):
+        spec["cond_emb.weight"] = (cfg["n_classes"], n_emb)
     _conv(spec, "stem_conv.voxel_conv.0.", pc, nf0, 3)
     _bn(spec, "stem_conv.voxel_conv.1.", nf0)
     _conv(spec, "stem_conv.voxel_conv.3.", nf0, nf0, 3)
@@ -345,7 +361,7 @@ class _Net:
     def batch_of(self, s):
         return torch.from_numpy(self.geo.level(s).coords[:, 0].astype(np.int64))
 
-    def forward(self, feats, t):
+    def forward(self, feats, t, c=None):
         cfg, sd = self.cfg, self.sd
         nf0 = cfg["down_blocks"][0][0][0]
         nl = cfg["num_layers"]
@@ -355,6 +371,8 @@ class _Net:
         e = torch.cat([e.sin(), e.cos()], dim=-1)
         emb = self.linear("emb_mlp.0.2.", F.silu(self.bn("emb_mlp.0.0.", e)))
         emb = self.linear("emb_mlp.1.1.", F.silu(emb))
+        if c is not None:                                  # CondSPVUnet: emb = emb_mlp(t) + cond_emb(c)
+            emb = emb + sd["cond_emb.weight"][c]
         self.rec("emb", emb)
         # initial voxelization, models/sparse_utils.py:60-73
         z = feats
@@ -405,10 +423,10 @@ class _Net:
         return self.linear("out_conv.2.", F.silu(self.bn("out_conv.0.", z)))    # models/spvd.py:457
 
 
-def forward(sd, cfg, coords: torch.Tensor, feats: torch.Tensor, t: torch.Tensor, *, training=False,
-            downsample_mode="spconv", scale_mode="mul", emulate_tf32=False, trace=None, geometry=None):
+def forward(sd, cfg, coords: torch.Tensor, feats: torch.Tensor, t: torch.Tensor, c: torch.Tensor = None, *,
+            training=False, downsample_mode="spconv", scale_mode="mul", emulate_tf32=False, trace=None, geometry=None):
     """SPVUnet.forward((SparseTensor(feats, coords), t)) on the CPU.  coords int32 [N,4]=(b,x,y,z) in
     units of ``pres``; feats [N,point_channels]; t int64 [B].  Returns the predicted noise [N,3]."""
     cfg = get_config(cfg)
     geo = geometry or Geometry(coords, cfg["pres"], cfg["voxel_size"], downsample_mode, scale_mode)
-    return _Net(sd, cfg, geo, training, emulate_tf32, trace).forward(feats, t)
+    return _Net(sd, cfg, geo, training, emulate_tf32, trace).forward(feats, t, c)

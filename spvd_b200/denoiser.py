@@ -154,7 +154,7 @@ class SPVUnet(nn.Module):
                  down_blocks=[[(64, 128, 192, 256, 384, 384), (True, True, True, True, False), (None, None, None, 8, 8)]],
                  up_blocks=[[(384, 384, 256), (True, True), (8, 8), (3, 3)],
                             [(256, 192, 128, 64), (True, True, False), (None, None, None), (3, 3, 3)]],
-                 num_layers=1, pres=1e-5, downsample_mode="spconv", scale_mode="mul"):
+                 num_layers=1, pres=1e-5, downsample_mode="spconv", scale_mode="mul", n_classes=None):
         super().__init__()
         self.pres, self.voxel_size = pres, voxel_size
         self.downsample_mode, self.scale_mode = downsample_mode, scale_mode
@@ -162,6 +162,8 @@ class SPVUnet(nn.Module):
         self.n_temb = nf0 = down_blocks[0][0][0]
         n_emb = nf0 * 4
         self.emb_mlp = nn.Sequential(_bn_silu_linear(self.n_temb, n_emb), nn.Sequential(nn.SiLU(), nn.Linear(n_emb, n_emb)))
+        if n_classes:        # CondSPVUnet (experiments/ConditionalGeneration.ipynb cell 4): model((x, t, c))
+            self.cond_emb = nn.Embedding(n_classes, n_emb)
         self.stem_conv = StemBlock(point_channels, nf0)
         self.down_stages = nn.ModuleList([SPVDownStage(n_emb, nfs, add_down, num_layers, attn)
                                           for nfs, add_down, attn in down_blocks])
@@ -303,7 +305,10 @@ class SPVUnet(nn.Module):
             raise RuntimeError("spvd_b200.SPVUnet runs on CUDA only (no CPU fallback)")
         geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0],
                                                                        int(getattr(x_in, "points_per_cloud", 0) or 0))
-        if self.use_executor and self._fast() and len(inp) == 2:
+        cls = inp[2] if len(inp) > 2 else None
+        if cls is not None and not hasattr(self, "cond_emb"):
+            raise RuntimeError("this model was built without n_classes; it takes (x, t)")
+        if self.use_executor and self._fast():
             from .runtime import Program
             key = (feats.shape[0], t.shape[0])
             prog = self._programs.get(key)
@@ -311,11 +316,11 @@ class SPVUnet(nn.Module):
                 prog = self._programs[key] = Program(self, *key)
             sink = getattr(self, "profile_sink", None)
             if sink is None:
-                return prog.run(geo, feats.contiguous().float(), t)
+                return prog.run(geo, feats.contiguous().float(), t, cls=cls)
             evs = [torch.cuda.Event(enable_timing=True) for _ in range(2 * len(prog.conv_meta))]
             for e in evs:
                 e.record()                      # materialises the cudaEvent_t handles
-            out = prog.run(geo, feats.contiguous().float(), t, conv_events=[e.cuda_event for e in evs])
+            out = prog.run(geo, feats.contiguous().float(), t, conv_events=[e.cuda_event for e in evs], cls=cls)
             pairs = {}
             for (kvol, cin, cout, rows_out, level, map_kind, kind) in prog.conv_meta:
                 if map_kind and (level, map_kind) not in pairs:
@@ -331,6 +336,8 @@ class SPVUnet(nn.Module):
         e = torch.cat([e.sin(), e.cos()], dim=-1)
         emb = self.emb_mlp[0][2](F.silu(self.emb_mlp[0][0](e)))
         emb = self.emb_mlp[1][1](F.silu(emb))
+        if cls is not None:
+            emb = emb + self.cond_emb(cls)
         emb_act = F.silu(emb)                      # every TimeEmbeddingBlock starts with SiLU(emb)
 
         def v2p(x, s):
@@ -392,7 +399,27 @@ PRESETS = {
                       down_blocks=[[(32, 32, 64, 64), (True, True, False), (None, 4, 4)]],
                       up_blocks=[[(64, 64), (True,), (4,), (3,)],
                                  [(64, 32, 32), (True, False), (None, None), (3, 3)]]),
+    # experiments/ConditionalGeneration.ipynb cell 4 (CondSPVUnet) and experiments/SuperResolution.ipynb cell 12
+    "COND_SPVD_L": dict(point_channels=3, voxel_size=0.1, num_layers=1, pres=1e-5, n_classes=55,
+                        down_blocks=[[(64, 128, 192, 256, 384, 384), (True, True, True, True, False), (None, None, None, 8, 8)]],
+                        up_blocks=[[(384, 384, 256), (True, True), (8, 8), (3, 3)],
+                                   [(256, 192, 128, 64), (True, True, False), (None, None, None), (3, 3, 3)]]),
+    "SUPERRES": dict(point_channels=4, voxel_size=0.1, num_layers=1, pres=1e-5,
+                     down_blocks=[[(64, 128, 192, 256, 256), (True, True, True, False), (None, None, None, None)]],
+                     up_blocks=[[(256, 256, 192), (True, True), (None, None), (3, 3)],
+                                [(192, 128, 64), (True, False), (None, None), (3, 3)]]),
+    "COND_TINY": dict(point_channels=3, voxel_size=0.1, num_layers=1, pres=1e-5, n_classes=7,
+                      down_blocks=[[(32, 32, 64, 64), (True, True, False), (None, 4, 4)]],
+                      up_blocks=[[(64, 64), (True,), (4,), (3,)],
+                                 [(64, 32, 32), (True, False), (None, None), (3, 3)]]),
 }
+
+
+class CondSPVUnet(SPVUnet):
+    """``model((x, t, c))`` with a class embedding added to the time embedding (ConditionalGeneration.ipynb cell 4)."""
+
+    def __init__(self, point_channels=3, voxel_size=0.1, n_classes=55, **kw):
+        super().__init__(point_channels=point_channels, voxel_size=voxel_size, n_classes=n_classes, **kw)
 
 
 def build_model(preset="SPVD", **overrides) -> SPVUnet:

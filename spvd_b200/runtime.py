@@ -334,7 +334,7 @@ class Program:
                 g.batch_offsets = geo.batch_offsets(s).data_ptr()
                 g.max_per_batch = max(lv.batch_counts_host)
 
-    def run(self, geo: Geometry, feats: torch.Tensor, t: torch.Tensor, conv_events=None):
+    def run(self, geo: Geometry, feats: torch.Tensor, t: torch.Tensor, conv_events=None, cls=None):
         m = self.model
         if feats.shape[0] != self.n_points or t.shape[0] != self.n_batch:
             raise RuntimeError("Program was compiled for a different number of points / clouds")
@@ -344,6 +344,8 @@ class Program:
         e = torch.cat([e.sin(), e.cos()], dim=-1)
         emb = m.emb_mlp[0][2](F.silu(m.emb_mlp[0][0](e)))
         emb = m.emb_mlp[1][1](F.silu(emb))
+        if cls is not None:
+            emb = emb + m.cond_emb(cls)
         self._view(self.in_emb, self.n_batch).copy_(F.silu(emb))
         self._view(self.in_feats, self.n_points).copy_(feats)
         self.fill_levels(geo)

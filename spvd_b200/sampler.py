@@ -124,7 +124,7 @@ class SparseScheduler:
 
     def sample_step(self, model, x_t, t, i, emb, shape, device):
         t_batch = torch.full((shape[0],), t, device=device, dtype=torch.long)
-        noise_pred = model((x_t, t_batch)) if emb is None else model((x_t, t_batch, emb))
+        noise_pred = model((x_t, t_batch)) if emb is None else model((x_t, t_batch, emb))   # emb = class ids [B]
         return self.update_rule(x_t, noise_pred, t, i, shape, device)
 
     @torch.no_grad()

@@ -109,3 +109,41 @@ def test_native_executor_matches_python_path_and_oracle(sp):
         assert rel_err(y_exec, y_py) < 1e-3        # Linear layers run as TF32 k=1 convs in the executor
         assert rel_err(y_exec, want32) < 1e-3
         assert rel_err(y_py, want) < 1e-4
+
+
+@pytest.mark.parametrize("preset,B,N,train", [("COND_TINY", 3, 512, False), ("COND_TINY", 4, 256, True),
+                                                 ("SPVD_L", 2, 512, False), ("COND_SPVD_L", 2, 512, False),
+                                                 ("SUPERRES", 2, 1024, False), ("SPVD", 1, 8192, False)])
+def test_other_configs_vs_oracle(sp, preset, B, N, train):
+    """BASELINE.json configs[2..4] as parity cases: SPVD-L, the conditional model (class embedding, 55 ShapeNet
+    categories), the 4-channel super-resolution topology, and a high-resolution cloud (8192 points)."""
+    from oracle import model as om
+    g = torch.Generator().manual_seed(len(preset) + N)
+    pts = torch.randn(B, N, 3, generator=g).clamp(-3, 3)
+    coords, feats, _ = om.torch2sparse(pts)
+    cfg = om.get_config(preset)
+    if cfg["point_channels"] == 4:                      # xyz + a 0/1 mask channel (utils/completion_schedulers.py:43-59)
+        feats = torch.cat([feats, (torch.rand(feats.shape[0], 1, generator=g) > 0.75).float()], 1)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    c = torch.randint(0, cfg["n_classes"], (B,), generator=g) if cfg.get("n_classes") else None
+    sd = om.make_state_dict(preset, seed=2)
+    m = sp.build_model(preset)
+    assert sum(p.numel() for p in m.parameters()) == om.num_params(preset)
+    m.load_state_dict(sd, strict=True)
+    m = m.cuda().train(train)
+    inp = (sp.SparseTensor(feats.cuda(), coords.cuda()), t.cuda()) + ((c.cuda(),) if c is not None else ())
+    if train:
+        params = {k: v.clone().requires_grad_(v.dtype.is_floating_point and "running" not in k) for k, v in sd.items()}
+        want = om.forward(params, preset, coords, feats, t, c, training=True)
+        want.square().mean().backward()
+        y = m(inp)
+        y.square().mean().backward()
+        assert rel_err(y.detach().cpu().numpy(), want.detach().numpy()) < 2e-3
+        gk = "cond_emb.weight"
+        assert rel_err(dict(m.named_parameters())[gk].grad.cpu().numpy(), params[gk].grad.numpy()) < 1e-2
+    else:
+        with torch.no_grad():
+            want = om.forward(sd, preset, coords, feats, t, c)
+            y = m(inp)
+        assert y.shape == (coords.shape[0], cfg["point_channels"])
+        assert rel_err(y.cpu().numpy(), want.numpy()) < 1e-3

@@ -14,6 +14,19 @@ from oracle import model as om
 from conftest import rel_err
 
 
+def test_conditional_and_superres_specs_match_the_reference_constructors():
+    """parameter names/shapes of the conditional (ConditionalGeneration.ipynb cell 4) and 4-channel super-resolution
+    (SuperResolution.ipynb cell 12) variants, and the product module tree, agree with oracle.model.param_spec"""
+    import spvd_b200.denoiser as d
+    for preset in ("COND_TINY", "COND_SPVD_L", "SUPERRES", "SPVD", "SPVD_L"):
+        m = d.build_model(preset)
+        spec = om.param_spec(preset)
+        sd = m.state_dict()
+        assert list(sd.keys()) == list(spec.keys())
+        assert all(tuple(sd[k].shape) == tuple(spec[k]) for k in spec)
+    assert om.num_params("COND_SPVD_L") == 88_103_366 + 55 * 256
+
+
 def test_param_counts():
     # models/__init__.py:8,24 ("32.9M", "88.1M"); experiments/ModelArchitecture.ipynb:631
     assert om.num_params("SPVD") == 32_894_054
