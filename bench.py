@@ -309,6 +309,10 @@ def run_reference(args):
     if rank != 0:
         return None, rank, world
     K, W = args.steps, args.warmup
+    try:        # torchrun exports OMP_NUM_THREADS=1; this arm is alone on the host: use every core it may run on
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        pass
     times = cpu_steps(args, K, W)
     total = sum(times)
     v = round(K / total, 4)
