@@ -143,8 +143,7 @@ def run_b200(args):
         st = sched.torch2sparse(x_pts, shape)
         tb = torch.full((B,), t, device=dev, dtype=torch.long)
         eps = model((st, tb))
-        new = strat.update(st.F, eps, t, i, lambda s: torch.randn(s, device=dev))
-        return sched.torch2sparse(new, shape)
+        return sched.update_rule(st, eps, t, i, shape, dev)        # DDPM update + re-sparsify (fused kernels)
 
     # ---- device-resident leg (value)
     xs_dev = [x.to(dev) for x in xs]
@@ -253,7 +252,7 @@ def run_b200(args):
             st = sched.torch2sparse(x, shape)
             tb = torch.full((B,), ts[j], device=dev, dtype=torch.long)
             eps = model((st, tb))
-            new = strat.update(st.F, eps, ts[j], j, lambda s: torch.randn(s, device=dev))
+            new = sched.update_rule(st, eps, ts[j], j, shape, dev).F
             pin_out.copy_(new.view(shape), non_blocking=True)             # D2H of the step's result
             torch.cuda.current_stream().synchronize()                     # the caller owns x_{t-1} on the host
         e2e_s = time.perf_counter() - t0

@@ -254,6 +254,16 @@ int spvd_attention_fwd(const float* qkv, const int32_t* batch_offsets, int n_bat
                        int heads, int act, float* out, spvd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * N1  per-step work of the sampling loop around the network, fused:
+ *   x_new = c1 * (x_t - c2 * eps) + sigma * z        DDPM.update_rule, utils/schedulers.py:78-89 (z NULL = last step)
+ *   coords = (cloud, floor((x_new - min_cloud x_new) / pres))   SparseSchedulerGPU.torch2sparse, utils/schedulers.py:249-257
+ * x_t / eps / z / x_new are [n_clouds*n_per_cloud, f] (xyz first); eps NULL = only re-sparsify x_t.  coords int32 [.,4] and/or
+ * pc float [.,4] (what SPVUnet.forward feeds the planner, x.C.float()) may be NULL; scratch >= 3*n_clouds int32. */
+int spvd_ddpm_step(const float* x_t, const float* eps, const float* z, float c1, float c2, float sigma, int n_clouds,
+                   int n_per_cloud, int f, float pres, float* x_new, int32_t* coords, float* pc, int32_t* scratch,
+                   spvd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Geometry planner: V1 + K1 + K2/K3 + V2/V3 for every tensor stride of the U-Net in one call, into
  * caller-owned buffers (level i has tensor stride 2^i; NULL pointers = not needed at that level).
  * Everything the reference caches lazily in _caches (models/sparse_utils.py:71,90,122-125 and the

@@ -51,6 +51,7 @@ SIGNATURES = {
     "spvd_attention_fwd": (_i, [_p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "spvd_program_run": (_i, [_p, _i, _p, _i, _i, _i, _p, _sz, _p, _p]),
     "spvd_segmented_unique": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "spvd_ddpm_step": (_i, [_p, _p, _p, _f, _f, _f, _i, _i, _i, _f, _p, _p, _p, _p, _p]),
     "spvd_plan_build": (_i, [_p, _i, _i, _i, _f, _f, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
 }
 

@@ -303,6 +303,9 @@ class SPVUnet(nn.Module):
         coords, feats = (x_in.C, x_in.F) if isinstance(x_in, SparseTensor) or hasattr(x_in, "C") else x_in
         if not feats.is_cuda:
             raise RuntimeError("spvd_b200.SPVUnet runs on CUDA only (no CPU fallback)")
+        cf = getattr(x_in, "coords_float", None)          # float copy of the coordinates, when the sampler made one
+        if cf is not None and cf.shape[0] == coords.shape[0]:
+            coords = cf
         geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0],
                                                                        int(getattr(x_in, "points_per_cloud", 0) or 0))
         cls = inp[2] if len(inp) > 2 else None

@@ -55,7 +55,7 @@ stats = _Stats()
 _K = {"point_voxel_coords": 1, "unique_coords": 22, "downsample_coords": 23, "hash_build": 1, "hash_query": 1,
       "kmap_subm3": 1, "kmap_down2": 1, "kmap_pairs": 3, "segmented_unique": 3, "batch_counts": 1, "point_voxel_query": 1, "devox_query": 1,
       "scatter_mean_fwd": 2, "scatter_mean_bwd": 1, "devoxelize_fwd": 1, "devoxelize_bwd": 1, "pack_weights": 1,
-      "transpose_weights": 1, "conv_fwd": 1, "conv_wgrad": 1, "round_tf32": 1, "affine_act": 1, "film": 1}
+      "transpose_weights": 1, "conv_fwd": 1, "conv_wgrad": 1, "ddpm_step": 2, "round_tf32": 1, "affine_act": 1, "film": 1}
 
 
 def _count(name):
@@ -339,3 +339,18 @@ def film(x, tt, coords):
     y = torch.empty_like(x)
     check(lib.spvd_film_fwd(_p(x, torch.float32), _p(tt, torch.float32), _p(coords, torch.int32), rows, c, _p(y), _s()))
     return y
+
+
+# --------------------------------------------------------------------------------------- sampler
+def ddpm_step(x_t, n_clouds, n_per_cloud, pres, eps=None, z=None, c1=1.0, c2=0.0, sigma=0.0):
+    """fused DDPM update + re-sparsification -> (x_new [M,F], coords int32 [M,4], pc float32 [M,4])"""
+    _count("ddpm_step")
+    m, f = x_t.shape
+    dev = x_t.device
+    x_new = torch.empty_like(x_t) if eps is not None else None
+    coords = torch.empty((m, 4), dtype=torch.int32, device=dev)
+    pc = torch.empty((m, 4), dtype=torch.float32, device=dev)
+    scratch = torch.empty(3 * n_clouds, dtype=torch.int32, device=dev)
+    check(lib.spvd_ddpm_step(_p(x_t, torch.float32), _p(eps), _p(z), float(c1), float(c2), float(sigma), n_clouds, n_per_cloud,
+                             f, float(pres), _p(x_new), _p(coords), _p(pc), _p(scratch), _s()))
+    return (x_new if eps is not None else x_t), coords, pc

@@ -72,8 +72,16 @@ class DDIM(DDPM):
 
 def torch2sparse(pts: torch.Tensor, pres: float = 1e-5, order: str = "keep") -> SparseTensor:
     """[B,N,F] points (xyz first) -> SparseTensor(coords int32 [M,4] = (b, floor((p - min_cloud p)/pres)), feats).
-    Reference: SparseSchedulerGPU.torch2sparse, utils/schedulers.py:249-257."""
+    Reference: SparseSchedulerGPU.torch2sparse, utils/schedulers.py:249-257.  On CUDA with order='keep' this is the
+    fused two-kernel path of libspvd_b200 (spvd_ddpm_step without an update)."""
     B, N, Fd = pts.shape
+    if order == "keep" and pts.is_cuda and pts.dtype == torch.float32:
+        from . import ops
+        feats = pts.reshape(-1, Fd).contiguous()
+        _, coords, pc = ops.ddpm_step(feats, B, N, pres)
+        st = SparseTensor(feats, coords)
+        st.points_per_cloud, st.coords_float = N, pc
+        return st
     c = pts[..., :3]
     c = c - c.amin(dim=1, keepdim=True)
     vs = torch.full((3,), pres, device=pts.device, dtype=pts.dtype)
@@ -119,7 +127,18 @@ class SparseScheduler:
         return x_t.F.detach().cpu().reshape(shape)
 
     def update_rule(self, x_t, noise_pred, t, i, shape, device):
-        new = self.strategy.update(x_t.F, noise_pred, t, i, self._noise(device))
+        s = self.strategy
+        if (self.order == "keep" and type(s) is DDPM and x_t.F.is_cuda and x_t.F.shape[1] == shape[2]
+                and x_t.F.shape[0] == shape[0] * shape[1]):
+            # fused: DDPM update + per-cloud min shift + quantisation in two kernels
+            from . import ops
+            z = self._noise(device)(x_t.F.shape) if t > 0 else None
+            new, coords, pc = ops.ddpm_step(x_t.F.contiguous(), shape[0], shape[1], self.pres, noise_pred.contiguous(), z,
+                                            s.c1[t], s.c2[t], s.sig[t])
+            st = SparseTensor(new, coords)
+            st.points_per_cloud, st.coords_float = shape[1], pc
+            return st
+        new = s.update(x_t.F, noise_pred, t, i, self._noise(device))
         return self.torch2sparse(new, shape)
 
     def sample_step(self, model, x_t, t, i, emb, shape, device):

@@ -24,6 +24,7 @@ class SparseTensor:
         self.feats, self.coords = feats, coords
         self.stride = make_ntuple(stride, 3)
         self.spatial_range = spatial_range
+        self.coords_float = None    # optional float32 copy of coords (saves the x.C.float() of models/spvd.py:436)
         self.points_per_cloud = 0   # optional hint: rows are batch-major with at most this many per cloud (0 = unknown)
         self._caches = TensorCache()
 

@@ -493,6 +493,26 @@ def test_layernorm_attention_cat_kernels(sp):
     assert torch.equal(y, torch.cat([a, b], 1))
 
 
+def test_fused_ddpm_step_matches_reference_formulas(sp):
+    """DDPM.update_rule (utils/schedulers.py:78-89) + torch2sparse (utils/schedulers.py:249-257) in two kernels"""
+    from spvd_b200.sampler import DDPM, torch2sparse
+    g = torch.Generator().manual_seed(9)
+    B, N = 5, 777
+    x, eps, z = (torch.randn(B * N, 3, generator=g) for _ in range(3))
+    s = DDPM()
+    for t in (999, 400, 0):
+        want = s.update(x, eps, t, 0, lambda shape: z)
+        want_sp = torch2sparse(want.view(B, N, 3), 1e-5, order="keep")           # CPU tensors -> torch path
+        new, coords, pc = sp.ops.ddpm_step(x.cuda(), B, N, 1e-5, eps.cuda(), z.cuda() if t > 0 else None, s.c1[t], s.c2[t], s.sig[t])
+        assert torch.allclose(new.cpu(), want, atol=1e-6, rtol=1e-6)
+        cpu_from_gpu = torch2sparse(new.cpu().view(B, N, 3), 1e-5, order="keep")  # same points -> identical integers
+        assert torch.equal(coords.cpu(), cpu_from_gpu.C)
+        assert torch.equal(pc.cpu(), cpu_from_gpu.C.float())
+        assert (coords.cpu() - want_sp.C).abs().max() <= 1                        # 1-ulp update differences move at most one cell
+    st = torch2sparse(x.view(B, N, 3).cuda(), 1e-5)                              # fused re-sparsify only
+    assert torch.equal(st.C.cpu(), torch2sparse(x.view(B, N, 3), 1e-5).C) and st.points_per_cloud == N
+
+
 def test_cpu_tensors_are_refused(sp):
     with pytest.raises(RuntimeError):
         sp.ops.point_voxel_coords(torch.zeros(4, 4), 1e-5, 0.1)
