@@ -170,3 +170,44 @@ class DDIMSparseSchedulerGPU(SparseScheduler):
     def __init__(self, beta_min=0.0001, beta_max=0.02, n_steps=1000, s_steps=100, s_mode="linear", mode="linear",
                  pres=1e-5, save_process=False, rng="cuda", order="keep"):
         super().__init__(DDIM(beta_min, beta_max, n_steps, mode, s_steps, s_mode), pres, save_process, rng, order)
+
+
+class DDPMSparseCompletionSchedulerGPU(SparseScheduler):
+    """Masked (inpainting-style) sampling for completion / super-resolution: the caller of BASELINE config 5.
+    Same surface as the reference (utils/completion_schedulers.py:7-93: ``complete(x0, model, n_points)``,
+    ``pad_noise``, ``update_rule``): points carry a 4th 0/1 channel, known points (mask 1) are kept, the rest follow the
+    DDPM update of the first three predicted channels."""
+
+    def __init__(self, beta_min=0.0001, beta_max=0.02, n_steps=1000, mode="linear", sigma="bt", pres=1e-5,
+                 save_process=False, rng="cuda", order="keep"):
+        super().__init__(DDPM(beta_min, beta_max, n_steps, mode, sigma), pres, save_process, rng, order)
+
+    def pad_noise(self, x0, n_points):
+        B, N, Fd = x0.shape
+        noise = self._noise(x0.device)((B, n_points - N, Fd))
+        mask = torch.zeros(B, n_points, 1, device=x0.device)
+        mask[:, :N] = 1
+        padded = torch.cat([torch.cat([x0, noise], dim=1), mask], dim=-1)
+        return self.torch2sparse(padded, padded.shape)
+
+    def update_rule(self, x_t, noise_pred, t, i, shape, device):
+        mask = x_t.F[:, -1:].bool()
+        new = self.strategy.update(x_t.F[:, :3], noise_pred[:, :3], t, i, self._noise(device))
+        x = torch.where(mask, x_t.F[:, :3], new)
+        return self.torch2sparse(torch.cat([x, mask.float()], dim=-1), shape)
+
+    def get_pc(self, x_t, shape):
+        return x_t.F.detach().cpu().reshape(shape)[:, :, :3]
+
+    @torch.no_grad()
+    def complete(self, x0, model, n_points, emb=None, save_process=False):
+        device = next(model.parameters()).device
+        x0 = x0.to(device)
+        shape = (x0.shape[0], n_points, x0.shape[-1] + 1)
+        x_t = self.pad_noise(x0, n_points)
+        preds = [self.get_pc(x_t, shape)] if save_process else None
+        for i, t in enumerate(self.strategy.steps):
+            x_t = self.sample_step(model, x_t, t, i, emb, shape, device)
+            if save_process:
+                preds.append(self.get_pc(x_t, shape))
+        return preds if save_process else self.get_pc(x_t, shape)
