@@ -99,7 +99,8 @@ struct UmmaCfg {
   static constexpr int kStageBytes = MT * kATileBytes + kBTileBytes;
   // pair-major tiles run only cin/32 iterations: keep the footprint small so that several CTAs share an SM and
   // one CTA's prologue / RED epilogue overlaps another's main loop
-  static constexpr int kStages = (kPairs || kLite) ? 2 : (4 * kStageBytes <= 200 * 1024) ? 4 : (3 * kStageBytes <= 200 * 1024) ? 3 : 2;
+  static constexpr int kLiteStages = (3 * kStageBytes + MT * 27 * BM * 4 + 1280 <= 113 * 1024) ? 3 : 2;   // still two CTAs per SM
+  static constexpr int kStages = kPairs ? 2 : kLite ? kLiteStages : (4 * kStageBytes <= 200 * 1024) ? 4 : (3 * kStageBytes <= 200 * 1024) ? 3 : 2;
   static constexpr int kRowsBytes = kPairs ? 2 * BM * 4 : MT * 27 * BM * 4;  // staged row indices
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kRowsBytes;
   // idesc: D=f32 (1<<4), A=B=tf32 (2<<7, 2<<10), both K-major, N>>3 at bit 17, M>>4 at bit 24
@@ -107,6 +108,27 @@ struct UmmaCfg {
                                      ((uint32_t)(BM >> 4) << 24);
   static_assert(kCols <= 512, "accumulators exceed TMEM");
 };
+
+__device__ __forceinline__ void bulk_g2s_multicast(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar,
+                                                   uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+      "l"(src), "r"(bytes), "r"(bar), "h"(cta_mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_multicast(uint32_t bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+               "h"(cta_mask)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
@@ -132,7 +154,11 @@ __device__ __forceinline__ void red_add_v4(float* addr, float4 v) {
 // output rows; the K loop runs over the channel slabs only and the epilogue scatters the 128 product rows with
 // vector RED into the zero-initialised output (bias / residual added by the centre-offset tiles, which cover
 // every output row exactly once).  Issued tensor-core rows = real pairs, instead of 128 x (active offsets).
-template <int BN, int MT, bool kAsyncA, bool kPairs = false, bool kLite = false>
+//
+// kCluster (2 or 4): the CTAs of a cluster own consecutive output tiles and walk the same (offset, slab) sequence; each
+// loads 1/kCluster of every weight tile and multicasts it into all of them (the weight stream is ~70% of the L2
+// traffic of the dense levels), a stage is recycled when every CTA of the cluster has consumed it.
+template <int BN, int MT, bool kAsyncA, bool kPairs = false, bool kLite = false, int kCluster = 1>
 __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __restrict__ in,
                                                                const float* __restrict__ w_packed,
                                                                const int* __restrict__ map_t, int ld,
@@ -146,6 +172,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   constexpr int kStages = Cfg::kStages;
   static_assert(kAsyncA || MT == 1, "the register gather path is instantiated for MT = 1 only");
   static_assert(!kPairs || MT == 1, "pair-major tiles: MT = 1");
+  static_assert(kCluster == 1 || (MT == 1 && !kPairs && (BN / kCluster) % 8 == 0), "cluster multicast: MT = 1, slices of 8 rows");
   pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
@@ -166,9 +193,10 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
     mask = 1u << (reinterpret_cast<const int*>(tile_mask)[blockIdx.x] & 31);   // the tile's single offset
   } else if (tile_mask) {
     unsigned u = 0;
+    const int t0 = kCluster > 1 ? ((int)blockIdx.x / kCluster) * kCluster : (int)blockIdx.x * MT;
 #pragma unroll
-    for (int t = 0; t < MT; ++t)
-      if ((int)blockIdx.x * MT + t < n_tiles) u |= tile_mask[blockIdx.x * MT + t];
+    for (int t = 0; t < (kCluster > 1 ? kCluster : MT); ++t)
+      if (t0 + t < n_tiles) u |= tile_mask[t0 + t];
     mask &= u;
   }
   const int total_iters = __popc(mask) * nchunks;
@@ -182,7 +210,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   if (tid == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(bar_base + 8 * s, kProducerThreads + 1);
-      mbar_init(bar_base + 8 * (kStages + s), 1);
+      mbar_init(bar_base + 8 * (kStages + s), kCluster);   // released by the MMA commit of every CTA of the cluster
     }
     mbar_init(bar_base + 8 * (2 * kStages), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -198,6 +226,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) cluster_sync_all();   // peers' barriers are initialised before anything remote arrives
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
 
@@ -248,8 +277,15 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
         const uint32_t a_s = base + stage * Cfg::kStageBytes;
         if (tid == 0) {
           mbar_arrive_expect_tx(bar_base + 8 * stage, Cfg::kBTileBytes);
-          bulk_g2s(a_s + MT * kATileBytes, w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK, Cfg::kBTileBytes,
-                   bar_base + 8 * stage);
+          const float* wsrc = w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK;
+          if constexpr (kCluster > 1) {
+            constexpr uint32_t kSlice = Cfg::kBTileBytes / kCluster;
+            const uint32_t rk = cluster_ctarank();
+            bulk_g2s_multicast(a_s + MT * kATileBytes + rk * kSlice, reinterpret_cast<const uint8_t*>(wsrc) + rk * kSlice,
+                               kSlice, bar_base + 8 * stage, (uint16_t)((1u << kCluster) - 1u));
+          } else {
+            bulk_g2s(a_s + MT * kATileBytes, wsrc, Cfg::kBTileBytes, bar_base + 8 * stage);
+          }
         }
 #pragma unroll
         for (int i = 0; i < MT * 8; ++i) {
@@ -292,8 +328,15 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
         const uint32_t a_s = base + stage * Cfg::kStageBytes;
         if (tid == 0) {
           mbar_arrive_expect_tx(bar_base + 8 * stage, Cfg::kBTileBytes);
-          bulk_g2s(a_s + MT * kATileBytes, w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK, Cfg::kBTileBytes,
-                   bar_base + 8 * stage);
+          const float* wsrc = w_packed + ((size_t)(k * nchunks + c) * cout + n0) * BK;
+          if constexpr (kCluster > 1) {
+            constexpr uint32_t kSlice = Cfg::kBTileBytes / kCluster;
+            const uint32_t rk = cluster_ctarank();
+            bulk_g2s_multicast(a_s + MT * kATileBytes + rk * kSlice, reinterpret_cast<const uint8_t*>(wsrc) + rk * kSlice,
+                               kSlice, bar_base + 8 * stage, (uint16_t)((1u << kCluster) - 1u));
+          } else {
+            bulk_g2s(a_s + MT * kATileBytes, wsrc, Cfg::kBTileBytes, bar_base + 8 * stage);
+          }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -383,7 +426,8 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
             umma_tf32(tmem_d + (uint32_t)(mt * BN), adesc + (uint64_t)(kk * 2), bdesc + (uint64_t)(kk * 2), Cfg::kIdesc,
                       (li > 0 || kk > 0) ? 1u : 0u);
         }
-        umma_commit(bar_base + 8 * (kStages + stage));
+        if constexpr (kCluster > 1) umma_commit_multicast(bar_base + 8 * (kStages + stage), (uint16_t)((1u << kCluster) - 1u));
+        else umma_commit(bar_base + 8 * (kStages + stage));
         if (li == num_iters - 1) umma_commit(bar_base + 8 * (2 * kStages));
       }
       __syncwarp();
@@ -391,6 +435,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (kCluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still write its smem / barriers
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
@@ -461,6 +506,38 @@ static int launch_umma_pairs(bool async_a, const float* in, const float* wp, con
                                                   cin, cout, bias, residual, out, s);
 }
 
+template <int BN, int kCluster>
+static int launch_umma_cluster(const float* in, const float* wp, const int32_t* map_t, int ld, const uint32_t* tile_mask,
+                               int n_out, int kvol, int cin, int cout, const float* bias, const float* residual, float* out,
+                               int nsplit, cudaStream_t s) {
+  using Cfg = UmmaCfg<BN, 1, false, true>;
+  auto kern = k_conv_fwd_umma<BN, 1, true, false, true, kCluster>;
+  static bool configured = false;
+  if (!configured) {
+    SPVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+    configured = true;
+  }
+  if (nsplit > 1) SPVD_CUDA(cudaMemsetAsync(out, 0, (size_t)n_out * cout * 4, s));
+  const int tiles = cdiv(cdiv(n_out, BM), kCluster) * kCluster;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(tiles, cout / BN, nsplit);
+  cfg.blockDim = dim3(kUmmaThreads);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = kCluster;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  SPVD_CUDA(cudaLaunchKernelEx(&cfg, kern, in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out,
+                               (const int*)nullptr, 0));
+  return SPVD_OK;
+}
+
 template <int BN>
 static int launch_umma_bn(bool async_a, int mt, const float* in, const float* wp, const int32_t* map_t, int ld,
                           const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
@@ -470,6 +547,10 @@ static int launch_umma_bn(bool async_a, int mt, const float* in, const float* wp
       return launch_umma<BN, 1, false, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
     return launch_umma<BN, 1, false>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
   }
+  if (mt == 4)   // lite + weight tiles multicast across a cluster of 2 CTAs
+    return launch_umma_cluster<BN, 2>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+  if (mt == 5)
+    return launch_umma_cluster<BN, 4>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
   if (mt == 3)   // one tile per CTA, two stages: small enough for two CTAs per SM
     return launch_umma<BN, 1, true, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
   if (mt >= 2)
@@ -495,9 +576,9 @@ static int pick_bn(int cout, int n_tiles = 1 << 30, int kvol = 27) {
 
 // split the (offset, slab) iterations over gridDim.z when the tiles alone cannot fill the GPU
 static int pick_split(int n_ctas, int max_iters) {
-  const int target = 2 * 148;
+  const int target = 2 * 148;   // two CTAs per SM: stay within ONE wave (a second, partial wave costs a full tile time)
   if (n_ctas >= 148) return 1;
-  int s = (target + n_ctas - 1) / n_ctas;
+  int s = target / n_ctas;
   int cap = max_iters / 6;  // keep >= 6 pipeline iterations per CTA
   if (s > cap) s = cap;
   return s < 1 ? 1 : s;
@@ -545,7 +626,7 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
   // prologue / epilogue overlaps the other's main loop -- measured 10-25% faster than two tiles per CTA sharing the
   // weight tile (tools/conv_bench.py)
   if (mt <= 0) mt = 3;
-  if (!aa && mt == 2) mt = 1;
+  if (!aa && (mt == 2 || mt >= 4)) mt = mt == 2 ? 1 : 3;
   if (nsplit <= 0) nsplit = pick_split(cdiv(n_out, BM * (mt == 2 ? 2 : 1)) * (cout / bn), max_iters);
   if (nsplit > max_iters) nsplit = max_iters;
   switch (bn) {

@@ -347,9 +347,11 @@ def test_conv_backward(sp, kind, cin, cout, impl):
     assert rel_err(bb.grad.cpu().numpy(), ba.grad.numpy()) < 1e-5
 
 
-@pytest.mark.parametrize("mt", [1, 2])
+@pytest.mark.parametrize("mt", [1, 2, 3, 4, 5])
 @pytest.mark.parametrize("cout", [32, 128, 192, 256])
-def test_conv_tcgen05_two_tiles_per_cta(sp, mt, cout):
+def test_conv_tcgen05_tile_configs(sp, mt, cout):
+    """mt: 1 = one tile/CTA, 2 = two tiles share each weight tile, 3 = lite (2 stages, 2 CTAs/SM), 4 / 5 = lite + weight
+    tiles multicast across a cluster of 2 / 4 CTAs"""
     x, w, b, m, n_out, km, oo = _conv_case(sp, "k3", 64, cout, 29)
     want = oo.conv_gather_gemm_scatter(x, w, m, n_out, b, emulate_tf32=True)
     xd = sp.ops.round_tf32(x.cuda())

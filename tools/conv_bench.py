@@ -41,7 +41,7 @@ for s, cin, cout in layers:
     bias = torch.randn(cout, device=dev)
     res = []
     bns = [b for b in (32, 64, 96, 128, 192, 256) if cout % b == 0]
-    for bn, mt, ns in itertools.product(bns, (1, 2, 3), (0, 1, 2, 4, 8)):
+    for bn, mt, ns in itertools.product(bns, (2, 3, 4, 5), (0, 1, 2, 4)):
         if bn * min(mt, 2) > 512: continue
         try:
             us = timeit(lambda: ops.conv_fwd(xin, w, wp, km.map_t, km.mask, lv.n, bias, ops.CONV_UMMA, bn=bn, nsplit=ns, a_tf32=True, mt=mt))
