@@ -215,6 +215,13 @@ int spvd_conv_fwd_pairs(const float* in, const float* w_packed, const int32_t* p
                         const int32_t* pair_out, const int32_t* tile_k, int n_pair_tiles, int center_k,
                         int n_out, int kvol, int cin, int cout, const float* bias, const float* residual,
                         float* out, int a_is_tf32, spvd_stream_t stream);
+/* Weight gradient on the tensor cores (tcgen05, TF32 operands -- round x and gout first with spvd_round_tf32 --,
+ * fp32 accumulate): both operands are gathered rows fed as MN-major SWIZZLE_128B tiles, the reduction runs over
+ * the pair lists of spvd_kmap_pairs (pair_in = rows of x, pair_out = rows of gout; all NULL with kvol == 1 =
+ * identity pairs over n_identity rows).  gw [kvol,cin,cout] is zero-filled inside; partial sums are RED-added. */
+int spvd_conv_wgrad_umma(const float* x, const float* gout, const int32_t* pair_in, const int32_t* pair_out,
+                         const int32_t* tile_k, int n_pair_tiles, int n_identity, int kvol, int cin, int cout,
+                         float* gw, spvd_stream_t stream);
 /* gw[k] = sum over pairs (i,o) of offset k of in[i]^T gout[o];  gw [kvol,cin,cout] zero-filled inside */
 int spvd_conv_wgrad(const float* in, const float* gout, const int32_t* map_t, int ld, int n_out,
                     int kvol, int cin, int cout, float* gw, spvd_stream_t stream);

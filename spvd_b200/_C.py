@@ -42,6 +42,7 @@ SIGNATURES = {
     "spvd_conv_fwd_umma": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
     "spvd_kmap_pairs": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "spvd_conv_fwd_pairs": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
+    "spvd_conv_wgrad_umma": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "spvd_conv_wgrad": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),
     "spvd_bn_silu_fwd": (_i, [_p, _p, _p, _ll, _i, _i, _p, _p]),
     "spvd_film_fwd": (_i, [_p, _p, _p, _ll, _i, _p, _p]),

@@ -56,7 +56,12 @@ class _SparseConv(torch.autograd.Function):
                               n_in, None, ops.CONV_AUTO if use_umma else ops.CONV_SIMT)
         if ctx.needs_input_grad[1]:
             n_out = kmap.n_out if kmap is not None else x.shape[0]
-            gw = ops.conv_wgrad(x, g, kmap.map_t if kmap is not None else None, n_out, kvol).view_as(weight)
+            if impl != ops.CONV_SIMT and ops.umma_supported(kvol, cin, cout):
+                # tensor cores: reduction over the pair lists, TF32 operands (rounded here), fp32 accumulation
+                gw = ops.conv_wgrad_umma(ops.round_tf32(x), ops.round_tf32(g), kmap.pairs() if kmap is not None else None,
+                                         n_out, kvol).view_as(weight)
+            else:
+                gw = ops.conv_wgrad(x, g, kmap.map_t if kmap is not None else None, n_out, kvol).view_as(weight)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             gb = g.sum(0)
         return gx, gw, gb, None, None, None, None

@@ -18,11 +18,20 @@ class KernelMap:
     """Offset-major map [kvol, ld] (+ per-128-row-tile offset mask) of one sparse convolution and the
     map of its data gradient."""
 
-    __slots__ = ("map_t", "mask", "n_out", "n_in", "kvol", "grad", "flip")
+    __slots__ = ("map_t", "mask", "n_out", "n_in", "kvol", "grad", "flip", "_pairs")
 
     def __init__(self, map_t, mask, n_out, n_in, kvol, flip):
         self.map_t, self.mask, self.n_out, self.n_in, self.kvol, self.flip = map_t, mask, n_out, n_in, kvol, flip
         self.grad = None   # KernelMap that produces d(in) from d(out)
+        self._pairs = None
+
+    def pairs(self):
+        """pair-major view (pair_in, pair_out, tile_k, n_tiles) of this map, built on first use (the weight-gradient
+        kernel reduces over it); costs one host read of the tile count."""
+        if self._pairs is None:
+            pin, pout, tk, nt, _ = ops.kmap_pairs(self.map_t, self.n_out, self.kvol)
+            self._pairs = (pin, pout, tk, int(nt.item()))
+        return self._pairs
 
 
 class Level:

@@ -316,6 +316,22 @@ def conv_wgrad(x, gout, map_t, n_out, kvol):
     return gw
 
 
+def conv_wgrad_umma(x, gout, pairs, n_rows, kvol):
+    """tensor-core weight gradient; x / gout must be TF32-representable.  pairs = (pair_in, pair_out, tile_k, n_tiles)
+    from kmap_pairs, or None for kernel size 1 (identity pairs over n_rows)."""
+    _count("conv_wgrad")
+    cin, cout = x.shape[1], gout.shape[1]
+    gw = torch.empty((kvol, cin, cout), dtype=torch.float32, device=x.device)
+    if pairs is None:
+        check(lib.spvd_conv_wgrad_umma(_p(x, torch.float32), _p(gout, torch.float32), None, None, None, 0, int(n_rows), kvol,
+                                       cin, cout, _p(gw), _s()))
+    else:
+        pin, pout, tk, nt = pairs
+        check(lib.spvd_conv_wgrad_umma(_p(x, torch.float32), _p(gout, torch.float32), _p(pin), _p(pout), _p(tk), int(nt), 0,
+                                       kvol, cin, cout, _p(gw), _s()))
+    return gw
+
+
 def round_tf32(x):
     _count("round_tf32")
     y = torch.empty_like(x)

@@ -343,7 +343,7 @@ def test_conv_backward(sp, kind, cin, cout, impl):
     sp.functional.sparse_conv(xb, wb, bb, km, sp.functional.PackedWeight(), code).backward(gout.cuda())
     tol = 1e-5 if impl == "simt" else 1e-3
     assert rel_err(xb.grad.cpu().numpy(), xa.grad.numpy()) < tol
-    assert rel_err(wb.grad.cpu().numpy().reshape(wa.shape), wa.grad.numpy()) < 1e-5     # wgrad is fp32 SIMT
+    assert rel_err(wb.grad.cpu().numpy().reshape(wa.shape), wa.grad.numpy()) < tol      # umma: tcgen05 wgrad (TF32 operands)
     assert rel_err(bb.grad.cpu().numpy(), ba.grad.numpy()) < 1e-5
 
 
@@ -438,6 +438,24 @@ def test_conv_tcgen05_split_and_async_gather(sp, nsplit, a_tf32):
     got = sp.ops.conv_fwd(xd, w.cuda(), wp, km.map_t, km.mask, n_out, b.cuda(), sp.ops.CONV_UMMA, nsplit=nsplit,
                           a_tf32=a_tf32)
     assert rel_err(got.cpu().numpy(), want.numpy()) < 2e-5
+
+
+@pytest.mark.parametrize("kind,cin,cout", [("k3", 32, 32), ("k3", 192, 128), ("k3", 320, 192), ("down", 64, 128),
+                                           ("up", 256, 192), ("k1", 192, 256), ("k1", 448, 256)])
+def test_conv_wgrad_tcgen05(sp, kind, cin, cout):
+    """weight gradient on the tensor cores (MN-major gathered operands) vs the fp32 oracle (autograd) and vs the oracle
+    with TF32-rounded operands"""
+    x, w, b, m, n_out, km, oo = _conv_case(sp, kind, cin, cout, 41)
+    g = torch.Generator().manual_seed(3)
+    gout = torch.randn(n_out, cout, generator=g)
+    wa = w.clone().requires_grad_(True)
+    oo.conv_gather_gemm_scatter(x, wa, m, n_out, None).backward(gout)
+    wt = w.clone().requires_grad_(True)
+    oo.conv_gather_gemm_scatter(oo.round_tf32(x), wt, m, n_out, None).backward(oo.round_tf32(gout))
+    xr, gr = sp.ops.round_tf32(x.cuda()), sp.ops.round_tf32(gout.cuda())
+    got = sp.ops.conv_wgrad_umma(xr, gr, km.pairs() if km is not None else None, n_out, w.shape[0]).cpu().numpy()
+    assert rel_err(got, wt.grad.numpy()) < 2e-5
+    assert rel_err(got, wa.grad.numpy()) < 1e-3
 
 
 def test_fused_glue(sp):
