@@ -454,9 +454,13 @@ __global__ void __launch_bounds__(1024) k_seg_sort(const int4* __restrict__ coor
     s_keys[i] = key;
   }
   __syncthreads();
-  for (int k = 2; k <= cap; k <<= 1) {
+  // bitonic sort of the first `n_sort` = next_pow2(cnt) keys (the rest is sentinel padding that already sits at the end).
+  // Steps with distance j <= 32 keep every warp inside its own 64-key block: they need __syncwarp only.
+  int n_sort = 64;
+  while (n_sort < cnt) n_sort <<= 1;
+  for (int k = 2; k <= n_sort; k <<= 1) {
     for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (cap >> 1); t += 1024) {
+      for (int t = tid; t < (n_sort >> 1); t += 1024) {
         const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));   // lower index of the pair
         const int l = i | j;
         const bool up = (i & k) == 0;
@@ -466,9 +470,12 @@ __global__ void __launch_bounds__(1024) k_seg_sort(const int4* __restrict__ coor
           s_keys[l] = a;
         }
       }
-      __syncthreads();
+      if (j > 32) __syncthreads();
+      else __syncwarp();
     }
+    if (k >= 64) __syncthreads();   // the next level starts with distance k > 32
   }
+  __syncthreads();
   // unique: each thread owns a contiguous run of cap/1024 (>= 1) elements
   const int per = (cap + 1023) >> 10;
   const int first = tid * per;
