@@ -249,6 +249,13 @@ int spvd_batch_counts(const int32_t* coords, int n_cap, const int32_t* n_dev, in
 int spvd_film_affine_fwd(const float* x, const float* tt, int ldt, const int32_t* coords,
                          const float* scale, const float* shift, long long rows, int c, int act,
                          float* y, spvd_stream_t stream);
+/* Timestep embedding of the denoiser in one launch (models/utils.py:15-19 sinusoid; models/spvd.py:380-392 emb_mlp =
+ * BatchNorm1d(eval) -> SiLU -> Linear(n_temb, n_emb) -> SiLU -> Linear(n_emb, n_emb); models/spvd.py cond_emb adds a
+ * class row): out[b] = act(W2 silu(W1 silu(bn(sincos(t[b] * freqs))) + b1) + b2 + cond_table[cls[b]]).
+ * params = freqs [n_temb/2] | bn scale [n_temb] | bn shift [n_temb] | W1 [n_emb,n_temb] | b1 | W2 [n_emb,n_emb] | b2;
+ * cls / cond_table may be NULL; act & 1 applies the SiLU every TimeEmbeddingBlock starts with. */
+int spvd_time_embed_fwd(const int64_t* t, const int64_t* cls, const float* params, const float* cond_table,
+                        int n_batch, int n_temb, int n_emb, int act, float* out, spvd_stream_t stream);
 /* torchsparse.cat (models/spvd.py:232): y = [a | b] along channels */
 int spvd_cat_fwd(const float* a, const float* b, long long rows, int ca, int cb, float* y,
                  spvd_stream_t stream);
@@ -315,6 +322,15 @@ int spvd_plan_build(const float* pc, int n_points, int n_batch, int max_cloud_ro
                     int32_t* summary_host, int summary_count, void* workspace, size_t workspace_bytes,
                     spvd_stream_t stream);
 
+/* The same for the levels [level_begin, level_end) only (the levels below level_begin must have been planned into
+ * the same buffers).  A forward can plan its finest levels, start the feature path on them, and plan the coarser ones
+ * on a second stream meanwhile; sync = 0 leaves the final copy of the summary asynchronous on `stream`. */
+int spvd_plan_build_range(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res,
+                          float after_res, int scale_mode, int downsample_mode, const spvd_plan_level_t* levels,
+                          int n_levels, int level_begin, int level_end, int ld, float* fcoords, int32_t* icoords,
+                          int32_t* status, const int32_t* summary_dev, int32_t* summary_host, int summary_count,
+                          int sync, void* workspace, size_t workspace_bytes, spvd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * M2  native inference executor: SPVUnet.forward (models/spvd.py:432-457, eval mode) as one call.
  * The host compiles the module tree once into spvd_op_t records whose operands are byte offsets
@@ -327,6 +343,8 @@ int spvd_plan_build(const float* pc, int n_points, int n_batch, int max_cloud_ro
 #define SPVD_OP_CAT 5          /* dst = [src0 (c0) | src1 (c1)]                                    */
 #define SPVD_OP_LAYERNORM 6    /* p0 = gamma, p1 = beta                                            */
 #define SPVD_OP_ATTENTION 7    /* src0 = qkv [rows,3*c1] -> dst [rows,c1]; i0 = heads              */
+#define SPVD_OP_TIME_EMBED 8   /* dst [batch,c1]; c0 = n_temb; w = params, p0 = class table or NULL,
+                                  p1 = t (int64 [batch]), bias = class ids (int64 [batch]) or NULL  */
 
 #define SPVD_MAP_NONE 0 /* kernel size 1 / nn.Linear */
 #define SPVD_MAP_K3 1

@@ -29,6 +29,7 @@ SIGNATURES = {
     "spvd_point_voxel_query": (_i, [_p, _i, _i, _p, _p, _i, _p, _p]),
     "spvd_devox_query": (_i, [_p, _i, _i, _p, _p, _i, _p, _p, _p]),
     "spvd_scatter_mean_fwd": (_i, [_p, _p, _i, _i, _p, _p, _i, _p]),
+    "spvd_time_embed_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "spvd_scatter_mean_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "spvd_devoxelize_fwd": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "spvd_devoxelize_bwd": (_i, [_p, _p, _p, _i, _i, _p, _i, _p]),
@@ -54,6 +55,7 @@ SIGNATURES = {
     "spvd_segmented_unique": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "spvd_ddpm_step": (_i, [_p, _p, _p, _f, _f, _f, _i, _i, _i, _f, _p, _p, _p, _p, _p]),
     "spvd_plan_build": (_i, [_p, _i, _i, _i, _f, _f, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "spvd_plan_build_range": (_i, [_p, _i, _i, _i, _f, _f, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _sz, _p]),
 }
 
 
@@ -61,7 +63,7 @@ def _load():
     path = _build.LIB
     try:
         path = _build.build()
-    except Exception as e:  # no nvcc on this machine: a prebuilt in-tree library is still fine
+    except _build.NvccMissing as e:  # no nvcc on this machine: a prebuilt in-tree library is still fine (compile errors raise)
         if not os.path.exists(path):
             raise ImportError(f"libspvd_b200.so is missing and could not be built: {e}") from e
     lib = C.CDLL(path)

@@ -23,8 +23,12 @@ NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", 
 def _nvcc() -> str:
     cand = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
     if not os.path.exists(cand):
-        raise RuntimeError("nvcc not found: libspvd_b200.so cannot be built")
+        raise NvccMissing("nvcc not found: libspvd_b200.so cannot be built")
     return cand
+
+
+class NvccMissing(RuntimeError):
+    pass
 
 
 def _digest() -> str:

@@ -54,18 +54,22 @@ int spvd_segmented_unique(const int32_t*, int, const int32_t*, int, int, int, in
     if (rc_ != SPVD_OK) return rc_; \
   } while (0)
 
-extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res, float after_res,
-                               int scale_mode, int downsample_mode, const spvd_plan_level_t* levels, int n_levels,
-                               int ld, float* fcoords, int32_t* icoords, int32_t* status, const int32_t* summary_dev,
-                               int32_t* summary_host, int summary_count, void* workspace, size_t workspace_bytes,
-                               spvd_stream_t stream) {
+extern "C" int spvd_plan_build_range(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res,
+                                     float after_res, int scale_mode, int downsample_mode, const spvd_plan_level_t* levels,
+                                     int n_levels, int level_begin, int level_end, int ld, float* fcoords, int32_t* icoords,
+                                     int32_t* status, const int32_t* summary_dev, int32_t* summary_host, int summary_count,
+                                     int sync, void* workspace, size_t workspace_bytes, spvd_stream_t stream) {
   SPVD_CHECK_ARG(pc && levels && fcoords && icoords && status && workspace && n_points > 0 && n_levels > 0,
                  "spvd_plan_build: bad arguments");
+  SPVD_CHECK_ARG(0 <= level_begin && level_begin < level_end && level_end <= n_levels, "spvd_plan_build: bad level range [%d,%d)",
+                 level_begin, level_end);
   SPVD_CHECK_ARG(ld % 128 == 0 && ld >= n_points, "spvd_plan_build: ld %d must be a multiple of 128 >= n_points", ld);
   cudaStream_t s = (cudaStream_t)stream;
-  SPVD_CUDA(cudaMemsetAsync(status, 0, 4, s));
-  SPVD_TRY(spvd_point_voxel_coords(pc, n_points, init_res, after_res, scale_mode, fcoords, icoords, stream));
-  for (int i = 0; i < n_levels; ++i) {
+  if (level_begin == 0) {
+    SPVD_CUDA(cudaMemsetAsync(status, 0, 4, s));
+    SPVD_TRY(spvd_point_voxel_coords(pc, n_points, init_res, after_res, scale_mode, fcoords, icoords, stream));
+  }
+  for (int i = level_begin; i < level_end; ++i) {
     const spvd_plan_level_t& L = levels[i];
     SPVD_CHECK_ARG(L.coords && L.count && L.keys && L.vals && L.capacity >= 2 * n_points,
                    "spvd_plan_build: level %d lacks coords / count / hash buffers", i);
@@ -92,7 +96,7 @@ extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, int m
                                  F.dpair_tile_k, F.dpair_counts, F.dpair_counts + 1, F.pair_scratch, stream));
     }
   }
-  for (int i = 0; i < n_levels; ++i) {
+  for (int i = level_begin; i < level_end; ++i) {
     const spvd_plan_level_t& L = levels[i];
     const int stride = 1 << i;
     if (L.kmap3) SPVD_TRY(spvd_kmap_subm3(L.coords, n_points, L.count, L.keys, L.vals, L.capacity, L.kmap3, ld, L.mask3, stream));
@@ -115,7 +119,17 @@ extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, int m
   SPVD_LAUNCH_CHECK();
   if (summary_dev && summary_host && summary_count > 0) {
     SPVD_CUDA(cudaMemcpyAsync(summary_host, summary_dev, (size_t)summary_count * 4, cudaMemcpyDeviceToHost, s));
-    SPVD_CUDA(cudaStreamSynchronize(s));
+    if (sync) SPVD_CUDA(cudaStreamSynchronize(s));
   }
   return SPVD_OK;
+}
+
+extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res, float after_res,
+                               int scale_mode, int downsample_mode, const spvd_plan_level_t* levels, int n_levels,
+                               int ld, float* fcoords, int32_t* icoords, int32_t* status, const int32_t* summary_dev,
+                               int32_t* summary_host, int summary_count, void* workspace, size_t workspace_bytes,
+                               spvd_stream_t stream) {
+  return spvd_plan_build_range(pc, n_points, n_batch, max_cloud_rows, init_res, after_res, scale_mode, downsample_mode, levels,
+                               n_levels, 0, n_levels, ld, fcoords, icoords, status, summary_dev, summary_host, summary_count, 1,
+                               workspace, workspace_bytes, stream);
 }

@@ -258,6 +258,62 @@ extern "C" int spvd_attention_fwd(const float* qkv, const int32_t* batch_offsets
 }
 
 // ------------------------------------------------------------------------------------------------
+// timestep embedding: sinusoid -> BatchNorm1d (eval) -> SiLU -> Linear -> SiLU -> Linear (+ class row) -> SiLU,
+// one CTA per cloud (models/utils.py:15-19, models/spvd.py:380-392); params = freqs[half] | bn scale, shift [n_temb]
+// | W1 [n_emb, n_temb] | b1 | W2 [n_emb, n_emb] | b2
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_time_embed(const long long* __restrict__ t, const long long* __restrict__ cls,
+                                                    const float* __restrict__ P, const float* __restrict__ cond, int n_temb,
+                                                    int n_emb, int act, float* __restrict__ out) {
+  extern __shared__ float sm_te[];
+  float* x = sm_te;            // [n_temb]
+  float* h = sm_te + n_temb;   // [n_emb]
+  const int b = blockIdx.x, half = n_temb / 2;
+  const float* freqs = P;
+  const float* bn_s = freqs + half;
+  const float* bn_b = bn_s + n_temb;
+  const float* W1 = bn_b + n_temb;
+  const float* b1 = W1 + (size_t)n_emb * n_temb;
+  const float* W2 = b1 + n_emb;
+  const float* b2 = W2 + (size_t)n_emb * n_emb;
+  const float tv = (float)t[b];
+  for (int i = threadIdx.x; i < 2 * half; i += blockDim.x) {
+    const float e = tv * freqs[i < half ? i : i - half];
+    const float v = i < half ? sinf(e) : cosf(e);
+    x[i] = silu_f(v * bn_s[i] + bn_b[i]);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+  for (int j = warp; j < n_emb; j += n_warps) {
+    float acc = 0.f;
+    for (int i = lane; i < n_temb; i += 32) acc = fmaf(W1[(size_t)j * n_temb + i], x[i], acc);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) h[j] = silu_f(acc + b1[j]);
+  }
+  __syncthreads();
+  const float* crow = (cond && cls) ? cond + (size_t)cls[b] * n_emb : nullptr;
+  for (int j = warp; j < n_emb; j += n_warps) {
+    float acc = 0.f;
+    for (int i = lane; i < n_emb; i += 32) acc = fmaf(W2[(size_t)j * n_emb + i], h[i], acc);
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      float v = acc + b2[j] + (crow ? crow[j] : 0.f);
+      out[(size_t)b * n_emb + j] = (act & 1) ? silu_f(v) : v;
+    }
+  }
+}
+
+extern "C" int spvd_time_embed_fwd(const int64_t* t, const int64_t* cls, const float* params, const float* cond_table,
+                                   int n_batch, int n_temb, int n_emb, int act, float* out, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(t && params && out && n_batch > 0 && n_temb > 0 && n_temb % 2 == 0 && n_emb > 0 && (n_temb + n_emb) * 4 <= 48 * 1024,
+                 "spvd_time_embed_fwd: bad arguments");
+  k_time_embed<<<n_batch, 256, (size_t)(n_temb + n_emb) * 4, (cudaStream_t)stream>>>(
+      (const long long*)t, (const long long*)cls, params, cond_table, n_temb, n_emb, act, out);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
 // program interpreter
 // ------------------------------------------------------------------------------------------------
 static inline long long rows_of(int kind, const spvd_level_geom_t* lv, int n_levels, int n_points, int n_batch) {
@@ -349,6 +405,10 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
         SPVD_CHECK_ARG(lv && lv->batch_offsets, "op %d: level %d has no per-cloud offsets", i, o.level);
         rc = spvd_attention_fwd(at(o.src0), lv->batch_offsets, n_batch, lv->max_per_batch, o.c1, o.i0, o.flags & 3,
                                 at(o.dst), stream);
+        break;
+      case SPVD_OP_TIME_EMBED:
+        rc = spvd_time_embed_fwd((const int64_t*)o.p1, (const int64_t*)o.bias, o.w, o.p0, n_batch, o.c0, o.c1, o.flags & 1,
+                                 at(o.dst), stream);
         break;
       default:
         set_error("spvd_program_run: op %d has unknown opcode %d", i, o.op);

@@ -11,6 +11,7 @@ below only own parameters; ``SPVUnet.forward`` drives them.
 from __future__ import annotations
 
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -178,6 +179,8 @@ class SPVUnet(nn.Module):
         self.use_executor = True
         self._plan_ws = {}           # (n_points, n_batch, device) -> [PlanWorkspace pool, cursor]
         self.geometry_pool = 2
+        self.plan_split_level = int(os.environ.get("SPVD_PLAN_SPLIT", "2"))   # levels the executor waits for before it starts
+        self._side_streams = {}
 
     # -- static description of which strides need which maps (so Geometry can build all of them up front)
     @staticmethod
@@ -280,7 +283,7 @@ class SPVUnet(nn.Module):
         return x
 
     # -- forward -------------------------------------------------------------------------------
-    def plan_geometry(self, coords: torch.Tensor, n_batch: int, max_cloud_rows: int = 0) -> Geometry:
+    def plan_geometry(self, coords: torch.Tensor, n_batch: int, max_cloud_rows: int = 0, split_level: int = 0) -> Geometry:
         """Plan every coordinate structure of the forward with one C call into persistent buffers.  Two
         buffer sets alternate, so the geometry of the previous call stays valid while the next one is
         planned (``geometry_pool`` > 2 keeps more alive, e.g. when several forwards precede one backward)."""
@@ -296,7 +299,12 @@ class SPVUnet(nn.Module):
         else:
             pool[1] = (pool[1] + 1) % len(pool[0])
             ws = pool[0][pool[1]]
-        return ws.build(pc, self.pres, self.voxel_size, self.scale_mode, self.downsample_mode, max_cloud_rows)
+        side = None
+        if split_level:
+            side = self._side_streams.get(pc.device)
+            if side is None:
+                side = self._side_streams[pc.device] = torch.cuda.Stream(device=pc.device, priority=-1)
+        return ws.build(pc, self.pres, self.voxel_size, self.scale_mode, self.downsample_mode, max_cloud_rows, split_level, side)
 
     def forward(self, inp, geometry: Geometry = None):
         x_in, t = inp[0], inp[1]
@@ -306,12 +314,15 @@ class SPVUnet(nn.Module):
         cf = getattr(x_in, "coords_float", None)          # float copy of the coordinates, when the sampler made one
         if cf is not None and cf.shape[0] == coords.shape[0]:
             coords = cf
-        geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0],
-                                                                       int(getattr(x_in, "points_per_cloud", 0) or 0))
         cls = inp[2] if len(inp) > 2 else None
         if cls is not None and not hasattr(self, "cond_emb"):
             raise RuntimeError("this model was built without n_classes; it takes (x, t)")
-        if self.use_executor and self._fast():
+        executor = self.use_executor and self._fast()
+        # executor: wait only for the finest levels; the coarser ones are planned on a side stream under the first ops
+        geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0],
+                                                                       int(getattr(x_in, "points_per_cloud", 0) or 0),
+                                                                       self.plan_split_level if executor else 0)
+        if executor:
             from .runtime import Program
             key = (feats.shape[0], t.shape[0])
             prog = self._programs.get(key)

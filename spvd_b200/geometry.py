@@ -137,7 +137,22 @@ class Geometry:
                 l.kmap_up = KernelMap(mu, ku, l.n, c.n, 8, flip=False)
                 l.kmap_down.grad, l.kmap_up.grad = l.kmap_up, l.kmap_down
 
+    _pending = None          # set by PlanWorkspace.build(split_level=...): finishes planning the coarser levels
+
+    def finish(self):
+        """Wait for (and collect) the levels that are still being planned on the side stream."""
+        f, self._pending = self._pending, None
+        if f is not None:
+            f()
+        return self
+
+    @property
+    def levels_ready(self):
+        return len(self.levels)
+
     def level(self, s):
+        if s not in self.levels:
+            self.finish()
         return self.levels[s]
 
     # ---- derived index tensors (geometry only, cached per level) --------------------------------
@@ -218,6 +233,8 @@ class PlanWorkspace:
         self.n_summary = nl + 1 + nl * n_batch + 4 * nl      # level counts | status | per-cloud counts | (pair tiles, pairs) x2
         self.summary = torch.zeros(self.n_summary, **i32)
         self.summary_host = torch.zeros(self.n_summary, dtype=torch.int32).pin_memory()
+        self.summary_host_b = torch.zeros(self.n_summary, dtype=torch.int32).pin_memory()   # coarse levels of a split build
+        self.fine_done = torch.cuda.Event()
         self.ws = torch.empty(max(_lib.spvd_unique_workspace_bytes(n_points), 256), dtype=torch.uint8, device=device)
         self.c_levels = (_PlanLevel * nl)()
         self.bufs = []
@@ -264,19 +281,52 @@ class PlanWorkspace:
         self.n_kernels = (1 + 22 + 23 * (nl - 1) + nl + (nl - 1) + len(k3_strides) + 2 * len(p2v_strides) + len(devox_strides) +
                           2 * nl + 3 * len(self.pair_strides) + 3 * (nl - 1))
 
-    def build(self, pc, pres, voxel_size, scale_mode="mul", downsample_mode="spconv", max_cloud_rows=0):
+    def build(self, pc, pres, voxel_size, scale_mode="mul", downsample_mode="spconv", max_cloud_rows=0, split_level=0,
+              side_stream=None):
         """max_cloud_rows > 0: the points are batch-major with at most that many per cloud (what torch2sparse
-        produces) -> per-cloud shared-memory sorts; 0: no assumption (global radix sort)."""
+        produces) -> per-cloud shared-memory sorts; 0: no assumption (global radix sort).
+        split_level = k > 0 with a side_stream: only the k finest levels are planned (and waited for) here; the coarser
+        ones are planned on side_stream while the caller already works on the fine ones, and ``Geometry.finish()`` (or
+        the first access to a coarser level) collects them."""
         if not pc.is_cuda or pc.dtype != torch.float32 or not pc.is_contiguous() or pc.shape != (self.n_points, 4):
             raise RuntimeError("PlanWorkspace.build needs a contiguous CUDA float32 [n_points,4] tensor")
-        _check(_lib.spvd_plan_build(
-            _C.c_void_p(pc.data_ptr()), self.n_points, self.n_batch, int(max_cloud_rows), pres, voxel_size, ops._SCALE[scale_mode],
-            ops._DOWNSAMPLE[downsample_mode], self.c_levels, len(self.strides), self.ld,
-            _C.c_void_p(self.fcoords.data_ptr()), _C.c_void_p(self.icoords.data_ptr()), _C.c_void_p(self.status.data_ptr()),
-            _C.c_void_p(self.summary.data_ptr()), _C.c_void_p(self.summary_host.data_ptr()), self.n_summary,
-            _C.c_void_p(self.ws.data_ptr()), self.ws.numel(), _C.c_void_p(torch.cuda.current_stream().cuda_stream)))
-        ops.stats.launches += self.n_kernels if not max_cloud_rows else self.n_kernels - 20 * len(self.strides)
-        host = self.summary_host.tolist()
+        nl = len(self.strides)
+
+        def launch(lo, hi, sync, stream, host=self.summary_host):
+            _check(_lib.spvd_plan_build_range(
+                _C.c_void_p(pc.data_ptr()), self.n_points, self.n_batch, int(max_cloud_rows), pres, voxel_size,
+                ops._SCALE[scale_mode], ops._DOWNSAMPLE[downsample_mode], self.c_levels, nl, lo, hi, self.ld,
+                _C.c_void_p(self.fcoords.data_ptr()), _C.c_void_p(self.icoords.data_ptr()), _C.c_void_p(self.status.data_ptr()),
+                _C.c_void_p(self.summary.data_ptr()), _C.c_void_p(host.data_ptr()), self.n_summary, int(sync),
+                _C.c_void_p(self.ws.data_ptr()), self.ws.numel(), _C.c_void_p(stream.cuda_stream)))
+
+        ops.stats.launches += self.n_kernels if not max_cloud_rows else self.n_kernels - 20 * nl
+        geo = Geometry.__new__(Geometry)
+        geo.n_points, geo.mode, geo.status = self.n_points, downsample_mode, self.status
+        geo.fcoords, geo.levels, geo.p2v, geo.devox = self.fcoords, {}, {}, {}
+        cur = torch.cuda.current_stream()
+        if not split_level or split_level >= nl or side_stream is None:
+            launch(0, nl, True, cur)
+            self._collect(geo, 0, nl)
+            return geo
+        # everything is enqueued before the host waits: fine levels on the current stream, then the coarse levels on the
+        # side stream behind an event, so the GPU never waits for the host to issue them
+        launch(0, split_level, False, cur)
+        self.fine_done.record(cur)
+        side_stream.wait_event(self.fine_done)
+        launch(split_level, nl, False, side_stream, self.summary_host_b)
+        self.fine_done.synchronize()
+        self._collect(geo, 0, split_level)
+
+        def finish():
+            side_stream.synchronize()
+            self._collect(geo, split_level, nl, self.summary_host_b)
+        geo._pending = finish
+        return geo
+
+    def _collect(self, geo, lo, hi, summary=None):
+        downsample_mode = geo.mode
+        host = (self.summary_host if summary is None else summary).tolist()
         nl, nb = len(self.strides), self.n_batch
         st = host[nl]
         if st:
@@ -284,10 +334,8 @@ class PlanWorkspace:
                                ("hash table full; " if st & 2 else "") +
                                ("a cloud has more points than the max_cloud_rows hint (or the points are not batch-major)"
                                 if st & 4 else ""))
-        geo = Geometry.__new__(Geometry)
-        geo.n_points, geo.mode, geo.status = self.n_points, downsample_mode, self.status
-        geo.fcoords, geo.levels, geo.p2v, geo.devox = self.fcoords, {}, {}, {}
-        for i, s in enumerate(self.strides):
+        for i in range(lo, hi):
+            s = self.strides[i]
             b = self.bufs[i]
             lv = Level(s, b["coords"], b["count"])
             lv.n = host[i]
@@ -301,22 +349,20 @@ class PlanWorkspace:
             if "pair_in" in b:
                 o = nl + 1 + nl * nb + 2 * i
                 lv.pairs = (b["pair_in"], b["pair_out"], b["pair_tile_k"], host[o], host[o + 1])   # (.., tiles, pairs)
-            if "dpair_in" in b:
-                o = nl + 1 + nl * nb + 2 * nl + 2 * i
-                lv.dpairs = (b["dpair_in"], b["dpair_out"], b["dpair_tile_k"], host[o], host[o + 1])
             geo.levels[s] = lv
             if "p2v" in b:
                 geo.p2v[s] = b["p2v"]
             if "devox_idx" in b:
                 geo.devox[s] = (b["devox_idx"], b["devox_w"])
-        for i, s in enumerate(self.strides):
-            b, lv = self.bufs[i], geo.levels[s]
             if "kmap3" in b:
                 lv.kmap3 = KernelMap(b["kmap3"], b["mask3"], lv.n, lv.n, 27, flip=True)
                 lv.kmap3.grad = lv.kmap3
+        for i in range(max(lo - 1, 0), hi - 1):           # stride-2 maps between level i and i + 1 (planned with level i + 1)
+            b, lv, c = self.bufs[i], geo.levels[self.strides[i]], geo.levels[self.strides[i + 1]]
+            if "dpair_in" in b:
+                o = nl + 1 + nl * nb + 2 * nl + 2 * i
+                lv.dpairs = (b["dpair_in"], b["dpair_out"], b["dpair_tile_k"], host[o], host[o + 1])
             if "kmap_down" in b:
-                c = geo.levels[2 * s]
                 lv.kmap_down = KernelMap(b["kmap_down"], b["mask_down"], c.n, lv.n, 8, flip=False)
                 lv.kmap_up = KernelMap(b["kmap_up"], b["mask_up"], lv.n, c.n, 8, flip=False)
                 lv.kmap_down.grad, lv.kmap_up.grad = lv.kmap_up, lv.kmap_down
-        return geo

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import time
 
 import torch
 import torch.nn.functional as F
@@ -19,12 +20,12 @@ from . import ops
 from ._C import check, lib
 from .geometry import Geometry
 
-OP_SCATTER_MEAN, OP_DEVOX, OP_CONV, OP_AFFINE, OP_FILM_AFFINE, OP_CAT, OP_LAYERNORM, OP_ATTENTION = range(8)
+OP_SCATTER_MEAN, OP_DEVOX, OP_CONV, OP_AFFINE, OP_FILM_AFFINE, OP_CAT, OP_LAYERNORM, OP_ATTENTION, OP_TIME_EMBED = range(9)
 MAP_NONE, MAP_K3, MAP_DOWN, MAP_UP = range(4)
 ROWS_POINTS, ROWS_BATCH = -1, -2
 FLAG_SILU, FLAG_ROUND, FLAG_A_TF32, FLAG_SIMT = 1, 2, 4, 8
 KERNELS_PER_OP = {OP_SCATTER_MEAN: 2, OP_DEVOX: 1, OP_CONV: 1, OP_AFFINE: 1, OP_FILM_AFFINE: 1, OP_CAT: 1,
-                  OP_LAYERNORM: 1, OP_ATTENTION: 1}
+                  OP_LAYERNORM: 1, OP_ATTENTION: 1, OP_TIME_EMBED: 1}
 
 
 class LevelGeom(C.Structure):
@@ -62,6 +63,7 @@ class Program:
         self.model, self.n_points, self.n_batch = model, n_points, n_batch
         self.dev = next(model.parameters()).device
         self.pair_density = 10.0  # use pair-major convs where a voxel has fewer active offsets than this on average
+        self.trace = None         # list -> run() appends (label, perf_counter) marks (tools/step_breakdown.py)
         self.keep = []            # prepared parameter tensors (kept alive; the ops hold raw pointers)
         self.recs = []            # dicts before register allocation
         self.regs = []
@@ -168,7 +170,14 @@ class Program:
         self.tt_width = col
         self.attn_levels = set()
         self.in_feats = self.reg(P, pc, "feats")
-        self.in_emb = self.reg(ROWS_BATCH, n_emb, "emb_act")
+        # silu(emb_mlp(sinusoid(t)) [+ cond_emb(cls)]) in one launch; t / cls pointers are patched in by run()
+        bn, l1, l2 = m.emb_mlp[0][0], m.emb_mlp[0][2], m.emb_mlp[1][1]
+        freqs = (-math.log(10000) * torch.linspace(0, 1, m.n_temb // 2, device=self.dev)).exp()
+        te = self._hold(torch.cat([freqs, *self._bn(bn), l1.weight.detach().reshape(-1), l1.bias.detach(),
+                                   l2.weight.detach().reshape(-1), l2.bias.detach()]))
+        self.in_emb = self.op(OP_TIME_EMBED, self.reg(ROWS_BATCH, n_emb, "emb_act"), None, flags=FLAG_SILU, level=-1,
+                              rows_in=ROWS_BATCH, rows_out=ROWS_BATCH, c0=m.n_temb, c1=n_emb, w=te,
+                              p0=self._hold(m.cond_emb.weight) if hasattr(m, "cond_emb") else None)
         wcat = torch.cat(ws, 0).t().unsqueeze(0)          # [1, n_emb, sum 2C]
         self.tt = self.conv(self.in_emb, self._conv_params(wcat, torch.cat(bs, 0), force_simt=True), 1, MAP_NONE, -1,
                             ROWS_BATCH, col)
@@ -287,7 +296,7 @@ class Program:
             o.op, o.flags, o.level, o.map_kind = rec["op"], rec.get("flags", 0), rec.get("level", -1), rec.get("map_kind", 0)
             o.rows_in, o.rows_out = rec["rows_in"], rec["rows_out"]
             o.c0, o.c1, o.kvol, o.i0, o.i1 = rec["c0"], rec["c1"], rec.get("kvol", 0), rec.get("i0", 0), rec.get("i1", 0)
-            o.src0 = rec["src0"].offset
+            o.src0 = rec["src0"].offset if rec["src0"] is not None else -1
             o.src1 = rec["src1"].offset if rec["src1"] is not None else -1
             o.dst = rec["dst"].offset
             o.aux = rec["aux"].offset if rec["aux"] is not None else -1
@@ -298,6 +307,14 @@ class Program:
             if rec["op"] == OP_CONV:
                 self.conv_meta.append((rec["kvol"], rec["c0"], rec["c1"], rec["rows_out"], rec["level"], rec["map_kind"],
                                        "umma" if (rec.get("w_packed") is not None) else "simt"))
+        # finest level an op can run with: it needs every level up to max(level, rows_in, rows_out) planned; the stride-2
+        # maps / pair lists of level l are planned together with level l + 1
+        self.op_max_level, self.convs_before, nconv = [], [], 0
+        for rec in self.recs:
+            top = max(rec.get("level", -1), rec["rows_in"], rec["rows_out"])
+            self.op_max_level.append(top)
+            self.convs_before.append(nconv)
+            nconv += rec["op"] == OP_CONV
         self.arena = torch.empty(self.arena_bytes, dtype=torch.uint8, device=self.dev)
         self.arena_f = self.arena.view(torch.float32)
         self.c_levels = (LevelGeom * len(self.strides))()
@@ -307,8 +324,8 @@ class Program:
         o = r.offset // 4
         return self.arena_f[o: o + rows * r.ch].view(rows, r.ch)
 
-    def fill_levels(self, geo: Geometry):
-        for i, s in enumerate(self.strides):
+    def fill_levels(self, geo: Geometry, upto=None):
+        for i, s in enumerate(self.strides[:upto]):
             lv, g = geo.level(s), self.c_levels[i]
             g.coords, g.n = lv.coords_cap.data_ptr(), lv.n
             if lv.kmap3 is not None:
@@ -325,7 +342,7 @@ class Program:
                 g.pair_in, g.pair_out, g.pair_tile_k, g.n_pair_tiles = pr[0].data_ptr(), pr[1].data_ptr(), pr[2].data_ptr(), pr[3]
             else:
                 g.pair_in, g.n_pair_tiles = None, 0
-            dp = getattr(lv, "dpairs", None)
+            dp = getattr(lv, "dpairs", None)          # planned together with the next coarser level
             if dp is not None:
                 g.dpair_in, g.dpair_out, g.dpair_tile_k, g.n_dpair_tiles = dp[0].data_ptr(), dp[1].data_ptr(), dp[2].data_ptr(), dp[3]
             else:
@@ -338,22 +355,45 @@ class Program:
         m = self.model
         if feats.shape[0] != self.n_points or t.shape[0] != self.n_batch:
             raise RuntimeError("Program was compiled for a different number of points / clouds")
-        # timestep embedding + MLP on [B, n_temb] (models/utils.py:15-19; models/spvd.py:391-392)
-        exponent = -math.log(10000) * torch.linspace(0, 1, m.n_temb // 2, device=t.device)
-        e = t[:, None].float() * exponent.exp()[None, :]
-        e = torch.cat([e.sin(), e.cos()], dim=-1)
-        emb = m.emb_mlp[0][2](F.silu(m.emb_mlp[0][0](e)))
-        emb = m.emb_mlp[1][1](F.silu(emb))
+        t = t.long().contiguous()
+        te = self.c_ops[0]                      # OP_TIME_EMBED reads this call's timesteps / class ids
+        assert te.op == OP_TIME_EMBED
+        te.p1 = t.data_ptr()
         if cls is not None:
-            emb = emb + m.cond_emb(cls)
-        self._view(self.in_emb, self.n_batch).copy_(F.silu(emb))
+            cls = cls.long().contiguous()
+            te.bias = cls.data_ptr()
+        else:
+            te.bias = None
         self._view(self.in_feats, self.n_points).copy_(feats)
-        self.fill_levels(geo)
         ev = None
         if conv_events is not None:
             ev = (C.c_void_p * len(conv_events))(*conv_events)
-        check(lib.spvd_program_run(self.c_ops, len(self.recs), self.c_levels, len(self.strides), self.n_points,
-                                   self.n_batch, C.c_void_p(self.arena.data_ptr()), self.arena_bytes, ev,
-                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def launch(lo, hi):
+            if hi <= lo:
+                return
+            evp = C.byref(ev, 2 * self.convs_before[lo] * C.sizeof(C.c_void_p)) if ev is not None else None
+            check(lib.spvd_program_run(C.byref(self.c_ops, lo * C.sizeof(Op)), hi - lo, self.c_levels, len(self.strides),
+                                       self.n_points, self.n_batch, C.c_void_p(self.arena.data_ptr()), self.arena_bytes, evp,
+                                       stream))
+
+        n, k = len(self.recs), 0
+        if geo._pending is not None:
+            # the finest levels are planned: run the ops that touch only those while the coarser ones are still being
+            # planned on the side stream, then collect them and run the rest
+            ready = geo.levels_ready
+            k = next((i for i, l in enumerate(self.op_max_level) if l >= ready), n)
+            self.fill_levels(geo, upto=ready)
+            launch(0, k)
+            if self.trace is not None:
+                self.trace.append(("part1 launched", time.perf_counter()))
+            geo.finish()
+            if self.trace is not None:
+                self.trace.append(("coarse levels collected", time.perf_counter()))
+        self.fill_levels(geo)
+        launch(k, n)
+        if self.trace is not None:
+            self.trace.append(("part2 launched", time.perf_counter()))
         ops.stats.launches += self.n_kernels
         return self._view(self.out, self.n_points).clone()

@@ -111,6 +111,67 @@ def test_native_executor_matches_python_path_and_oracle(sp):
         assert rel_err(y_py, want) < 1e-4
 
 
+def test_split_planning_matches_one_shot_planning(sp):
+    """Planning the coarse levels on a side stream under the first ops (plan_split_level) must give the same geometry
+    and the same output as planning everything up front."""
+    from oracle import model as om
+    g = torch.Generator().manual_seed(11)
+    pts = torch.randn(4, 2048, 3, generator=g).clamp(-3, 3)
+    coords, feats, _ = om.torch2sparse(pts)
+    t = torch.tensor([999, 640, 77, 0]).cuda()
+    m, _ = make_model(sp, "SPVD", 3, "spconv", "mul", sp.ops.CONV_AUTO)
+    m.eval()
+    x = sp.SparseTensor(feats.cuda(), coords.cuda())
+    outs, geos = {}, {}
+    with torch.no_grad():
+        for split in (0, 1, 2, 3):
+            m.plan_split_level = split
+            for _ in range(2):                      # twice: the second call reuses the other workspace of the pool
+                outs[split] = m((x, t)).cpu()
+            geo = m.plan_geometry(coords.cuda().float(), 4, 0, split)
+            assert (geo._pending is not None) == (split > 0) and geo.levels_ready == (split or 5)
+            geo.finish()
+            geos[split] = {s: (lv.n, lv.coords.cpu(), lv.kmap3.map_t[:, :lv.n].cpu(),
+                               None if lv.kmap_down is None else lv.kmap_down.map_t[:, :lv.kmap_down.n_out].cpu(),
+                               getattr(lv, "dpairs", (0,) * 5)[3:])
+                           for s, lv in geo.levels.items()}
+    for split in (1, 2, 3):
+        assert rel_err(outs[split].numpy(), outs[0].numpy()) < 5e-4      # run-to-run (atomics order + TF32 flips) is ~1e-4
+        for s, ref in geos[0].items():
+            got = geos[split][s]
+            assert got[0] == ref[0] and torch.equal(got[1], ref[1]) and torch.equal(got[2], ref[2]) and got[4] == ref[4]
+            assert (ref[3] is None and got[3] is None) or torch.equal(got[3], ref[3])
+
+
+@pytest.mark.parametrize("preset", ["SPVD", "COND_SPVD_L"])
+def test_time_embedding_kernel_vs_torch(sp, preset):
+    """spvd_time_embed_fwd (one launch) against the module-by-module torch evaluation of emb_mlp / cond_emb."""
+    import math
+    import torch.nn.functional as F
+    from spvd_b200.runtime import Program
+    m, _ = make_model(sp, preset, 2, "spconv", "mul", sp.ops.CONV_AUTO)
+    m.eval()
+    B = 7
+    t = torch.tensor([999, 998, 500, 37, 2, 1, 0]).cuda()
+    cls = torch.tensor([0, 54, 3, 3, 17, 1, 9]).cuda() if hasattr(m, "cond_emb") else None
+    prog = Program(m, 64 * B, B)
+    te = prog.recs[0]
+    out = torch.empty(B, te["c1"], device="cuda")
+    from spvd_b200._C import lib, check
+    check(lib.spvd_time_embed_fwd(t.data_ptr(), cls.data_ptr() if cls is not None else None, te["w"].data_ptr(),
+                                  te["p0"].data_ptr() if te["p0"] is not None else None, B, te["c0"], te["c1"], 1,
+                                  out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    with torch.no_grad():
+        exponent = -math.log(10000) * torch.linspace(0, 1, m.n_temb // 2, device="cuda")
+        e = t[:, None].float() * exponent.exp()[None, :]
+        e = torch.cat([e.sin(), e.cos()], dim=-1)
+        emb = m.emb_mlp[1](m.emb_mlp[0](e))
+        if cls is not None:
+            emb = emb + m.cond_emb(cls)
+        want = F.silu(emb)
+    assert rel_err(out.cpu().numpy(), want.cpu().numpy()) < 1e-5
+
+
 @pytest.mark.parametrize("preset,B,N,train", [("COND_TINY", 3, 512, False), ("COND_TINY", 4, 256, True),
                                                  ("SPVD_L", 2, 512, False), ("COND_SPVD_L", 2, 512, False),
                                                  ("SUPERRES", 2, 1024, False), ("SPVD", 1, 8192, False)])

@@ -24,8 +24,10 @@ with torch.no_grad():
         st = sched.torch2sparse(xs[j], shape)
         tb = torch.full((32,), ts[j], device=dev, dtype=torch.long)
         e1.record()
-        geo = model.plan_geometry(st.C, 32, st.points_per_cloud)
+        geo = model.plan_geometry(st.coords_float, 32, st.points_per_cloud, model.plan_split_level)
         c1 = time.perf_counter(); e2.record()
+        for p in model._programs.values():
+            p.trace = [("geometry returned", c1)]
         eps = model((st, tb), geometry=geo)
         new = strat.update(st.F, eps, ts[j], j, lambda s: torch.randn(s, device=dev))
         sched.torch2sparse(new, shape)
@@ -33,6 +35,8 @@ with torch.no_grad():
         torch.cuda.synchronize(); c3 = time.perf_counter()
         if j >= W:
             rows.append((e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), (c1 - c0) * 1e3, (c2 - c1) * 1e3, (c3 - c0) * 1e3))
+for p in model._programs.values():
+    print("last step, ms after the geometry call returned:", [(k, round((v - p.trace[0][1]) * 1e3, 3)) for k, v in p.trace[1:]])
 import statistics
 names = ["gpu t2s", "gpu geometry(incl sync)", "gpu feature path", "cpu till geometry done", "cpu launch feature path", "wall total"]
 for i, n in enumerate(names):
