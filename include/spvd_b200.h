@@ -331,6 +331,31 @@ int spvd_plan_build_range(const float* pc, int n_points, int n_batch, int max_cl
                           int32_t* status, const int32_t* summary_dev, int32_t* summary_host, int summary_count,
                           int sync, void* workspace, size_t workspace_bytes, spvd_stream_t stream);
 
+/* Level groups [bounds[g], bounds[g+1]), g < n_groups, planned by one host call that never waits: group 0 on `stream`,
+ * the others on `side_stream` behind it; events[g] (a cudaEvent_t) is recorded after group g's summary reached
+ * summary_hosts[g].  The caller waits on events[0], starts the feature path on the finest levels, and collects the
+ * coarser groups as their events complete. */
+int spvd_plan_build_groups(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res,
+                           float after_res, int scale_mode, int downsample_mode, const spvd_plan_level_t* levels,
+                           int n_levels, const int32_t* bounds, int n_groups, int ld, float* fcoords,
+                           int32_t* icoords, int32_t* status, const int32_t* summary_dev,
+                           int32_t* const* summary_hosts, int summary_count, void* const* events, void* workspace,
+                           size_t workspace_bytes, spvd_stream_t stream, spvd_stream_t side_stream);
+
+/* The same as CUDA graphs.  The planner's launch sequence depends only on capacities (grids are sized by n_points, row
+ * counts stay on the device), so it is captured once per buffer set -- one graph per level group -- and replayed with one
+ * launch per group.  pc_stage [n_points,4] is a buffer of the caller that launch() copies the points into. */
+typedef struct spvd_plan_graph spvd_plan_graph_t;
+int spvd_plan_graph_create(int n_points, int n_batch, int max_cloud_rows, float init_res, float after_res,
+                           int scale_mode, int downsample_mode, const spvd_plan_level_t* levels, int n_levels,
+                           const int32_t* bounds, int n_groups, int ld, float* pc_stage, float* fcoords,
+                           int32_t* icoords, int32_t* status, const int32_t* summary_dev,
+                           int32_t* const* summary_hosts, int summary_count, void* workspace,
+                           size_t workspace_bytes, spvd_plan_graph_t** out);
+int spvd_plan_graph_launch(spvd_plan_graph_t* g, const float* pc, void* const* events, spvd_stream_t stream,
+                           spvd_stream_t side_stream);
+void spvd_plan_graph_destroy(spvd_plan_graph_t* g);
+
 /* ------------------------------------------------------------------------------------------------
  * M2  native inference executor: SPVUnet.forward (models/spvd.py:432-457, eval mode) as one call.
  * The host compiles the module tree once into spvd_op_t records whose operands are byte offsets

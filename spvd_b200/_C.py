@@ -55,6 +55,11 @@ SIGNATURES = {
     "spvd_segmented_unique": (_i, [_p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "spvd_ddpm_step": (_i, [_p, _p, _p, _f, _f, _f, _i, _i, _i, _f, _p, _p, _p, _p, _p]),
     "spvd_plan_build": (_i, [_p, _i, _i, _i, _f, _f, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "spvd_plan_build_groups": (_i, [_p, _i, _i, _i, _f, _f, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _i, _p, _p, _sz,
+                                    _p, _p]),
+    "spvd_plan_graph_create": (_i, [_i, _i, _i, _f, _f, _i, _i, _p, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _i, _p, _sz, _p]),
+    "spvd_plan_graph_launch": (_i, [_p, _p, _p, _p, _p]),
+    "spvd_plan_graph_destroy": (None, [_p]),
     "spvd_plan_build_range": (_i, [_p, _i, _i, _i, _f, _f, _i, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p, _sz, _p]),
 }
 

@@ -133,3 +133,103 @@ extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, int m
                                n_levels, 0, n_levels, ld, fcoords, icoords, status, summary_dev, summary_host, summary_count, 1,
                                workspace, workspace_bytes, stream);
 }
+
+// Level groups [bounds[g], bounds[g+1]) planned with ONE host call and no host wait: group 0 on `stream`, the others on
+// `side_stream` behind group 0; events[g] (cudaEvent_t) is recorded after group g's summary copy into summary_hosts[g].
+extern "C" int spvd_plan_build_groups(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res,
+                                      float after_res, int scale_mode, int downsample_mode, const spvd_plan_level_t* levels,
+                                      int n_levels, const int32_t* bounds, int n_groups, int ld, float* fcoords,
+                                      int32_t* icoords, int32_t* status, const int32_t* summary_dev,
+                                      int32_t* const* summary_hosts, int summary_count, void* const* events, void* workspace,
+                                      size_t workspace_bytes, spvd_stream_t stream, spvd_stream_t side_stream) {
+  SPVD_CHECK_ARG(bounds && summary_hosts && events && n_groups >= 1 && bounds[0] == 0 && bounds[n_groups] == n_levels,
+                 "spvd_plan_build_groups: bounds must run from 0 to n_levels");
+  for (int g = 0; g < n_groups; ++g) {
+    SPVD_CHECK_ARG(summary_hosts[g] && events[g], "spvd_plan_build_groups: group %d lacks a summary buffer / event", g);
+    spvd_stream_t st = g == 0 ? stream : side_stream;
+    SPVD_TRY(spvd_plan_build_range(pc, n_points, n_batch, max_cloud_rows, init_res, after_res, scale_mode, downsample_mode,
+                                   levels, n_levels, bounds[g], bounds[g + 1], ld, fcoords, icoords, status, summary_dev,
+                                   summary_hosts[g], summary_count, 0, workspace, workspace_bytes, st));
+    SPVD_CUDA(cudaEventRecord((cudaEvent_t)events[g], (cudaStream_t)st));
+    if (g == 0 && n_groups > 1) SPVD_CUDA(cudaStreamWaitEvent((cudaStream_t)side_stream, (cudaEvent_t)events[0], 0));
+  }
+  return SPVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The planner as CUDA graphs: its launch sequence depends only on capacities (every grid is sized by n_points, the row
+// counts stay on the device), so one capture per workspace replaces ~65 launches by one graph launch per level group.
+// ------------------------------------------------------------------------------------------------
+struct spvd_plan_graph {
+  int n_groups = 0;
+  size_t pc_bytes = 0;
+  float* pc_stage = nullptr;
+  cudaGraphExec_t exec[8] = {};
+  cudaStream_t capture = nullptr;
+};
+
+extern "C" void spvd_plan_graph_destroy(spvd_plan_graph* g) {
+  if (!g) return;
+  for (int i = 0; i < g->n_groups; ++i)
+    if (g->exec[i]) cudaGraphExecDestroy(g->exec[i]);
+  if (g->capture) cudaStreamDestroy(g->capture);
+  delete g;
+}
+
+extern "C" int spvd_plan_graph_create(int n_points, int n_batch, int max_cloud_rows, float init_res, float after_res,
+                                      int scale_mode, int downsample_mode, const spvd_plan_level_t* levels, int n_levels,
+                                      const int32_t* bounds, int n_groups, int ld, float* pc_stage, float* fcoords,
+                                      int32_t* icoords, int32_t* status, const int32_t* summary_dev,
+                                      int32_t* const* summary_hosts, int summary_count, void* workspace,
+                                      size_t workspace_bytes, spvd_plan_graph** out) {
+  SPVD_CHECK_ARG(out && pc_stage && bounds && summary_hosts && n_groups >= 1 && n_groups <= 8 && bounds[0] == 0 &&
+                     bounds[n_groups] == n_levels,
+                 "spvd_plan_graph_create: bad arguments (1..8 groups, bounds from 0 to n_levels)");
+  *out = nullptr;
+  spvd_plan_graph* g = new spvd_plan_graph();
+  g->pc_stage = pc_stage;
+  g->pc_bytes = (size_t)n_points * 4 * sizeof(float);
+  cudaError_t e = cudaStreamCreateWithFlags(&g->capture, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    set_error("spvd_plan_graph_create: cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    delete g;
+    return SPVD_ERR_CUDA;
+  }
+  for (int i = 0; i < n_groups; ++i) {
+    e = cudaStreamBeginCapture(g->capture, cudaStreamCaptureModeRelaxed);
+    int rc = SPVD_OK;
+    if (e == cudaSuccess)
+      rc = spvd_plan_build_range(pc_stage, n_points, n_batch, max_cloud_rows, init_res, after_res, scale_mode, downsample_mode,
+                                 levels, n_levels, bounds[i], bounds[i + 1], ld, fcoords, icoords, status, summary_dev,
+                                 summary_hosts[i], summary_count, 0, workspace, workspace_bytes, (spvd_stream_t)g->capture);
+    cudaGraph_t graph = nullptr;
+    cudaError_t e2 = e == cudaSuccess ? cudaStreamEndCapture(g->capture, &graph) : e;
+    if (rc == SPVD_OK && e2 == cudaSuccess) e2 = cudaGraphInstantiate(&g->exec[i], graph, 0);
+    if (graph) cudaGraphDestroy(graph);
+    g->n_groups = i + 1;
+    if (rc != SPVD_OK || e2 != cudaSuccess) {
+      if (rc == SPVD_OK) set_error("spvd_plan_graph_create: capture of level group %d failed: %s", i, cudaGetErrorString(e2));
+      cudaGetLastError();
+      spvd_plan_graph_destroy(g);
+      return rc != SPVD_OK ? rc : SPVD_ERR_CUDA;
+    }
+  }
+  *out = g;
+  return SPVD_OK;
+}
+
+// group 0 on `stream`, the others on `side_stream` behind it; events[i] (cudaEvent_t) is recorded after group i
+extern "C" int spvd_plan_graph_launch(spvd_plan_graph* g, const float* pc, void* const* events, spvd_stream_t stream,
+                                      spvd_stream_t side_stream) {
+  SPVD_CHECK_ARG(g && pc && events, "spvd_plan_graph_launch: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream, side = (cudaStream_t)side_stream;
+  SPVD_CUDA(cudaMemcpyAsync(g->pc_stage, pc, g->pc_bytes, cudaMemcpyDeviceToDevice, s));
+  for (int i = 0; i < g->n_groups; ++i) {
+    SPVD_CHECK_ARG(events[i], "spvd_plan_graph_launch: group %d has no event", i);
+    cudaStream_t st = i == 0 ? s : side;
+    SPVD_CUDA(cudaGraphLaunch(g->exec[i], st));
+    SPVD_CUDA(cudaEventRecord((cudaEvent_t)events[i], st));
+    if (i == 0 && g->n_groups > 1) SPVD_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)events[0], 0));
+  }
+  return SPVD_OK;
+}

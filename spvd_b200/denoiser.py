@@ -179,7 +179,9 @@ class SPVUnet(nn.Module):
         self.use_executor = True
         self._plan_ws = {}           # (n_points, n_batch, device) -> [PlanWorkspace pool, cursor]
         self.geometry_pool = 2
-        self.plan_split_level = int(os.environ.get("SPVD_PLAN_SPLIT", "2"))   # levels the executor waits for before it starts
+        # level groups of the executor's planning: it waits for the first group only, the others are planned under the
+        # ops of the finer levels ("1,2" = level 0 | level 1 | the rest; "0" = plan everything up front)
+        self.plan_split_level = tuple(int(v) for v in os.environ.get("SPVD_PLAN_SPLIT", "1,3").split(","))
         self._side_streams = {}
 
     # -- static description of which strides need which maps (so Geometry can build all of them up front)
@@ -283,7 +285,7 @@ class SPVUnet(nn.Module):
         return x
 
     # -- forward -------------------------------------------------------------------------------
-    def plan_geometry(self, coords: torch.Tensor, n_batch: int, max_cloud_rows: int = 0, split_level: int = 0) -> Geometry:
+    def plan_geometry(self, coords: torch.Tensor, n_batch: int, max_cloud_rows: int = 0, split_level=0) -> Geometry:
         """Plan every coordinate structure of the forward with one C call into persistent buffers.  Two
         buffer sets alternate, so the geometry of the previous call stays valid while the next one is
         planned (``geometry_pool`` > 2 keeps more alive, e.g. when several forwards precede one backward)."""
@@ -300,7 +302,7 @@ class SPVUnet(nn.Module):
             pool[1] = (pool[1] + 1) % len(pool[0])
             ws = pool[0][pool[1]]
         side = None
-        if split_level:
+        if split_level and split_level != (0,):
             side = self._side_streams.get(pc.device)
             if side is None:
                 side = self._side_streams[pc.device] = torch.cuda.Stream(device=pc.device, priority=-1)

@@ -137,13 +137,15 @@ class Geometry:
                 l.kmap_up = KernelMap(mu, ku, l.n, c.n, 8, flip=False)
                 l.kmap_down.grad, l.kmap_up.grad = l.kmap_up, l.kmap_down
 
-    _pending = None          # set by PlanWorkspace.build(split_level=...): finishes planning the coarser levels
+    _pending = None          # PlanWorkspace.build(split_level=...): [collect the next group of coarser levels, ...]
 
-    def finish(self):
-        """Wait for (and collect) the levels that are still being planned on the side stream."""
-        f, self._pending = self._pending, None
-        if f is not None:
-            f()
+    def finish(self, upto=None):
+        """Wait for (and collect) level groups that are still being planned on the side stream: all of them, or just
+        enough to have ``upto`` levels."""
+        while self._pending and (upto is None or len(self.levels) < upto):
+            self._pending.pop(0)()
+        if not self._pending:
+            self._pending = None
         return self
 
     @property
@@ -196,6 +198,8 @@ class Geometry:
 # One-call planner (spvd_plan_build): persistent buffers + a single C call per forward
 # --------------------------------------------------------------------------------------------------
 import ctypes as _C
+import os
+import time
 
 from ._C import check as _check, lib as _lib
 
@@ -233,8 +237,13 @@ class PlanWorkspace:
         self.n_summary = nl + 1 + nl * n_batch + 4 * nl      # level counts | status | per-cloud counts | (pair tiles, pairs) x2
         self.summary = torch.zeros(self.n_summary, **i32)
         self.summary_host = torch.zeros(self.n_summary, dtype=torch.int32).pin_memory()
-        self.summary_host_b = torch.zeros(self.n_summary, dtype=torch.int32).pin_memory()   # coarse levels of a split build
-        self.fine_done = torch.cuda.Event()
+        # one host copy of the summary per level group of a split build
+        self.summary_hosts = [self.summary_host] + [torch.zeros(self.n_summary, dtype=torch.int32).pin_memory() for _ in range(nl - 1)]
+        self._graphs, self.pc_stage = {}, None
+        self.use_graphs = os.environ.get("SPVD_PLAN_GRAPH", "1") != "0"
+        self.group_done = [torch.cuda.Event() for _ in range(nl)]
+        self._events_live = False
+        self.trace = None            # list -> build() appends (label, perf_counter) marks (tools/step_breakdown.py)
         self.ws = torch.empty(max(_lib.spvd_unique_workspace_bytes(n_points), 256), dtype=torch.uint8, device=device)
         self.c_levels = (_PlanLevel * nl)()
         self.bufs = []
@@ -285,44 +294,89 @@ class PlanWorkspace:
               side_stream=None):
         """max_cloud_rows > 0: the points are batch-major with at most that many per cloud (what torch2sparse
         produces) -> per-cloud shared-memory sorts; 0: no assumption (global radix sort).
-        split_level = k > 0 with a side_stream: only the k finest levels are planned (and waited for) here; the coarser
-        ones are planned on side_stream while the caller already works on the fine ones, and ``Geometry.finish()`` (or
-        the first access to a coarser level) collects them."""
+        split_level = k > 0 (or increasing cuts (k0, k1, ..)) with a side_stream: only the k finest levels are planned
+        (and waited for) here; the coarser groups are planned on side_stream while the caller already works on the fine
+        ones, and ``Geometry.finish()`` (or the first access to a coarser level) collects them."""
         if not pc.is_cuda or pc.dtype != torch.float32 or not pc.is_contiguous() or pc.shape != (self.n_points, 4):
             raise RuntimeError("PlanWorkspace.build needs a contiguous CUDA float32 [n_points,4] tensor")
         nl = len(self.strides)
-
-        def launch(lo, hi, sync, stream, host=self.summary_host):
-            _check(_lib.spvd_plan_build_range(
-                _C.c_void_p(pc.data_ptr()), self.n_points, self.n_batch, int(max_cloud_rows), pres, voxel_size,
-                ops._SCALE[scale_mode], ops._DOWNSAMPLE[downsample_mode], self.c_levels, nl, lo, hi, self.ld,
-                _C.c_void_p(self.fcoords.data_ptr()), _C.c_void_p(self.icoords.data_ptr()), _C.c_void_p(self.status.data_ptr()),
-                _C.c_void_p(self.summary.data_ptr()), _C.c_void_p(host.data_ptr()), self.n_summary, int(sync),
-                _C.c_void_p(self.ws.data_ptr()), self.ws.numel(), _C.c_void_p(stream.cuda_stream)))
 
         ops.stats.launches += self.n_kernels if not max_cloud_rows else self.n_kernels - 20 * nl
         geo = Geometry.__new__(Geometry)
         geo.n_points, geo.mode, geo.status = self.n_points, downsample_mode, self.status
         geo.fcoords, geo.levels, geo.p2v, geo.devox = self.fcoords, {}, {}, {}
         cur = torch.cuda.current_stream()
-        if not split_level or split_level >= nl or side_stream is None:
-            launch(0, nl, True, cur)
-            self._collect(geo, 0, nl)
-            return geo
-        # everything is enqueued before the host waits: fine levels on the current stream, then the coarse levels on the
-        # side stream behind an event, so the GPU never waits for the host to issue them
-        launch(0, split_level, False, cur)
-        self.fine_done.record(cur)
-        side_stream.wait_event(self.fine_done)
-        launch(split_level, nl, False, side_stream, self.summary_host_b)
-        self.fine_done.synchronize()
-        self._collect(geo, 0, split_level)
-
-        def finish():
-            side_stream.synchronize()
-            self._collect(geo, split_level, nl, self.summary_host_b)
-        geo._pending = finish
+        cuts = (split_level,) if isinstance(split_level, int) else tuple(split_level)
+        cuts = sorted({c for c in cuts if 0 < c < nl}) if side_stream is not None else []
+        # level groups [0,c0) [c0,c1) ... : one C call enqueues everything before the host waits -- the finest group on
+        # the current stream, the others on the side stream behind an event -- so the GPU never waits for the host
+        bounds = [0] + cuts + [nl]
+        ng = len(bounds) - 1
+        if not self._events_live:
+            for e in self.group_done:
+                e.record(cur)                                   # materialises the cudaEvent_t handles
+            self._events_live = True
+        c_events = (_C.c_void_p * ng)(*[e.cuda_event for e in self.group_done[:ng]])
+        side = side_stream.cuda_stream if side_stream is not None else cur.cuda_stream
+        key = (int(max_cloud_rows), float(pres), float(voxel_size), scale_mode, downsample_mode, tuple(bounds))
+        graph = self._graphs.get(key) if self.use_graphs else None
+        if graph is None and self.use_graphs and key not in self._graphs:
+            graph = self._graphs[key] = self._capture(key)
+        if graph is not None:
+            _check(_lib.spvd_plan_graph_launch(graph, pc.data_ptr(), c_events, cur.cuda_stream, side))
+        else:
+            c_bounds = (_C.c_int32 * (ng + 1))(*bounds)
+            c_hosts = (_C.c_void_p * ng)(*[h.data_ptr() for h in self.summary_hosts[:ng]])
+            _check(_lib.spvd_plan_build_groups(
+                pc.data_ptr(), self.n_points, self.n_batch, int(max_cloud_rows), pres, voxel_size, ops._SCALE[scale_mode],
+                ops._DOWNSAMPLE[downsample_mode], self.c_levels, nl, c_bounds, ng, self.ld, self.fcoords.data_ptr(),
+                self.icoords.data_ptr(), self.status.data_ptr(), self.summary.data_ptr(), c_hosts, self.n_summary, c_events,
+                self.ws.data_ptr(), self.ws.numel(), cur.cuda_stream, side))
+        if self.trace is not None:
+            self.trace.append(("plan enqueued", time.perf_counter()))
+        pending = []
+        for g in range(1, ng):
+            def collect(g=g, lo=bounds[g], hi=bounds[g + 1]):
+                self.group_done[g].synchronize()
+                self._collect(geo, lo, hi, self.summary_hosts[g])
+            pending.append(collect)
+        self.group_done[0].synchronize()
+        if self.trace is not None:
+            self.trace.append(("finest group done", time.perf_counter()))
+        self._collect(geo, 0, bounds[1])
+        if self.trace is not None:
+            self.trace.append(("finest group collected", time.perf_counter()))
+        geo._pending = pending or None
         return geo
+
+    def _capture(self, key):
+        """The planner for one (mode, level grouping) as CUDA graphs (spvd_plan_graph_create); None if capture fails."""
+        max_cloud_rows, pres, voxel_size, scale_mode, downsample_mode, bounds = key
+        ng, nl = len(bounds) - 1, len(self.strides)
+        if self.pc_stage is None:
+            self.pc_stage = torch.empty((self.n_points, 4), dtype=torch.float32, device=self.fcoords.device)
+        c_bounds = (_C.c_int32 * (ng + 1))(*bounds)
+        c_hosts = (_C.c_void_p * ng)(*[h.data_ptr() for h in self.summary_hosts[:ng]])
+        handle = _C.c_void_p()
+        torch.cuda.synchronize()
+        rc = _lib.spvd_plan_graph_create(self.n_points, self.n_batch, max_cloud_rows, pres, voxel_size, ops._SCALE[scale_mode],
+                                         ops._DOWNSAMPLE[downsample_mode], self.c_levels, nl, c_bounds, ng, self.ld,
+                                         self.pc_stage.data_ptr(), self.fcoords.data_ptr(), self.icoords.data_ptr(),
+                                         self.status.data_ptr(), self.summary.data_ptr(), c_hosts, self.n_summary,
+                                         self.ws.data_ptr(), self.ws.numel(), _C.byref(handle))
+        if rc != 0:
+            import warnings
+            warnings.warn("spvd_b200: planner graph capture failed (" + _lib.spvd_last_error().decode() + "); launching directly")
+            return None
+        return handle
+
+    def __del__(self):
+        for g in getattr(self, "_graphs", {}).values():
+            if g is not None:
+                try:
+                    _lib.spvd_plan_graph_destroy(g)
+                except Exception:
+                    pass
 
     def _collect(self, geo, lo, hi, summary=None):
         downsample_mode = geo.mode

@@ -379,18 +379,19 @@ class Program:
                                        stream))
 
         n, k = len(self.recs), 0
-        if geo._pending is not None:
+        while geo._pending is not None:
             # the finest levels are planned: run the ops that touch only those while the coarser ones are still being
-            # planned on the side stream, then collect them and run the rest
+            # planned on the side stream, then collect the next group of levels and go on
             ready = geo.levels_ready
-            k = next((i for i, l in enumerate(self.op_max_level) if l >= ready), n)
+            k2 = next((i for i, l in enumerate(self.op_max_level) if l >= ready), n)
             self.fill_levels(geo, upto=ready)
-            launch(0, k)
+            launch(k, k2)
+            k = k2
             if self.trace is not None:
-                self.trace.append(("part1 launched", time.perf_counter()))
-            geo.finish()
+                self.trace.append((f"ops on {ready} levels launched", time.perf_counter()))
+            geo.finish(upto=ready + 1)
             if self.trace is not None:
-                self.trace.append(("coarse levels collected", time.perf_counter()))
+                self.trace.append((f"{geo.levels_ready} levels collected", time.perf_counter()))
         self.fill_levels(geo)
         launch(k, n)
         if self.trace is not None:

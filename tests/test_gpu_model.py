@@ -124,18 +124,19 @@ def test_split_planning_matches_one_shot_planning(sp):
     x = sp.SparseTensor(feats.cuda(), coords.cuda())
     outs, geos = {}, {}
     with torch.no_grad():
-        for split in (0, 1, 2, 3):
+        for split in (0, 1, 2, 3, (1, 2), (1, 3, 4)):
             m.plan_split_level = split
             for _ in range(2):                      # twice: the second call reuses the other workspace of the pool
                 outs[split] = m((x, t)).cpu()
             geo = m.plan_geometry(coords.cuda().float(), 4, 0, split)
-            assert (geo._pending is not None) == (split > 0) and geo.levels_ready == (split or 5)
+            first = split[0] if isinstance(split, tuple) else split
+            assert (geo._pending is not None) == (first > 0) and geo.levels_ready == (first or 5)
             geo.finish()
             geos[split] = {s: (lv.n, lv.coords.cpu(), lv.kmap3.map_t[:, :lv.n].cpu(),
                                None if lv.kmap_down is None else lv.kmap_down.map_t[:, :lv.kmap_down.n_out].cpu(),
                                getattr(lv, "dpairs", (0,) * 5)[3:])
                            for s, lv in geo.levels.items()}
-    for split in (1, 2, 3):
+    for split in (1, 2, 3, (1, 2), (1, 3, 4)):
         assert rel_err(outs[split].numpy(), outs[0].numpy()) < 5e-4      # run-to-run (atomics order + TF32 flips) is ~1e-4
         for s, ref in geos[0].items():
             got = geos[split][s]

@@ -24,7 +24,12 @@ with torch.no_grad():
         st = sched.torch2sparse(xs[j], shape)
         tb = torch.full((32,), ts[j], device=dev, dtype=torch.long)
         e1.record()
+        for pool in model._plan_ws.values():
+            for w in pool[0]:
+                w.trace = []
+        cg = time.perf_counter()
         geo = model.plan_geometry(st.coords_float, 32, st.points_per_cloud, model.plan_split_level)
+        gtrace = [(k, round((v - cg) * 1e3, 3)) for pool in model._plan_ws.values() for w in pool[0] for k, v in (w.trace or [])]
         c1 = time.perf_counter(); e2.record()
         for p in model._programs.values():
             p.trace = [("geometry returned", c1)]
@@ -35,6 +40,7 @@ with torch.no_grad():
         torch.cuda.synchronize(); c3 = time.perf_counter()
         if j >= W:
             rows.append((e0.elapsed_time(e1), e1.elapsed_time(e2), e2.elapsed_time(e3), (c1 - c0) * 1e3, (c2 - c1) * 1e3, (c3 - c0) * 1e3))
+print("last step, ms after plan_geometry was entered:", gtrace)
 for p in model._programs.values():
     print("last step, ms after the geometry call returned:", [(k, round((v - p.trace[0][1]) * 1e3, 3)) for k, v in p.trace[1:]])
 import statistics
