@@ -195,7 +195,19 @@ int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, in
  * a_is_tf32 != 0 promises that `in` is already TF32-representable (spvd_round_tf32, or a producer
  * that rounds, e.g. spvd_bn_silu_fwd with act & 2): the gather then runs as cp.async with kStages
  * slabs in flight instead of through registers with cvt.rna;
- * mt = 128-row output tiles per CTA sharing each weight tile (1 or 2; 0 = choose; 2 needs a_is_tf32). */
+ * mt = 128-row output tiles per CTA sharing each weight tile (1 or 2; 0 = choose; 2 needs a_is_tf32).
+ *
+ * f16 operands (a_is_tf32 = SPVD_A_F32_TO_F16 or SPVD_A_F16): same tiles with A and B in IEEE half -- an 11-bit
+ * significand, i.e. TF32's precision, fp32 accumulation -- on tcgen05.mma.kind::f16: twice the TF32 issue rate and 64
+ * input channels per 128-byte slab, so half the iterations and half the operand bytes.  w_packed must then be the
+ * spvd_conv_pack_weights_f16 image; `in` is fp32 (converted on the fly, clamped to the finite half range) for
+ * SPVD_A_F32_TO_F16, or an f16 [rows, cin] tensor (a producer with act & 4) for SPVD_A_F16; mt is ignored. */
+#define SPVD_A_F32 0        /* fp32 rows, rounded to TF32 while gathered          */
+#define SPVD_A_TF32 1       /* fp32 rows that are already TF32-representable      */
+#define SPVD_A_F32_TO_F16 2 /* fp32 rows, converted to f16 while gathered         */
+#define SPVD_A_F16 3        /* f16 rows                                           */
+size_t spvd_conv_packed_weight_count_f16(int kvol, int cin, int cout); /* in halves */
+int spvd_conv_pack_weights_f16(const float* w, int kvol, int cin, int cout, void* w_packed, spvd_stream_t stream);
 int spvd_conv_fwd_umma(const float* in, const float* w_packed, const int32_t* map_t, int ld,
                        const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
                        const float* bias, const float* residual, float* out, int bn, int nsplit,
@@ -383,6 +395,8 @@ void spvd_plan_graph_destroy(spvd_plan_graph_t* g);
 #define SPVD_FLAG_ROUND 2  /* producer rounds its output to TF32                                    */
 #define SPVD_FLAG_A_TF32 4 /* CONV: src0 is TF32-representable (cp.async gather)                   */
 #define SPVD_FLAG_SIMT 8   /* CONV: force the fp32 SIMT kernel                                     */
+#define SPVD_FLAG_F16 16   /* CONV: f16 operands (w_packed = f16 image; with A_TF32: src0 is f16);
+                              AFFINE / FILM_AFFINE / LAYERNORM / ATTENTION: write dst as f16       */
 
 typedef struct spvd_level_geom {
   const int32_t* coords; /* [n,4] */

@@ -48,6 +48,20 @@ static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b)
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
+// two floats -> packed f16x2 (round to nearest even, clamped to the largest finite half: no infinities reach the MMA);
+// the low half is `lo`
+__device__ __forceinline__ uint32_t pack_half2_sat(float lo, float hi) {
+  lo = fminf(fmaxf(lo, -65504.f), 65504.f);
+  hi = fminf(fmaxf(hi, -65504.f), 65504.f);
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+// float4 number t of a row-major tensor stored as f16: 8 bytes at half offset 4*t
+__device__ __forceinline__ void store_half4(void* y, long long t, float4 v) {
+  reinterpret_cast<uint2*>(y)[t] = make_uint2(pack_half2_sat(v.x, v.y), pack_half2_sat(v.z, v.w));
+}
+
 template <typename... KArgs, typename... Args>
 static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s,
                                      Args... args) {

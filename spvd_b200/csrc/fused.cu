@@ -13,7 +13,7 @@ __device__ __forceinline__ float rna_tf32(float x) {
   return __uint_as_float(r);
 }
 
-// y = act(x * scale[c] + shift[c]);  act bit 0: SiLU, bit 1: round the result to TF32 (rna)
+// y = act(x * scale[c] + shift[c]);  act bit 0: SiLU, bit 1: round the result to TF32 (rna), bit 2: store y as f16
 __global__ void k_affine_act4(const float4* __restrict__ x, const float4* __restrict__ scale,
                               const float4* __restrict__ shift, long long total4, int c4, int act,
                               float4* __restrict__ y) {
@@ -32,6 +32,10 @@ __global__ void k_affine_act4(const float4* __restrict__ x, const float4* __rest
     v.y = silu(v.y);
     v.z = silu(v.z);
     v.w = silu(v.w);
+  }
+  if (act & 4) {
+    store_half4(y, t, v);
+    return;
   }
   if (act & 2) {
     v.x = rna_tf32(v.x);
@@ -103,6 +107,7 @@ extern "C" int spvd_bn_silu_fwd(const float* x, const float* scale, const float*
   if (rows == 0) return SPVD_OK;
   cudaStream_t s = (cudaStream_t)stream;
   bool v4 = c % 4 == 0 && (((size_t)x | (size_t)y | (size_t)scale | (size_t)shift) & 15) == 0;
+  SPVD_CHECK_ARG(v4 || !(act & 4), "spvd_bn_silu_fwd: f16 output needs c %% 4 == 0 and 16-byte aligned pointers");
   if (v4)
     SPVD_CUDA(launch_pdl(k_affine_act4, dim3(cdiv(rows * (c / 4), 256)), dim3(256), 0, s, (const float4*)x,
                          (const float4*)scale, (const float4*)shift, rows * (c / 4), c / 4, act, (float4*)y));

@@ -7,6 +7,7 @@
 // BatchNorm+SiLU (models/modules/graph.py:35-41 + models/ddpm_unet_attn.py:57), channel concat.
 #include <math.h>
 
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace spvd {
@@ -38,6 +39,10 @@ __global__ void k_film_affine4(const float4* __restrict__ x, const float* __rest
   v.w = fmaf(fmaf(1.f + sc.w, v.w, sh.w), s.w, o.w);
   if (act & 1) {
     v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+  }
+  if (act & 4) {
+    store_half4(y, t, v);
+    return;
   }
   if (act & 2) {
     v.x = rna_tf32_f(v.x); v.y = rna_tf32_f(v.y); v.z = rna_tf32_f(v.z); v.w = rna_tf32_f(v.w);
@@ -80,7 +85,8 @@ __global__ void k_layernorm(const float* __restrict__ x, const float* __restrict
   float rstd = rsqrtf(v / c + eps);
   for (int i = lane; i < c; i += 32) {
     float r = (xr[i] - mean) * rstd * gamma[i] + beta[i];
-    y[(size_t)row * c + i] = (act & 2) ? rna_tf32_f(r) : r;
+    if (act & 4) reinterpret_cast<__half*>(y)[(size_t)row * c + i] = __float2half_rn(fminf(fmaxf(r, -65504.f), 65504.f));
+    else y[(size_t)row * c + i] = (act & 2) ? rna_tf32_f(r) : r;
   }
 }
 
@@ -171,6 +177,10 @@ __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ qkv
 #pragma unroll
     for (int i = 0; i < D / 4; ++i) {
       float4 o = make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
+      if (act & 4) {
+        store_half4(out, ((long long)(r0 + qi) * C + h * D) / 4 + i, o);
+        continue;
+      }
       if (act & 2) {
         o.x = rna_tf32_f(o.x); o.y = rna_tf32_f(o.y); o.z = rna_tf32_f(o.z); o.w = rna_tf32_f(o.w);
       }
@@ -366,20 +376,23 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
           SPVD_CHECK_ARG(map, "op %d: level %d lacks kernel map kind %d", i, o.level, o.map_kind);
         }
         if (conv_events) SPVD_CUDA(cudaEventRecord((cudaEvent_t)conv_events[2 * conv_index], (cudaStream_t)stream));
+        // operand mode of the tcgen05 kernels: TF32 or f16 weights image, src0 pre-converted by its producer or not
+        const int a_mode = (o.flags & SPVD_FLAG_F16) ? ((o.flags & SPVD_FLAG_A_TF32) ? SPVD_A_F16 : SPVD_A_F32_TO_F16)
+                                                     : ((o.flags & SPVD_FLAG_A_TF32) ? SPVD_A_TF32 : SPVD_A_F32);
         if (o.w_packed && o.map_kind == SPVD_MAP_K3 && (o.flags & SPVD_FLAG_A_TF32) && !(o.flags & SPVD_FLAG_SIMT) &&
             lv->n_pair_tiles > 0 && lv->pair_in)
           rc = spvd_conv_fwd_pairs(at(o.src0), o.w_packed, lv->pair_in, lv->pair_out, lv->pair_tile_k, lv->n_pair_tiles,
-                                   o.kvol / 2, (int)rout, o.kvol, o.c0, o.c1, o.bias, at(o.src1), at(o.dst), 1, stream);
+                                   o.kvol / 2, (int)rout, o.kvol, o.c0, o.c1, o.bias, at(o.src1), at(o.dst), a_mode, stream);
         else if (o.w_packed && (o.map_kind == SPVD_MAP_DOWN || o.map_kind == SPVD_MAP_UP) && !(o.flags & SPVD_FLAG_SIMT) &&
                  lv->n_dpair_tiles > 0 && lv->dpair_in && !o.bias && o.src1 < 0)
           // stride-2 conv: (fine -> coarse) pairs; its transpose runs on the same lists with the roles swapped
           rc = spvd_conv_fwd_pairs(at(o.src0), o.w_packed, o.map_kind == SPVD_MAP_DOWN ? lv->dpair_in : lv->dpair_out,
                                    o.map_kind == SPVD_MAP_DOWN ? lv->dpair_out : lv->dpair_in, lv->dpair_tile_k,
                                    lv->n_dpair_tiles, -1, (int)rout, o.kvol, o.c0, o.c1, nullptr, nullptr, at(o.dst),
-                                   (o.flags & SPVD_FLAG_A_TF32) ? 1 : 0, stream);
+                                   a_mode, stream);
         else if (o.w_packed && !(o.flags & SPVD_FLAG_SIMT))
           rc = spvd_conv_fwd_umma(at(o.src0), o.w_packed, map, ld, mask, (int)rout, o.kvol, o.c0, o.c1, o.bias,
-                                  at(o.src1), at(o.dst), 0, 0, (o.flags & SPVD_FLAG_A_TF32) ? 1 : 0, 0, stream);
+                                  at(o.src1), at(o.dst), 0, 0, a_mode, 0, stream);
         else
           rc = spvd_conv_fwd_simt(at(o.src0), o.w, map, ld, mask, (int)rout, o.kvol, o.c0, o.c1, o.bias, at(o.src1),
                                   at(o.dst), stream);
@@ -388,22 +401,22 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
         break;
       }
       case SPVD_OP_AFFINE:
-        rc = spvd_bn_silu_fwd(at(o.src0), o.p0, o.p1, rin, o.c0, o.flags & 3, at(o.dst), stream);
+        rc = spvd_bn_silu_fwd(at(o.src0), o.p0, o.p1, rin, o.c0, (o.flags & 3) | ((o.flags & SPVD_FLAG_F16) ? 4 : 0), at(o.dst), stream);
         break;
       case SPVD_OP_FILM_AFFINE:
         SPVD_CHECK_ARG(lv, "op %d: FiLM without a level", i);
-        rc = spvd_film_affine_fwd(at(o.src0), at(o.src1) + o.i1, o.i0, lv->coords, o.p0, o.p1, rin, o.c0, o.flags & 3,
+        rc = spvd_film_affine_fwd(at(o.src0), at(o.src1) + o.i1, o.i0, lv->coords, o.p0, o.p1, rin, o.c0, (o.flags & 3) | ((o.flags & SPVD_FLAG_F16) ? 4 : 0),
                                   at(o.dst), stream);
         break;
       case SPVD_OP_CAT:
         rc = spvd_cat_fwd(at(o.src0), at(o.src1), rin, o.c0, o.c1, at(o.dst), stream);
         break;
       case SPVD_OP_LAYERNORM:
-        rc = spvd_layernorm_fwd(at(o.src0), o.p0, o.p1, (int)rin, o.c0, 1e-5f, o.flags & 3, at(o.dst), stream);
+        rc = spvd_layernorm_fwd(at(o.src0), o.p0, o.p1, (int)rin, o.c0, 1e-5f, (o.flags & 3) | ((o.flags & SPVD_FLAG_F16) ? 4 : 0), at(o.dst), stream);
         break;
       case SPVD_OP_ATTENTION:
         SPVD_CHECK_ARG(lv && lv->batch_offsets, "op %d: level %d has no per-cloud offsets", i, o.level);
-        rc = spvd_attention_fwd(at(o.src0), lv->batch_offsets, n_batch, lv->max_per_batch, o.c1, o.i0, o.flags & 3,
+        rc = spvd_attention_fwd(at(o.src0), lv->batch_offsets, n_batch, lv->max_per_batch, o.c1, o.i0, (o.flags & 3) | ((o.flags & SPVD_FLAG_F16) ? 4 : 0),
                                 at(o.dst), stream);
         break;
       case SPVD_OP_TIME_EMBED:

@@ -183,6 +183,9 @@ class SPVUnet(nn.Module):
         # ops of the finer levels ("1,2" = level 0 | level 1 | the rest; "0" = plan everything up front)
         self.plan_split_level = tuple(int(v) for v in os.environ.get("SPVD_PLAN_SPLIT", "1,3").split(","))
         self._side_streams = {}
+        # tensor-core operand format of the executor: "f16" = IEEE half operands (the 11-bit significand of TF32, fp32
+        # accumulation, twice the issue rate and half the operand bytes) or "tf32"; training always uses TF32
+        self.executor_operands = os.environ.get("SPVD_EXEC_OPERANDS", "f16")
 
     # -- static description of which strides need which maps (so Geometry can build all of them up front)
     @staticmethod
@@ -326,10 +329,10 @@ class SPVUnet(nn.Module):
                                                                        self.plan_split_level if executor else 0)
         if executor:
             from .runtime import Program
-            key = (feats.shape[0], t.shape[0])
+            key = (feats.shape[0], t.shape[0], self.executor_operands)
             prog = self._programs.get(key)
             if prog is None:
-                prog = self._programs[key] = Program(self, *key)
+                prog = self._programs[key] = Program(self, *key[:2])
             sink = getattr(self, "profile_sink", None)
             if sink is None:
                 return prog.run(geo, feats.contiguous().float(), t, cls=cls)

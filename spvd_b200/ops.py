@@ -244,6 +244,15 @@ def pack_weights(w3):
     return wp
 
 
+def pack_weights_f16(w3):
+    """w3 [kvol, cin, cout] -> f16 tensor-core tile image (cin padded to a multiple of 64)"""
+    _count("pack_weights")
+    kvol, cin, cout = w3.shape
+    wp = torch.empty(lib.spvd_conv_packed_weight_count_f16(kvol, cin, cout), dtype=torch.float16, device=w3.device)
+    check(lib.spvd_conv_pack_weights_f16(_p(w3, torch.float32), kvol, cin, cout, _p(wp), _s()))
+    return wp
+
+
 def transpose_weights(w3, flip):
     _count("transpose_weights")
     kvol, cin, cout = w3.shape
@@ -267,8 +276,12 @@ def conv_fwd(x, w3, w_packed, map_t, mask, n_out, bias=None, impl=CONV_AUTO, bn=
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
     if impl == CONV_UMMA or (impl == CONV_AUTO and w_packed is not None and umma_supported(kvol, cin, cout)):
-        check(lib.spvd_conv_fwd_umma(_p(x, torch.float32), _p(w_packed, torch.float32), _p(map_t), ld, _p(mask), n_out, kvol,
-                                     cin, cout, _p(bias), _p(residual), _p(out), int(bn), int(nsplit), int(bool(a_tf32)), int(mt), _s()))
+        # operand mode from the dtypes: f16 weight image -> f16 operands (x f16 or fp32 converted on the fly)
+        a_mode = ((3 if x.dtype == torch.float16 else 2) if w_packed.dtype == torch.float16 else int(bool(a_tf32)))
+        if x.dtype == torch.float16 and w_packed.dtype != torch.float16:
+            raise RuntimeError("an f16 input needs the f16 weight image (pack_weights_f16)")
+        check(lib.spvd_conv_fwd_umma(_p(x), _p(w_packed), _p(map_t), ld, _p(mask), n_out, kvol,
+                                     cin, cout, _p(bias), _p(residual), _p(out), int(bn), int(nsplit), a_mode, int(mt), _s()))
     else:
         check(lib.spvd_conv_fwd_simt(_p(x, torch.float32), _p(w3, torch.float32), _p(map_t), ld, _p(mask), n_out, kvol, cin,
                                      cout, _p(bias), _p(residual), _p(out), _s()))
@@ -301,9 +314,10 @@ def conv_fwd_pairs(x, w3, w_packed, pair_in, pair_out, tile_k, n_tiles, n_out, b
     kvol, cin, cout = w3.shape
     out = torch.empty((n_out, cout), dtype=torch.float32, device=x.device)
     center = (kvol // 2 if kvol % 2 else -1) if center is None else center
-    check(lib.spvd_conv_fwd_pairs(_p(x, torch.float32), _p(w_packed, torch.float32), _p(pair_in), _p(pair_out), _p(tile_k),
+    a_mode = ((3 if x.dtype == torch.float16 else 2) if w_packed.dtype == torch.float16 else int(bool(a_tf32)))
+    check(lib.spvd_conv_fwd_pairs(_p(x), _p(w_packed), _p(pair_in), _p(pair_out), _p(tile_k),
                                   int(n_tiles), center, n_out, kvol, cin, cout, _p(bias), _p(residual), _p(out),
-                                  int(bool(a_tf32)), _s()))
+                                  a_mode, _s()))
     return out
 
 

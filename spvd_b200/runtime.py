@@ -23,7 +23,7 @@ from .geometry import Geometry
 OP_SCATTER_MEAN, OP_DEVOX, OP_CONV, OP_AFFINE, OP_FILM_AFFINE, OP_CAT, OP_LAYERNORM, OP_ATTENTION, OP_TIME_EMBED = range(9)
 MAP_NONE, MAP_K3, MAP_DOWN, MAP_UP = range(4)
 ROWS_POINTS, ROWS_BATCH = -1, -2
-FLAG_SILU, FLAG_ROUND, FLAG_A_TF32, FLAG_SIMT = 1, 2, 4, 8
+FLAG_SILU, FLAG_ROUND, FLAG_A_TF32, FLAG_SIMT, FLAG_F16 = 1, 2, 4, 8, 16
 KERNELS_PER_OP = {OP_SCATTER_MEAN: 2, OP_DEVOX: 1, OP_CONV: 1, OP_AFFINE: 1, OP_FILM_AFFINE: 1, OP_CAT: 1,
                   OP_LAYERNORM: 1, OP_ATTENTION: 1, OP_TIME_EMBED: 1}
 
@@ -48,10 +48,10 @@ class Op(C.Structure):
 
 
 class _Reg:
-    __slots__ = ("rows", "ch", "offset", "last", "name")
+    __slots__ = ("rows", "ch", "offset", "last", "name", "half")
 
     def __init__(self, rows, ch, name=""):
-        self.rows, self.ch, self.offset, self.last, self.name = rows, ch, -1, -1, name
+        self.rows, self.ch, self.offset, self.last, self.name, self.half = rows, ch, -1, -1, name, False
 
 
 def _ptr(t):
@@ -68,6 +68,8 @@ class Program:
         self.recs = []            # dicts before register allocation
         self.regs = []
         self.strides = list(model._plan["strides"])
+        # tensor-core operands of the executor: "f16" (IEEE half, TF32's 11-bit significand, kind::f16) or "tf32"
+        self.f16 = getattr(model, "executor_operands", "f16") == "f16"
         self._emit()
         self._allocate()
         self._finalize()
@@ -87,7 +89,7 @@ class Program:
         w3 = self._hold(w3)
         wp = None
         if not force_simt and ops.umma_supported(*w3.shape):
-            wp = ops.pack_weights(w3)
+            wp = ops.pack_weights_f16(w3) if self.f16 else ops.pack_weights(w3)
             self.keep.append(wp)
         return w3, wp, (self._hold(bias) if bias is not None else None)
 
@@ -109,19 +111,32 @@ class Program:
         self.recs.append(dict(op=op, dst=dst, src0=src0, src1=src1, aux=aux, **kw))
         return dst
 
+    def _half(self, cin, cout, kvol=1):
+        """should the producer of a [.., cin] tensor write it as f16?  (its only consumer is that tensor-core conv)"""
+        return self.f16 and bool(ops.umma_supported(kvol, cin, cout))
+
     def conv(self, x, params, kvol, map_kind, level, rows_out, cout, residual=None, a_tf32=False):
         w3, wp, bias = params
-        flags = (FLAG_A_TF32 if (a_tf32 and wp is not None) else 0) | (FLAG_SIMT if wp is None else 0)
+        if x.half and wp is None:
+            raise RuntimeError("an f16 activation reached a convolution without a tensor-core path")
+        pre = x.half if self.f16 else a_tf32            # src0 already in the operand format of the tensor-core kernel
+        flags = (FLAG_A_TF32 if (pre and wp is not None) else 0) | (FLAG_SIMT if wp is None else 0) | \
+                (FLAG_F16 if (self.f16 and wp is not None) else 0)
         return self.op(OP_CONV, self.reg(rows_out, cout), x, residual, flags=flags, level=level, map_kind=map_kind,
                        rows_in=x.rows, rows_out=rows_out, c0=x.ch, c1=cout, kvol=kvol, w=w3, w_packed=wp, bias=bias)
 
     def linear(self, x, lin, residual=None, a_tf32=False):
         return self.conv(x, self._linear_params(lin), 1, MAP_NONE, -1, x.rows, lin.out_features, residual, a_tf32)
 
-    def affine(self, x, bn, silu=True, rnd=False):
+    def _fmt(self, rnd, half):
+        return FLAG_F16 if half else FLAG_ROUND if rnd else 0
+
+    def affine(self, x, bn, silu=True, rnd=False, half=False):
         s, b = self._bn(bn)
-        return self.op(OP_AFFINE, self.reg(x.rows, x.ch), x, flags=(FLAG_SILU if silu else 0) | (FLAG_ROUND if rnd else 0),
-                       level=-1, rows_in=x.rows, rows_out=x.rows, c0=x.ch, c1=x.ch, p0=s, p1=b)
+        y = self.op(OP_AFFINE, self.reg(x.rows, x.ch), x, flags=(FLAG_SILU if silu else 0) | self._fmt(rnd, half),
+                    level=-1, rows_in=x.rows, rows_out=x.rows, c0=x.ch, c1=x.ch, p0=s, p1=b)
+        y.half = half
+        return y
 
     def _umma_ok(self, lin_or_conv_in, cout):
         return lin_or_conv_in % 32 == 0 and cout % 32 == 0
@@ -129,27 +144,30 @@ class Program:
     def point_block(self, pb, z1, z):
         lin = pb.conv[2]
         rnd = self._umma_ok(lin.in_features, lin.out_features)
-        a = self.affine(z, pb.conv[0], True, rnd)
+        a = self.affine(z, pb.conv[0], True, rnd, rnd and self._half(lin.in_features, lin.out_features))
         return self.linear(a, lin, residual=z1, a_tf32=rnd)
 
     def res_block(self, blk, x, lvl):
         c1, c2 = blk.conv1[2], blk.conv2[2]
         nf = c1.out_channels
-        a1 = self.affine(x, blk.conv1[0], True, True)
+        a1 = self.affine(x, blk.conv1[0], True, True, self._half(x.ch, nf, 27))
         h1 = self.conv(a1, self._conv_params(c1.kernel, c1.bias), 27, MAP_K3, lvl, lvl, nf, a_tf32=True)
         s2, b2 = self._bn(blk.conv2[0])
         off = self.tt_offsets[id(blk)]
-        a2 = self.op(OP_FILM_AFFINE, self.reg(lvl, nf), h1, self.tt, flags=FLAG_SILU | FLAG_ROUND, level=lvl, rows_in=lvl,
-                     rows_out=lvl, c0=nf, c1=nf, i0=self.tt_width, i1=off, p0=s2, p1=b2)
+        a2 = self.op(OP_FILM_AFFINE, self.reg(lvl, nf), h1, self.tt, flags=FLAG_SILU | self._fmt(True, self._half(nf, nf, 27)),
+                     level=lvl, rows_in=lvl, rows_out=lvl, c0=nf, c1=nf, i0=self.tt_width, i1=off, p0=s2, p1=b2)
+        a2.half = self._half(nf, nf, 27)
         res = self.linear(x, blk.idconv) if hasattr(blk, "idconv") else x
         h2 = self.conv(a2, self._conv_params(c2.kernel, c2.bias), 27, MAP_K3, lvl, lvl, nf, residual=res, a_tf32=True)
         if hasattr(blk, "attn"):
             at = blk.attn
-            ln = self.op(OP_LAYERNORM, self.reg(lvl, nf), h2, flags=FLAG_ROUND, level=-1, rows_in=lvl, rows_out=lvl,
-                         c0=nf, c1=nf, p0=self._hold(at.norm1.weight), p1=self._hold(at.norm1.bias))
+            ln = self.op(OP_LAYERNORM, self.reg(lvl, nf), h2, flags=self._fmt(True, self._half(nf, 3 * nf)), level=-1,
+                         rows_in=lvl, rows_out=lvl, c0=nf, c1=nf, p0=self._hold(at.norm1.weight), p1=self._hold(at.norm1.bias))
+            ln.half = self._half(nf, 3 * nf)
             qkv = self.linear(ln, at.attn.qkv, a_tf32=True)
-            ao = self.op(OP_ATTENTION, self.reg(lvl, nf), qkv, flags=FLAG_ROUND, level=lvl, rows_in=lvl, rows_out=lvl,
-                         c0=3 * nf, c1=nf, i0=at.attn.num_heads)
+            ao = self.op(OP_ATTENTION, self.reg(lvl, nf), qkv, flags=self._fmt(True, self._half(nf, nf)), level=lvl,
+                         rows_in=lvl, rows_out=lvl, c0=3 * nf, c1=nf, i0=at.attn.num_heads)
+            ao.half = self._half(nf, nf)
             h2 = self.linear(ao, at.attn.proj, residual=h2, a_tf32=True)
             self.attn_levels.add(lvl)
         return h2
@@ -195,7 +213,7 @@ class Program:
         st = m.stem_conv
         c0, c3 = st.voxel_conv[0], st.voxel_conv[3]
         x = self.conv(x, self._conv_params(c0.kernel, c0.bias), 27, MAP_K3, 0, 0, c0.out_channels)
-        x = self.affine(x, st.voxel_conv[1], True, True)
+        x = self.affine(x, st.voxel_conv[1], True, True, self._half(c3.in_channels, c3.out_channels, 27))
         x = self.conv(x, self._conv_params(c3.kernel, c3.bias), 27, MAP_K3, 0, 0, c3.out_channels, a_tf32=True)
         z = self.point_block(st.point_conv, devox(x, 0), z)
         x = scatter(z, 0)

@@ -319,6 +319,23 @@ def test_conv_forward_tcgen05(sp, kind, cin, cout):
     assert rel_err(got, want.numpy()) < 1e-3                # BASELINE.json tolerance vs plain fp32
 
 
+@pytest.mark.parametrize("pre", [False, True])      # fp32 rows converted while gathered / rows already f16
+@pytest.mark.parametrize("kind,cin,cout", SHAPES + [("k3", 96, 64), ("k1", 32, 256), ("k3", 160, 128)])
+def test_conv_forward_tcgen05_f16_operands(sp, kind, cin, cout, pre):
+    """kind::f16 path: operands rounded to IEEE half (the significand of TF32), fp32 accumulation; 64-channel slabs with
+    a half-empty last slab when cin % 64 == 32"""
+    x, w, b, m, n_out, km, oo = _conv_case(sp, kind, cin, cout, 19)
+    want = oo.conv_gather_gemm_scatter(x, w, m, n_out, b)
+    want_f16 = oo.conv_gather_gemm_scatter(x.half().float(), w.half().float(), m, n_out, b)
+    wp = sp.ops.pack_weights_f16(w.cuda())
+    xd = x.cuda().half() if pre else x.cuda()
+    for nsplit in (0, 1, 5):
+        got = sp.ops.conv_fwd(xd, w.cuda(), wp, km.map_t if km is not None else None, km.mask if km is not None else None,
+                              n_out, b.cuda(), sp.ops.CONV_UMMA, nsplit=nsplit).cpu().numpy()
+        assert rel_err(got, want_f16.numpy()) < 2e-5        # same operand rounding as the emulation
+        assert rel_err(got, want.numpy()) < 1e-3            # BASELINE.json tolerance vs plain fp32
+
+
 @pytest.mark.parametrize("bn,cout", [(32, 384), (64, 384), (96, 384), (128, 384), (192, 384), (256, 256)])
 def test_conv_tcgen05_slice_widths(sp, bn, cout):
     x, w, b, m, n_out, km, oo = _conv_case(sp, "k3", 64, cout, 17)
@@ -394,6 +411,12 @@ def test_conv_pair_major(sp, stride, cin, cout):
     want = oo.conv_gather_gemm_scatter(x, w, m, n, b, emulate_tf32=True) + res
     y = sp.ops.conv_fwd_pairs(x.cuda(), w.cuda(), sp.ops.pack_weights(w.cuda()), pin, pout, tk, T, n, b.cuda(), res.cuda())
     assert rel_err(y.cpu().numpy(), want.numpy()) < 2e-5
+    # the same tiles with f16 operands (rows already f16, and fp32 rows converted while gathered)
+    want16 = oo.conv_gather_gemm_scatter(x.half().float(), w.half().float(), m, n, b) + res
+    wp16 = sp.ops.pack_weights_f16(w.cuda())
+    for xd in (x.cuda().half(), x.cuda()):
+        y16 = sp.ops.conv_fwd_pairs(xd, w.cuda(), wp16, pin, pout, tk, T, n, b.cuda(), res.cuda())
+        assert rel_err(y16.cpu().numpy(), want16.numpy()) < 2e-5
 
 
 @pytest.mark.parametrize("a_tf32", [True, False])
