@@ -429,6 +429,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
     const bool first = kPairs ? (active_k[0] == center_k) : (blockIdx.z == 0);
     const bool add_bias = bias != nullptr && first;
     const bool add_res = residual != nullptr && first;
+    const bool wide = ((reinterpret_cast<size_t>(out) | reinterpret_cast<size_t>(residual)) & 31) == 0;   // 256-bit accesses
 #pragma unroll 1
     for (int mt = 0; mt < MT; ++mt) {
       int row = m0 + mt * BM + warp * 32 + lane;
@@ -436,6 +437,19 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
         row = s_rows[BM + warp * 32 + lane];
         if (row < 0) row = n_out;   // padding pair: nothing to write
       }
+      // residual of the row, one 32-column chunk ahead of its use (the loads fly under tcgen05.ld and the stores)
+      const bool pre_res = add_res && !split && wide && row < n_out;
+      float q[32];
+      auto load_res = [&](int cb) {
+        const float* rp = residual + (size_t)row * cout + n0 + cb * 32;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("ld.global.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                       : "=f"(q[8 * j]), "=f"(q[8 * j + 1]), "=f"(q[8 * j + 2]), "=f"(q[8 * j + 3]), "=f"(q[8 * j + 4]),
+                         "=f"(q[8 * j + 5]), "=f"(q[8 * j + 6]), "=f"(q[8 * j + 7])
+                       : "l"(rp + 8 * j));
+      };
+      if (pre_res) load_res(0);
 #pragma unroll 1
       for (int cb = 0; cb < BN / 32; ++cb) {
         uint32_t r[32];
@@ -459,21 +473,44 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
         }
         if (row < n_out) {
           float* dstf = out + (size_t)row * cout + n0 + cb * 32;
-          const float4* bp = add_bias ? reinterpret_cast<const float4*>(bias + n0 + cb * 32) : nullptr;
+          const float* bp = add_bias ? bias + n0 + cb * 32 : nullptr;
+          const float* rp = add_res ? residual + (size_t)row * cout + n0 + cb * 32 : nullptr;
+          if (!split && wide) {
+            // one full 32-byte sector per lane and instruction (LDG/STG.256)
+            if (pre_res) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                   __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-            if (bp) {
-              float4 b = __ldg(bp + j);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              for (int e = 0; e < 32; ++e) r[e] = __float_as_uint(__uint_as_float(r[e]) + q[e]);
+              if (cb + 1 < BN / 32) load_res(cb + 1);
             }
-            if (add_res) {
-              float4 b = *reinterpret_cast<const float4*>(residual + (size_t)row * cout + n0 + cb * 32 + 4 * j);
-              o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float o[8];
+#pragma unroll
+              for (int e = 0; e < 8; ++e) o[e] = __uint_as_float(r[8 * j + e]);
+              if (bp) {
+                const float4 b0 = __ldg(reinterpret_cast<const float4*>(bp) + 2 * j), b1 = __ldg(reinterpret_cast<const float4*>(bp) + 2 * j + 1);
+                o[0] += b0.x; o[1] += b0.y; o[2] += b0.z; o[3] += b0.w; o[4] += b1.x; o[5] += b1.y; o[6] += b1.z; o[7] += b1.w;
+              }
+              asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dstf + 8 * j), "f"(o[0]), "f"(o[1]), "f"(o[2]),
+                           "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7])
+                           : "memory");
             }
-            if (split) red_add_v4(dstf + 4 * j, o);
-            else reinterpret_cast<float4*>(dstf)[j] = o;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float4 o = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                     __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+              if (bp) {
+                float4 b = __ldg(reinterpret_cast<const float4*>(bp) + j);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (rp) {
+                float4 b = *reinterpret_cast<const float4*>(rp + 4 * j);
+                o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+              }
+              if (split) red_add_v4(dstf + 4 * j, o);
+              else reinterpret_cast<float4*>(dstf)[j] = o;
+            }
           }
         }
       }

@@ -92,20 +92,25 @@ __global__ void k_layernorm(const float* __restrict__ x, const float* __restrict
 
 // Per-cloud multi-head attention over the voxels of one level.  qkv [rows, 3C] with channel layout
 // which*C + head*D + d (the reference's reshape(B,N,3,H,D)); rows of a cloud are contiguous
-// (batch-major voxel order).  One query per thread, keys/values staged in shared memory 128 at a
+// (batch-major voxel order).  Four lanes per query, keys/values staged in shared memory 128 at a
 // time, online softmax (the reference's exp(x)*mask/sum is the same function).
 template <int D>
 __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ qkv, const int* __restrict__ offsets,
                                                    int C, float scale, int act, float* __restrict__ out) {
+  // 32 queries per CTA, 4 lanes per query: lane s of a query visits the keys j = s (mod 4) and the four partial
+  // (max, sum, weighted values) states are merged with two shuffles at the end (the clouds are short -- a few hundred
+  // rows -- so one thread per query leaves most of the GPU idle)
   constexpr int KB = D <= 32 ? 128 : 64;   // static shared memory stays under 48 KB
+  constexpr int QB = 32, S = 4;
   __shared__ float4 Ks[KB][D / 4];
   __shared__ float4 Vs[KB][D / 4];
   pdl_trigger();
   pdl_wait();
   const int b = blockIdx.z, h = blockIdx.y;
   const int r0 = offsets[b], L = offsets[b + 1] - r0;
-  if ((int)blockIdx.x * 128 >= L) return;
-  const int qi = blockIdx.x * 128 + threadIdx.x;
+  if ((int)blockIdx.x * QB >= L) return;
+  const int slice = threadIdx.x & (S - 1);
+  const int qi = blockIdx.x * QB + (threadIdx.x >> 2);
   const bool valid = qi < L;
   float q[D], acc[D];
   {
@@ -129,16 +134,16 @@ __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ qkv
       Vs[j][i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(kp) + C)[i];
     }
     __syncthreads();
-    for (int j0 = 0; j0 < nk; j0 += 8) {
+    for (int j0 = slice; j0 < nk; j0 += 8 * S) {
       float s[8], mc = -INFINITY;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
         float d = -INFINITY;
-        if (j0 + jj < nk) {
+        if (j0 + jj * S < nk) {
           d = 0.f;
 #pragma unroll
           for (int i = 0; i < D / 4; ++i) {
-            float4 k4 = Ks[j0 + jj][i];
+            float4 k4 = Ks[j0 + jj * S][i];
             d = fmaf(q[4 * i], k4.x, d);
             d = fmaf(q[4 * i + 1], k4.y, d);
             d = fmaf(q[4 * i + 2], k4.z, d);
@@ -156,12 +161,12 @@ __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ qkv
       for (int i = 0; i < D; ++i) acc[i] *= alpha;
 #pragma unroll
       for (int jj = 0; jj < 8; ++jj) {
-        if (j0 + jj < nk) {
+        if (j0 + jj * S < nk) {
           float p = __expf(s[jj] - mn);
           l += p;
 #pragma unroll
           for (int i = 0; i < D / 4; ++i) {
-            float4 v4 = Vs[j0 + jj][i];
+            float4 v4 = Vs[j0 + jj * S][i];
             acc[4 * i] = fmaf(p, v4.x, acc[4 * i]);
             acc[4 * i + 1] = fmaf(p, v4.y, acc[4 * i + 1]);
             acc[4 * i + 2] = fmaf(p, v4.z, acc[4 * i + 2]);
@@ -171,11 +176,23 @@ __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ qkv
       }
     }
   }
+  // merge the four key slices of the query (a slice that saw no key has m = -inf, l = 0: weight 0)
+#pragma unroll
+  for (int o = 1; o < S; o <<= 1) {
+    const float m_o = __shfl_xor_sync(0xffffffffu, m, o), l_o = __shfl_xor_sync(0xffffffffu, l, o);
+    const float mn = fmaxf(m, m_o);
+    const float wa = m == -INFINITY ? 0.f : __expf(m - mn), wb = m_o == -INFINITY ? 0.f : __expf(m_o - mn);
+    l = l * wa + l_o * wb;
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = acc[i] * wa + __shfl_xor_sync(0xffffffffu, acc[i], o) * wb;
+    m = mn;
+  }
   if (valid) {
     float inv = 1.f / l;
     float4* op = reinterpret_cast<float4*>(out + (size_t)(r0 + qi) * C + h * D);
 #pragma unroll
     for (int i = 0; i < D / 4; ++i) {
+      if ((i & (S - 1)) != slice) continue;     // the four lanes hold the same result: each writes a quarter of it
       float4 o = make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
       if (act & 4) {
         store_half4(out, ((long long)(r0 + qi) * C + h * D) / 4 + i, o);
@@ -192,7 +209,7 @@ __global__ void __launch_bounds__(128) k_attention(const float* __restrict__ qkv
 template <int D>
 static void launch_attention(const float* qkv, const int* offsets, int C, int heads, int nb, int max_len, int act,
                              float* out, cudaStream_t s) {
-  dim3 grid(cdiv(max_len, 128), heads, nb);
+  dim3 grid(cdiv(max_len, 32), heads, nb);
   launch_pdl(k_attention<D>, grid, dim3(128), 0, s, qkv, offsets, C, 1.0f / sqrtf((float)D), act, out);
 }
 

@@ -24,16 +24,16 @@ def timeit(fn, reps=7):
         a.record(); fn(); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b) * 1e3)
     return min(ts)
-for s, cin, cout in [(4, 320, 192), (4, 192, 192), (4, 128, 128), (8, 192, 192), (8, 384, 192), (16, 448, 256), (16, 256, 256)]:
+for s, cin, cout in [(2, 128, 128), (2, 192, 128), (4, 320, 192), (4, 192, 192), (4, 128, 128), (8, 192, 192), (8, 384, 192), (16, 448, 256), (16, 256, 256)]:
     lv = geo.level(s); km = lv.kmap3
     w = torch.randn(27, cin, cout, device=dev) / (27 * cin) ** 0.5
-    wp = ops.pack_weights(w)
-    xin = ops.round_tf32(torch.randn(lv.n, cin, device=dev))
+    wp = ops.pack_weights_f16(w)
+    xin = torch.randn(lv.n, cin, device=dev).half()
     bias = torch.randn(cout, device=dev)
     out = []
     for bn in [b for b in (64, 96, 128, 192, 256) if cout % b == 0]:
-        for mt in (1, 2, 3):
-            for ns in (0, 1, 2, 3, 4, 8):
+        for mt in (3,):
+            for ns in (0, 1, 2, 3, 4, 6, 8, 12):
                 if bn * (2 if mt == 2 else 1) > 512: continue
                 try:
                     us = timeit(lambda: ops.conv_fwd(xin, w, wp, km.map_t, km.mask, lv.n, bias, ops.CONV_UMMA, bn=bn, nsplit=ns, a_tf32=True, mt=mt))
@@ -42,5 +42,5 @@ for s, cin, cout in [(4, 320, 192), (4, 192, 192), (4, 128, 128), (8, 192, 192),
                 out.append((us, bn, mt, ns))
     auto = timeit(lambda: ops.conv_fwd(xin, w, wp, km.map_t, km.mask, lv.n, bias, ops.CONV_UMMA, a_tf32=True))
     print(f"s={s} n={lv.n} tiles={(lv.n+127)//128} {cin}->{cout} auto={auto:.1f}")
-    for mt in (1, 2, 3):
+    for mt in (3,):
         print("   mt", mt, " ".join(f"bn{bn}/ns{ns}:{us:.0f}" for us, bn, m, ns in sorted(out, key=lambda r: (r[1], r[3])) if m == mt))

@@ -36,12 +36,27 @@ for s, cin, cout in [(1, 32, 32), (1, 64, 64), (2, 64, 64), (2, 128, 128), (2, 1
     err = float((got - ref).abs().max() / ref.abs().max())
     tot += auto
     print(f"s={s} n={lv.n} {cin}->{cout} auto={auto:.1f} relerr={err:.1e}")
-for rows, cin, cout in [(65536, 32, 256), (65536, 256, 192), (64035, 192, 128), (55435, 320, 192), (8259, 192, 576), (1849, 256, 768)]:
+for rows, cin, cout in [(65536, 32, 256), (65536, 256, 192), (64035, 192, 128), (55435, 320, 192), (64035, 96, 64), (8259, 192, 576), (1849, 256, 768)]:
     w = torch.randn(1, cin, cout, device=dev) / cin ** 0.5
     wp = ops.pack_weights(w)
     xin = ops.round_tf32(torch.randn(rows, cin, device=dev))
     bias = torch.randn(cout, device=dev)
-    auto = timeit(lambda: ops.conv_fwd(xin, w, wp, None, None, rows, bias, ops.CONV_UMMA, a_tf32=True))
+    res = torch.randn(rows, cout, device=dev)
+    auto = timeit(lambda: ops.conv_fwd(xin, w, wp, None, None, rows, bias, ops.CONV_UMMA, a_tf32=True, residual=res))
+    wp16 = ops.pack_weights_f16(w); x16 = xin.half()
+    f16 = timeit(lambda: ops.conv_fwd(x16, w, wp16, None, None, rows, bias, ops.CONV_UMMA, residual=res))
+    f16c = timeit(lambda: ops.conv_fwd(xin, w, wp16, None, None, rows, bias, ops.CONV_UMMA, residual=res))
+    mb = rows * (cin * 2 + cout * 8) / 1e6
     tot += auto
-    print(f"linear rows={rows} {cin}->{cout} auto={auto:.1f}")
+    print(f"linear rows={rows} {cin}->{cout} tf32={auto:.1f} f16={f16:.1f} f16(convert)={f16c:.1f}  ideal(f16 in, res+out fp32)={mb/6.4e3*1e3/1e3:.1f}us")
 print("total", round(tot, 1))
+print("bn sweep for the point-level linears (f16 rows, residual)")
+for rows, cin, cout in [(65536, 32, 256), (65536, 256, 192), (64035, 192, 128), (55435, 320, 192)]:
+    w = torch.randn(1, cin, cout, device=dev) / cin ** 0.5
+    wp16 = ops.pack_weights_f16(w); x16 = torch.randn(rows, cin, device=dev).half()
+    bias = torch.randn(cout, device=dev); res = torch.randn(rows, cout, device=dev)
+    out = []
+    for bn in (32, 64, 96, 128, 192, 256):
+        if cout % bn: continue
+        out.append((bn, timeit(lambda: ops.conv_fwd(x16, w, wp16, None, None, rows, bias, ops.CONV_UMMA, residual=res, bn=bn))))
+    print(rows, cin, cout, " ".join(f"bn{b}:{u:.1f}" for b, u in out))
