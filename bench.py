@@ -228,10 +228,12 @@ def run_b200(args):
         except Exception:
             pass
         ach = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
-        roof = {"bound": "tensor", "kernel": "k_conv_fwd_umma (tcgen05 kind::tf32)", "achieved": round(ach, 2),
+        f16 = model.executor_operands == "f16"
+        roof = {"bound": "tensor", "kernel": "k_conv_fwd_umma (tcgen05 kind::%s)" % ("f16" if f16 else "tf32"), "achieved": round(ach, 2),
                 "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained",
-                "note": "TF32 operands (kind::tf32 runs at half the bf16 rate, so frac <= 0.5 by construction); durations from "
+                "note": ("f16 operands (same tensor-core rate as the bf16 peak), fp32 accumulate; " if f16 else
+                         "TF32 operands (kind::tf32 runs at half the bf16 rate, so frac <= 0.5 by construction); ") + "durations from "
                         "CUDA events around each launch in an instrumented replay of the timed steps",
                 "launches": n, "avg_launch_us": round(ms * 1e3 / max(n, 1), 2),
                 "algorithmic_gflop_per_step": round(flops / K / 1e9, 1),
@@ -266,7 +268,8 @@ def run_b200(args):
         nbytes = B * N * 3 * 4
         out = {"metric": METRIC, "value": round(world * K / (total_ms * 1e-3), 3), "unit": UNIT, "n_gpus": world,
                "steps": K, "warmup": W, "ms_per_step": round(total_ms / K, 4), "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": "f32 (tf32 tensor-core operands, f32 accumulate)",
+               "scaling": "weak", "vs_baseline": None, "dtype": ("f32 activations / accumulate, f16 tensor-core operands (11-bit significand, as TF32)"
+                         if model.executor_operands == "f16" else "f32 (tf32 tensor-core operands, f32 accumulate)"),
                "data": "synthetic",
                "config": {"workload": f"{args.preset} DDPM sampling step (forward + update + re-sparsify), open-loop replay over t=999..0, "
                                       f"B={B}x{N} points per GPU, random-init weights, downsample_mode={args.downsample_mode}",

@@ -227,6 +227,11 @@ int spvd_conv_fwd_pairs(const float* in, const float* w_packed, const int32_t* p
                         const int32_t* pair_out, const int32_t* tile_k, int n_pair_tiles, int center_k,
                         int n_out, int kvol, int cin, int cout, const float* bias, const float* residual,
                         float* out, int a_is_tf32, spvd_stream_t stream);
+/* The fp32 SIMT version for the network input (cin <= 4, e.g. the 3 -> 32 stem convolution): one warp instruction per
+ * pair, RED into the zero-filled output, bias added by the centre-offset tiles. */
+int spvd_conv_fwd_pairs_simt(const float* in, const float* w, const int32_t* pair_in, const int32_t* pair_out,
+                             const int32_t* tile_k, int n_pair_tiles, int center_k, int n_out, int kvol, int cin,
+                             int cout, const float* bias, float* out, spvd_stream_t stream);
 /* Weight gradient on the tensor cores (tcgen05, TF32 operands -- round x and gout first with spvd_round_tf32 --,
  * fp32 accumulate): both operands are gathered rows fed as MN-major SWIZZLE_128B tiles, the reduction runs over
  * the pair lists of spvd_kmap_pairs (pair_in = rows of x, pair_out = rows of gout; all NULL with kvol == 1 =

@@ -54,22 +54,24 @@ int spvd_segmented_unique(const int32_t*, int, const int32_t*, int, int, int, in
     if (rc_ != SPVD_OK) return rc_; \
   } while (0)
 
-extern "C" int spvd_plan_build_range(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res,
-                                     float after_res, int scale_mode, int downsample_mode, const spvd_plan_level_t* levels,
-                                     int n_levels, int level_begin, int level_end, int ld, float* fcoords, int32_t* icoords,
-                                     int32_t* status, const int32_t* summary_dev, int32_t* summary_host, int summary_count,
-                                     int sync, void* workspace, size_t workspace_bytes, spvd_stream_t stream) {
+// phases: 1 = the coordinate chain (voxel sets, hash tables, stride-2 maps), 2 = what hangs off it per level (3^3 maps,
+// pair lists, point queries) and the summary copy; the coarser levels need only phase 1 of the finer ones
+static int plan_range(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res, float after_res,
+                      int scale_mode, int downsample_mode, const spvd_plan_level_t* levels, int n_levels, int level_begin,
+                      int level_end, int phases, int ld, float* fcoords, int32_t* icoords, int32_t* status,
+                      const int32_t* summary_dev, int32_t* summary_host, int summary_count, int sync, void* workspace,
+                      size_t workspace_bytes, spvd_stream_t stream) {
   SPVD_CHECK_ARG(pc && levels && fcoords && icoords && status && workspace && n_points > 0 && n_levels > 0,
                  "spvd_plan_build: bad arguments");
   SPVD_CHECK_ARG(0 <= level_begin && level_begin < level_end && level_end <= n_levels, "spvd_plan_build: bad level range [%d,%d)",
                  level_begin, level_end);
   SPVD_CHECK_ARG(ld % 128 == 0 && ld >= n_points, "spvd_plan_build: ld %d must be a multiple of 128 >= n_points", ld);
   cudaStream_t s = (cudaStream_t)stream;
-  if (level_begin == 0) {
+  if (level_begin == 0 && (phases & 1)) {
     SPVD_CUDA(cudaMemsetAsync(status, 0, 4, s));
     SPVD_TRY(spvd_point_voxel_coords(pc, n_points, init_res, after_res, scale_mode, fcoords, icoords, stream));
   }
-  for (int i = level_begin; i < level_end; ++i) {
+  for (int i = level_begin; i < level_end && (phases & 1); ++i) {
     const spvd_plan_level_t& L = levels[i];
     SPVD_CHECK_ARG(L.coords && L.count && L.keys && L.vals && L.capacity >= 2 * n_points,
                    "spvd_plan_build: level %d lacks coords / count / hash buffers", i);
@@ -91,12 +93,13 @@ extern "C" int spvd_plan_build_range(const float* pc, int n_points, int n_batch,
       if (F.kmap_down || F.kmap_up)
         SPVD_TRY(spvd_kmap_down2(F.coords, n_points, F.count, L.keys, L.vals, L.capacity, F.kmap_down, ld, F.mask_down,
                                  F.kmap_up, ld, F.mask_up, nullptr, nullptr, stream));
-      if (F.kmap_down && F.dpair_in && F.dpair_out && F.dpair_tile_k && F.dpair_counts && F.pair_scratch)
+      // (scratch of the COARSE level: the fine level's own scratch may be in use by its 3^3 pair list on another stream)
+      if (F.kmap_down && F.dpair_in && F.dpair_out && F.dpair_tile_k && F.dpair_counts && L.pair_scratch)
         SPVD_TRY(spvd_kmap_pairs(F.kmap_down, ld, n_points, L.count, 8, F.dpair_tile_cap, F.dpair_in, F.dpair_out,
-                                 F.dpair_tile_k, F.dpair_counts, F.dpair_counts + 1, F.pair_scratch, stream));
+                                 F.dpair_tile_k, F.dpair_counts, F.dpair_counts + 1, L.pair_scratch, stream));
     }
   }
-  for (int i = level_begin; i < level_end; ++i) {
+  for (int i = level_begin; i < level_end && (phases & 2); ++i) {
     const spvd_plan_level_t& L = levels[i];
     const int stride = 1 << i;
     if (L.kmap3) SPVD_TRY(spvd_kmap_subm3(L.coords, n_points, L.count, L.keys, L.vals, L.capacity, L.kmap3, ld, L.mask3, stream));
@@ -117,11 +120,21 @@ extern "C" int spvd_plan_build_range(const float* pc, int n_points, int n_batch,
     }
   }
   SPVD_LAUNCH_CHECK();
-  if (summary_dev && summary_host && summary_count > 0) {
+  if ((phases & 2) && summary_dev && summary_host && summary_count > 0) {
     SPVD_CUDA(cudaMemcpyAsync(summary_host, summary_dev, (size_t)summary_count * 4, cudaMemcpyDeviceToHost, s));
     if (sync) SPVD_CUDA(cudaStreamSynchronize(s));
   }
   return SPVD_OK;
+}
+
+extern "C" int spvd_plan_build_range(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res,
+                                     float after_res, int scale_mode, int downsample_mode, const spvd_plan_level_t* levels,
+                                     int n_levels, int level_begin, int level_end, int ld, float* fcoords, int32_t* icoords,
+                                     int32_t* status, const int32_t* summary_dev, int32_t* summary_host, int summary_count,
+                                     int sync, void* workspace, size_t workspace_bytes, spvd_stream_t stream) {
+  return plan_range(pc, n_points, n_batch, max_cloud_rows, init_res, after_res, scale_mode, downsample_mode, levels, n_levels,
+                    level_begin, level_end, 3, ld, fcoords, icoords, status, summary_dev, summary_host, summary_count, sync,
+                    workspace, workspace_bytes, stream);
 }
 
 extern "C" int spvd_plan_build(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res, float after_res,
@@ -165,6 +178,8 @@ struct spvd_plan_graph {
   size_t pc_bytes = 0;
   float* pc_stage = nullptr;
   cudaGraphExec_t exec[8] = {};
+  cudaGraphExec_t exec0_tail = nullptr;   // with several groups: exec[0] = coordinate chain of group 0, this = the rest of it
+  cudaEvent_t chain_done = nullptr;       // the coarser groups start behind the coordinate chain, not behind all of group 0
   cudaStream_t capture = nullptr;
 };
 
@@ -172,6 +187,8 @@ extern "C" void spvd_plan_graph_destroy(spvd_plan_graph* g) {
   if (!g) return;
   for (int i = 0; i < g->n_groups; ++i)
     if (g->exec[i]) cudaGraphExecDestroy(g->exec[i]);
+  if (g->exec0_tail) cudaGraphExecDestroy(g->exec0_tail);
+  if (g->chain_done) cudaEventDestroy(g->chain_done);
   if (g->capture) cudaStreamDestroy(g->capture);
   delete g;
 }
@@ -195,20 +212,30 @@ extern "C" int spvd_plan_graph_create(int n_points, int n_batch, int max_cloud_r
     delete g;
     return SPVD_ERR_CUDA;
   }
-  for (int i = 0; i < n_groups; ++i) {
+  if (n_groups > 1) e = cudaEventCreateWithFlags(&g->chain_done, cudaEventDisableTiming);
+  if (e != cudaSuccess) {
+    set_error("spvd_plan_graph_create: cudaEventCreate failed: %s", cudaGetErrorString(e));
+    spvd_plan_graph_destroy(g);
+    return SPVD_ERR_CUDA;
+  }
+  // graphs: one per level group; group 0 of a split plan is two (coordinate chain | the rest)
+  for (int i = 0; i < n_groups + (n_groups > 1 ? 1 : 0); ++i) {
+    const int grp = i < n_groups ? i : 0;
+    const int phases = n_groups == 1 ? 3 : (i == 0 ? 1 : (i == n_groups ? 2 : 3));
     e = cudaStreamBeginCapture(g->capture, cudaStreamCaptureModeRelaxed);
     int rc = SPVD_OK;
     if (e == cudaSuccess)
-      rc = spvd_plan_build_range(pc_stage, n_points, n_batch, max_cloud_rows, init_res, after_res, scale_mode, downsample_mode,
-                                 levels, n_levels, bounds[i], bounds[i + 1], ld, fcoords, icoords, status, summary_dev,
-                                 summary_hosts[i], summary_count, 0, workspace, workspace_bytes, (spvd_stream_t)g->capture);
+      rc = plan_range(pc_stage, n_points, n_batch, max_cloud_rows, init_res, after_res, scale_mode, downsample_mode, levels,
+                      n_levels, bounds[grp], bounds[grp + 1], phases, ld, fcoords, icoords, status, summary_dev,
+                      summary_hosts[grp], summary_count, 0, workspace, workspace_bytes, (spvd_stream_t)g->capture);
     cudaGraph_t graph = nullptr;
     cudaError_t e2 = e == cudaSuccess ? cudaStreamEndCapture(g->capture, &graph) : e;
-    if (rc == SPVD_OK && e2 == cudaSuccess) e2 = cudaGraphInstantiate(&g->exec[i], graph, 0);
+    cudaGraphExec_t* slot = i < n_groups ? &g->exec[i] : &g->exec0_tail;
+    if (rc == SPVD_OK && e2 == cudaSuccess) e2 = cudaGraphInstantiate(slot, graph, 0);
     if (graph) cudaGraphDestroy(graph);
-    g->n_groups = i + 1;
+    if (i < n_groups) g->n_groups = i + 1;
     if (rc != SPVD_OK || e2 != cudaSuccess) {
-      if (rc == SPVD_OK) set_error("spvd_plan_graph_create: capture of level group %d failed: %s", i, cudaGetErrorString(e2));
+      if (rc == SPVD_OK) set_error("spvd_plan_graph_create: capture of level group %d failed: %s", grp, cudaGetErrorString(e2));
       cudaGetLastError();
       spvd_plan_graph_destroy(g);
       return rc != SPVD_OK ? rc : SPVD_ERR_CUDA;
@@ -228,8 +255,13 @@ extern "C" int spvd_plan_graph_launch(spvd_plan_graph* g, const float* pc, void*
     SPVD_CHECK_ARG(events[i], "spvd_plan_graph_launch: group %d has no event", i);
     cudaStream_t st = i == 0 ? s : side;
     SPVD_CUDA(cudaGraphLaunch(g->exec[i], st));
+    if (i == 0 && g->n_groups > 1) {
+      // the coarser groups wait for group 0's coordinate chain only and run beside its maps and point queries
+      SPVD_CUDA(cudaEventRecord(g->chain_done, s));
+      SPVD_CUDA(cudaStreamWaitEvent(side, g->chain_done, 0));
+      SPVD_CUDA(cudaGraphLaunch(g->exec0_tail, s));
+    }
     SPVD_CUDA(cudaEventRecord((cudaEvent_t)events[i], st));
-    if (i == 0 && g->n_groups > 1) SPVD_CUDA(cudaStreamWaitEvent(side, (cudaEvent_t)events[0], 0));
   }
   return SPVD_OK;
 }

@@ -227,6 +227,8 @@ int spvd_conv_fwd_umma(const float*, const float*, const int32_t*, int, const ui
 int spvd_bn_silu_fwd(const float*, const float*, const float*, long long, int, int, float*, spvd_stream_t);
 int spvd_conv_fwd_pairs(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int,
                         int, const float*, const float*, float*, int, spvd_stream_t);
+int spvd_conv_fwd_pairs_simt(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int,
+                             int, int, const float*, float*, spvd_stream_t);
 }
 
 extern "C" int spvd_film_affine_fwd(const float* x, const float* tt, int ldt, const int32_t* coords,
@@ -410,6 +412,9 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
         else if (o.w_packed && !(o.flags & SPVD_FLAG_SIMT))
           rc = spvd_conv_fwd_umma(at(o.src0), o.w_packed, map, ld, mask, (int)rout, o.kvol, o.c0, o.c1, o.bias,
                                   at(o.src1), at(o.dst), 0, 0, a_mode, 0, stream);
+        else if (o.map_kind == SPVD_MAP_K3 && o.c0 <= 4 && o.src1 < 0 && lv->n_pair_tiles > 0 && lv->pair_in)
+          rc = spvd_conv_fwd_pairs_simt(at(o.src0), o.w, lv->pair_in, lv->pair_out, lv->pair_tile_k, lv->n_pair_tiles,
+                                        o.kvol / 2, (int)rout, o.kvol, o.c0, o.c1, o.bias, at(o.dst), stream);
         else
           rc = spvd_conv_fwd_simt(at(o.src0), o.w, map, ld, mask, (int)rout, o.kvol, o.c0, o.c1, o.bias, at(o.src1),
                                   at(o.dst), stream);

@@ -276,8 +276,8 @@ class PlanWorkspace:
                 b["dpair_tile_k"] = torch.empty(dcap, **i32)
                 o = nl + 1 + nl * n_batch + 2 * nl + 2 * i
                 b["dpair_counts"] = self.summary[o: o + 2]
-            if tile_cap or dcap:
-                b["pair_scratch"] = torch.empty(32 + 27 * ((n_points + 4095) // 4096 + 1), **i32)
+            # (every level: the stride-2 pair list of level i - 1 is built in the scratch of level i)
+            b["pair_scratch"] = torch.empty(32 + 27 * ((n_points + 4095) // 4096 + 1), **i32)
             self.bufs.append(b)
             L = self.c_levels[i]
             for name, t in b.items():
