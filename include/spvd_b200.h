@@ -273,6 +273,11 @@ int spvd_film_affine_fwd(const float* x, const float* tt, int ldt, const int32_t
  * cls / cond_table may be NULL; act & 1 applies the SiLU every TimeEmbeddingBlock starts with. */
 int spvd_time_embed_fwd(const int64_t* t, const int64_t* cls, const float* params, const float* cond_table,
                         int n_batch, int n_temb, int n_emb, int act, float* out, spvd_stream_t stream);
+/* torchsparse.cat (models/spvd.py:232) fused with the BatchNorm+SiLU that follows it in the up-path EmbResBlock
+ * (models/ddpm_unet_attn.py:24-28): cat_f16 = [a | b] and y_f16 = act([a | b] * scale + shift), both stored as f16 -- the
+ * operands of the block's 1x1 shortcut and of its first 3^3 convolution. */
+int spvd_cat_affine_f16_fwd(const float* a, const float* b, long long rows, int ca, int cb, const float* scale,
+                            const float* shift, int act, void* cat_f16, void* y_f16, spvd_stream_t stream);
 /* torchsparse.cat (models/spvd.py:232): y = [a | b] along channels */
 int spvd_cat_fwd(const float* a, const float* b, long long rows, int ca, int cb, float* y,
                  spvd_stream_t stream);
@@ -387,6 +392,7 @@ void spvd_plan_graph_destroy(spvd_plan_graph_t* g);
 #define SPVD_OP_ATTENTION 7    /* src0 = qkv [rows,3*c1] -> dst [rows,c1]; i0 = heads              */
 #define SPVD_OP_TIME_EMBED 8   /* dst [batch,c1]; c0 = n_temb; w = params, p0 = class table or NULL,
                                   p1 = t (int64 [batch]), bias = class ids (int64 [batch]) or NULL  */
+#define SPVD_OP_CAT_AFFINE 9   /* dst = f16 act([src0|src1]*p0+p1), aux = f16 [src0|src1]          */
 
 #define SPVD_MAP_NONE 0 /* kernel size 1 / nn.Linear */
 #define SPVD_MAP_K3 1

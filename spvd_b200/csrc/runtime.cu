@@ -245,6 +245,39 @@ extern "C" int spvd_film_affine_fwd(const float* x, const float* tt, int ldt, co
   return SPVD_OK;
 }
 
+// [a | b] -> (i) the concatenation as f16 (operand of the block's 1x1 shortcut convolution) and (ii)
+// act(cat * scale + shift) as f16 (operand of its first 3^3 convolution): the up-path blocks need both and nothing else
+__global__ void k_cat_affine4_f16(const float4* __restrict__ a, const float4* __restrict__ b, long long rows, int ca4, int cb4,
+                                  const float4* __restrict__ scale, const float4* __restrict__ shift, int act,
+                                  void* __restrict__ raw, void* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int c4 = ca4 + cb4;
+  if (t >= rows * c4) return;
+  const long long row = t / c4;
+  const int q = (int)(t % c4);
+  float4 v = q < ca4 ? a[row * ca4 + q] : b[row * cb4 + (q - ca4)];
+  store_half4(raw, t, v);
+  const float4 s = __ldg(scale + q), o = __ldg(shift + q);
+  v.x = fmaf(v.x, s.x, o.x); v.y = fmaf(v.y, s.y, o.y); v.z = fmaf(v.z, s.z, o.z); v.w = fmaf(v.w, s.w, o.w);
+  if (act & 1) {
+    v.x = silu_f(v.x); v.y = silu_f(v.y); v.z = silu_f(v.z); v.w = silu_f(v.w);
+  }
+  store_half4(y, t, v);
+}
+
+extern "C" int spvd_cat_affine_f16_fwd(const float* a, const float* b, long long rows, int ca, int cb, const float* scale,
+                                       const float* shift, int act, void* cat_f16, void* y_f16, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(a && b && scale && shift && cat_f16 && y_f16 && rows >= 0 && ca > 0 && cb > 0 && ca % 4 == 0 && cb % 4 == 0,
+                 "spvd_cat_affine_f16_fwd: bad arguments (channel counts multiples of 4)");
+  if (rows == 0) return SPVD_OK;
+  SPVD_CUDA(launch_pdl(k_cat_affine4_f16, dim3(cdiv(rows * ((ca + cb) / 4), 256)), dim3(256), 0, (cudaStream_t)stream,
+                       (const float4*)a, (const float4*)b, rows, ca / 4, cb / 4, (const float4*)scale, (const float4*)shift, act,
+                       cat_f16, y_f16));
+  return SPVD_OK;
+}
+
 extern "C" int spvd_cat_fwd(const float* a, const float* b, long long rows, int ca, int cb, float* y,
                             spvd_stream_t stream) {
   SPVD_CHECK_ARG(a && b && y && rows >= 0 && ca > 0 && cb > 0 && ca % 4 == 0 && cb % 4 == 0,
@@ -367,7 +400,7 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
       set_error("spvd_program_run: op %d has a bad row space", i);
       return SPVD_ERR_INVALID;
     }
-    const long long need = o.dst + rout * (long long)(o.op == SPVD_OP_CAT ? o.c0 + o.c1 : o.c1) * 4;  // c1 = output channels
+    const long long need = o.dst + rout * (long long)((o.op == SPVD_OP_CAT || o.op == SPVD_OP_CAT_AFFINE) ? o.c0 + o.c1 : o.c1) * 4;  // c1 = output channels
     if (o.dst < 0 || (size_t)need > arena_bytes) {
       set_error("spvd_program_run: op %d writes past the arena (%lld > %zu)", i, need, arena_bytes);
       return SPVD_ERR_WORKSPACE;
@@ -432,6 +465,10 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
         break;
       case SPVD_OP_CAT:
         rc = spvd_cat_fwd(at(o.src0), at(o.src1), rin, o.c0, o.c1, at(o.dst), stream);
+        break;
+      case SPVD_OP_CAT_AFFINE:
+        SPVD_CHECK_ARG(o.aux >= 0 && o.p0 && o.p1, "op %d: cat+affine needs the second output and the affine", i);
+        rc = spvd_cat_affine_f16_fwd(at(o.src0), at(o.src1), rin, o.c0, o.c1, o.p0, o.p1, o.flags & 1, at(o.aux), at(o.dst), stream);
         break;
       case SPVD_OP_LAYERNORM:
         rc = spvd_layernorm_fwd(at(o.src0), o.p0, o.p1, (int)rin, o.c0, 1e-5f, (o.flags & 3) | ((o.flags & SPVD_FLAG_F16) ? 4 : 0), at(o.dst), stream);

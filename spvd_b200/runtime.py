@@ -20,12 +20,12 @@ from . import ops
 from ._C import check, lib
 from .geometry import Geometry
 
-OP_SCATTER_MEAN, OP_DEVOX, OP_CONV, OP_AFFINE, OP_FILM_AFFINE, OP_CAT, OP_LAYERNORM, OP_ATTENTION, OP_TIME_EMBED = range(9)
+OP_SCATTER_MEAN, OP_DEVOX, OP_CONV, OP_AFFINE, OP_FILM_AFFINE, OP_CAT, OP_LAYERNORM, OP_ATTENTION, OP_TIME_EMBED, OP_CAT_AFFINE = range(10)
 MAP_NONE, MAP_K3, MAP_DOWN, MAP_UP = range(4)
 ROWS_POINTS, ROWS_BATCH = -1, -2
 FLAG_SILU, FLAG_ROUND, FLAG_A_TF32, FLAG_SIMT, FLAG_F16 = 1, 2, 4, 8, 16
 KERNELS_PER_OP = {OP_SCATTER_MEAN: 2, OP_DEVOX: 1, OP_CONV: 1, OP_AFFINE: 1, OP_FILM_AFFINE: 1, OP_CAT: 1,
-                  OP_LAYERNORM: 1, OP_ATTENTION: 1, OP_TIME_EMBED: 1}
+                  OP_LAYERNORM: 1, OP_ATTENTION: 1, OP_TIME_EMBED: 1, OP_CAT_AFFINE: 1}
 
 
 class LevelGeom(C.Structure):
@@ -147,10 +147,14 @@ class Program:
         a = self.affine(z, pb.conv[0], True, rnd, rnd and self._half(lin.in_features, lin.out_features))
         return self.linear(a, lin, residual=z1, a_tf32=rnd)
 
-    def res_block(self, blk, x, lvl):
+    def res_block(self, blk, x, lvl, pre=None):
+        """pre = (a1, x as f16) when the caller fused cat + BN + SiLU (up path)"""
         c1, c2 = blk.conv1[2], blk.conv2[2]
         nf = c1.out_channels
-        a1 = self.affine(x, blk.conv1[0], True, True, self._half(x.ch, nf, 27))
+        if pre is not None:
+            a1, x = pre
+        else:
+            a1 = self.affine(x, blk.conv1[0], True, True, self._half(x.ch, nf, 27))
         h1 = self.conv(a1, self._conv_params(c1.kernel, c1.bias), 27, MAP_K3, lvl, lvl, nf, a_tf32=True)
         s2, b2 = self._bn(blk.conv2[0])
         off = self.tt_offsets[id(blk)]
@@ -236,9 +240,20 @@ class Program:
             for blk in stage.ups:
                 for r in blk.resnets:
                     skip = saved.pop()
-                    xc = self.op(OP_CAT, self.reg(lvl, x.ch + skip.ch), x, skip, flags=0, level=-1, rows_in=lvl,
-                                 rows_out=lvl, c0=x.ch, c1=skip.ch)
-                    x = self.res_block(r, xc, lvl)
+                    cc, nf = x.ch + skip.ch, r.conv1[2].out_channels
+                    if hasattr(r, "idconv") and self._half(cc, nf, 27) and self._half(cc, nf, 1):
+                        # cat + BN + SiLU in one pass, both results as f16: the block reads the concatenation only through
+                        # its two tensor-core convolutions (first 3^3 conv, 1x1 shortcut)
+                        s1, b1 = self._bn(r.conv1[0])
+                        xc16 = self.reg(lvl, cc, "cat_f16")
+                        a1 = self.op(OP_CAT_AFFINE, self.reg(lvl, cc), x, skip, aux=xc16, flags=FLAG_SILU | FLAG_F16, level=-1,
+                                     rows_in=lvl, rows_out=lvl, c0=x.ch, c1=skip.ch, p0=s1, p1=b1)
+                        a1.half = xc16.half = True
+                        x = self.res_block(r, None, lvl, pre=(a1, xc16))
+                    else:
+                        xc = self.op(OP_CAT, self.reg(lvl, cc), x, skip, flags=0, level=-1, rows_in=lvl,
+                                     rows_out=lvl, c0=x.ch, c1=skip.ch)
+                        x = self.res_block(r, xc, lvl)
                 u = blk.up
                 if blk.add_up:
                     lvl -= 1

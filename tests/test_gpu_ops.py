@@ -534,6 +534,22 @@ def test_layernorm_attention_cat_kernels(sp):
     y = torch.empty(100, 96).cuda()
     check(lib.spvd_cat_fwd(P(a), P(b), 100, 64, 32, P(y), S))
     assert torch.equal(y, torch.cat([a, b], 1))
+    # cat + BN + SiLU with both results stored as f16 (the up-path blocks of the executor), and the f16 stores of the
+    # other producers (act & 4)
+    sc, sh = torch.randn(96, generator=g).cuda(), torch.randn(96, generator=g).cuda()
+    raw16, y16 = torch.empty(100, 96, dtype=torch.float16).cuda(), torch.empty(100, 96, dtype=torch.float16).cuda()
+    check(lib.spvd_cat_affine_f16_fwd(P(a), P(b), 100, 64, 32, P(sc), P(sh), 1, P(raw16), P(y16), S))
+    assert torch.equal(raw16, y.half())
+    assert torch.equal(y16, torch.nn.functional.silu(y * sc + sh).half()) or \
+        rel_err(y16.float().cpu().numpy(), torch.nn.functional.silu(y * sc + sh).cpu().numpy()) < 1e-3
+    h = torch.empty(100, 96, dtype=torch.float16).cuda()
+    check(lib.spvd_bn_silu_fwd(P(y), P(sc), P(sh), 100, 96, 1 | 4, P(h), S))
+    assert rel_err(h.float().cpu().numpy(), torch.nn.functional.silu(y * sc + sh).cpu().numpy()) < 1e-3
+    big = torch.full((4, 8), 1e6).cuda()
+    hb = torch.empty(4, 8, dtype=torch.float16).cuda()
+    one, zero = torch.ones(8).cuda(), torch.zeros(8).cuda()
+    check(lib.spvd_bn_silu_fwd(P(big), P(one), P(zero), 4, 8, 4, P(hb), S))
+    assert float(hb.max()) == 65504.0                      # clamped to the largest finite half, never inf
 
 
 def test_fused_ddpm_step_matches_reference_formulas(sp):
