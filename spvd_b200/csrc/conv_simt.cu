@@ -135,11 +135,16 @@ __global__ void __launch_bounds__(128) k_conv_fwd_small_cin_pairs(const float* _
   pdl_wait();
   __syncthreads();
   const bool add_bias = bias != nullptr && k == center_k;
+  // every lane fetches the input row of ITS pair (32 independent loads in flight), then the warp walks the 32 pairs
+  float mx[4] = {0.f, 0.f, 0.f, 0.f};
+  if (my_in >= 0)
+    for (int ci = 0; ci < cin; ++ci) mx[ci] = __ldg(in + (size_t)my_in * cin + ci);
   for (int j = 0; j < 32; ++j) {
-    const int ri = __shfl_sync(0xffffffffu, my_in, j), ro = __shfl_sync(0xffffffffu, my_out, j);
-    if (ri < 0 || ro < 0) continue;
-    float x[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int ci = 0; ci < cin; ++ci) x[ci] = __ldg(in + (size_t)ri * cin + ci);
+    const int ro = __shfl_sync(0xffffffffu, my_in < 0 ? -1 : my_out, j);
+    float x[4];
+#pragma unroll
+    for (int ci = 0; ci < 4; ++ci) x[ci] = __shfl_sync(0xffffffffu, mx[ci], j);
+    if (ro < 0) continue;
     for (int c = lane; c < cout; c += 32) {
       float acc = add_bias ? bias[c] : 0.f;
       for (int ci = 0; ci < cin; ++ci) acc = fmaf(x[ci], s_wk[ci * cout + c], acc);

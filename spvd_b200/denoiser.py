@@ -183,6 +183,8 @@ class SPVUnet(nn.Module):
         # ops of the finer levels ("1,2" = level 0 | level 1 | the rest; "0" = plan everything up front)
         self.plan_split_level = tuple(int(v) for v in os.environ.get("SPVD_PLAN_SPLIT", "1,3").split(","))
         self._side_streams = {}
+        self._aux_streams = {}
+        self.side_prologue = os.environ.get("SPVD_SIDE_PROLOGUE", "0") == "1"
         # tensor-core operand format of the executor: "f16" = IEEE half operands (the 11-bit significand of TF32, fp32
         # accumulation, twice the issue rate and half the operand bytes) or "tf32"; training always uses TF32
         self.executor_operands = os.environ.get("SPVD_EXEC_OPERANDS", "f16")
@@ -323,16 +325,25 @@ class SPVUnet(nn.Module):
         if cls is not None and not hasattr(self, "cond_emb"):
             raise RuntimeError("this model was built without n_classes; it takes (x, t)")
         executor = self.use_executor and self._fast()
-        # executor: wait only for the finest levels; the coarser ones are planned on a side stream under the first ops
-        geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0],
-                                                                       int(getattr(x_in, "points_per_cloud", 0) or 0),
-                                                                       self.plan_split_level if executor else 0)
+        prog = None
         if executor:
             from .runtime import Program
             key = (feats.shape[0], t.shape[0], self.executor_operands)
             prog = self._programs.get(key)
             if prog is None:
                 prog = self._programs[key] = Program(self, *key[:2])
+            if (geometry is None and getattr(self, "profile_sink", None) is None and self.plan_split_level not in (0, (0,))
+                    and self.side_prologue):
+                # timestep-only ops run on a side stream beside the geometry planning
+                aux = self._aux_streams.get(feats.device)
+                if aux is None:
+                    aux = self._aux_streams[feats.device] = torch.cuda.Stream(device=feats.device, priority=-1)
+                prog.prologue(t, cls, aux)
+        # executor: wait only for the finest levels; the coarser ones are planned on a side stream under the first ops
+        geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0],
+                                                                       int(getattr(x_in, "points_per_cloud", 0) or 0),
+                                                                       self.plan_split_level if executor else 0)
+        if executor:
             sink = getattr(self, "profile_sink", None)
             if sink is None:
                 return prog.run(geo, feats.contiguous().float(), t, cls=cls)

@@ -350,6 +350,11 @@ class Program:
             nconv += rec["op"] == OP_CONV
         self.arena = torch.empty(self.arena_bytes, dtype=torch.uint8, device=self.dev)
         self.arena_f = self.arena.view(torch.float32)
+        # leading ops that read nothing but the timestep / class ids: time embedding and the FiLM projection GEMM
+        self.n_prologue = 2 if (n >= 2 and self.recs[0]["op"] == OP_TIME_EMBED and self.recs[1]["op"] == OP_CONV and
+                                self.recs[1]["src0"] is self.in_emb and self.recs[1]["dst"] is self.tt) else 0
+        self.prologue_done = torch.cuda.Event()
+        self._prologue_launched, self._time_keep = False, None
         self.c_levels = (LevelGeom * len(self.strides))()
 
     # ------------------------------------------------------------------------------ execution
@@ -384,19 +389,41 @@ class Program:
                 g.batch_offsets = geo.batch_offsets(s).data_ptr()
                 g.max_per_batch = max(lv.batch_counts_host)
 
+    def _bind_time(self, t, cls):
+        if t.shape[0] != self.n_batch:
+            raise RuntimeError("Program was compiled for a different number of clouds")
+        t = t.long().contiguous()
+        cls = cls.long().contiguous() if cls is not None else None
+        te = self.c_ops[0]                      # OP_TIME_EMBED reads this call's timesteps / class ids
+        assert te.op == OP_TIME_EMBED
+        te.p1 = t.data_ptr()
+        te.bias = cls.data_ptr() if cls is not None else None
+        self._time_keep = (t, cls)              # the op holds raw pointers
+
+    def prologue(self, t, cls, side_stream):
+        """The ops that depend on the timestep only (embedding MLP, all FiLM projections) on a side stream, to run beside
+        the geometry planning instead of in front of the stem; ``run`` then starts behind them."""
+        if self.n_prologue == 0:
+            return
+        self._bind_time(t, cls)
+        cur = torch.cuda.current_stream()
+        side_stream.wait_stream(cur)            # the previous forward still reads the FiLM table
+        check(lib.spvd_program_run(self.c_ops, self.n_prologue, self.c_levels, len(self.strides), self.n_points, self.n_batch,
+                                   C.c_void_p(self.arena.data_ptr()), self.arena_bytes, None, C.c_void_p(side_stream.cuda_stream)))
+        self.prologue_done.record(side_stream)
+        self._prologue_launched = True
+
     def run(self, geo: Geometry, feats: torch.Tensor, t: torch.Tensor, conv_events=None, cls=None):
         m = self.model
         if feats.shape[0] != self.n_points or t.shape[0] != self.n_batch:
             raise RuntimeError("Program was compiled for a different number of points / clouds")
-        t = t.long().contiguous()
-        te = self.c_ops[0]                      # OP_TIME_EMBED reads this call's timesteps / class ids
-        assert te.op == OP_TIME_EMBED
-        te.p1 = t.data_ptr()
-        if cls is not None:
-            cls = cls.long().contiguous()
-            te.bias = cls.data_ptr()
+        first = 0
+        if self._prologue_launched and conv_events is None:
+            torch.cuda.current_stream().wait_event(self.prologue_done)
+            first = self.n_prologue
         else:
-            te.bias = None
+            self._bind_time(t, cls)
+        self._prologue_launched = False
         self._view(self.in_feats, self.n_points).copy_(feats)
         ev = None
         if conv_events is not None:
@@ -411,7 +438,7 @@ class Program:
                                        self.n_points, self.n_batch, C.c_void_p(self.arena.data_ptr()), self.arena_bytes, evp,
                                        stream))
 
-        n, k = len(self.recs), 0
+        n, k = len(self.recs), first
         while geo._pending is not None:
             # the finest levels are planned: run the ops that touch only those while the coarser ones are still being
             # planned on the side stream, then collect the next group of levels and go on
