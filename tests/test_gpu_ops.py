@@ -216,8 +216,18 @@ def test_one_call_planner_matches_op_by_op_geometry(sp):
     for mode in ("spconv", "floor"):
         ref = sp.Geometry(pc, 1e-5, 0.1, n_batch=4, downsample_mode=mode, **kw)
         ws = sp.geometry.PlanWorkspace(pc.shape[0], 4, kw["strides"], kw["strides"], kw["p2v_strides"], kw["devox_strides"], pc.device)
-        for hint in (0, 0, 2048):                            # buffers are reused; last: per-cloud smem sort path
-            geo = ws.build(pc, 1e-5, 0.1, "mul", mode, max_cloud_rows=hint)
+        # buffers are reused; hint 2048 = per-cloud smem sort path; the planner is replayed from CUDA graphs (one capture per
+        # mode / hint / level grouping) or launched kernel by kernel; level groups on a side stream
+        side = torch.cuda.Stream()
+        for graphs, hint, split in ((False, 0, 0), (True, 0, 0), (True, 0, 0), (False, 2048, (1, 3)), (True, 2048, (1, 3)),
+                                    (True, 2048, (1, 3)), (True, 2048, 0)):
+            ws.use_graphs = graphs
+            geo = ws.build(pc, 1e-5, 0.1, "mul", mode, max_cloud_rows=hint, split_level=split, side_stream=side).finish()
+            _check_same_geometry(geo, ref, kw)
+
+
+def _check_same_geometry(geo, ref, kw):
+    if True:
         assert torch.equal(geo.fcoords, ref.fcoords)
         for s in kw["strides"]:
             a, b = geo.level(s), ref.level(s)
@@ -417,6 +427,29 @@ def test_conv_pair_major(sp, stride, cin, cout):
     for xd in (x.cuda().half(), x.cuda()):
         y16 = sp.ops.conv_fwd_pairs(xd, w.cuda(), wp16, pin, pout, tk, T, n, b.cuda(), res.cuda())
         assert rel_err(y16.cpu().numpy(), want16.numpy()) < 2e-5
+
+
+def test_conv_pair_major_simt_stem(sp):
+    """the 3 -> 32 stem convolution on the pair list (fp32 SIMT, RED scatter) equals the oracle"""
+    import ctypes
+    from spvd_b200._C import lib, check
+    from oracle import model as om, ops as oo
+    coords, _ = cloud_points(4, 2048, 41)
+    og = om.Geometry(coords, 1e-5, 0.1, "spconv", "mul")
+    geo = sp.Geometry(coords.float().cuda(), 1e-5, 0.1, strides=(1,), p2v_strides=(1,), devox_strides=(1,))
+    km = geo.level(1).kmap3
+    n = km.n_out
+    pin, pout, tk, nt, _ = sp.ops.kmap_pairs(km.map_t, n)
+    g = torch.Generator().manual_seed(3)
+    for cin, cout in ((3, 32), (4, 48)):
+        x, w, b = torch.randn(n, cin, generator=g), torch.randn(27, cin, cout, generator=g), torch.randn(cout, generator=g)
+        want = oo.conv_gather_gemm_scatter(x, w, og.kmap3(1), n, b)
+        xd, wd, bd = x.cuda(), w.cuda(), b.cuda()
+        out = torch.empty(n, cout, device="cuda")
+        P = lambda t: ctypes.c_void_p(t.data_ptr())
+        check(lib.spvd_conv_fwd_pairs_simt(P(xd), P(wd), P(pin), P(pout), P(tk), int(nt.item()), 13, n, 27, cin, cout, P(bd), P(out),
+                                           ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        assert rel_err(out.cpu().numpy(), want.numpy()) < 1e-5
 
 
 @pytest.mark.parametrize("a_tf32", [True, False])
