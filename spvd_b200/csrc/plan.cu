@@ -54,6 +54,28 @@ int spvd_segmented_unique(const int32_t*, int, const int32_t*, int, int, int, in
     if (rc_ != SPVD_OK) return rc_; \
   } while (0)
 
+// A second stream + two events per (host thread, device): inside one level group the point queries (point->voxel index,
+// trilinear corners) depend only on the hash table and run beside the 3^3 map and its pair list.  Works the same when the
+// caller's stream is being captured (the fork / join become graph edges).
+struct ForkCtx {
+  cudaStream_t stream = nullptr;
+  cudaEvent_t fork = nullptr, join = nullptr;
+};
+static int fork_ctx(ForkCtx** out) {
+  static thread_local ForkCtx ctx[64];
+  int dev = 0;
+  SPVD_CUDA(cudaGetDevice(&dev));
+  SPVD_CHECK_ARG(dev >= 0 && dev < 64, "device index %d out of range", dev);
+  ForkCtx& c = ctx[dev];
+  if (!c.stream) {
+    SPVD_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    SPVD_CUDA(cudaEventCreateWithFlags(&c.fork, cudaEventDisableTiming));
+    SPVD_CUDA(cudaEventCreateWithFlags(&c.join, cudaEventDisableTiming));
+  }
+  *out = &c;
+  return SPVD_OK;
+}
+
 // phases: 1 = the coordinate chain (voxel sets, hash tables, stride-2 maps), 2 = what hangs off it per level (3^3 maps,
 // pair lists, point queries) and the summary copy; the coarser levels need only phase 1 of the finer ones
 static int plan_range(const float* pc, int n_points, int n_batch, int max_cloud_rows, float init_res, float after_res,
@@ -99,25 +121,42 @@ static int plan_range(const float* pc, int n_points, int n_batch, int max_cloud_
                                  F.dpair_tile_k, F.dpair_counts, F.dpair_counts + 1, L.pair_scratch, stream));
     }
   }
-  for (int i = level_begin; i < level_end && (phases & 2); ++i) {
-    const spvd_plan_level_t& L = levels[i];
-    const int stride = 1 << i;
-    if (L.kmap3) SPVD_TRY(spvd_kmap_subm3(L.coords, n_points, L.count, L.keys, L.vals, L.capacity, L.kmap3, ld, L.mask3, stream));
-    if (L.kmap3 && L.pair_in && L.pair_out && L.pair_tile_k && L.pair_counts && L.pair_scratch)
-      SPVD_TRY(spvd_kmap_pairs(L.kmap3, ld, n_points, L.count, 27, L.pair_tile_cap, L.pair_in, L.pair_out, L.pair_tile_k,
-                               L.pair_counts, L.pair_counts + 1, L.pair_scratch, stream));
-    if (L.p2v) {
-      SPVD_TRY(spvd_point_voxel_query(fcoords, n_points, stride, L.keys, L.vals, L.capacity, L.p2v, stream));
-      // misses go to row 0: idx_query.clamp_(0), models/sparse_utils.py:93
-      k_clamp_min0<<<cdiv(n_points, 256), 256, 0, s>>>(L.p2v, n_points);
+  if (phases & 2) {
+    ForkCtx* fk = nullptr;
+    SPVD_TRY(fork_ctx(&fk));
+    bool forked = false;
+    for (int i = level_begin; i < level_end; ++i) forked = forked || levels[i].p2v || (levels[i].devox_idx && levels[i].devox_w);
+    if (forked) {
+      // point queries of the group on the side branch
+      SPVD_CUDA(cudaEventRecord(fk->fork, s));
+      SPVD_CUDA(cudaStreamWaitEvent(fk->stream, fk->fork, 0));
+      for (int i = level_begin; i < level_end; ++i) {
+        const spvd_plan_level_t& L = levels[i];
+        const int stride = 1 << i;
+        if (L.p2v) {
+          SPVD_TRY(spvd_point_voxel_query(fcoords, n_points, stride, L.keys, L.vals, L.capacity, L.p2v, (spvd_stream_t)fk->stream));
+          // misses go to row 0: idx_query.clamp_(0), models/sparse_utils.py:93
+          k_clamp_min0<<<cdiv(n_points, 256), 256, 0, fk->stream>>>(L.p2v, n_points);
+        }
+        if (L.devox_idx && L.devox_w)
+          SPVD_TRY(spvd_devox_query(fcoords, n_points, stride, L.keys, L.vals, L.capacity, L.devox_idx, L.devox_w,
+                                    (spvd_stream_t)fk->stream));
+      }
+      SPVD_CUDA(cudaEventRecord(fk->join, fk->stream));
     }
-    if (L.devox_idx && L.devox_w)
-      SPVD_TRY(spvd_devox_query(fcoords, n_points, stride, L.keys, L.vals, L.capacity, L.devox_idx, L.devox_w, stream));
-    const bool seg = max_cloud_rows > 0 && max_cloud_rows <= 16384 && n_batch > 0 && L.batch_counts;
-    if (L.batch_counts && !seg) {
-      SPVD_TRY(spvd_batch_counts(L.coords, n_points, L.count, n_batch, L.batch_counts, stream));
-      if (L.batch_offsets) k_batch_offsets<<<1, 32, 0, s>>>(L.batch_counts, n_batch, L.batch_offsets);
+    for (int i = level_begin; i < level_end; ++i) {
+      const spvd_plan_level_t& L = levels[i];
+      if (L.kmap3) SPVD_TRY(spvd_kmap_subm3(L.coords, n_points, L.count, L.keys, L.vals, L.capacity, L.kmap3, ld, L.mask3, stream));
+      if (L.kmap3 && L.pair_in && L.pair_out && L.pair_tile_k && L.pair_counts && L.pair_scratch)
+        SPVD_TRY(spvd_kmap_pairs(L.kmap3, ld, n_points, L.count, 27, L.pair_tile_cap, L.pair_in, L.pair_out, L.pair_tile_k,
+                                 L.pair_counts, L.pair_counts + 1, L.pair_scratch, stream));
+      const bool seg = max_cloud_rows > 0 && max_cloud_rows <= 16384 && n_batch > 0 && L.batch_counts;
+      if (L.batch_counts && !seg) {
+        SPVD_TRY(spvd_batch_counts(L.coords, n_points, L.count, n_batch, L.batch_counts, stream));
+        if (L.batch_offsets) k_batch_offsets<<<1, 32, 0, s>>>(L.batch_counts, n_batch, L.batch_offsets);
+      }
     }
+    if (forked) SPVD_CUDA(cudaStreamWaitEvent(s, fk->join, 0));
   }
   SPVD_LAUNCH_CHECK();
   if ((phases & 2) && summary_dev && summary_host && summary_count > 0) {

@@ -362,16 +362,27 @@ class Program:
         o = r.offset // 4
         return self.arena_f[o: o + rows * r.ch].view(rows, r.ch)
 
-    def fill_levels(self, geo: Geometry, upto=None):
-        for i, s in enumerate(self.strides[:upto]):
+    def fill_levels(self, geo: Geometry, upto=None, start=0):
+        """(Re)write the level records [start, upto); level start - 1 gets only what is planned together with its coarser
+        neighbour (stride-2 maps and pair lists), which is all that can have changed for it."""
+        n_levels = len(self.strides) if upto is None else upto
+        for i in range(max(start - 1, 0), n_levels):
+            s = self.strides[i]
             lv, g = geo.level(s), self.c_levels[i]
-            g.coords, g.n = lv.coords_cap.data_ptr(), lv.n
-            if lv.kmap3 is not None:
-                g.kmap3, g.mask3, g.ld3 = lv.kmap3.map_t.data_ptr(), lv.kmap3.mask.data_ptr(), lv.kmap3.map_t.shape[1]
             if lv.kmap_down is not None:
                 g.kmap_down, g.mask_down, g.ld_down = (lv.kmap_down.map_t.data_ptr(), lv.kmap_down.mask.data_ptr(),
                                                        lv.kmap_down.map_t.shape[1])
                 g.kmap_up, g.mask_up, g.ld_up = lv.kmap_up.map_t.data_ptr(), lv.kmap_up.mask.data_ptr(), lv.kmap_up.map_t.shape[1]
+            dp = getattr(lv, "dpairs", None)          # planned together with the next coarser level
+            if dp is not None:
+                g.dpair_in, g.dpair_out, g.dpair_tile_k, g.n_dpair_tiles = dp[0].data_ptr(), dp[1].data_ptr(), dp[2].data_ptr(), dp[3]
+            else:
+                g.dpair_in, g.n_dpair_tiles = None, 0
+            if i < start:
+                continue
+            g.coords, g.n = lv.coords_cap.data_ptr(), lv.n
+            if lv.kmap3 is not None:
+                g.kmap3, g.mask3, g.ld3 = lv.kmap3.map_t.data_ptr(), lv.kmap3.mask.data_ptr(), lv.kmap3.map_t.shape[1]
             g.p2v = geo.p2v[s].data_ptr() if s in geo.p2v else None
             if s in geo.devox:
                 g.devox_idx, g.devox_w = geo.devox[s][0].data_ptr(), geo.devox[s][1].data_ptr()
@@ -380,11 +391,6 @@ class Program:
                 g.pair_in, g.pair_out, g.pair_tile_k, g.n_pair_tiles = pr[0].data_ptr(), pr[1].data_ptr(), pr[2].data_ptr(), pr[3]
             else:
                 g.pair_in, g.n_pair_tiles = None, 0
-            dp = getattr(lv, "dpairs", None)          # planned together with the next coarser level
-            if dp is not None:
-                g.dpair_in, g.dpair_out, g.dpair_tile_k, g.n_dpair_tiles = dp[0].data_ptr(), dp[1].data_ptr(), dp[2].data_ptr(), dp[3]
-            else:
-                g.dpair_in, g.n_dpair_tiles = None, 0
             if i in self.attn_levels:
                 g.batch_offsets = geo.batch_offsets(s).data_ptr()
                 g.max_per_batch = max(lv.batch_counts_host)
@@ -438,13 +444,14 @@ class Program:
                                        self.n_points, self.n_batch, C.c_void_p(self.arena.data_ptr()), self.arena_bytes, evp,
                                        stream))
 
-        n, k = len(self.recs), first
+        n, k, filled = len(self.recs), first, 0
         while geo._pending is not None:
             # the finest levels are planned: run the ops that touch only those while the coarser ones are still being
             # planned on the side stream, then collect the next group of levels and go on
             ready = geo.levels_ready
             k2 = next((i for i, l in enumerate(self.op_max_level) if l >= ready), n)
-            self.fill_levels(geo, upto=ready)
+            self.fill_levels(geo, upto=ready, start=filled)
+            filled = ready
             launch(k, k2)
             k = k2
             if self.trace is not None:
@@ -452,7 +459,7 @@ class Program:
             geo.finish(upto=ready + 1)
             if self.trace is not None:
                 self.trace.append((f"{geo.levels_ready} levels collected", time.perf_counter()))
-        self.fill_levels(geo)
+        self.fill_levels(geo, start=filled)
         launch(k, n)
         if self.trace is not None:
             self.trace.append(("part2 launched", time.perf_counter()))
