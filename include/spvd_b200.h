@@ -201,7 +201,8 @@ int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, in
  * significand, i.e. TF32's precision, fp32 accumulation -- on tcgen05.mma.kind::f16: twice the TF32 issue rate and 64
  * input channels per 128-byte slab, so half the iterations and half the operand bytes.  w_packed must then be the
  * spvd_conv_pack_weights_f16 image; `in` is fp32 (converted on the fly, clamped to the finite half range) for
- * SPVD_A_F32_TO_F16, or an f16 [rows, cin] tensor (a producer with act & 4) for SPVD_A_F16; mt is ignored. */
+ * SPVD_A_F32_TO_F16, or an f16 [rows, cin] tensor (a producer with act & 4) for SPVD_A_F16; mt is ignored, except
+ * mt = 6 with SPVD_A_F16 and a map: the experimental persistent stream-K kernel (equal iteration shares per CTA). */
 #define SPVD_A_F32 0        /* fp32 rows, rounded to TF32 while gathered          */
 #define SPVD_A_TF32 1       /* fp32 rows that are already TF32-representable      */
 #define SPVD_A_F32_TO_F16 2 /* fp32 rows, converted to f16 while gathered         */

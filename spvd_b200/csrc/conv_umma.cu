@@ -6,7 +6,7 @@ namespace spvd {
 // conv_umma_f16.cu
 int conv_fwd_umma_f16(const void* in, bool a_half, const void* w_packed, const int32_t* map_t, int ld,
                       const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
-                      const float* residual, float* out, int bn, int nsplit, cudaStream_t s);
+                      const float* residual, float* out, int bn, int nsplit, int mt, cudaStream_t s);
 int conv_fwd_pairs_f16(const void* in, bool a_half, const void* w_packed, const int32_t* pair_in, const int32_t* pair_out,
                        const int32_t* tile_k, int n_pair_tiles, int center_k, int n_out, int kvol, int cin, int cout,
                        const float* bias, const float* residual, float* out, cudaStream_t s);
@@ -46,7 +46,7 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
   cudaStream_t s = (cudaStream_t)stream;
   if (a_is_tf32 >= SPVD_A_F32_TO_F16)   // f16 operands: w_packed is the spvd_conv_pack_weights_f16 image
     return conv_fwd_umma_f16(in, a_is_tf32 == SPVD_A_F16, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual,
-                             out, bn, nsplit, s);
+                             out, bn, nsplit, mt, s);
   if (bn <= 0) bn = pick_bn(cout, cdiv(n_out, BM), kvol);
   SPVD_CHECK_ARG(cout % bn == 0, "spvd_conv_fwd_umma: slice width %d does not divide cout %d", bn, cout);
   const int max_iters = kvol * (cin / 32);
