@@ -154,6 +154,12 @@ int spvd_scatter_mean_fwd(const float* src, const int32_t* idx, int n, int c, fl
                           float* counts, int nv, spvd_stream_t stream);
 int spvd_scatter_mean_bwd(const float* gout, const int32_t* idx, const float* counts, int n, int c,
                           float* gsrc, spvd_stream_t stream);
+/* The same mean with the weight 1 / (points in the point's voxel) precomputed once per level (spvd_point_mean_weights;
+ * counts = int32 scratch [nv_cap]): spvd_scatter_wmean_fwd is then one zero-fill and one RED pass -- no count accumulation,
+ * no divide pass over the voxel rows.  Differs from spvd_scatter_mean_fwd by the rounding of x/n vs x*(1/n) only. */
+int spvd_point_mean_weights(const int32_t* idx, int n, int nv_cap, int32_t* counts, float* w, spvd_stream_t stream);
+int spvd_scatter_wmean_fwd(const float* src, const int32_t* idx, const float* w, int n, int c, float* out, int nv,
+                           spvd_stream_t stream);
 
 /* torchsparse.nn.functional.spdevoxelize          reference: models/sparse_utils.py:119,128
  * out[p] = sum_j w8[p,j] * feats[idx8[p,j]] (idx -1 skipped); backward scatter-adds into gfeats
@@ -334,6 +340,8 @@ typedef struct spvd_plan_level {
   int32_t* dpair_out;     /*                               coarse rows */
   int32_t* dpair_tile_k;
   int32_t* dpair_counts;  /* [2] */
+  float* p2v_w;           /* [n_points] 1 / (points sharing the point's voxel), with p2v; or NULL */
+  int32_t* p2v_cnt;       /* [n_points] scratch of the above */
   int32_t capacity, pair_tile_cap, dpair_tile_cap, pad;
 } spvd_plan_level_t;
 
@@ -428,6 +436,7 @@ typedef struct spvd_level_geom {
   const int32_t* dpair_in;      /* pair-major view of kmap_down (fine rows) or NULL */
   const int32_t* dpair_out;     /* coarse rows */
   const int32_t* dpair_tile_k;
+  const float* p2v_w;       /* per-point mean weights (spvd_point_mean_weights) or NULL */
   int32_t n, ld3, ld_down, ld_up, max_per_batch, n_pair_tiles; /* n_pair_tiles > 0: 3^3 convs run pair-major */
   int32_t n_dpair_tiles, pad;   /* > 0: the stride-2 / transposed convs of this level run pair-major */
 } spvd_level_geom_t;

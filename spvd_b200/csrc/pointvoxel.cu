@@ -49,6 +49,37 @@ __global__ void k_divide_rows(float* __restrict__ out, const float* __restrict__
   out[t] = __fdiv_rn(out[t], cnt);
 }
 
+// ---- scatter_mean with the 1/count of every point's voxel precomputed at planning time: one zero-fill + one RED pass,
+// no count accumulation and no divide pass over the voxel rows ------------------------------------------------------
+__global__ void k_voxel_point_count(const int* __restrict__ idx, int n, int* __restrict__ counts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = i < n ? idx[i] : -1;
+  if (v < 0) return;
+  const unsigned peers = __match_any_sync(__activemask(), v);       // one atomic per distinct voxel of the warp
+  if ((threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(counts + v, __popc(peers));
+}
+
+__global__ void k_point_mean_weight(const int* __restrict__ idx, const int* __restrict__ counts, int n, float* __restrict__ w) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int v = idx[i];
+  w[i] = v >= 0 ? __fdiv_rn(1.0f, (float)counts[v]) : 0.f;
+}
+
+__global__ void k_scatter_wadd4(const float4* __restrict__ src, const int* __restrict__ idx, const float* __restrict__ w, int n,
+                                int c4, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n * c4) return;
+  const int p = (int)(t / c4), q = (int)(t % c4);
+  const int v = idx[p];
+  if (v < 0) return;
+  const float wp = w[p];
+  const float4 x = src[t];
+  red_add_v4(out + ((size_t)v * c4 + q) * 4, make_float4(x.x * wp, x.y * wp, x.z * wp, x.w * wp));
+}
+
 __global__ void k_scatter_mean_bwd(const float* __restrict__ gout, const int* __restrict__ idx,
                                    const float* __restrict__ counts, int n, int c, float* __restrict__ gsrc) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -151,6 +182,30 @@ extern "C" int spvd_scatter_mean_fwd(const float* src, const int32_t* idx, int n
       k_scatter_add1<<<cdiv((long long)n * c, 256), 256, 0, s>>>(src, idx, n, c, out, counts);
   }
   SPVD_CUDA(launch_pdl(k_divide_rows, dim3(cdiv((long long)nv * c, 256)), dim3(256), 0, s, out, counts, nv, c));
+  return SPVD_OK;
+}
+
+extern "C" int spvd_point_mean_weights(const int32_t* idx, int n, int nv_cap, int32_t* counts, float* w, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(idx && counts && w && n >= 0 && nv_cap >= 0, "spvd_point_mean_weights: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  SPVD_CUDA(cudaMemsetAsync(counts, 0, (size_t)nv_cap * 4, s));
+  if (n == 0) return SPVD_OK;
+  k_voxel_point_count<<<cdiv(n, 256), 256, 0, s>>>(idx, n, counts);
+  k_point_mean_weight<<<cdiv(n, 256), 256, 0, s>>>(idx, counts, n, w);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_scatter_wmean_fwd(const float* src, const int32_t* idx, const float* w, int n, int c, float* out, int nv,
+                                      spvd_stream_t stream) {
+  SPVD_CHECK_ARG(src && idx && w && out && n >= 0 && c > 0 && c % 4 == 0 && nv >= 0, "spvd_scatter_wmean_fwd: bad arguments (c %% 4 == 0)");
+  SPVD_CHECK_ARG(aligned16(src) && aligned16(out), "spvd_scatter_wmean_fwd: pointers must be 16-byte aligned");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (nv == 0) return SPVD_OK;
+  SPVD_CUDA(cudaMemsetAsync(out, 0, (size_t)nv * c * 4, s));
+  if (n > 0)
+    SPVD_CUDA(launch_pdl(k_scatter_wadd4, dim3(cdiv((long long)n * (c / 4), 256)), dim3(256), 0, s, (const float4*)src, idx, w, n,
+                         c / 4, out));
   return SPVD_OK;
 }
 

@@ -33,7 +33,7 @@ class LevelGeom(C.Structure):
                 ("mask_down", C.c_void_p), ("kmap_up", C.c_void_p), ("mask_up", C.c_void_p), ("p2v", C.c_void_p),
                 ("devox_idx", C.c_void_p), ("devox_w", C.c_void_p), ("batch_offsets", C.c_void_p),
                 ("pair_in", C.c_void_p), ("pair_out", C.c_void_p), ("pair_tile_k", C.c_void_p),
-                ("dpair_in", C.c_void_p), ("dpair_out", C.c_void_p), ("dpair_tile_k", C.c_void_p),
+                ("dpair_in", C.c_void_p), ("dpair_out", C.c_void_p), ("dpair_tile_k", C.c_void_p), ("p2v_w", C.c_void_p),
                 ("n", C.c_int32), ("ld3", C.c_int32), ("ld_down", C.c_int32), ("ld_up", C.c_int32),
                 ("max_per_batch", C.c_int32), ("n_pair_tiles", C.c_int32), ("n_dpair_tiles", C.c_int32), ("pad", C.c_int32)]
 
@@ -384,6 +384,8 @@ class Program:
             if lv.kmap3 is not None:
                 g.kmap3, g.mask3, g.ld3 = lv.kmap3.map_t.data_ptr(), lv.kmap3.mask.data_ptr(), lv.kmap3.map_t.shape[1]
             g.p2v = geo.p2v[s].data_ptr() if s in geo.p2v else None
+            pw = getattr(geo, "p2v_w", None)
+            g.p2v_w = pw[s].data_ptr() if pw and s in pw else None
             if s in geo.devox:
                 g.devox_idx, g.devox_w = geo.devox[s][0].data_ptr(), geo.devox[s][1].data_ptr()
             pr = getattr(lv, "pairs", None)

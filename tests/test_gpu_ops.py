@@ -514,6 +514,29 @@ def test_conv_wgrad_tcgen05(sp, kind, cin, cout):
     assert rel_err(got, wa.grad.numpy()) < 1e-3
 
 
+def test_weighted_scatter_mean_equals_scatter_mean(sp):
+    """planner-side 1/count weights + one RED pass (spvd_scatter_wmean_fwd) against spvd_scatter_mean_fwd"""
+    import ctypes
+    from spvd_b200._C import lib, check
+    g = torch.Generator().manual_seed(1)
+    n, nv, c = 50000, 3000, 64
+    idx = torch.randint(0, nv, (n,), generator=g).int()
+    idx[:5000] = 0                                      # the crowded row-0 sink of unmatched points
+    idx[idx == 5] = 6                                   # voxel 5 gets no point
+    src = torch.randn(n, c, generator=g)
+    P = lambda t: ctypes.c_void_p(t.data_ptr())
+    S = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    d_idx, d_src = idx.cuda(), src.cuda()
+    cnt, w = torch.empty(nv, dtype=torch.int32, device="cuda"), torch.empty(n, device="cuda")
+    check(lib.spvd_point_mean_weights(P(d_idx), n, nv, P(cnt), P(w), S))
+    counts = torch.bincount(idx.long(), minlength=nv)
+    assert torch.equal(cnt.cpu().long(), counts) and torch.equal(w.cpu(), 1.0 / counts[idx.long()].float())
+    out = torch.empty(nv, c, device="cuda")
+    check(lib.spvd_scatter_wmean_fwd(P(d_src), P(d_idx), P(w), n, c, P(out), nv, S))
+    want, _ = sp.ops.scatter_mean_fwd(d_src, d_idx, nv)
+    assert rel_err(out.cpu().numpy(), want.cpu().numpy()) < 1e-6 and float(out[5].abs().max()) == 0.0
+
+
 def test_fused_glue(sp):
     g = torch.Generator().manual_seed(0)
     x = torch.randn(1000, 64, generator=g).cuda()
