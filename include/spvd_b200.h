@@ -208,7 +208,9 @@ int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, in
  * input channels per 128-byte slab, so half the iterations and half the operand bytes.  w_packed must then be the
  * spvd_conv_pack_weights_f16 image; `in` is fp32 (converted on the fly, clamped to the finite half range) for
  * SPVD_A_F32_TO_F16, or an f16 [rows, cin] tensor (a producer with act & 4) for SPVD_A_F16; mt is ignored, except
- * mt = 6 with SPVD_A_F16 and a map: the experimental persistent stream-K kernel (equal iteration shares per CTA). */
+ * mt = 6 with SPVD_A_F16 and a map: the experimental persistent stream-K kernel (equal iteration shares per CTA);
+ * mt = 7 with SPVD_A_F16: CTA pairs (tcgen05 cta_group::2, M = 256 over two SMs, each CTA loads half of every weight tile).
+ * Both are correct and tested but slower than the default on the SPVD shapes. */
 #define SPVD_A_F32 0        /* fp32 rows, rounded to TF32 while gathered          */
 #define SPVD_A_TF32 1       /* fp32 rows that are already TF32-representable      */
 #define SPVD_A_F32_TO_F16 2 /* fp32 rows, converted to f16 while gathered         */

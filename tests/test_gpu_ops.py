@@ -339,7 +339,8 @@ def test_conv_forward_tcgen05_f16_operands(sp, kind, cin, cout, pre):
     want_f16 = oo.conv_gather_gemm_scatter(x.half().float(), w.half().float(), m, n_out, b)
     wp = sp.ops.pack_weights_f16(w.cuda())
     xd = x.cuda().half() if pre else x.cuda()
-    for nsplit, mt in ((0, 0), (1, 0), (5, 0), (0, 6)):      # mt = 6: the persistent stream-K kernel (f16 rows only)
+    # mt = 6: the persistent stream-K kernel, mt = 7: CTA pairs (cta_group::2); both for f16 rows only
+    for nsplit, mt in ((0, 0), (1, 0), (5, 0), (0, 6), (0, 7), (1, 7), (3, 7)):
         got = sp.ops.conv_fwd(xd, w.cuda(), wp, km.map_t if km is not None else None, km.mask if km is not None else None,
                               n_out, b.cuda(), sp.ops.CONV_UMMA, nsplit=nsplit, mt=mt).cpu().numpy()
         assert rel_err(got, want_f16.numpy()) < 2e-5        # same operand rounding as the emulation

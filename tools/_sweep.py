@@ -31,9 +31,9 @@ for s, cin, cout in [(2, 128, 128), (2, 192, 128), (4, 320, 192), (4, 192, 192),
     xin = torch.randn(lv.n, cin, device=dev).half()
     bias = torch.randn(cout, device=dev)
     out = []
-    for bn in [b for b in (64, 96, 128, 192, 256) if cout % b == 0]:
-        for mt in (3,):
-            for ns in (0, 1, 2, 3, 4, 6, 8, 12):
+    for bn in [b for b in (96, 128, 192, 256) if cout % b == 0]:
+        for mt in (3, 7):
+            for ns in (0, 1, 2, 4, 8):
                 if bn * (2 if mt == 2 else 1) > 512: continue
                 try:
                     us = timeit(lambda: ops.conv_fwd(xin, w, wp, km.map_t, km.mask, lv.n, bias, ops.CONV_UMMA, bn=bn, nsplit=ns, a_tf32=True, mt=mt))
@@ -42,5 +42,5 @@ for s, cin, cout in [(2, 128, 128), (2, 192, 128), (4, 320, 192), (4, 192, 192),
                 out.append((us, bn, mt, ns))
     auto = timeit(lambda: ops.conv_fwd(xin, w, wp, km.map_t, km.mask, lv.n, bias, ops.CONV_UMMA, a_tf32=True))
     print(f"s={s} n={lv.n} tiles={(lv.n+127)//128} {cin}->{cout} auto={auto:.1f}")
-    for mt in (3,):
+    for mt in (3, 7):
         print("   mt", mt, " ".join(f"bn{bn}/ns{ns}:{us:.0f}" for us, bn, m, ns in sorted(out, key=lambda r: (r[1], r[3])) if m == mt))
