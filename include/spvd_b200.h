@@ -160,6 +160,16 @@ int spvd_scatter_mean_bwd(const float* gout, const int32_t* idx, const float* co
 int spvd_point_mean_weights(const int32_t* idx, int n, int nv_cap, int32_t* counts, float* w, spvd_stream_t stream);
 int spvd_scatter_wmean_fwd(const float* src, const int32_t* idx, const float* w, int n, int c, float* out, int nv,
                            spvd_stream_t stream);
+/* The same mean as a segmented reduction, for levels where many points share a voxel (same-address RED serialises: at
+ * stride 16 a voxel holds ~35 points and row 0, the sink of unmatched points, thousands).  spvd_group_points_by_voxel (once
+ * per level): counts [nv_cap + 2], start / cursor [nv_cap], order [n] = point ids voxel by voxel (voxel v owns
+ * order[start[v] .. start[v] + counts[v])), units [2 * (nv_cap + n / 32 + 1)] = (voxel, chunk) records, one per <= 32 points
+ * of a voxel.  spvd_segment_mean_fwd: zero-fill, then one thread per (unit, 4 channels) sums the unit's rows and adds its
+ * share of the mean with one vector RED.  c % 4 == 0. */
+int spvd_group_points_by_voxel(const int32_t* idx, int n, int nv_cap, const int32_t* nv_dev, int32_t* counts,
+                               int32_t* start, int32_t* cursor, int32_t* order, int32_t* units, spvd_stream_t stream);
+int spvd_segment_mean_fwd(const float* src, const int32_t* start, const int32_t* counts, const int32_t* order,
+                          const int32_t* units, int n, int nv_cap, int c, float* out, int nv, spvd_stream_t stream);
 
 /* torchsparse.nn.functional.spdevoxelize          reference: models/sparse_utils.py:119,128
  * out[p] = sum_j w8[p,j] * feats[idx8[p,j]] (idx -1 skipped); backward scatter-adds into gfeats
@@ -343,7 +353,11 @@ typedef struct spvd_plan_level {
   int32_t* dpair_tile_k;
   int32_t* dpair_counts;  /* [2] */
   float* p2v_w;           /* [n_points] 1 / (points sharing the point's voxel), with p2v; or NULL */
-  int32_t* p2v_cnt;       /* [n_points] scratch of the above */
+  int32_t* p2v_cnt;       /* [n_points + 2] points per voxel (+ 2 counters) */
+  int32_t* p2v_start;     /* [n_points] with p2v_order / p2v_cursor / p2v_units: points grouped by voxel */
+  int32_t* p2v_cursor;    /* [n_points] (spvd_group_points_by_voxel); NULL = not wanted for this level */
+  int32_t* p2v_order;     /* [n_points] */
+  int32_t* p2v_units;     /* [2 * (n_points + n_points / 32 + 1)] */
   int32_t capacity, pair_tile_cap, dpair_tile_cap, pad;
 } spvd_plan_level_t;
 
@@ -439,6 +453,10 @@ typedef struct spvd_level_geom {
   const int32_t* dpair_out;     /* coarse rows */
   const int32_t* dpair_tile_k;
   const float* p2v_w;       /* per-point mean weights (spvd_point_mean_weights) or NULL */
+  const int32_t* p2v_cnt;   /* points grouped by voxel (spvd_group_points_by_voxel) or NULL */
+  const int32_t* p2v_start;
+  const int32_t* p2v_order;
+  const int32_t* p2v_units;
   int32_t n, ld3, ld_down, ld_up, max_per_batch, n_pair_tiles; /* n_pair_tiles > 0: 3^3 convs run pair-major */
   int32_t n_dpair_tiles, pad;   /* > 0: the stride-2 / transposed convs of this level run pair-major */
 } spvd_level_geom_t;

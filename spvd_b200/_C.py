@@ -33,6 +33,8 @@ SIGNATURES = {
     "spvd_conv_pack_weights_f16": (_i, [_p, _i, _i, _i, _p, _p]),
     "spvd_conv_fwd_pairs_simt": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p]),
     "spvd_cat_affine_f16_fwd": (_i, [_p, _p, C.c_longlong, _i, _i, _p, _p, _i, _p, _p, _p]),
+    "spvd_group_points_by_voxel": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "spvd_segment_mean_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p]),
     "spvd_point_mean_weights": (_i, [_p, _i, _i, _p, _p, _p]),
     "spvd_scatter_wmean_fwd": (_i, [_p, _p, _p, _i, _i, _p, _i, _p]),
     "spvd_time_embed_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),

@@ -45,6 +45,8 @@ int spvd_batch_counts(const int32_t*, int, const int32_t*, int, int32_t*, spvd_s
 int spvd_kmap_pairs(const int32_t*, int, int, const int32_t*, int, int, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*,
                     int32_t*, spvd_stream_t);
 int spvd_point_mean_weights(const int32_t*, int, int, int32_t*, float*, spvd_stream_t);
+int spvd_group_points_by_voxel(const int32_t*, int, int, const int32_t*, int32_t*, int32_t*, int32_t*, int32_t*, int32_t*,
+                               spvd_stream_t);
 int spvd_segmented_unique(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, int32_t*, int32_t*, int32_t*,
                           int32_t*, void*, size_t, spvd_stream_t);
 }
@@ -138,7 +140,10 @@ static int plan_range(const float* pc, int n_points, int n_batch, int max_cloud_
           SPVD_TRY(spvd_point_voxel_query(fcoords, n_points, stride, L.keys, L.vals, L.capacity, L.p2v, (spvd_stream_t)fk->stream));
           // misses go to row 0: idx_query.clamp_(0), models/sparse_utils.py:93
           k_clamp_min0<<<cdiv(n_points, 256), 256, 0, fk->stream>>>(L.p2v, n_points);
-          if (L.p2v_w && L.p2v_cnt)
+          if (L.p2v_cnt && L.p2v_start && L.p2v_cursor && L.p2v_order && L.p2v_units)
+            SPVD_TRY(spvd_group_points_by_voxel(L.p2v, n_points, n_points, L.count, L.p2v_cnt, L.p2v_start, L.p2v_cursor,
+                                                L.p2v_order, L.p2v_units, (spvd_stream_t)fk->stream));
+          else if (L.p2v_w && L.p2v_cnt)
             SPVD_TRY(spvd_point_mean_weights(L.p2v, n_points, n_points, L.p2v_cnt, L.p2v_w, (spvd_stream_t)fk->stream));
         }
         if (L.devox_idx && L.devox_w)

@@ -80,6 +80,80 @@ __global__ void k_scatter_wadd4(const float4* __restrict__ src, const int* __res
   red_add_v4(out + ((size_t)v * c4 + q) * 4, make_float4(x.x * wp, x.y * wp, x.z * wp, x.w * wp));
 }
 
+// ---- scatter_mean as a segmented reduction: the planner groups the points by voxel (disjoint ranges of an order array,
+// handed out warp by warp from one cursor) and cuts every voxel into units of <= kUnit points; the feature pass sums each
+// unit's rows with plain loads and adds its share of the mean with ONE vector RED per 4 channels.  At stride 16 a voxel
+// holds ~35 points (hundreds early in sampling) and the row-0 sink of unmatched points thousands: per-point same-address
+// RED serialises there (145 us for C = 256 in ncu). -------------------------------------------------------------------
+constexpr int kUnit = 32;
+
+// counts [nv] (from k_voxel_point_count), meta = {next free order slot, next free unit}
+__global__ void k_group_alloc(const int* __restrict__ counts, const int* __restrict__ nv_dev, int nv_cap, int* __restrict__ meta,
+                              int* __restrict__ start, int* __restrict__ cursor, int2* __restrict__ units) {
+  const int nv = resolve_n(nv_dev, nv_cap);
+  const int v = blockIdx.x * blockDim.x + threadIdx.x;
+  const int c = v < nv ? counts[v] : 0;
+  const int nu = (c + kUnit - 1) / kUnit;
+  const int lane = threadIdx.x & 31;
+  int incl = c, uincl = nu;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, incl, o), tu = __shfl_up_sync(0xffffffffu, uincl, o);
+    if (lane >= o) incl += t, uincl += tu;
+  }
+  int base = 0, ubase = 0;
+  if (lane == 31 && incl > 0) base = atomicAdd(meta, incl), ubase = atomicAdd(meta + 1, uincl);
+  base = __shfl_sync(0xffffffffu, base, 31);
+  ubase = __shfl_sync(0xffffffffu, ubase, 31);
+  if (v < nv) {
+    start[v] = cursor[v] = base + incl - c;
+    const int u0 = ubase + uincl - nu;
+    for (int u = 0; u < nu; ++u) units[u0 + u] = make_int2(v, u);
+  }
+}
+
+__global__ void k_group_fill(const int* __restrict__ idx, int n, int* __restrict__ cursor, int* __restrict__ order) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int v = i < n ? idx[i] : -1;
+  if (v < 0) return;
+  const unsigned peers = __match_any_sync(__activemask(), v);
+  const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(cursor + v, __popc(peers));
+  base = __shfl_sync(peers, base, leader);
+  order[base + __popc(peers & ((1u << lane) - 1u))] = i;
+}
+
+// one thread per (unit, 4 channels); the output was zero-filled
+__global__ void k_segment_mean4(const float4* __restrict__ src, const int* __restrict__ start, const int* __restrict__ counts,
+                                const int* __restrict__ order, const int2* __restrict__ units, const int* __restrict__ meta,
+                                int c4, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int u = (int)(t / c4), q = (int)(t % c4);
+  if (u >= meta[1]) return;
+  const int2 rec = units[u];
+  const int v = rec.x, cnt = counts[v];
+  const int lo = start[v] + rec.y * kUnit, hi = min(start[v] + cnt, lo + kUnit);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  int j = lo;
+  for (; j + 4 <= hi; j += 4) {
+    const int o0 = order[j], o1 = order[j + 1], o2 = order[j + 2], o3 = order[j + 3];
+    const float4 f0 = src[(size_t)o0 * c4 + q], f1 = src[(size_t)o1 * c4 + q];
+    const float4 f2 = src[(size_t)o2 * c4 + q], f3 = src[(size_t)o3 * c4 + q];
+    acc.x += (f0.x + f1.x) + (f2.x + f3.x);
+    acc.y += (f0.y + f1.y) + (f2.y + f3.y);
+    acc.z += (f0.z + f1.z) + (f2.z + f3.z);
+    acc.w += (f0.w + f1.w) + (f2.w + f3.w);
+  }
+  for (; j < hi; ++j) {
+    const float4 f = src[(size_t)order[j] * c4 + q];
+    acc.x += f.x; acc.y += f.y; acc.z += f.z; acc.w += f.w;
+  }
+  const float inv = __fdiv_rn(1.0f, (float)cnt);
+  red_add_v4(out + ((size_t)v * c4 + q) * 4, make_float4(acc.x * inv, acc.y * inv, acc.z * inv, acc.w * inv));
+}
+
 __global__ void k_scatter_mean_bwd(const float* __restrict__ gout, const int* __restrict__ idx,
                                    const float* __restrict__ counts, int n, int c, float* __restrict__ gsrc) {
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,6 +267,32 @@ extern "C" int spvd_point_mean_weights(const int32_t* idx, int n, int nv_cap, in
   k_voxel_point_count<<<cdiv(n, 256), 256, 0, s>>>(idx, n, counts);
   k_point_mean_weight<<<cdiv(n, 256), 256, 0, s>>>(idx, counts, n, w);
   SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_group_points_by_voxel(const int32_t* idx, int n, int nv_cap, const int32_t* nv_dev, int32_t* counts,
+                                          int32_t* start, int32_t* cursor, int32_t* order, int32_t* units, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(idx && counts && start && cursor && order && units && n >= 0 && nv_cap >= 0, "spvd_group_points_by_voxel: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  SPVD_CUDA(cudaMemsetAsync(counts, 0, (size_t)(nv_cap + 2) * 4, s));   // counts [nv_cap] | next free slot | units
+  if (n > 0) k_voxel_point_count<<<cdiv(n, 256), 256, 0, s>>>(idx, n, counts);
+  if (nv_cap > 0) k_group_alloc<<<cdiv(nv_cap, 256), 256, 0, s>>>(counts, nv_dev, nv_cap, counts + nv_cap, start, cursor, (int2*)units);
+  if (n > 0) k_group_fill<<<cdiv(n, 256), 256, 0, s>>>(idx, n, cursor, order);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_segment_mean_fwd(const float* src, const int32_t* start, const int32_t* counts, const int32_t* order,
+                                     const int32_t* units, int n, int nv_cap, int c, float* out, int nv, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(src && start && counts && order && units && out && c > 0 && c % 4 == 0 && nv >= 0 && nv <= nv_cap && n >= 0,
+                 "spvd_segment_mean_fwd: bad arguments (c %% 4 == 0)");
+  SPVD_CHECK_ARG(aligned16(src) && aligned16(out), "spvd_segment_mean_fwd: pointers must be 16-byte aligned");
+  if (nv == 0) return SPVD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  SPVD_CUDA(cudaMemsetAsync(out, 0, (size_t)nv * c * 4, s));
+  const long long max_units = (long long)nv + n / 32;                  // ceil(cnt / 32) summed over the voxels
+  SPVD_CUDA(launch_pdl(k_segment_mean4, dim3(cdiv(max_units * (c / 4), 256)), dim3(256), 0, s, (const float4*)src, start, counts,
+                       order, (const int2*)units, counts + nv_cap, c / 4, out));
   return SPVD_OK;
 }
 

@@ -221,6 +221,8 @@ extern "C" {
 int spvd_scatter_mean_fwd(const float*, const int32_t*, int, int, float*, float*, int, spvd_stream_t);
 int spvd_devoxelize_fwd(const float*, const int32_t*, const float*, int, int, float*, spvd_stream_t);
 int spvd_scatter_wmean_fwd(const float*, const int32_t*, const float*, int, int, float*, int, spvd_stream_t);
+int spvd_segment_mean_fwd(const float*, const int32_t*, const int32_t*, const int32_t*, const int32_t*, int, int, int, float*,
+                          int, spvd_stream_t);
 int spvd_conv_fwd_simt(const float*, const float*, const int32_t*, int, const uint32_t*, int, int, int, int,
                        const float*, const float*, float*, spvd_stream_t);
 int spvd_conv_fwd_umma(const float*, const float*, const int32_t*, int, const uint32_t*, int, int, int, int,
@@ -411,7 +413,10 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
     switch (o.op) {
       case SPVD_OP_SCATTER_MEAN:
         SPVD_CHECK_ARG(lv && lv->p2v, "op %d: level %d has no point->voxel index", i, o.level);
-        if (lv->p2v_w && o.c0 % 4 == 0)
+        if (lv->p2v_cnt && lv->p2v_start && lv->p2v_order && lv->p2v_units && o.c0 % 4 == 0)
+          rc = spvd_segment_mean_fwd(at(o.src0), lv->p2v_start, lv->p2v_cnt, lv->p2v_order, lv->p2v_units, n_points, n_points,
+                                     o.c0, at(o.dst), lv->n, stream);
+        else if (lv->p2v_w && o.c0 % 4 == 0)
           rc = spvd_scatter_wmean_fwd(at(o.src0), lv->p2v, lv->p2v_w, n_points, o.c0, at(o.dst), lv->n, stream);
         else
           rc = spvd_scatter_mean_fwd(at(o.src0), lv->p2v, n_points, o.c0, at(o.dst), at(o.aux), lv->n, stream);

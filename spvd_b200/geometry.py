@@ -209,7 +209,7 @@ class _PlanLevel(_C.Structure):
                                            "kmap_up", "mask_up", "p2v", "devox_idx", "devox_w", "batch_counts",
                                            "batch_offsets", "pair_in", "pair_out", "pair_tile_k", "pair_counts",
                                            "pair_scratch", "dpair_in", "dpair_out", "dpair_tile_k", "dpair_counts",
-                                           "p2v_w", "p2v_cnt")] + \
+                                           "p2v_w", "p2v_cnt", "p2v_start", "p2v_cursor", "p2v_order", "p2v_units")] + \
                [("capacity", _C.c_int32), ("pair_tile_cap", _C.c_int32), ("dpair_tile_cap", _C.c_int32), ("pad", _C.c_int32)]
 
 
@@ -261,7 +261,11 @@ class PlanWorkspace:
             if s in p2v_strides:
                 b["p2v"] = torch.empty(n_points, **i32)
                 b["p2v_w"] = torch.empty(n_points, dtype=torch.float32, device=device)   # 1 / points per voxel, per point
-                b["p2v_cnt"] = torch.empty(n_points, **i32)
+                b["p2v_cnt"] = torch.empty(n_points + 2, **i32)
+                if s > 1:           # many points per voxel: segmented reduction instead of RED (stride 1 has ~1 point per voxel)
+                    for name in ("p2v_start", "p2v_cursor", "p2v_order"):
+                        b[name] = torch.empty(n_points, **i32)
+                    b["p2v_units"] = torch.empty(2 * (n_points + n_points // 32 + 1), **i32)
             if s in devox_strides:
                 b["devox_idx"] = torch.empty((n_points, 8), **i32)
                 b["devox_w"] = torch.empty((n_points, 8), dtype=torch.float32, device=device)
@@ -307,7 +311,7 @@ class PlanWorkspace:
         ops.stats.launches += self.n_kernels if not max_cloud_rows else self.n_kernels - 20 * nl
         geo = Geometry.__new__(Geometry)
         geo.n_points, geo.mode, geo.status = self.n_points, downsample_mode, self.status
-        geo.fcoords, geo.levels, geo.p2v, geo.devox, geo.p2v_w = self.fcoords, {}, {}, {}, {}
+        geo.fcoords, geo.levels, geo.p2v, geo.devox, geo.p2v_w, geo.p2v_groups = self.fcoords, {}, {}, {}, {}, {}
         cur = torch.cuda.current_stream()
         cuts = (split_level,) if isinstance(split_level, int) else tuple(split_level)
         cuts = sorted({c for c in cuts if 0 < c < nl}) if side_stream is not None else []
@@ -410,6 +414,8 @@ class PlanWorkspace:
             if "p2v" in b:
                 geo.p2v[s] = b["p2v"]
                 geo.p2v_w[s] = b["p2v_w"]
+                if "p2v_order" in b:
+                    geo.p2v_groups[s] = (b["p2v_cnt"], b["p2v_start"], b["p2v_order"], b["p2v_units"])
             if "devox_idx" in b:
                 geo.devox[s] = (b["devox_idx"], b["devox_w"])
             if "kmap3" in b:

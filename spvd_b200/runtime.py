@@ -34,6 +34,7 @@ class LevelGeom(C.Structure):
                 ("devox_idx", C.c_void_p), ("devox_w", C.c_void_p), ("batch_offsets", C.c_void_p),
                 ("pair_in", C.c_void_p), ("pair_out", C.c_void_p), ("pair_tile_k", C.c_void_p),
                 ("dpair_in", C.c_void_p), ("dpair_out", C.c_void_p), ("dpair_tile_k", C.c_void_p), ("p2v_w", C.c_void_p),
+                ("p2v_cnt", C.c_void_p), ("p2v_start", C.c_void_p), ("p2v_order", C.c_void_p), ("p2v_units", C.c_void_p),
                 ("n", C.c_int32), ("ld3", C.c_int32), ("ld_down", C.c_int32), ("ld_up", C.c_int32),
                 ("max_per_batch", C.c_int32), ("n_pair_tiles", C.c_int32), ("n_dpair_tiles", C.c_int32), ("pad", C.c_int32)]
 
@@ -386,6 +387,8 @@ class Program:
             g.p2v = geo.p2v[s].data_ptr() if s in geo.p2v else None
             pw = getattr(geo, "p2v_w", None)
             g.p2v_w = pw[s].data_ptr() if pw and s in pw else None
+            grp = getattr(geo, "p2v_groups", {}).get(s)
+            g.p2v_cnt, g.p2v_start, g.p2v_order, g.p2v_units = [t.data_ptr() for t in grp] if grp is not None else [None] * 4
             if s in geo.devox:
                 g.devox_idx, g.devox_w = geo.devox[s][0].data_ptr(), geo.devox[s][1].data_ptr()
             pr = getattr(lv, "pairs", None)

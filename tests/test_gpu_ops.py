@@ -536,6 +536,24 @@ def test_weighted_scatter_mean_equals_scatter_mean(sp):
     check(lib.spvd_scatter_wmean_fwd(P(d_src), P(d_idx), P(w), n, c, P(out), nv, S))
     want, _ = sp.ops.scatter_mean_fwd(d_src, d_idx, nv)
     assert rel_err(out.cpu().numpy(), want.cpu().numpy()) < 1e-6 and float(out[5].abs().max()) == 0.0
+    # the same as a segmented reduction over points grouped by voxel (voxels 0 and 7 hold thousands / hundreds of points: many units)
+    idx2 = idx.clone()
+    idx2[5000:5100] = 7
+    counts2 = torch.bincount(idx2.long(), minlength=nv)
+    d_idx2 = idx2.cuda()
+    gc, gs, gcur, go, gh = (torch.empty(k, dtype=torch.int32, device="cuda") for k in (nv + 2, nv, nv, n, 2 * (nv + n // 32 + 1)))
+    check(lib.spvd_group_points_by_voxel(P(d_idx2), n, nv, None, P(gc), P(gs), P(gcur), P(go), P(gh), S))
+    o, st = go.cpu().long(), gs.cpu().tolist()
+    assert torch.equal(gc[:nv].cpu().long(), counts2) and int(gc[nv]) == n and sorted(o.tolist()) == list(range(n))
+    assert all(bool((idx2.long()[o[st[v]: st[v] + int(counts2[v])]] == v).all()) for v in range(nv))
+    n_units = int(gc[nv + 1])
+    assert n_units == int(((counts2 + 31) // 32).sum())
+    recs = gh.cpu()[: 2 * n_units].view(-1, 2).tolist()                       # (voxel, chunk) records, one per <= 32 points
+    assert sorted(map(tuple, recs)) == sorted((v, u) for v in range(nv) for u in range((int(counts2[v]) + 31) // 32))
+    out2 = torch.empty(nv, c, device="cuda")
+    check(lib.spvd_segment_mean_fwd(P(d_src), P(gs), P(gc), P(go), P(gh), n, nv, c, P(out2), nv, S))
+    want2, _ = sp.ops.scatter_mean_fwd(d_src, d_idx2, nv)
+    assert rel_err(out2.cpu().numpy(), want2.cpu().numpy()) < 1e-5 and float(out2[5].abs().max()) == 0.0
 
 
 def test_fused_glue(sp):
