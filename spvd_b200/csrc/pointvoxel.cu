@@ -164,31 +164,41 @@ __global__ void k_scatter_mean_bwd(const float* __restrict__ gout, const int* __
 }
 
 // ---- devoxelize -----------------------------------------------------------------------------
+// kSlots float4 channel slots per thread (q, q + c4/kSlots, ...): the 8 corner indices / weights are loaded once and
+// 8 * kSlots gathers are in flight per thread -- with one slot the kernel is bound by (dependent-load latency) x (waves)
+template <int kSlots>
 __global__ void k_devox_fwd4(const float4* __restrict__ feats, const int* __restrict__ idx8,
                              const float* __restrict__ w8, int n, int c4, float4* __restrict__ out) {
   pdl_trigger();
   pdl_wait();
+  const int cq = c4 / kSlots;
   long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= (long long)n * c4) return;
-  int p = (int)(t / c4), q = (int)(t % c4);
+  if (t >= (long long)n * cq) return;
+  int p = (int)(t / cq), q = (int)(t % cq);
   const int4* ip = reinterpret_cast<const int4*>(idx8 + (size_t)p * 8);
   const float4* wp = reinterpret_cast<const float4*>(w8 + (size_t)p * 8);
   int4 i0 = ip[0], i1 = ip[1];
   float4 w0 = wp[0], w1 = wp[1];
   int id[8] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w};
   float w[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 acc[kSlots];
+#pragma unroll
+  for (int h = 0; h < kSlots; ++h) acc[h] = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     if (id[j] >= 0) {
-      float4 f = feats[(size_t)id[j] * c4 + q];
-      acc.x = fmaf(w[j], f.x, acc.x);
-      acc.y = fmaf(w[j], f.y, acc.y);
-      acc.z = fmaf(w[j], f.z, acc.z);
-      acc.w = fmaf(w[j], f.w, acc.w);
+#pragma unroll
+      for (int h = 0; h < kSlots; ++h) {
+        float4 f = feats[(size_t)id[j] * c4 + q + h * cq];
+        acc[h].x = fmaf(w[j], f.x, acc[h].x);
+        acc[h].y = fmaf(w[j], f.y, acc[h].y);
+        acc[h].z = fmaf(w[j], f.z, acc[h].z);
+        acc[h].w = fmaf(w[j], f.w, acc[h].w);
+      }
     }
   }
-  out[t] = acc;
+#pragma unroll
+  for (int h = 0; h < kSlots; ++h) out[(size_t)p * c4 + q + h * cq] = acc[h];
 }
 
 __global__ void k_devox_fwd1(const float* __restrict__ feats, const int* __restrict__ idx8,
@@ -324,8 +334,18 @@ extern "C" int spvd_devoxelize_fwd(const float* feats, const int32_t* idx8, cons
   if (n == 0) return SPVD_OK;
   cudaStream_t s = (cudaStream_t)stream;
   if (c % 4 == 0 && aligned16(feats) && aligned16(out))
-    SPVD_CUDA(launch_pdl(k_devox_fwd4, dim3(cdiv((long long)n * (c / 4), 256)), dim3(256), 0, s, (const float4*)feats, idx8,
-                         w8, n, c / 4, (float4*)out));
+  {
+    const int c4 = c / 4;
+    if (c4 % 4 == 0 && c4 >= 32)
+      SPVD_CUDA(launch_pdl(k_devox_fwd4<4>, dim3(cdiv((long long)n * (c4 / 4), 256)), dim3(256), 0, s, (const float4*)feats, idx8,
+                           w8, n, c4, (float4*)out));
+    else if (c4 % 2 == 0)
+      SPVD_CUDA(launch_pdl(k_devox_fwd4<2>, dim3(cdiv((long long)n * (c4 / 2), 256)), dim3(256), 0, s, (const float4*)feats, idx8,
+                           w8, n, c4, (float4*)out));
+    else
+      SPVD_CUDA(launch_pdl(k_devox_fwd4<1>, dim3(cdiv((long long)n * c4, 256)), dim3(256), 0, s, (const float4*)feats, idx8,
+                           w8, n, c4, (float4*)out));
+  }
   else
     SPVD_CUDA(launch_pdl(k_devox_fwd1, dim3(cdiv((long long)n * c, 256)), dim3(256), 0, s, feats, idx8, w8, n, c, out));
   return SPVD_OK;
