@@ -14,36 +14,48 @@ __device__ __forceinline__ float rna_tf32(float x) {
 }
 
 // y = act(x * scale[c] + shift[c]);  act bit 0: SiLU, bit 1: round the result to TF32 (rna), bit 2: store y as f16
-__global__ void k_affine_act4(const float4* __restrict__ x, const float4* __restrict__ scale,
-                              const float4* __restrict__ shift, long long total4, int c4, int act,
-                              float4* __restrict__ y) {
+// kPer float4 per thread (a block's elements 256 apart, all loads issued before the first store): large tensors stream
+// faster with two loads in flight per thread, small ones want as many threads as they can get
+template <int kPer>
+__global__ void __launch_bounds__(256) k_affine_act4(const float4* __restrict__ x, const float4* __restrict__ scale,
+                                                     const float4* __restrict__ shift, long long total4, int c4, int act,
+                                                     float4* __restrict__ y) {
   pdl_trigger();
   pdl_wait();
-  long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= total4) return;
-  int q = (int)(t % c4);
-  float4 v = x[t], s = __ldg(scale + q), b = __ldg(shift + q);
-  v.x = fmaf(v.x, s.x, b.x);
-  v.y = fmaf(v.y, s.y, b.y);
-  v.z = fmaf(v.z, s.z, b.z);
-  v.w = fmaf(v.w, s.w, b.w);
-  if (act & 1) {
-    v.x = silu(v.x);
-    v.y = silu(v.y);
-    v.z = silu(v.z);
-    v.w = silu(v.w);
+  const long long t0 = (long long)blockIdx.x * (256 * kPer) + threadIdx.x;
+  float4 v[kPer];
+#pragma unroll
+  for (int e = 0; e < kPer; ++e)
+    if (t0 + e * 256 < total4) v[e] = x[t0 + e * 256];
+#pragma unroll
+  for (int e = 0; e < kPer; ++e) {
+    const long long t = t0 + e * 256;
+    if (t >= total4) break;
+    const int q = (int)(t % c4);
+    const float4 s = __ldg(scale + q), b = __ldg(shift + q);
+    float4 r = v[e];
+    r.x = fmaf(r.x, s.x, b.x);
+    r.y = fmaf(r.y, s.y, b.y);
+    r.z = fmaf(r.z, s.z, b.z);
+    r.w = fmaf(r.w, s.w, b.w);
+    if (act & 1) {
+      r.x = silu(r.x);
+      r.y = silu(r.y);
+      r.z = silu(r.z);
+      r.w = silu(r.w);
+    }
+    if (act & 4) {
+      store_half4(y, t, r);
+      continue;
+    }
+    if (act & 2) {
+      r.x = rna_tf32(r.x);
+      r.y = rna_tf32(r.y);
+      r.z = rna_tf32(r.z);
+      r.w = rna_tf32(r.w);
+    }
+    y[t] = r;
   }
-  if (act & 4) {
-    store_half4(y, t, v);
-    return;
-  }
-  if (act & 2) {
-    v.x = rna_tf32(v.x);
-    v.y = rna_tf32(v.y);
-    v.z = rna_tf32(v.z);
-    v.w = rna_tf32(v.w);
-  }
-  y[t] = v;
 }
 
 __global__ void k_affine_act1(const float* __restrict__ x, const float* __restrict__ scale,
@@ -108,10 +120,14 @@ extern "C" int spvd_bn_silu_fwd(const float* x, const float* scale, const float*
   cudaStream_t s = (cudaStream_t)stream;
   bool v4 = c % 4 == 0 && (((size_t)x | (size_t)y | (size_t)scale | (size_t)shift) & 15) == 0;
   SPVD_CHECK_ARG(v4 || !(act & 4), "spvd_bn_silu_fwd: f16 output needs c %% 4 == 0 and 16-byte aligned pointers");
-  if (v4)
-    SPVD_CUDA(launch_pdl(k_affine_act4, dim3(cdiv(rows * (c / 4), 256)), dim3(256), 0, s, (const float4*)x,
-                         (const float4*)scale, (const float4*)shift, rows * (c / 4), c / 4, act, (float4*)y));
-  else
+  if (v4) {
+    if (rows * (c / 4) >= (1 << 20))
+      SPVD_CUDA(launch_pdl(k_affine_act4<2>, dim3(cdiv(rows * (c / 4), 512)), dim3(256), 0, s, (const float4*)x,
+                           (const float4*)scale, (const float4*)shift, rows * (c / 4), c / 4, act, (float4*)y));
+    else
+      SPVD_CUDA(launch_pdl(k_affine_act4<1>, dim3(cdiv(rows * (c / 4), 256)), dim3(256), 0, s, (const float4*)x,
+                           (const float4*)scale, (const float4*)shift, rows * (c / 4), c / 4, act, (float4*)y));
+  } else
     SPVD_CUDA(launch_pdl(k_affine_act1, dim3(cdiv(rows * c, 256)), dim3(256), 0, s, x, scale, shift, rows * c, c, act, y));
   return SPVD_OK;
 }
