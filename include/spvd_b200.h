@@ -479,6 +479,25 @@ int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_level_geom_t* l
                      int n_points, int n_batch, void* arena, size_t arena_bytes,
                      void* const* conv_events, spvd_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * N4  evaluation distances between point clouds xyz1 [B,n,3], xyz2 [B,m,3] (fp32, row-major).
+ * Chamfer (metrics/chamfer_dist/chamfer.cu:15-229): dist1[b,i] = min_j |xyz1_i - xyz2_j|^2 with its first argmin idx1, and
+ * the same from xyz2 to xyz1; the backward scatters 2 g (a - b) to both ends of every nearest-neighbour pair.
+ * Approximate earth mover's distance (metrics/PyTorchEMD/cuda/emd_kernel.cu:26-330): approxmatch = auction-style soft
+ * matching over the levels -4^7 .. -4^-1, 0 into match [B,m,n]; matchcost = sum match * squared distance, and its
+ * gradients w.r.t. both clouds.  workspace: spvd_emd_workspace_floats(B, n, m) floats. */
+int spvd_chamfer_fwd(const float* xyz1, const float* xyz2, int n_batch, int n, int m, float* dist1, float* dist2,
+                     int32_t* idx1, int32_t* idx2, spvd_stream_t stream);
+int spvd_chamfer_bwd(const float* xyz1, const float* xyz2, const int32_t* idx1, const int32_t* idx2, const float* gdist1,
+                     const float* gdist2, int n_batch, int n, int m, float* gxyz1, float* gxyz2, spvd_stream_t stream);
+size_t spvd_emd_workspace_floats(int n_batch, int n, int m);
+int spvd_emd_approxmatch(const float* xyz1, const float* xyz2, int n_batch, int n, int m, float* match, float* workspace,
+                         spvd_stream_t stream);
+int spvd_emd_matchcost_fwd(const float* xyz1, const float* xyz2, const float* match, int n_batch, int n, int m, float* cost,
+                           spvd_stream_t stream);
+int spvd_emd_matchcost_bwd(const float* grad_cost, const float* xyz1, const float* xyz2, const float* match, int n_batch, int n,
+                           int m, float* grad1, float* grad2, spvd_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

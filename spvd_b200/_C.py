@@ -37,6 +37,12 @@ SIGNATURES = {
     "spvd_segment_mean_fwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _p, _i, _p]),
     "spvd_point_mean_weights": (_i, [_p, _i, _i, _p, _p, _p]),
     "spvd_scatter_wmean_fwd": (_i, [_p, _p, _p, _i, _i, _p, _i, _p]),
+    "spvd_chamfer_fwd": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p]),
+    "spvd_chamfer_bwd": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
+    "spvd_emd_workspace_floats": (_sz, [_i, _i, _i]),
+    "spvd_emd_approxmatch": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "spvd_emd_matchcost_fwd": (_i, [_p, _p, _p, _i, _i, _i, _p, _p]),
+    "spvd_emd_matchcost_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _p, _p]),
     "spvd_time_embed_fwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p, _p]),
     "spvd_scatter_mean_bwd": (_i, [_p, _p, _p, _i, _i, _p, _p]),
     "spvd_devoxelize_fwd": (_i, [_p, _p, _p, _i, _i, _p, _p]),

@@ -1,0 +1,65 @@
+"""Chamfer / approximate EMD kernels against the CPU restatement in oracle/metrics.py."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("B,n,m", [(3, 500, 700), (2, 2048, 2048), (1, 37, 1500)])
+def test_chamfer_forward_backward(B, n, m):
+    from oracle import metrics as om
+    from spvd_b200 import metrics as gm
+    g = torch.Generator().manual_seed(n + m)
+    a, b = torch.randn(B, n, 3, generator=g), torch.randn(B, m, 3, generator=g)
+    d1, d2, i1, i2 = om.chamfer(a, b)
+    ad, bd = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    g1, g2, j1, j2 = gm.chamfer_3DDist()(ad, bd)
+    assert np.allclose(g1.detach().cpu().numpy(), d1.numpy(), rtol=1e-5, atol=1e-7)
+    assert np.allclose(g2.detach().cpu().numpy(), d2.numpy(), rtol=1e-5, atol=1e-7)
+    # argmin: identical except on exact ties; the distance at the returned index is the minimum
+    assert (j1.cpu() == i1).float().mean() > 0.999 and (j2.cpu() == i2).float().mean() > 0.999
+    picked = ((a - torch.gather(b, 1, j1.cpu().long()[..., None].expand(-1, -1, 3))) ** 2).sum(-1)
+    assert np.allclose(picked.numpy(), d1.numpy(), rtol=1e-5, atol=1e-7)
+    # gradients of the reference's loss (mean + mean) against autograd through the oracle's gather formulation
+    ac, bc = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    dd = ((ac[:, :, None] - bc[:, None]) ** 2).sum(-1)
+    (dd.min(2)[0].mean() + dd.min(1)[0].mean()).backward()
+    gm.ChamferDistanceL2()(ad, bd).backward()
+    assert rel_err(ad.grad.cpu().numpy(), ac.grad.numpy()) < 1e-5 and rel_err(bd.grad.cpu().numpy(), bc.grad.numpy()) < 1e-5
+
+
+@pytest.mark.parametrize("B,n,m", [(2, 256, 256), (3, 512, 256), (1, 300, 900), (2, 1024, 1024)])
+def test_emd_match_cost_and_gradients(B, n, m):
+    from oracle import metrics as om
+    from spvd_b200 import metrics as gm
+    g = torch.Generator().manual_seed(7 * n + m)
+    a, b = torch.rand(B, n, 3, generator=g) - 0.5, torch.rand(B, m, 3, generator=g) - 0.5
+    match = om.approxmatch(a, b)
+    want = om.matchcost(a, b, match)
+    ad, bd = a.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    cost = gm.earth_mover_distance(ad, bd, transpose=False)
+    assert rel_err(cost.detach().cpu().numpy(), want.numpy()) < 1e-3          # __expf vs exp over ten levels
+    # the matching is (nearly) a transport plan: every point of the smaller-multiplicity side is matched once
+    ws = torch.empty(gm.lib.spvd_emd_workspace_floats(B, n, m), device="cuda")
+    mt = torch.empty(B, m, n, device="cuda")
+    gm.check(gm.lib.spvd_emd_approxmatch(gm._ptr(ad.detach()), gm._ptr(bd.detach()), B, n, m, gm._ptr(mt), gm._ptr(ws), gm._stream()))
+    assert rel_err(mt.cpu().numpy(), match.numpy()) < 2e-3
+    multi_l = 1.0 if n >= m else float(m // n)
+    assert np.allclose(mt.sum(1).cpu().numpy(), multi_l, atol=2e-2)
+    # gradients: matchcost is bilinear in the squared distances with the matching held fixed
+    cost.sum().backward()
+    ac, bc = a.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    om.matchcost(ac, bc, match).sum().backward()
+    assert rel_err(ad.grad.cpu().numpy(), ac.grad.numpy()) < 2e-3 and rel_err(bd.grad.cpu().numpy(), bc.grad.numpy()) < 2e-3
+    # transposed input convention of the reference ([B,3,n])
+    c2 = gm.EMD(a.cuda().transpose(1, 2).contiguous(), b.cuda().transpose(1, 2).contiguous())
+    assert torch.allclose(c2, cost.detach(), rtol=1e-6)
+
+
+def test_metrics_refuse_cpu_tensors():
+    from spvd_b200 import metrics as gm
+    with pytest.raises(RuntimeError):
+        gm.chamfer_3DDist()(torch.zeros(1, 8, 3), torch.zeros(1, 8, 3))
