@@ -63,3 +63,23 @@ def test_metrics_refuse_cpu_tensors():
     from spvd_b200 import metrics as gm
     with pytest.raises(RuntimeError):
         gm.chamfer_3DDist()(torch.zeros(1, 8, 3), torch.zeros(1, 8, 3))
+
+
+def test_reference_extension_names_resolve_to_this_library():
+    """`import chamfer` / `import emd_cuda` (the reference's compiled extensions) after spvd_b200.compat.install()"""
+    import spvd_b200.compat as compat
+    from spvd_b200 import metrics as gm
+    compat.install()
+    import chamfer, emd_cuda
+    g = torch.Generator().manual_seed(3)
+    a, b = torch.rand(2, 300, 3, generator=g).cuda(), torch.rand(2, 400, 3, generator=g).cuda()
+    d1, d2, i1, i2 = chamfer.forward(a, b)
+    w1, w2, j1, j2 = gm.chamfer_3DDist()(a, b)
+    assert torch.equal(d1, w1) and torch.equal(d2, w2) and torch.equal(i1, j1) and torch.equal(i2, j2)
+    g1, g2 = chamfer.backward(a, b, i1, i2, torch.ones_like(d1), torch.ones_like(d2))
+    assert g1.shape == a.shape and g2.shape == b.shape and torch.isfinite(g1).all()
+    match = emd_cuda.approxmatch_forward(a, b)
+    cost = emd_cuda.matchcost_forward(a, b, match)
+    assert torch.allclose(cost, gm.EMD(a, b, transpose=False), rtol=1e-6)
+    ga, gb = emd_cuda.matchcost_backward(torch.ones_like(cost), a, b, match)
+    assert ga.shape == a.shape and gb.shape == b.shape
