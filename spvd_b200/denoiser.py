@@ -296,12 +296,15 @@ class SPVUnet(nn.Module):
         planned (``geometry_pool`` > 2 keeps more alive, e.g. when several forwards precede one backward)."""
         p = self._plan
         pc = (coords.float() if coords.dtype != torch.float32 else coords).contiguous()
-        key = (pc.shape[0], n_batch, pc.device)
+        key = (pc.shape[0], n_batch, pc.device, self.training)
         pool = self._plan_ws.get(key)
         if pool is None:
             pool = self._plan_ws[key] = [[], 0]
         if len(pool[0]) < self.geometry_pool:
-            pool[0].append(PlanWorkspace(pc.shape[0], n_batch, p["strides"], p["strides"], p["p2v"], p["devox"], pc.device))
+            # training: pair lists at every level (the weight gradient reduces over them); inference: only where the
+            # executor can choose pair-major convolutions
+            pool[0].append(PlanWorkspace(pc.shape[0], n_batch, p["strides"], p["strides"], p["p2v"], p["devox"], pc.device,
+                                         pair_strides=None if self.training else (1, 2)))
             ws = pool[0][-1]
         else:
             pool[1] = (pool[1] + 1) % len(pool[0])

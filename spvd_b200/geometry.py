@@ -226,9 +226,11 @@ class PlanWorkspace:
     """All buffers of one Geometry for a fixed (n_points, n_batch, plan), allocated once; ``build`` fills them
     with one C call and returns a Geometry that VIEWS them (valid until the workspace is built again)."""
 
-    def __init__(self, n_points, n_batch, strides, k3_strides, p2v_strides, devox_strides, device, pair_strides=(1, 2)):
+    def __init__(self, n_points, n_batch, strides, k3_strides, p2v_strides, devox_strides, device, pair_strides=None):
         self.n_points, self.n_batch, self.strides = n_points, n_batch, tuple(strides)
-        self.pair_strides = tuple(s for s in pair_strides if s in k3_strides)
+        # pair lists at every level: the executor picks pair-major or dense per level from the pair count, the training path's
+        # weight gradient reduces over them
+        self.pair_strides = tuple(s for s in (k3_strides if pair_strides is None else pair_strides) if s in k3_strides)
         assert all(s == 1 << i for i, s in enumerate(self.strides)), "strides must be 1,2,4,..."
         i32 = dict(dtype=torch.int32, device=device)
         nl, ld = len(self.strides), ops.round128(n_points)
@@ -421,6 +423,8 @@ class PlanWorkspace:
             if "kmap3" in b:
                 lv.kmap3 = KernelMap(b["kmap3"], b["mask3"], lv.n, lv.n, 27, flip=True)
                 lv.kmap3.grad = lv.kmap3
+                if "pair_in" in b:       # the weight-gradient kernel reduces over the planner's pair list: no lazy build, no sync
+                    lv.kmap3._pairs = lv.pairs[:4]
         for i in range(max(lo - 1, 0), hi - 1):           # stride-2 maps between level i and i + 1 (planned with level i + 1)
             b, lv, c = self.bufs[i], geo.levels[self.strides[i]], geo.levels[self.strides[i + 1]]
             if "dpair_in" in b:
@@ -430,3 +434,7 @@ class PlanWorkspace:
                 lv.kmap_down = KernelMap(b["kmap_down"], b["mask_down"], c.n, lv.n, 8, flip=False)
                 lv.kmap_up = KernelMap(b["kmap_up"], b["mask_up"], lv.n, c.n, 8, flip=False)
                 lv.kmap_down.grad, lv.kmap_up.grad = lv.kmap_up, lv.kmap_down
+                if "dpair_in" in b:      # one (fine, coarse) pair list serves the strided conv and, roles swapped, its transpose
+                    dp = lv.dpairs
+                    lv.kmap_down._pairs = (dp[0], dp[1], dp[2], dp[3])
+                    lv.kmap_up._pairs = (dp[1], dp[0], dp[2], dp[3])
