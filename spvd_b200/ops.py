@@ -34,7 +34,9 @@ def _p(t, dtype=None):
 
 
 def _s():
-    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # torch.cuda.current_stream() costs ~15 us of Python per call (hundreds of calls per training step); the raw getter is
+    # a plain C call returning the same cudaStream_t
+    return ctypes.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 class _Stats:
