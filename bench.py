@@ -119,7 +119,6 @@ def run_b200(args):
     import spvd_b200
     from spvd_b200 import ops
     from spvd_b200.sampler import DDPMSparseSchedulerGPU
-    from oracle import model as om          # deterministic random-init weights (names/shapes of the reference)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -131,8 +130,8 @@ def run_b200(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     B, N, K, W = args.batch, args.points, args.steps, args.warmup
-    model = spvd_b200.build_model(args.preset, downsample_mode=args.downsample_mode)
-    model.load_state_dict(om.make_state_dict(args.preset, seed=0))
+    torch.manual_seed(0)                     # random-init weights of the named architecture (the module's own initialisers;
+    model = spvd_b200.build_model(args.preset, downsample_mode=args.downsample_mode)   # nothing of oracle/ is on this arm)
     model = model.to(dev).eval()
     sched = DDPMSparseSchedulerGPU()
     strat, xs, ts = make_workload(K + W, B, N, seed=1234 + rank)
