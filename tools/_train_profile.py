@@ -3,9 +3,8 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, spvd_b200
 from spvd_b200.sampler import torch2sparse
-from oracle import model as om
 dev = torch.device("cuda", 0)
-model = spvd_b200.build_model("SPVD"); model.load_state_dict(om.make_state_dict("SPVD", 0)); model = model.to(dev).train()
+torch.manual_seed(0); model = spvd_b200.build_model("SPVD"); model = model.to(dev).train()
 opt = torch.optim.Adam(model.parameters(), lr=1e-4)
 strat, xs, ts = bench.make_workload(6, 32, 2048, 7)
 def step(j):

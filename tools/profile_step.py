@@ -6,14 +6,13 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench
 import spvd_b200
 from spvd_b200.sampler import DDPMSparseSchedulerGPU
-from oracle import model as om
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 warm = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 preset = os.environ.get("SPVD_PRESET", "SPVD")
 dev = torch.device("cuda", 0)
+torch.manual_seed(0)
 model = spvd_b200.build_model(preset)
-model.load_state_dict(om.make_state_dict(preset, seed=0))
 model = model.to(dev).eval()
 sched = DDPMSparseSchedulerGPU()
 strat, xs, ts = bench.make_workload(steps + warm, 32, 2048, 1234)

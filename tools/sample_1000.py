@@ -6,11 +6,10 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import spvd_b200
 from spvd_b200.sampler import DDPMSparseSchedulerGPU
-from oracle import model as om
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+torch.manual_seed(0)
 model = spvd_b200.build_model("SPVD")
-model.load_state_dict(om.make_state_dict("SPVD", seed=0))
 model = model.cuda().eval()
 sched = DDPMSparseSchedulerGPU(n_steps=steps)
 torch.manual_seed(0)

@@ -4,11 +4,10 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, spvd_b200
 from spvd_b200.sampler import DDPMSparseSchedulerGPU
-from oracle import model as om
 
 dev = torch.device("cuda", 0)
 preset = os.environ.get("SPVD_PRESET", "SPVD")
-model = spvd_b200.build_model(preset); model.load_state_dict(om.make_state_dict(preset, 0)); model = model.to(dev).eval()
+torch.manual_seed(0); model = spvd_b200.build_model(preset); model = model.to(dev).eval()
 sched = DDPMSparseSchedulerGPU()
 K, W = 10, 3
 strat, xs, ts = bench.make_workload(K + W, 32, 2048, 1234)

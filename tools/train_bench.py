@@ -5,12 +5,11 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, spvd_b200
 from spvd_b200.sampler import torch2sparse, DDPM
 from spvd_b200.parallel import train_step
-from oracle import model as om
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 B = int(os.environ.get("SPVD_BATCH", "32"))
 dev = torch.device("cuda", 0)
-model = spvd_b200.build_model("SPVD"); model.load_state_dict(om.make_state_dict("SPVD", 0)); model = model.to(dev).train()
+torch.manual_seed(0); model = spvd_b200.build_model("SPVD"); model = model.to(dev).train()
 opt = torch.optim.Adam(model.parameters(), lr=1e-4)
 strat, xs, ts = bench.make_workload(steps + 2, B, 2048, 7)
 E = lambda: torch.cuda.Event(enable_timing=True)

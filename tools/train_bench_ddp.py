@@ -7,7 +7,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, spvd_b200
 from spvd_b200.sampler import torch2sparse
 from spvd_b200.parallel import GradientAllReduce, train_step
-from oracle import model as om
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -15,7 +14,7 @@ torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
-model = spvd_b200.build_model("SPVD"); model.load_state_dict(om.make_state_dict("SPVD", 0)); model = model.to(dev).train()
+torch.manual_seed(0); model = spvd_b200.build_model("SPVD"); model = model.to(dev).train()
 opt = torch.optim.Adam(model.parameters(), lr=1e-4)
 red = GradientAllReduce(model.parameters()) if world > 1 else None
 W = 3
