@@ -115,6 +115,55 @@ __global__ void __launch_bounds__(256) k_conv_fwd_small_cin(const float* __restr
   out[t] = acc;
 }
 
+// nn.Linear with a tiny input or output width (the 3 -> 32 point embedding, the 32 -> 3 output head; 65536 rows):
+// pure streaming.  kLinIn: one thread per (row, 4 output channels), 128-bit residual loads and stores.
+// kLinOut: one thread per row, the row read as float4, cout <= 4 dot products.
+__global__ void __launch_bounds__(256) k_linear_small_cin4(const float* __restrict__ in, const float* __restrict__ w, int n_out,
+                                                           int cin, int cout4, const float* __restrict__ bias,
+                                                           const float* __restrict__ residual, float* __restrict__ out) {
+  extern __shared__ float4 s_w4[];   // [cin][cout4]
+  pdl_trigger();
+  for (int i = threadIdx.x; i < cin * cout4; i += blockDim.x) s_w4[i] = reinterpret_cast<const float4*>(w)[i];
+  pdl_wait();
+  __syncthreads();
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)n_out * cout4) return;
+  const int o = (int)(t / cout4), q = (int)(t % cout4);
+  float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+  if (residual) {
+    const float4 r = reinterpret_cast<const float4*>(residual)[t];
+    acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
+  }
+  for (int ci = 0; ci < cin; ++ci) {
+    const float x = __ldg(in + (size_t)o * cin + ci);
+    const float4 wv = s_w4[ci * cout4 + q];
+    acc.x = fmaf(x, wv.x, acc.x); acc.y = fmaf(x, wv.y, acc.y); acc.z = fmaf(x, wv.z, acc.z); acc.w = fmaf(x, wv.w, acc.w);
+  }
+  reinterpret_cast<float4*>(out)[t] = acc;
+}
+
+__global__ void __launch_bounds__(256) k_linear_small_cout(const float* __restrict__ in, const float* __restrict__ w, int n_out,
+                                                           int cin4, int cout, const float* __restrict__ bias,
+                                                           const float* __restrict__ residual, float* __restrict__ out) {
+  extern __shared__ float s_wo[];   // [cin][cout]
+  pdl_trigger();
+  for (int i = threadIdx.x; i < cin4 * 4 * cout; i += blockDim.x) s_wo[i] = w[i];
+  pdl_wait();
+  __syncthreads();
+  const int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= n_out) return;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int c = 0; c < cout; ++c) acc[c] = (bias ? bias[c] : 0.f) + (residual ? residual[(size_t)o * cout + c] : 0.f);
+  const float4* xr = reinterpret_cast<const float4*>(in) + (size_t)o * cin4;
+  for (int i = 0; i < cin4; ++i) {
+    const float4 x = xr[i];
+    const float* wr = s_wo + (size_t)i * 4 * cout;
+    for (int c = 0; c < cout; ++c)
+      acc[c] = fmaf(x.w, wr[3 * cout + c], fmaf(x.z, wr[2 * cout + c], fmaf(x.y, wr[cout + c], fmaf(x.x, wr[c], acc[c]))));
+  }
+  for (int c = 0; c < cout; ++c) out[(size_t)o * cout + c] = acc[c];
+}
+
 // The same on a pair list (spvd_kmap_pairs): one CTA per tile of 128 (input row, output row) pairs of ONE offset, one
 // warp instruction per pair (lanes = output channels), vector-free RED into the zero-filled output; the centre-offset
 // tiles, which cover every output row exactly once, add the bias.  At stride 1 a voxel has ~2 of 27 neighbours, so this
@@ -244,6 +293,17 @@ extern "C" int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t
   SPVD_CHECK_ARG(map_t || kvol == 1, "spvd_conv_fwd: a NULL map needs kvol == 1");
   SPVD_CHECK_ARG(!map_t || ld >= n_out, "spvd_conv_fwd: ld %d < n_out %d", ld, n_out);
   if (n_out == 0) return SPVD_OK;
+  const bool al16 = (((size_t)in | (size_t)w | (size_t)out | (size_t)bias | (size_t)residual) & 15) == 0;
+  if (!map_t && kvol == 1 && cin <= 4 && cout % 4 == 0 && cin * cout * 4 <= 40 * 1024 && al16) {
+    SPVD_CUDA(launch_pdl(k_linear_small_cin4, dim3(cdiv((long long)n_out * (cout / 4), 256)), dim3(256), (size_t)cin * cout * 4,
+                         (cudaStream_t)stream, in, w, n_out, cin, cout / 4, bias, residual, out));
+    return SPVD_OK;
+  }
+  if (!map_t && kvol == 1 && cout <= 4 && cin % 4 == 0 && cin * cout * 4 <= 40 * 1024 && al16) {
+    SPVD_CUDA(launch_pdl(k_linear_small_cout, dim3(cdiv(n_out, 256)), dim3(256), (size_t)cin * cout * 4, (cudaStream_t)stream, in, w,
+                         n_out, cin / 4, cout, bias, residual, out));
+    return SPVD_OK;
+  }
   if (cin <= 4 && (size_t)kvol * cin * cout * 4 <= 40 * 1024) {
     SPVD_CUDA(launch_pdl(k_conv_fwd_small_cin, dim3(cdiv((long long)n_out * cout, 256)), dim3(256),
                          (size_t)kvol * cin * cout * 4, (cudaStream_t)stream, in, w, map_t, ld, n_out, kvol, cin, cout, bias,

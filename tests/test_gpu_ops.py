@@ -430,6 +430,17 @@ def test_conv_pair_major(sp, stride, cin, cout):
         assert rel_err(y16.cpu().numpy(), want16.numpy()) < 2e-5
 
 
+@pytest.mark.parametrize("cin,cout", [(3, 32), (4, 64), (32, 3), (64, 4), (3, 3)])
+def test_linear_tiny_width_simt(sp, cin, cout):
+    """the streaming kernels of the 3 -> 32 point embedding and the 32 -> 3 output head (and the generic fallback)"""
+    g = torch.Generator().manual_seed(cin * 100 + cout)
+    n = 5000
+    x, w, b, r = torch.randn(n, cin, generator=g), torch.randn(1, cin, cout, generator=g), torch.randn(cout, generator=g), torch.randn(n, cout, generator=g)
+    want = x @ w[0] + b + r
+    got = sp.ops.conv_fwd(x.cuda(), w.cuda(), None, None, None, n, b.cuda(), sp.ops.CONV_SIMT, residual=r.cuda())
+    assert rel_err(got.cpu().numpy(), want.numpy()) < 1e-6
+
+
 def test_conv_pair_major_simt_stem(sp):
     """the 3 -> 32 stem convolution on the pair list (fp32 SIMT, RED scatter) equals the oracle"""
     import ctypes
