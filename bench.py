@@ -53,10 +53,24 @@ def parse():
 
 
 # ------------------------------------------------------------------------------------- workload
+def _schedule():
+    """spvd_b200/schedule.py loaded by path: torch-only coefficient tables, so that the CPU arm never imports the
+    spvd_b200 package (which would map libspvd_b200.so into the process)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_spvd_schedule", os.path.join(ROOT, "spvd_b200", "schedule.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def workload_name(args):
+    return (f"{args.preset} DDPM sampling step (forward + update + re-sparsify), open-loop replay over t=999..0, "
+            f"B={args.batch}x{args.points} points per GPU, random-init weights, downsample_mode={args.downsample_mode}")
+
+
 def make_workload(n_steps, B, N, seed):
     """Host tensors: per step the noisy cloud x_t [B,N,3] and its timestep."""
-    from spvd_b200.sampler import DDPM
-    strat = DDPM()
+    strat = _schedule().DDPM()
     g = torch.Generator().manual_seed(seed)
     x0 = torch.randn(B, N, 3, generator=g)
     x0 = x0 / x0.norm(dim=-1, keepdim=True) * math.sqrt(3.0)
@@ -270,8 +284,7 @@ def run_b200(args):
                "scaling": "weak", "vs_baseline": None, "dtype": ("f32 activations / accumulate, f16 tensor-core operands (11-bit significand, as TF32)"
                          if model.executor_operands == "f16" else "f32 (tf32 tensor-core operands, f32 accumulate)"),
                "data": "synthetic",
-               "config": {"workload": f"{args.preset} DDPM sampling step (forward + update + re-sparsify), open-loop replay over t=999..0, "
-                                      f"B={B}x{N} points per GPU, random-init weights, downsample_mode={args.downsample_mode}",
+               "config": {"workload": workload_name(args),
                           "preset": args.preset, "batch_per_gpu": B, "points": N, "parallelism": f"dp{world} (clouds sharded, no collective)",
                           "l2": "256 MiB flush write between timed steps" if flush is not None else "no flush (per-step working set > L2)"},
                "e2e": {"value": round(world * K / e2e_s, 3), "unit": UNIT, "h2d_bytes_per_step": nbytes,
@@ -284,7 +297,6 @@ def run_b200(args):
 def cpu_steps(args, n_steps, warmup, seed=1234):
     """The reference algorithm restated on the CPU (oracle/), timed on the host cores."""
     from oracle import model as om
-    from spvd_b200.sampler import DDPM  # coefficient tables only (pure python/torch-CPU)
     B, N = args.batch, args.points
     strat, xs, ts = make_workload(n_steps + warmup, B, N, seed)
     sd = om.make_state_dict(args.preset, seed=0)
@@ -322,8 +334,7 @@ def run_reference(args):
     out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
            "ms_per_step": round(total / K * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "f32", "data": "synthetic",
-           "config": {"workload": f"{args.preset} DDPM sampling step (forward + update + re-sparsify), open-loop replay over t=999..0, "
-                                  f"B={args.batch}x{args.points} points, random-init weights, downsample_mode={args.downsample_mode}",
+           "config": {"workload": workload_name(args),
                       "preset": args.preset, "batch_per_gpu": args.batch, "points": args.points,
                       "note": "reference's torchsparse path cannot run on CPU (GPUHashTable, models/sparse_utils.py:43) "
                               "and torchsparse is not installed: this arm is the CPU oracle port (oracle/model.py)"},

@@ -231,6 +231,47 @@ int spvd_conv_fwd_umma(const float* in, const float* w_packed, const int32_t* ma
                        const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
                        const float* bias, const float* residual, float* out, int bn, int nsplit,
                        int a_is_tf32, int mt, spvd_stream_t stream);
+/* Same kernels on mask-sorted tiles (spvd_kmap_sort): map_t / tile_mask are in the sorted row order and tile row j
+ * writes output row out_rows[j] (a permutation of 0..n_out-1; NULL = identity, i.e. spvd_conv_fwd_umma).  Rows that share
+ * their set of active kernel offsets sit in the same 128-row tile, so far fewer (tile, offset) steps multiply zero rows --
+ * what torchsparse calls a "sorted implicit GEMM"; replaces the conv launch inside spnn.Conv3d (models/spvd.py:35,38).
+ * mt = 4 with SPVD_A_F16 / SPVD_A_TF32: clusters of two CTAs multicast each half of every weight tile to both. */
+int spvd_conv_fwd_umma_rows(const float* in, const float* w_packed, const int32_t* map_t, int ld,
+                            const uint32_t* tile_mask, const int32_t* out_rows, int n_out, int kvol, int cin, int cout,
+                            const float* bias, const float* residual, float* out, int bn, int nsplit,
+                            int a_is_tf32, int mt, spvd_stream_t stream);
+/* Mask-sorted view of a kernel map: rows sorted by the bit set of their active offsets (stable: ties keep row order).
+ * map_sorted [kvol,ld] = the map with its columns in that order, mask_sorted [ld/128] = per-tile OR of the row masks,
+ * perm [ld] = sorted position -> original row (-1 past the row count).  workspace >= spvd_kmap_sort_workspace_bytes(n_cap). */
+size_t spvd_kmap_sort_workspace_bytes(int n_cap);
+int spvd_kmap_sort(const int32_t* map_t, int ld, int n_cap, const int32_t* n_dev, int kvol, int32_t* map_sorted,
+                   uint32_t* mask_sorted, int32_t* perm, void* workspace, size_t workspace_bytes, spvd_stream_t stream);
+/* Persistent sorted-tile convolution with a fused epilogue (csrc/conv_sp_f16.cu), f16 operands, fp32 accumulate:
+ *   v[o] = sum_k in[map_t[k][j]] W[k] (+ in2[o] W2) (+ bias) (+ residual[o]);  FiLM: v = (1 + film[b(o)][c]) v + film[b(o)][cout + c]
+ *   out32[o] = v;   out16[o] = f16(act(v * aff_scale + aff_shift))     (o = out_rows[j], or j when out_rows is NULL)
+ * in / in2 are f16 row-major, w / w2 spvd_conv_pack_weights_f16 images ([kvol,cin,cout] and [1,cin2,cout]); map_t NULL =
+ * identity (kvol 1).  Replaces spnn.Conv3d + the FiLM / BatchNorm / SiLU / shortcut glue of EmbResBlock.forward
+ * (models/ddpm_unet_attn.py:48-65).  bn = output slice width (0 = choose), stages = stage-ring cap (0 = choose). */
+typedef struct spvd_conv_sp_args {
+  const void* in;
+  const void* w;
+  const int32_t* map_t;
+  const uint32_t* tile_mask;
+  const int32_t* out_rows;
+  const void* in2;
+  const void* w2;
+  const float* bias;
+  const float* residual;
+  const float* film;     /* [n_batch, film_ld]: scale at column c, shift at column cout + c */
+  const int32_t* coords; /* [n_out,4], column 0 = cloud index (FiLM only) */
+  const float* aff_scale;
+  const float* aff_shift;
+  float* out32;
+  void* out16;
+  int32_t ld, n_out, kvol, cin, cout, cin2, film_ld, act; /* act bit 0 = SiLU on the f16 output */
+  int32_t n_in, pad;                                       /* rows of `in` (bound of the gather; 0 = unknown) */
+} spvd_conv_sp_args_t;
+int spvd_conv_sp_f16(const spvd_conv_sp_args_t* args, int bn, int stages, spvd_stream_t stream);
 /* Pair-major view of a kernel map, for sparse levels (few active offsets per voxel): per offset the valid
  * (input row, output row) pairs compacted into tiles of 128 pairs, ordered by offset then output row.
  * pair_in / pair_out [tile_cap*128] (-1 = padding), tile_k [tile_cap] = offset of each tile,
@@ -358,7 +399,17 @@ typedef struct spvd_plan_level {
   int32_t* p2v_cursor;    /* [n_points] (spvd_group_points_by_voxel); NULL = not wanted for this level */
   int32_t* p2v_order;     /* [n_points] */
   int32_t* p2v_units;     /* [2 * (n_points + n_points / 32 + 1)] */
-  int32_t capacity, pair_tile_cap, dpair_tile_cap, pad;
+  int32_t* kmap3_sorted;      /* mask-sorted views (spvd_kmap_sort) of kmap3 / kmap_down / kmap_up: [kvol,ld] maps in sorted  */
+  uint32_t* mask3_sorted;     /* row order, their per-tile offset masks [ld/128] and the row permutations [ld]; NULL = not   */
+  int32_t* perm3;             /* wanted.  sort_ws (>= spvd_kmap_sort_workspace_bytes(n_points)) is this level's scratch.     */
+  int32_t* kmap_down_sorted;
+  uint32_t* mask_down_sorted;
+  int32_t* perm_down;
+  int32_t* kmap_up_sorted;
+  uint32_t* mask_up_sorted;
+  int32_t* perm_up;
+  void* sort_ws;
+  int32_t capacity, pair_tile_cap, dpair_tile_cap, sort_ws_bytes;
 } spvd_plan_level_t;
 
 /* max_cloud_rows > 0: the caller promises batch-major points with at most that many per cloud (the
@@ -418,6 +469,9 @@ void spvd_plan_graph_destroy(spvd_plan_graph_t* g);
 #define SPVD_OP_TIME_EMBED 8   /* dst [batch,c1]; c0 = n_temb; w = params, p0 = class table or NULL,
                                   p1 = t (int64 [batch]), bias = class ids (int64 [batch]) or NULL  */
 #define SPVD_OP_CAT_AFFINE 9   /* dst = f16 act([src0|src1]*p0+p1), aux = f16 [src0|src1]          */
+#define SPVD_OP_CONV_SP 10     /* spvd_conv_sp_f16: src0 f16 [rows_in,c0] (+ src2 f16 [rows_out,c2]) -> v = conv + bias
+                                  + src1 residual, FiLM(src3); dst = v as fp32 (or -1), aux = f16 act(v * p0 + p1) (or
+                                  -1; p0 NULL = no affine, SPVD_FLAG_SILU = SiLU)                                  */
 
 #define SPVD_MAP_NONE 0 /* kernel size 1 / nn.Linear */
 #define SPVD_MAP_K3 1
@@ -457,6 +511,15 @@ typedef struct spvd_level_geom {
   const int32_t* p2v_start;
   const int32_t* p2v_order;
   const int32_t* p2v_units;
+  const int32_t* kmap3_sorted;   /* mask-sorted views (spvd_kmap_sort) or NULL */
+  const uint32_t* mask3_sorted;
+  const int32_t* perm3;
+  const int32_t* kmap_down_sorted;
+  const uint32_t* mask_down_sorted;
+  const int32_t* perm_down;
+  const int32_t* kmap_up_sorted;
+  const uint32_t* mask_up_sorted;
+  const int32_t* perm_up;
   int32_t n, ld3, ld_down, ld_up, max_per_batch, n_pair_tiles; /* n_pair_tiles > 0: 3^3 convs run pair-major */
   int32_t n_dpair_tiles, pad;   /* > 0: the stride-2 / transposed convs of this level run pair-major */
 } spvd_level_geom_t;
@@ -471,6 +534,11 @@ typedef struct spvd_op {
   const float* bias;
   const float* p0;
   const float* p1;
+  /* SPVD_OP_CONV_SP only: src2 = second operand source (f16 [rows_out, c2], identity rows; -1 = none) with its packed
+   * k = 1 weight image w2_packed; src3 = FiLM table (row stride i0 floats, column offset i1; -1 = none) */
+  int64_t src2, src3;
+  const float* w2_packed;
+  int32_t c2, pad2;
 } spvd_op_t;
 
 /* conv_events: NULL, or 2 CUDA events (cudaEvent_t) per SPVD_OP_CONV in program order, recorded

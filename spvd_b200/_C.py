@@ -55,6 +55,10 @@ SIGNATURES = {
     "spvd_conv_fwd": (_i, [_p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _i, _p]),
     "spvd_conv_fwd_simt": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _p]),
     "spvd_conv_fwd_umma": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "spvd_conv_fwd_umma_rows": (_i, [_p, _p, _p, _i, _p, _p, _i, _i, _i, _i, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "spvd_kmap_sort_workspace_bytes": (_sz, [_i]),
+    "spvd_kmap_sort": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
+    "spvd_conv_sp_f16": (_i, [_p, _i, _i, _p]),
     "spvd_kmap_pairs": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "spvd_conv_fwd_pairs": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "spvd_conv_wgrad_umma": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),

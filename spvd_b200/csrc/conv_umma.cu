@@ -6,7 +6,8 @@ namespace spvd {
 // conv_umma_f16.cu
 int conv_fwd_umma_f16(const void* in, bool a_half, const void* w_packed, const int32_t* map_t, int ld,
                       const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
-                      const float* residual, float* out, int bn, int nsplit, int mt, cudaStream_t s);
+                      const float* residual, float* out, int bn, int nsplit, int mt, cudaStream_t s,
+                      const int32_t* out_rows = nullptr);
 int conv_fwd_pairs_f16(const void* in, bool a_half, const void* w_packed, const int32_t* pair_in, const int32_t* pair_out,
                        const int32_t* tile_k, int n_pair_tiles, int center_k, int n_out, int kvol, int cin, int cout,
                        const float* bias, const float* residual, float* out, cudaStream_t s);
@@ -34,6 +35,14 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
                                   const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout,
                                   const float* bias, const float* residual, float* out, int bn, int nsplit,
                                   int a_is_tf32, int mt, spvd_stream_t stream) {
+  return spvd_conv_fwd_umma_rows(in, w_packed, map_t, ld, tile_mask, nullptr, n_out, kvol, cin, cout, bias, residual, out, bn,
+                                 nsplit, a_is_tf32, mt, stream);
+}
+
+extern "C" int spvd_conv_fwd_umma_rows(const float* in, const float* w_packed, const int32_t* map_t, int ld,
+                                       const uint32_t* tile_mask, const int32_t* out_rows, int n_out, int kvol, int cin,
+                                       int cout, const float* bias, const float* residual, float* out, int bn, int nsplit,
+                                       int a_is_tf32, int mt, spvd_stream_t stream) {
   SPVD_CHECK_ARG(in && w_packed && out && n_out >= 0, "spvd_conv_fwd_umma: bad arguments");
   SPVD_CHECK_ARG(residual != out || residual == nullptr, "spvd_conv_fwd_umma: residual must not alias out");
   SPVD_CHECK_ARG(spvd_conv_umma_supported(kvol, cin, cout), "spvd_conv_fwd_umma: unsupported shape %dx%dx%d", kvol, cin, cout);
@@ -46,7 +55,7 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
   cudaStream_t s = (cudaStream_t)stream;
   if (a_is_tf32 >= SPVD_A_F32_TO_F16)   // f16 operands: w_packed is the spvd_conv_pack_weights_f16 image
     return conv_fwd_umma_f16(in, a_is_tf32 == SPVD_A_F16, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual,
-                             out, bn, nsplit, mt, s);
+                             out, bn, nsplit, mt, s, out_rows);
   if (bn <= 0) bn = pick_bn(cout, cdiv(n_out, BM), kvol);
   SPVD_CHECK_ARG(cout % bn == 0, "spvd_conv_fwd_umma: slice width %d does not divide cout %d", bn, cout);
   const int max_iters = kvol * (cin / 32);
@@ -59,12 +68,12 @@ extern "C" int spvd_conv_fwd_umma(const float* in, const float* w_packed, const 
   if (nsplit <= 0) nsplit = pick_split(cdiv(n_out, BM * (mt == 2 ? 2 : 1)) * (cout / bn), max_iters);
   if (nsplit > max_iters) nsplit = max_iters;
   switch (bn) {
-    case 32: return launch_umma_bn<32>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 64: return launch_umma_bn<64>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 96: return launch_umma_bn<96>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 128: return launch_umma_bn<128>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 192: return launch_umma_bn<192>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 256: return launch_umma_bn<256>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 32: return launch_umma_bn<32>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
+    case 64: return launch_umma_bn<64>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
+    case 96: return launch_umma_bn<96>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
+    case 128: return launch_umma_bn<128>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
+    case 192: return launch_umma_bn<192>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
+    case 256: return launch_umma_bn<256>(aa, mt, in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
   }
   set_error("spvd_conv_fwd_umma: slice width %d is not instantiated", bn);
   return SPVD_ERR_INVALID;

@@ -889,20 +889,26 @@ static int launch_2sm(const void* in, const void* wp, const int32_t* map_t, int 
 template <int BN>
 static int launch_f16_bn(bool a_half, const float* in, const float* wp, const int32_t* map_t, int ld, const uint32_t* tile_mask,
                          int n_out, int kvol, int cin, int cout, const float* bias, const float* residual, float* out,
-                         int nsplit, cudaStream_t s) {
+                         int nsplit, cudaStream_t s, int mt, const int32_t* out_rows) {
+  if (a_half && mt == 4)   // weight tiles multicast across a cluster of 2 CTAs
+    return launch_umma_cluster<BN, 2, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
+  if constexpr (BN <= 256) {
+    if (a_half && mt == 2)   // two tiles per CTA share every weight tile
+      return launch_umma<BN, 2, true, false, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
+  }
   if (a_half)
-    return launch_umma<BN, 1, true, true, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-  return launch_umma<BN, 1, false, true, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    return launch_umma<BN, 1, true, true, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
+  return launch_umma<BN, 1, false, true, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
 }
 
 int conv_fwd_umma_f16(const void* in, bool a_half, const void* w_packed, const int32_t* map_t, int ld,
                       const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
-                      const float* residual, float* out, int bn, int nsplit, int mt, cudaStream_t s) {
+                      const float* residual, float* out, int bn, int nsplit, int mt, cudaStream_t s, const int32_t* out_rows) {
   const float* inf = reinterpret_cast<const float*>(in);
   const float* wp = reinterpret_cast<const float*>(w_packed);
   // f16 rows, one slice over all output channels, automatic configuration: the persistent stream-K kernel
   // mt == 7: CTA pairs (cta_group::2), each CTA loads half of every weight tile
-  if (mt == 7 && a_half && cdiv(n_out, BM) >= 2) {
+  if (mt == 7 && a_half && !out_rows && cdiv(n_out, BM) >= 2) {
     int b = bn > 0 ? bn : pick_bn(cout, cdiv(n_out, BM), kvol);
     const int max_iters = kvol * ((cin + 63) / 64);
     int ns = nsplit > 0 ? nsplit : pick_split(cdiv(cdiv(n_out, BM), 2) * 2 * (cout / b), max_iters);
@@ -917,7 +923,7 @@ int conv_fwd_umma_f16(const void* in, bool a_half, const void* w_packed, const i
     }
   }
   // mt == 6 (experimental, slower than the one-tile kernel on every SPVD layer -- see DESIGN.md 4.1): persistent stream-K
-  if (mt == 6 && a_half && map_t && kvol > 1 && cdiv(n_out, BM) <= kSkMaxTiles) {
+  if (mt == 6 && a_half && !out_rows && map_t && kvol > 1 && cdiv(n_out, BM) <= kSkMaxTiles) {
     switch (cout) {
       case 64: return launch_streamk<64>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, s);
       case 96: return launch_streamk<96>(in, w_packed, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, s);
@@ -930,15 +936,15 @@ int conv_fwd_umma_f16(const void* in, bool a_half, const void* w_packed, const i
   if (bn <= 0) bn = pick_bn(cout, cdiv(n_out, BM), kvol);
   SPVD_CHECK_ARG(cout % bn == 0, "spvd_conv_fwd_umma: slice width %d does not divide cout %d", bn, cout);
   const int max_iters = kvol * ((cin + 63) / 64);
-  if (nsplit <= 0) nsplit = pick_split(cdiv(n_out, BM) * (cout / bn), max_iters);
+  if (nsplit <= 0) nsplit = pick_split(cdiv(n_out, BM * (mt == 2 ? 2 : 1)) * (cout / bn), max_iters);
   if (nsplit > max_iters) nsplit = max_iters;
   switch (bn) {
-    case 32: return launch_f16_bn<32>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 64: return launch_f16_bn<64>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 96: return launch_f16_bn<96>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 128: return launch_f16_bn<128>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 192: return launch_f16_bn<192>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    case 256: return launch_f16_bn<256>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    case 32: return launch_f16_bn<32>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, mt, out_rows);
+    case 64: return launch_f16_bn<64>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, mt, out_rows);
+    case 96: return launch_f16_bn<96>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, mt, out_rows);
+    case 128: return launch_f16_bn<128>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, mt, out_rows);
+    case 192: return launch_f16_bn<192>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, mt, out_rows);
+    case 256: return launch_f16_bn<256>(a_half, inf, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, mt, out_rows);
   }
   set_error("spvd_conv_fwd_umma: slice width %d is not instantiated", bn);
   return SPVD_ERR_INVALID;

@@ -20,6 +20,38 @@
 
 namespace spvd {
 
+// tools/conv_trace.cu compiles this header with -DSPVD_TRACE: per-CTA clock marks of the pipeline phases
+#ifdef SPVD_TRACE
+__device__ unsigned long long* g_spvd_trace = nullptr;     // [ctas][32]
+#define SPVD_MARK(slot)                                                                                          \
+  do {                                                                                                           \
+    if (g_spvd_trace) g_spvd_trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (slot)] = clock64(); \
+  } while (0)
+#define SPVD_ACC(slot, v)                                                                                        \
+  do {                                                                                                           \
+    if (g_spvd_trace) g_spvd_trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (slot)] += (v); \
+  } while (0)
+#define SPVD_CLK() clock64()
+#define SPVD_GMARK(slot)                                                                                         \
+  do {                                                                                                           \
+    unsigned long long t_;                                                                                       \
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_));                                                       \
+    if (g_spvd_trace) g_spvd_trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (slot)] = t_; \
+  } while (0)
+#define SPVD_SMID(slot)                                                                                          \
+  do {                                                                                                           \
+    unsigned s_;                                                                                                 \
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(s_));                                                              \
+    if (g_spvd_trace) g_spvd_trace[((size_t)(blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 32 + (slot)] = s_; \
+  } while (0)
+#else
+#define SPVD_GMARK(slot) do {} while (0)
+#define SPVD_SMID(slot) do {} while (0)
+#define SPVD_MARK(slot) do {} while (0)
+#define SPVD_ACC(slot, v) do {} while (0)
+#define SPVD_CLK() 0ll
+#endif
+
 constexpr int BM = 128;
 constexpr int BK = 32;
 constexpr int kStages = 4;
@@ -187,8 +219,13 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   static_assert(kAsyncA || MT == 1, "the register gather path is instantiated for MT = 1 only");
   static_assert(!kPairs || MT == 1, "pair-major tiles: MT = 1");
   static_assert(kCluster == 1 || (MT == 1 && !kPairs && (BN / kCluster) % 8 == 0), "cluster multicast: MT = 1, slices of 8 rows");
-  static_assert(!kF16 || (MT == 1 && kCluster == 1), "f16 operands: one tile per CTA, no cluster");
+  static_assert(!kF16 || kAsyncA || (MT == 1 && kCluster == 1), "f16 operands converted on the fly: one tile per CTA, no cluster");
   pdl_trigger();
+  if (threadIdx.x == 0) {
+    SPVD_MARK(0);
+    SPVD_GMARK(10);
+    SPVD_SMID(12);
+  }
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw = smem_u32(smem_raw);
   const uint32_t base = (raw + 1023u) & ~1023u;
@@ -248,6 +285,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
   if constexpr (kCluster > 1) cluster_sync_all();   // peers' barriers are initialised before anything remote arrives
   tc_fence_after();
   const uint32_t tmem_d = *tmem_slot;
+  if (threadIdx.x == 0) SPVD_MARK(1);
 
   // stage the input-row indices of every offset this CTA will visit (one coalesced pass; the per-iteration
   // critical path then has no dependent global load in front of the gather)
@@ -259,20 +297,31 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
       s_rows[BM + tid] = __ldg(pair_out + (size_t)blockIdx.x * BM + tid);    // output rows
     }
   } else {
-    for (int e = tid; e < (ka_end - ka_begin) * (MT * BM); e += kUmmaThreads) {
-      const int slot = e / (MT * BM), r = e - slot * (MT * BM);
-      const int o = m0 + r;
-      int v = -1;
-      if (map_t) {
-        if (o < ld) v = __ldg(map_t + (size_t)active_k[ka_begin + slot] * ld + o);
-      } else if (o < n_out) {
-        v = o;
+    if (map_t) {
+      // 16-byte asynchronous copies (512 B of one offset's map row per 32 lanes), all in flight at once: the dependent
+      // __ldg loop this replaces cost ~20k cycles per CTA with 27 active offsets (tools/_conv_trace.py)
+      constexpr int kChunks = MT * BM / 4;
+      for (int e = tid; e < (ka_end - ka_begin) * kChunks; e += kUmmaThreads) {
+        const int slot = e / kChunks, q = e - slot * kChunks;
+        const int o = m0 + 4 * q;
+        int* dst = s_rows + slot * (MT * BM) + 4 * q;
+        if (o < ld) cp_async16(smem_u32(dst), map_t + (size_t)active_k[ka_begin + slot] * ld + o, 16u);
+        else dst[0] = dst[1] = dst[2] = dst[3] = -1;
       }
-      s_rows[e] = v;
+      asm volatile("cp.async.wait_all;" ::: "memory");
+    } else {
+      for (int e = tid; e < (ka_end - ka_begin) * (MT * BM); e += kUmmaThreads) {
+        const int r = e % (MT * BM);
+        s_rows[e] = (m0 + r < n_out) ? m0 + r : -1;
+      }
     }
   }
   pdl_wait();   // everything above read geometry and weights only; activations follow
   __syncthreads();
+  if (threadIdx.x == 0) {
+    SPVD_MARK(2);
+    SPVD_ACC(16, (unsigned long long)num_iters);
+  }
 
   if (warp < 4) {
     // ------------------------------------------------------------------ producers
@@ -292,7 +341,9 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
         const int ka = it / nchunks, c = it - ka * nchunks;
         const int k = active_k[ka];
         if (c == 0 || li == 0) load_rows(ka);
+        const long long tw0 = SPVD_CLK();
         mbar_wait(bar_base + 8 * (kStages + stage), parity ^ 1u);
+        if (tid == 0) SPVD_ACC(17, (unsigned long long)(SPVD_CLK() - tw0));
         const uint32_t a_s = base + stage * Cfg::kStageBytes;
         if (tid == 0) {
           mbar_arrive_expect_tx(bar_base + 8 * stage, Cfg::kBTileBytes);
@@ -316,7 +367,9 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
           cp_async16(dst, src, ok ? 16u : 0u);
         }
         cp_async_mbar_arrive_noinc(bar_base + 8 * stage);
+        if (tid == 0 && li == 0) SPVD_MARK(3);
       }
+      if (tid == 0) SPVD_MARK(4);
     } else if constexpr (kF16) {
       // fp32 rows converted on the fly: this thread's 16-byte f16 piece of a row is 8 input channels = two float4
       float4 v[16];
@@ -426,6 +479,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
       mbar_wait(bar_base + 8 * (2 * kStages), 0);
       tc_fence_after();
     }
+    if (tid == 0) SPVD_MARK(7);
     const bool first = kPairs ? (active_k[0] == center_k) : (blockIdx.z == 0);
     const bool add_bias = bias != nullptr && first;
     const bool add_res = residual != nullptr && first;
@@ -436,6 +490,9 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
       if constexpr (kPairs) {
         row = s_rows[BM + warp * 32 + lane];
         if (row < 0) row = n_out;   // padding pair: nothing to write
+      } else if (pair_out) {
+        // mask-sorted tiles (spvd_kmap_sort): tile row j is output row pair_out[j]
+        row = row < n_out ? __ldg(pair_out + row) : n_out;
       }
       // residual of the row, one 32-column chunk ahead of its use (the loads fly under tcgen05.ld and the stores)
       const bool pre_res = add_res && !split && wide && row < n_out;
@@ -515,12 +572,18 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
         }
       }
     }
+    if (tid == 0) SPVD_MARK(8);
   } else {
     // ------------------------------------------------------------------ MMA issuer (warp 4)
     for (int li = 0; li < num_iters; ++li) {
       const int stage = li % kStages;
       const uint32_t parity = (uint32_t)(li / kStages) & 1u;
+      const long long tw0 = SPVD_CLK();
       mbar_wait(bar_base + 8 * stage, parity);
+      if (lane == 0) {
+        SPVD_ACC(18, (unsigned long long)(SPVD_CLK() - tw0));
+        if (li == 0) SPVD_MARK(5);
+      }
       if constexpr (kAsyncA) fence_proxy_async();   // cp.async wrote the A tiles through the generic proxy
       tc_fence_after();
       if (lane == 0) {
@@ -544,9 +607,14 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
       }
       __syncwarp();
     }
+    if (lane == 0) SPVD_MARK(6);
   }
   tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) {
+    SPVD_MARK(9);
+    SPVD_GMARK(11);
+  }
   if constexpr (kCluster > 1) cluster_sync_all();   // no CTA leaves while a peer may still write its smem / barriers
   if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
@@ -572,7 +640,7 @@ static __global__ void k_pack_weights(const float* __restrict__ w, int kvol, int
 template <int BN, int MT, bool kAsyncA, bool kLite = false, bool kF16 = false>
 static int launch_umma(const float* in, const float* wp, const int32_t* map_t, int ld, const uint32_t* tile_mask,
                        int n_out, int kvol, int cin, int cout, const float* bias, const float* residual, float* out,
-                       int nsplit, cudaStream_t s) {
+                       int nsplit, cudaStream_t s, const int32_t* out_rows = nullptr) {
   using Cfg = UmmaCfg<BN, MT, false, kLite>;
   static bool configured = false;
   if (!configured) {
@@ -584,7 +652,7 @@ static int launch_umma(const float* in, const float* wp, const int32_t* map_t, i
   dim3 grid(cdiv(n_out, BM * MT), cout / BN, nsplit);
   SPVD_CUDA(launch_pdl(k_conv_fwd_umma<BN, MT, kAsyncA, false, kLite, 1, kF16>, grid, dim3(kUmmaThreads),
                        (size_t)Cfg::kSmemBytes, s, in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out,
-                       (const int*)nullptr, 0));
+                       (const int*)out_rows, 0));
   return SPVD_OK;
 }
 
@@ -619,12 +687,12 @@ static int launch_umma_pairs(bool async_a, const float* in, const float* wp, con
                                                   cin, cout, bias, residual, out, s);
 }
 
-template <int BN, int kCluster>
+template <int BN, int kCluster, bool kF16 = false>
 static int launch_umma_cluster(const float* in, const float* wp, const int32_t* map_t, int ld, const uint32_t* tile_mask,
                                int n_out, int kvol, int cin, int cout, const float* bias, const float* residual, float* out,
-                               int nsplit, cudaStream_t s) {
+                               int nsplit, cudaStream_t s, const int32_t* out_rows = nullptr) {
   using Cfg = UmmaCfg<BN, 1, false, true>;
-  auto kern = k_conv_fwd_umma<BN, 1, true, false, true, kCluster>;
+  auto kern = k_conv_fwd_umma<BN, 1, true, false, true, kCluster, kF16>;
   static bool configured = false;
   if (!configured) {
     SPVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -647,28 +715,28 @@ static int launch_umma_cluster(const float* in, const float* wp, const int32_t* 
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   SPVD_CUDA(cudaLaunchKernelEx(&cfg, kern, in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out,
-                               (const int*)nullptr, 0));
+                               (const int*)out_rows, 0));
   return SPVD_OK;
 }
 
 template <int BN>
 static int launch_umma_bn(bool async_a, int mt, const float* in, const float* wp, const int32_t* map_t, int ld,
                           const uint32_t* tile_mask, int n_out, int kvol, int cin, int cout, const float* bias,
-                          const float* residual, float* out, int nsplit, cudaStream_t s) {
+                          const float* residual, float* out, int nsplit, cudaStream_t s, const int32_t* out_rows = nullptr) {
   if (!async_a) {
     if (mt == 3)
-      return launch_umma<BN, 1, false, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-    return launch_umma<BN, 1, false>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+      return launch_umma<BN, 1, false, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
+    return launch_umma<BN, 1, false>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
   }
   if (mt == 4)   // lite + weight tiles multicast across a cluster of 2 CTAs
-    return launch_umma_cluster<BN, 2>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    return launch_umma_cluster<BN, 2>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
   if (mt == 5)
-    return launch_umma_cluster<BN, 4>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    return launch_umma_cluster<BN, 4>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
   if (mt == 3)   // one tile per CTA, two stages: small enough for two CTAs per SM
-    return launch_umma<BN, 1, true, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    return launch_umma<BN, 1, true, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
   if (mt >= 2)
-    return launch_umma<BN, 2, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
-  return launch_umma<BN, 1, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s);
+    return launch_umma<BN, 2, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
+  return launch_umma<BN, 1, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
 }
 
 // widest instantiated slice that divides cout: the A tile is gathered once per slice, so fewer is better

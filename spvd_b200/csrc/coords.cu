@@ -172,9 +172,9 @@ __global__ void k_digit_hist(const u64* __restrict__ keys, SortState* st) {
     if (h[i]) atomicAdd(g + i, h[i]);
 }
 
-__global__ void k_sort_plan(SortState* st) {
+__global__ void k_sort_plan(SortState* st, int first_pass = 0) {
   __shared__ int uniform[8];
-  if (threadIdx.x < 8) uniform[threadIdx.x] = 0;
+  if (threadIdx.x < 8) uniform[threadIdx.x] = threadIdx.x < first_pass ? 1 : 0;   // digits the input is already sorted by
   __syncthreads();
   unsigned n = (unsigned)st->n;
   for (int p = 0; p < 8; ++p)
@@ -364,7 +364,7 @@ static int sorted_unique(const SortWs& w, int n_cap, int4* out_coords, int* out_
   if (grid > 296) grid = 296;
   if (grid < 1) grid = 1;
   k_digit_hist<<<grid, 256, 0, s>>>(w.buf[0], w.st);
-  k_sort_plan<<<1, 256, 0, s>>>(w.st);
+  k_sort_plan<<<1, 256, 0, s>>>(w.st, 0);
   for (int p = 0; p < 8; ++p) {
     k_tile_hist<<<w.n_tiles, kSortThreads, 0, s>>>(w.buf[0], w.buf[1], w.st, p, w.n_tiles, w.tile_hist);
     k_scatter<<<w.n_tiles, kSortThreads, 0, s>>>(w.buf[0], w.buf[1], w.st, p, w.n_tiles, w.tile_hist);
@@ -374,6 +374,44 @@ static int sorted_unique(const SortWs& w, int n_cap, int4* out_coords, int* out_
                                                     out_count);
   SPVD_LAUNCH_CHECK();
   return SPVD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Mask-sorted view of a kernel map (what torchsparse calls the "sorted implicit GEMM" order): output rows sorted by the
+// bit set of their active kernel offsets, so that the 128 rows of a tile share (most of) their offsets and an
+// output-stationary convolution tile issues few zero rows.  Key = (mask << 32) | row: the input is already sorted by
+// the low 32 bits and every pass of the LSD sort is stable, so only the four mask digits are sorted.
+// ---------------------------------------------------------------------------------------------
+__global__ void k_mask_keys(const int* __restrict__ map_t, int ld, int kvol, const SortState* __restrict__ st,
+                            u64* __restrict__ keys) {
+  const int n = st->n;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  unsigned m = 0;
+  for (int k = 0; k < kvol; ++k) m |= (__ldg(map_t + (size_t)k * ld + i) >= 0 ? 1u : 0u) << k;
+  keys[i] = ((u64)m << 32) | (u64)(unsigned)i;
+}
+
+__global__ void __launch_bounds__(128) k_sorted_map(const u64* __restrict__ b0, const u64* __restrict__ b1,
+                                                    const SortState* __restrict__ st, const int* __restrict__ map_t, int ld,
+                                                    int kvol, int* __restrict__ map_sorted, unsigned* __restrict__ mask_sorted,
+                                                    int* __restrict__ perm) {
+  __shared__ unsigned wm[4];
+  const u64* src = st->parity[8] ? b1 : b0;
+  const int n = st->n, j = blockIdx.x * 128 + threadIdx.x;
+  int row = -1;
+  unsigned m = 0;
+  if (j < n) {
+    const u64 key = src[j];
+    row = (int)(unsigned)(key & 0xffffffffull);
+    m = (unsigned)(key >> 32);
+  }
+  perm[j] = row;
+  for (int k = 0; k < kvol; ++k) map_sorted[(size_t)k * ld + j] = row >= 0 ? __ldg(map_t + (size_t)k * ld + row) : -1;
+  m = __reduce_or_sync(0xffffffffu, m);
+  if ((threadIdx.x & 31) == 0) wm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x == 0) mask_sorted[blockIdx.x] = wm[0] | wm[1] | wm[2] | wm[3];
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -648,4 +686,31 @@ extern "C" int spvd_downsample_coords(const int32_t* coords, int n_cap, const in
   }
   k_parent_keys<<<cdiv(n_cap, 256), 256, 0, s>>>((const int4*)coords, w.st, mode, w.buf[0], status);
   return sorted_unique(w, n_cap, (int4*)out_coords, out_count, s);
+}
+
+extern "C" size_t spvd_kmap_sort_workspace_bytes(int n_cap) { return sort_ws_bytes(n_cap); }
+
+extern "C" int spvd_kmap_sort(const int32_t* map_t, int ld, int n_cap, const int32_t* n_dev, int kvol, int32_t* map_sorted,
+                              uint32_t* mask_sorted, int32_t* perm, void* workspace, size_t workspace_bytes,
+                              spvd_stream_t stream) {
+  SPVD_CHECK_ARG(map_t && map_sorted && mask_sorted && perm && workspace && n_cap > 0 && kvol >= 1 && kvol <= 32,
+                 "spvd_kmap_sort: bad arguments");
+  SPVD_CHECK_ARG(ld % 128 == 0 && ld >= n_cap, "spvd_kmap_sort: ld %d must be a multiple of 128 >= n_cap", ld);
+  SPVD_CHECK_ARG(workspace_bytes >= sort_ws_bytes(n_cap), "spvd_kmap_sort: workspace too small (%zu < %zu)", workspace_bytes,
+                 sort_ws_bytes(n_cap));
+  cudaStream_t s = (cudaStream_t)stream;
+  SortWs w = carve_ws(workspace, n_cap);
+  k_state_init<<<1, 256, 0, s>>>(w.st, n_cap, n_dev);
+  k_mask_keys<<<cdiv(n_cap, 256), 256, 0, s>>>(map_t, ld, kvol, w.st, w.buf[0]);
+  int grid = cdiv(n_cap, 1024);
+  if (grid > 296) grid = 296;
+  k_digit_hist<<<grid, 256, 0, s>>>(w.buf[0], w.st);
+  k_sort_plan<<<1, 256, 0, s>>>(w.st, 4);
+  for (int p = 4; p < 4 + (kvol + 7) / 8; ++p) {
+    k_tile_hist<<<w.n_tiles, kSortThreads, 0, s>>>(w.buf[0], w.buf[1], w.st, p, w.n_tiles, w.tile_hist);
+    k_scatter<<<w.n_tiles, kSortThreads, 0, s>>>(w.buf[0], w.buf[1], w.st, p, w.n_tiles, w.tile_hist);
+  }
+  k_sorted_map<<<ld / 128, 128, 0, s>>>(w.buf[0], w.buf[1], w.st, map_t, ld, kvol, map_sorted, mask_sorted, perm);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
 }

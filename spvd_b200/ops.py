@@ -6,6 +6,7 @@ libspvd_b200.so.  All wrappers require CUDA tensors -- there is no CPU path in t
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 
@@ -57,7 +58,7 @@ stats = _Stats()
 _K = {"point_voxel_coords": 1, "unique_coords": 22, "downsample_coords": 23, "hash_build": 1, "hash_query": 1,
       "kmap_subm3": 1, "kmap_down2": 1, "kmap_pairs": 3, "segmented_unique": 3, "batch_counts": 1, "point_voxel_query": 1, "devox_query": 1,
       "scatter_mean_fwd": 2, "scatter_mean_bwd": 1, "devoxelize_fwd": 1, "devoxelize_bwd": 1, "pack_weights": 1,
-      "transpose_weights": 1, "conv_fwd": 1, "conv_wgrad": 1, "ddpm_step": 2, "round_tf32": 1, "affine_act": 1, "film": 1}
+      "transpose_weights": 1, "conv_fwd": 1, "conv_wgrad": 1, "ddpm_step": 2, "round_tf32": 1, "affine_act": 1, "film": 1, "kmap_sort": 13}
 
 
 def _count(name):
@@ -263,7 +264,8 @@ def transpose_weights(w3, flip):
     return wt
 
 
-def conv_fwd(x, w3, w_packed, map_t, mask, n_out, bias=None, impl=CONV_AUTO, bn=0, nsplit=0, a_tf32=False, residual=None, mt=0):
+def conv_fwd(x, w3, w_packed, map_t, mask, n_out, bias=None, impl=CONV_AUTO, bn=0, nsplit=0, a_tf32=False, residual=None, mt=0,
+             out_rows=None):
     """x [n_in, cin]; w3 [kvol, cin, cout] (may be None when w_packed is given and the UMMA path applies);
     map_t [kvol, ld] or None (identity)."""
     if w3 is not None:
@@ -282,8 +284,8 @@ def conv_fwd(x, w3, w_packed, map_t, mask, n_out, bias=None, impl=CONV_AUTO, bn=
         a_mode = ((3 if x.dtype == torch.float16 else 2) if w_packed.dtype == torch.float16 else int(bool(a_tf32)))
         if x.dtype == torch.float16 and w_packed.dtype != torch.float16:
             raise RuntimeError("an f16 input needs the f16 weight image (pack_weights_f16)")
-        check(lib.spvd_conv_fwd_umma(_p(x), _p(w_packed), _p(map_t), ld, _p(mask), n_out, kvol,
-                                     cin, cout, _p(bias), _p(residual), _p(out), int(bn), int(nsplit), a_mode, int(mt), _s()))
+        check(lib.spvd_conv_fwd_umma_rows(_p(x), _p(w_packed), _p(map_t), ld, _p(mask), _p(out_rows), n_out, kvol,
+                                          cin, cout, _p(bias), _p(residual), _p(out), int(bn), int(nsplit), a_mode, int(mt), _s()))
     else:
         check(lib.spvd_conv_fwd_simt(_p(x, torch.float32), _p(w3, torch.float32), _p(map_t), ld, _p(mask), n_out, kvol, cin,
                                      cout, _p(bias), _p(residual), _p(out), _s()))
@@ -386,3 +388,50 @@ def ddpm_step(x_t, n_clouds, n_per_cloud, pres, eps=None, z=None, c1=1.0, c2=0.0
     check(lib.spvd_ddpm_step(_p(x_t, torch.float32), _p(eps), _p(z), float(c1), float(c2), float(sigma), n_clouds, n_per_cloud,
                              f, float(pres), _p(x_new), _p(coords), _p(pc), _p(scratch), _s()))
     return (x_new if eps is not None else x_t), coords, pc
+
+
+# ------------------------------------------------------------------------------- sorted tiles + fused persistent conv
+class ConvSpArgs(ctypes.Structure):
+    """spvd_conv_sp_args_t (include/spvd_b200.h)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("inp", "w", "map_t", "tile_mask", "out_rows", "in2", "w2", "bias", "residual",
+                                               "film", "coords", "aff_scale", "aff_shift", "out32", "out16")] + \
+               [(n, ctypes.c_int32) for n in ("ld", "n_out", "kvol", "cin", "cout", "cin2", "film_ld", "act", "n_in", "pad")]
+
+
+def kmap_sort(map_t, n, kvol, n_dev=None):
+    """-> (map_sorted [kvol, ld], mask_sorted [ld/128], perm [ld]) : rows sorted by their active-offset bit set"""
+    _count("kmap_sort")
+    ld = map_t.shape[1]
+    dev = map_t.device
+    ms = torch.empty((kvol, ld), dtype=torch.int32, device=dev)
+    tm = torch.empty(ld // 128, dtype=torch.int32, device=dev)
+    perm = torch.empty(ld, dtype=torch.int32, device=dev)
+    ws = torch.empty(lib.spvd_kmap_sort_workspace_bytes(int(n)), dtype=torch.uint8, device=dev)
+    check(lib.spvd_kmap_sort(_p(map_t, torch.int32), ld, int(n), _p(n_dev), kvol, _p(ms), _p(tm), _p(perm), _p(ws), ws.numel(), _s()))
+    return ms, tm, perm
+
+
+def conv_sp(x16, w_packed, kvol, cin, cout, n_out, map_t=None, tile_mask=None, out_rows=None, bias=None, residual=None,
+            in2=None, w2_packed=None, film=None, coords=None, aff=None, silu=False, want32=True, want16=False, bn=0, stages=0):
+    """spvd_conv_sp_f16: persistent sorted-tile convolution with fused epilogue.  x16 / in2 f16; returns (out32, out16)."""
+    _count("conv_fwd")
+    dev = x16.device
+    if x16.dtype != torch.float16 or w_packed.dtype != torch.float16:
+        raise RuntimeError("conv_sp needs f16 rows and the f16 weight image")
+    a = ConvSpArgs()
+    out32 = torch.empty((n_out, cout), dtype=torch.float32, device=dev) if want32 else None
+    out16 = torch.empty((n_out, cout), dtype=torch.float16, device=dev) if want16 else None
+    a.inp, a.w, a.map_t, a.tile_mask, a.out_rows = _p(x16), _p(w_packed), _p(map_t), _p(tile_mask), _p(out_rows)
+    a.in2, a.w2 = _p(in2), _p(w2_packed)
+    a.bias, a.residual, a.coords = _p(bias), _p(residual), _p(coords)
+    a.film = ctypes.c_void_p(film.data_ptr()) if film is not None else None     # may be a column slice of a wider table
+    a.aff_scale, a.aff_shift = (_p(aff[0]), _p(aff[1])) if aff is not None else (None, None)
+    a.out32, a.out16 = _p(out32), _p(out16)
+    a.ld = map_t.shape[1] if map_t is not None else 0
+    a.n_out, a.kvol, a.cin, a.cout = int(n_out), int(kvol), int(cin), int(cout)
+    a.cin2 = in2.shape[1] if in2 is not None else 0
+    a.film_ld = film.stride(0) if film is not None else 0
+    a.act = 1 if silu else 0
+    a.n_in = x16.shape[0]
+    check(lib.spvd_conv_sp_f16(ctypes.byref(a), int(bn), int(stages), _s()))
+    return out32, out16
