@@ -209,18 +209,16 @@ def run_b200(args):
         table = {}
         strides = model._plan["strides"]
         for evs, meta, pairs, sizes in sink:
-            for ci, (kvol, cin, cout, rows_out, level, map_kind, kind) in enumerate(meta):
+            for ci, (kvol, cin, cout, rows_out, level, map_kind, kind, cin2) in enumerate(meta):
                 dt = evs[2 * ci].elapsed_time(evs[2 * ci + 1])
-                if map_kind == 0:
-                    P = B * N if rows_out == -1 else (B if rows_out == -2 else sizes[rows_out])
-                else:
-                    P = pairs[(level, map_kind)]
-                fl = 2.0 * P * cin * cout
+                n_rows = B * N if rows_out == -1 else (B if rows_out == -2 else sizes[rows_out])
+                P = n_rows if map_kind == 0 else pairs[(level, map_kind)]
+                fl = 2.0 * P * cin * cout + 2.0 * n_rows * cin2 * cout       # + the 1x1 shortcut folded into the K loop
                 e = table.setdefault((kind, kvol, cin, cout, strides[level] if level >= 0 else rows_out), [0, 0.0, 0.0])
                 e[0] += 1
                 e[1] += dt
                 e[2] += fl
-                if kind == "umma":
+                if kind in ("umma", "sp"):
                     flops += fl
                     ms += dt
                     n += 1

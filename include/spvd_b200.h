@@ -548,6 +548,52 @@ int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_level_geom_t* l
                      void* const* conv_events, spvd_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * TR  training-mode glue (csrc/train.cu): what a training step of the denoiser needs between the sparse convolutions,
+ * so that forward + backward run on this library only (train_generation.py:98-112 drives it; the modules are
+ * models/ddpm_unet_attn.py:24-65, models/modules/graph.py:19-41, models/modules/transformer.py:40-67,102-125).
+ * `workspace` everywhere: >= 2 * c doubles (1 for spvd_mse_loss), ZERO on entry; every call leaves it zero again. */
+/* nn.BatchNorm1d in training mode (+ SiLU when act & 1): batch statistics over `rows`, y = act(x * scale + shift);
+ * save_mean / save_invstd / scale / shift [c] are outputs; running_mean / running_var (may be NULL) are updated in place
+ * with `momentum` and the unbiased variance, exactly like torch. */
+int spvd_bn_train_fwd(const float* x, long long rows, int c, const float* gamma, const float* beta, float eps,
+                      float momentum, float* running_mean, float* running_var, float* save_mean, float* save_invstd,
+                      float* scale, float* shift, int act, float* y, double* workspace, spvd_stream_t stream);
+int spvd_bn_train_bwd(const float* x, const float* gy, long long rows, int c, const float* gamma, const float* beta,
+                      const float* save_mean, const float* save_invstd, int act, float* gx, float* ggamma, float* gbeta,
+                      double* workspace, spvd_stream_t stream);
+/* out[c] = sum over rows of g[., c]  (bias gradients) */
+int spvd_colsum(const float* g, long long rows, int c, float* out, double* workspace, spvd_stream_t stream);
+/* backward of y = (1 + tt[b, c]) * x + tt[b, C + c] (spvd_film_fwd): gx, and gtt [n_batch, ldg] += the per-cloud sums
+ * (gtt zero-filled by the caller); rows of cloud b are [batch_offsets[b], batch_offsets[b+1]). */
+int spvd_film_bwd(const float* x, const float* gy, const float* tt, int ldt, const int32_t* batch_offsets, int n_batch,
+                  int max_rows_per_cloud, int c, float* gx, float* gtt, int ldg, spvd_stream_t stream);
+int spvd_layernorm_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int c, float eps, float* y,
+                             float* mean, float* rstd, spvd_stream_t stream);
+int spvd_layernorm_bwd(const float* x, const float* gy, const float* gamma, const float* mean, const float* rstd, int rows,
+                       int c, float* gx, float* ggamma, float* gbeta, double* workspace, spvd_stream_t stream);
+/* spvd_attention_fwd that also saves the log-sum-exp [rows, heads]; backward: gqkv [rows, 3c], delta [rows, heads] scratch */
+int spvd_attention_train_fwd(const float* qkv, const int32_t* batch_offsets, int n_batch, int max_len, int c, int heads,
+                             float* out, float* lse, spvd_stream_t stream);
+int spvd_attention_bwd(const float* qkv, const float* out, const float* gout, const float* lse, const int32_t* batch_offsets,
+                       int n_batch, int max_len, int c, int heads, float* gqkv, float* delta, spvd_stream_t stream);
+/* torchsparse.cat (models/spvd.py:232) for any channel counts, and its backward (channel split) */
+int spvd_cat_any_fwd(const float* a, const float* b, long long rows, int ca, int cb, float* y, spvd_stream_t stream);
+int spvd_split_fwd(const float* g, long long rows, int ca, int cb, float* ga, float* gb, spvd_stream_t stream);
+int spvd_silu_fwd(const float* x, long long n, float* y, spvd_stream_t stream);
+int spvd_silu_bwd(const float* x, const float* gy, long long n, float* gx, spvd_stream_t stream);
+int spvd_add_fwd(const float* a, const float* b, long long n, float* y, spvd_stream_t stream);
+/* out[b] = table[idx[b]] (+ base[b]): the class embedding added to the time embedding (ConditionalGeneration.ipynb cell 4);
+ * backward: gtable[idx[b]] += g[b] (gtable zero-filled by the caller) */
+int spvd_embedding_fwd(const float* table, const int64_t* idx, const float* base, int n_batch, int e, float* out,
+                       spvd_stream_t stream);
+int spvd_embedding_bwd(const float* g, const int64_t* idx, int n_batch, int e, float* gtable, spvd_stream_t stream);
+/* models/utils.py:15-19: out[b] = [sin(t_b * f_i), cos(t_b * f_i)], f_i = exp(-ln(1e4) * i / (d/2 - 1)) */
+int spvd_timestep_embedding(const int64_t* t, int n_batch, int d, float* out, spvd_stream_t stream);
+/* nn.MSELoss (train_generation.py:104): loss[0] = mean((pred - target)^2); gpred (may be NULL) = grad_scale * d loss / d pred */
+int spvd_mse_loss(const float* pred, const float* target, long long n, float grad_scale, float* loss, float* gpred,
+                  double* workspace, spvd_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * N4  evaluation distances between point clouds xyz1 [B,n,3], xyz2 [B,m,3] (fp32, row-major).
  * Chamfer (metrics/chamfer_dist/chamfer.cu:15-229): dist1[b,i] = min_j |xyz1_i - xyz2_j|^2 with its first argmin idx1, and
  * the same from xyz2 to xyz1; the backward scatters 2 g (a - b) to both ends of every nearest-neighbour pair.

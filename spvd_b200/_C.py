@@ -59,6 +59,23 @@ SIGNATURES = {
     "spvd_kmap_sort_workspace_bytes": (_sz, [_i]),
     "spvd_kmap_sort": (_i, [_p, _i, _i, _p, _i, _p, _p, _p, _p, _sz, _p]),
     "spvd_conv_sp_f16": (_i, [_p, _i, _i, _p]),
+    "spvd_bn_train_fwd": (_i, [_p, _ll, _i, _p, _p, _f, _f, _p, _p, _p, _p, _p, _p, _i, _p, _p, _p]),
+    "spvd_bn_train_bwd": (_i, [_p, _p, _ll, _i, _p, _p, _p, _p, _i, _p, _p, _p, _p, _p]),
+    "spvd_colsum": (_i, [_p, _ll, _i, _p, _p, _p]),
+    "spvd_film_bwd": (_i, [_p, _p, _p, _i, _p, _i, _i, _i, _p, _p, _i, _p]),
+    "spvd_layernorm_train_fwd": (_i, [_p, _p, _p, _i, _i, _f, _p, _p, _p, _p]),
+    "spvd_layernorm_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _p, _p, _p, _p, _p]),
+    "spvd_attention_train_fwd": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "spvd_attention_bwd": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _p, _p, _p]),
+    "spvd_cat_any_fwd": (_i, [_p, _p, _ll, _i, _i, _p, _p]),
+    "spvd_split_fwd": (_i, [_p, _ll, _i, _i, _p, _p, _p]),
+    "spvd_silu_fwd": (_i, [_p, _ll, _p, _p]),
+    "spvd_silu_bwd": (_i, [_p, _p, _ll, _p, _p]),
+    "spvd_add_fwd": (_i, [_p, _p, _ll, _p, _p]),
+    "spvd_embedding_fwd": (_i, [_p, _p, _p, _i, _i, _p, _p]),
+    "spvd_embedding_bwd": (_i, [_p, _p, _i, _i, _p, _p]),
+    "spvd_timestep_embedding": (_i, [_p, _i, _i, _p, _p]),
+    "spvd_mse_loss": (_i, [_p, _p, _ll, _f, _p, _p, _p, _p]),
     "spvd_kmap_pairs": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "spvd_conv_fwd_pairs": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "spvd_conv_wgrad_umma": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),

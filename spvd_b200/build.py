@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libspvd_b200.so")
-SOURCES = ["error.cu", "coords.cu", "hash.cu", "pointvoxel.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_f16.cu", "conv_sp_f16.cu", "fused.cu", "runtime.cu", "plan.cu", "sampler.cu", "conv_wgrad_umma.cu", "metrics.cu"]
+SOURCES = ["error.cu", "coords.cu", "hash.cu", "pointvoxel.cu", "conv_simt.cu", "conv_umma.cu", "conv_umma_f16.cu", "conv_sp_f16.cu", "fused.cu", "runtime.cu", "plan.cu", "sampler.cu", "conv_wgrad_umma.cu", "metrics.cu", "train.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]
 

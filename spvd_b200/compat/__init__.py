@@ -191,38 +191,11 @@ class SiLU(tnn.SiLU):
 
 
 # ------------------------------------------------------------ numpy-side input format (CPU, datasets / CPU scheduler)
-def ravel_hash(x):
-    x = (x - x.min(axis=0)).astype(np.uint64)
-    xmax = x.max(axis=0).astype(np.uint64) + 1
-    h = np.zeros(x.shape[0], dtype=np.uint64)
-    for k in range(x.shape[1] - 1):
-        h += x[:, k]
-        h *= xmax[k + 1]
-    return h + x[:, -1]
-
-
-def sparse_quantize(coords, voxel_size=1, *, return_index=False, return_inverse=False):
-    coords = np.floor(coords / np.asarray(make_ntuple(voxel_size, 3))).astype(np.int32)
-    _, ind, inv = np.unique(ravel_hash(coords), return_index=True, return_inverse=True)
-    out = [coords[ind]] + ([ind] if return_index else []) + ([inv] if return_inverse else [])
-    return out[0] if len(out) == 1 else out
-
-
-def sparse_collate(inputs):
-    coords = [torch.cat((torch.full((x.coords.shape[0], 1), k, dtype=torch.int), x.coords.int()), dim=1)
-              for k, x in enumerate(inputs)]
-    return SparseTensor(torch.cat([x.feats for x in inputs], 0), torch.cat(coords, 0), inputs[0].stride)
+from ..data import collate as _collate, ravel_hash, sparse_collate, sparse_quantize  # noqa: E402,F401
 
 
 def sparse_collate_fn(inputs):
-    if isinstance(inputs[0], dict):
-        out = {}
-        for name in inputs[0]:
-            v = [d[name] for d in inputs]
-            out[name] = sparse_collate(v) if isinstance(v[0], SparseTensor) else (
-                torch.stack(v, 0) if isinstance(v[0], torch.Tensor) else v)
-        return out
-    return inputs
+    return _collate(inputs) if isinstance(inputs[0], dict) else inputs
 
 
 # ------------------------------------------------------------------------ tiny third-party names

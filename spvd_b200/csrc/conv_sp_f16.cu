@@ -15,19 +15,18 @@
 //     the fp32 result and / or the f16 operand of the next convolution;
 //   * a second operand source extends the K loop: the 1x1 shortcut (idconv, models/ddpm_unet_attn.py:61) of a residual
 //     block runs as extra slabs of its second 3^3 convolution instead of as a launch of its own.
-//   * the input rows are gathered by the TMA (cp.async.bulk.tensor ... tile::gather4: four rows of the f16 activation
-//     matrix per instruction, 128-byte swizzle applied by the copy engine, out-of-range row index -1 = zero fill) instead
-//     of per-thread cp.async: LDGSTS gathers kept about one stage in flight per SM however deep the ring was
-//     (tools/_conv_trace.py: ~1000 cycles of every ~1300-cycle iteration went into issuing them); one warp now feeds
-//     the whole ring and the copy engine keeps every stage in flight.
-#include <cuda.h>
+//   * map rows reach the producers through a ring of 512-byte segments that thread 0 bulk-copies (cp.async.bulk) eight
+//     (tile, offset) steps ahead, and the offset masks of a CTA's tiles are staged once: no role has a dependent global
+//     load on its critical path.
+// Measured and rejected: gathering the rows with the TMA (cp.async.bulk.tensor ... tile::gather4, 512 B per instruction)
+// is correct but about twice as slow as the per-thread cp.async gather on every SPVD layer (profiles/README.md).
 #include <cuda_fp16.h>
 
 #include "conv_umma_impl.cuh"
 
 namespace spvd {
 
-constexpr int kSpThreads = 32 * 6;   // warp 0 producer (TMA), 1 MMA issuer, 2-5 epilogue
+constexpr int kSpThreads = 32 * 9;   // warps 0-3 producers, 4 MMA issuer, 5-8 epilogue
 constexpr int kSpMaxStages = 8;
 constexpr int kSpIdxSlots = 8;       // ring of map-row segments (512 B each) prefetched ahead of the gathers
 constexpr int kSpMaskCache = 256;    // offset masks of this CTA's tiles, staged once
@@ -46,22 +45,8 @@ struct SpCfg {
 
 __device__ __forceinline__ float sp_silu(float v) { return v / (1.f + __expf(-v)); }
 
-struct alignas(64) SpKernelArgs {
-  CUtensorMap tm_in, tm_in2;     // f16 [rows, cin] with box {64, 1}, SWIZZLE_128B (gather4 takes the four row coordinates)
-  spvd_conv_sp_args_t a;
-};
-
-__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap* tm, int col, int r0, int r1, int r2, int r3,
-                                            uint32_t bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, %6}], [%7];" ::"r"(dst),
-      "l"(tm), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
-      : "memory");
-}
-
 template <int BN>
-__global__ void __launch_bounds__(kSpThreads, 2) k_conv_sp_f16(const __grid_constant__ SpKernelArgs p, int S) {
-  const spvd_conv_sp_args_t& a = p.a;
+__global__ void __launch_bounds__(kSpThreads, 2) k_conv_sp_f16(const __grid_constant__ spvd_conv_sp_args_t a, int S) {
   using Cfg = SpCfg<BN>;
   constexpr int NB = Cfg::kBufs;
   pdl_trigger();
@@ -86,7 +71,7 @@ __global__ void __launch_bounds__(kSpThreads, 2) k_conv_sp_f16(const __grid_cons
 
   if (tid == 0) {
     for (int s = 0; s < S; ++s) {
-      mbar_init(bar_full + 8 * s, 1);
+      mbar_init(bar_full + 8 * s, kProducerThreads + 1);
       mbar_init(bar_empty + 8 * s, 1);
     }
     for (int b = 0; b < 2; ++b) {
@@ -102,7 +87,7 @@ __global__ void __launch_bounds__(kSpThreads, 2) k_conv_sp_f16(const __grid_cons
       const int tile = blockIdx.x + i * gridDim.x;
       s_mask[i] = tile < n_tiles ? (a.tile_mask[tile] & kmask) : 0u;
     }
-  if (warp == 1) {
+  if (warp == 4) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
                  "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
@@ -120,27 +105,36 @@ __global__ void __launch_bounds__(kSpThreads, 2) k_conv_sp_f16(const __grid_cons
     return i < kSpMaskCache ? s_mask[i] : (a.tile_mask[tile] & kmask);
   };
 
-  if (warp == 0) {
-    // ------------------------------------------------------------------ producer (one warp: lane l owns tile rows 4l .. 4l+3)
+  if (warp < 4) {
+    // ------------------------------------------------------------------ producers (thread t: 16-byte piece t & 7 of rows (t >> 3) + 16 i)
+    const int chunk16 = tid & 7, r0 = tid >> 3;
     const uint8_t* w_b = reinterpret_cast<const uint8_t*>(a.w);
     int li = 0;
-    auto fill = [&](const CUtensorMap* tm, const int* rows, const uint8_t* wsrc, int c) {
+    auto fill = [&](const uint8_t* src, uint32_t row_bytes, const int* rows, const uint8_t* wsrc, int c) {
       const int stage = li % S;
       const uint32_t parity = (uint32_t)(li / S) & 1u;
       const uint32_t a_s = base + stage * Cfg::kStageBytes;
       mbar_wait(bar_empty + 8 * stage, parity ^ 1u);
-      if (lane == 0) {
-        mbar_arrive_expect_tx(bar_full + 8 * stage, kATileBytes + Cfg::kBTileBytes);
+      if (tid == 0) {
+        mbar_arrive_expect_tx(bar_full + 8 * stage, Cfg::kBTileBytes);
         bulk_g2s(a_s + kATileBytes, wsrc, Cfg::kBTileBytes, bar_full + 8 * stage);
       }
       __syncwarp();
-      tma_gather4(a_s + lane * 512, tm, c * 64, rows[0], rows[1], rows[2], rows[3], bar_full + 8 * stage);
+      const uint32_t col_b = (uint32_t)c * 128u + (uint32_t)chunk16 * 16u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 16 * i;
+        const uint32_t dst = a_s + r * 128 + ((chunk16 ^ (r & 7)) << 4);
+        const bool ok = rows[i] >= 0 && col_b < row_bytes;
+        cp_async16(dst, ok ? src + (size_t)rows[i] * row_bytes + col_b : src, ok ? 16u : 0u);
+      }
+      cp_async_mbar_arrive_noinc(bar_full + 8 * stage);
       ++li;
     };
-    // map rows travel through a ring of 512-byte segments, bulk-copied kSpIdxSlots (tile, offset) steps ahead by lane 0
-    int pf_i = 0, pf_tile = blockIdx.x, pf_q = 0;      // prefetch cursor (lane 0): i-th tile of this CTA, remaining offsets
+    // map rows travel through a ring of 512-byte segments, bulk-copied kSpIdxSlots (tile, offset) steps ahead by thread 0
+    int pf_i = 0, pf_tile = blockIdx.x, pf_q = 0;      // prefetch cursor (thread 0): i-th tile of this CTA, remaining offsets
     unsigned pf_rem = (a.map_t && pf_tile < n_tiles) ? tile_mask_of(pf_tile, 0) : 0u;
-    auto prefetch_one = [&]() {                         // lane 0 only
+    auto prefetch_one = [&]() {                         // thread 0 only
       while (pf_tile < n_tiles && pf_rem == 0u) {
         pf_tile += gridDim.x;
         ++pf_i;
@@ -150,17 +144,17 @@ __global__ void __launch_bounds__(kSpThreads, 2) k_conv_sp_f16(const __grid_cons
       const int k = __ffs(pf_rem) - 1;
       pf_rem &= pf_rem - 1;
       const int slot = pf_q % kSpIdxSlots;
-      fence_proxy_async();   // the generic-proxy reads of this segment (ordered by __syncwarp) precede the async-proxy refill
+      fence_proxy_async();   // the generic-proxy reads of this segment (ordered by the barrier) precede the async-proxy refill
       mbar_arrive_expect_tx(bar_idx + 8 * slot, 512u);
       bulk_g2s(smem_u32(s_idx + slot * BM), a.map_t + (size_t)k * a.ld + (size_t)pf_tile * BM, 512u, bar_idx + 8 * slot);
       ++pf_q;
     };
-    if (a.map_t && lane == 0)
+    if (a.map_t && tid == 0)
       for (int i = 0; i < kSpIdxSlots; ++i) prefetch_one();
     __syncwarp();
     int q = 0, ti = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++ti) {
-      int rows[4];
+      int rows[8];
       if (a.map_t) {
         unsigned rem = tile_mask_of(tile, ti);
         while (rem) {
@@ -168,36 +162,43 @@ __global__ void __launch_bounds__(kSpThreads, 2) k_conv_sp_f16(const __grid_cons
           rem &= rem - 1;
           const int slot = q % kSpIdxSlots;
           mbar_wait(bar_idx + 8 * slot, (uint32_t)(q / kSpIdxSlots) & 1u);
-          // (volatile asm: the load must stay in front of the __syncwarp below, which releases the segment for refill)
-          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];"
-                       : "=r"(rows[0]), "=r"(rows[1]), "=r"(rows[2]), "=r"(rows[3])
-                       : "r"(smem_u32(s_idx + slot * BM + 4 * lane))
-                       : "memory");
+          // (volatile asm: these loads must stay in front of the barrier below, which releases the segment for refill --
+          //  as plain loads they were sunk behind it and a handful of rows per launch gathered a refilled segment)
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            asm volatile("ld.shared.b32 %0, [%1];" : "=r"(rows[i]) : "r"(smem_u32(s_idx + slot * BM + r0 + 16 * i)) : "memory");
           ++q;
+          // warp 0 diverges around thread 0's bulk copies: reconverge first (an aligned barrier reached by a split warp is
+          // undefined) and use the unaligned form
           __syncwarp();
-          if (lane == 0) prefetch_one();
+          asm volatile("barrier.sync 1, 128;" ::: "memory");
+          if (tid == 0) prefetch_one();
           __syncwarp();
-          for (int c = 0; c < nchunks; ++c) fill(&p.tm_in, rows, w_b + ((size_t)(k * nchunks + c) * a.cout + n0) * 128, c);
+          for (int c = 0; c < nchunks; ++c)
+            fill(reinterpret_cast<const uint8_t*>(a.in), (uint32_t)a.cin * 2u, rows,
+                 w_b + ((size_t)(k * nchunks + c) * a.cout + n0) * 128, c);
         }
       } else {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int o = tile * BM + 4 * lane + i;
+        for (int i = 0; i < 8; ++i) {
+          const int o = tile * BM + r0 + 16 * i;
           rows[i] = o < a.n_out ? o : -1;
         }
-        for (int c = 0; c < nchunks; ++c) fill(&p.tm_in, rows, w_b + ((size_t)c * a.cout + n0) * 128, c);
+        for (int c = 0; c < nchunks; ++c)
+          fill(reinterpret_cast<const uint8_t*>(a.in), (uint32_t)a.cin * 2u, rows, w_b + ((size_t)c * a.cout + n0) * 128, c);
       }
       if (a.in2) {   // K extension: rows of the second source are the tile's own output rows
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int o = tile * BM + 4 * lane + i;
+        for (int i = 0; i < 8; ++i) {
+          const int o = tile * BM + r0 + 16 * i;
           rows[i] = o < a.n_out ? (a.out_rows ? __ldg(a.out_rows + o) : o) : -1;
         }
         for (int c = 0; c < nchunks2; ++c)
-          fill(&p.tm_in2, rows, reinterpret_cast<const uint8_t*>(a.w2) + ((size_t)c * a.cout + n0) * 128, c);
+          fill(reinterpret_cast<const uint8_t*>(a.in2), (uint32_t)a.cin2 * 2u, rows,
+               reinterpret_cast<const uint8_t*>(a.w2) + ((size_t)c * a.cout + n0) * 128, c);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 4) {
     // ------------------------------------------------------------------ MMA issuer
     int li = 0, t = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++t) {
@@ -212,7 +213,8 @@ __global__ void __launch_bounds__(kSpThreads, 2) k_conv_sp_f16(const __grid_cons
       }
       for (int it = 0; it < iters; ++it, ++li) {
         const int stage = li % S;
-        mbar_wait(bar_full + 8 * stage, (uint32_t)(li / S) & 1u);   // TMA wrote both tiles (async proxy): no proxy fence
+        mbar_wait(bar_full + 8 * stage, (uint32_t)(li / S) & 1u);
+        fence_proxy_async();     // cp.async wrote the A tile through the generic proxy
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_s = base + stage * Cfg::kStageBytes;
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(kSpThreads, 2) k_conv_sp_f16(const __grid_cons
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 4) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"((uint32_t)Cfg::kTmemCols)
                  : "memory");
   }
@@ -326,35 +328,6 @@ static int sp_num_sms() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
   if (n_sm[dev] == 0 && cudaDeviceGetAttribute(&n_sm[dev], cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n_sm[dev] = 148;
   return n_sm[dev];
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-// f16 [rows, cin] row-major as a 2-D tensor map with a {64 channels, 1 row} box: 128-byte rows, SWIZZLE_128B; channels past
-// cin and rows outside [0, rows) read as zero (cin = 32: the upper half of every slab; row index -1 = "no neighbour")
-static int make_row_map(CUtensorMap* tm, const void* ptr, int cin, long long rows) {
-  static EncodeTiledFn encode = nullptr;
-  if (!encode) {
-    void* fn = nullptr;
-    cudaDriverEntryPointQueryResult qr;
-    SPVD_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr));
-    SPVD_CHECK_ARG(fn && qr == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available in this driver");
-    encode = (EncodeTiledFn)fn;
-  }
-  const cuuint64_t gdim[2] = {(cuuint64_t)cin, (cuuint64_t)(rows > 0 ? rows : 1)};
-  const cuuint64_t gstride[1] = {(cuuint64_t)cin * 2};
-  const cuuint32_t box[2] = {64, 1};
-  const cuuint32_t estride[2] = {1, 1};
-  const CUresult r = encode(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box, estride,
-                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) {
-    set_error("cuTensorMapEncodeTiled failed (%d) for a [%lld, %d] f16 matrix", (int)r, rows, cin);
-    return SPVD_ERR_CUDA;
-  }
-  return SPVD_OK;
 }
 
 template <int BN>
@@ -381,14 +354,7 @@ static int launch_sp(const spvd_conv_sp_args_t& a, int stages, cudaStream_t s) {
   if (stages > 0 && stages < S) S = stages;
   SPVD_CHECK_ARG(S >= 2, "spvd_conv_sp_f16: no room for two pipeline stages at BN = %d", BN);
   const size_t smem = (size_t)S * Cfg::kStageBytes + 1024 + kSpTailBytes;
-  SpKernelArgs p;
-  p.a = a;
-  const long long rows_in = a.n_in > 0 ? a.n_in : (1ll << 30);
-  int rc = make_row_map(&p.tm_in, a.in, a.cin, rows_in);
-  if (rc != SPVD_OK) return rc;
-  p.tm_in2 = p.tm_in;
-  if (a.in2 && (rc = make_row_map(&p.tm_in2, a.in2, a.cin2, a.n_out)) != SPVD_OK) return rc;
-  SPVD_CUDA(launch_pdl(kern, dim3(ctas, slices), dim3(kSpThreads), smem, s, p, S));
+  SPVD_CUDA(launch_pdl(kern, dim3(ctas, slices), dim3(kSpThreads), smem, s, a, S));
   return SPVD_OK;
 }
 

@@ -49,6 +49,7 @@ int spvd_group_points_by_voxel(const int32_t*, int, int, const int32_t*, int32_t
                                spvd_stream_t);
 int spvd_segmented_unique(const int32_t*, int, const int32_t*, int, int, int, int, int32_t*, int32_t*, int32_t*, int32_t*,
                           int32_t*, void*, size_t, spvd_stream_t);
+int spvd_kmap_sort(const int32_t*, int, int, const int32_t*, int, int32_t*, uint32_t*, int32_t*, void*, size_t, spvd_stream_t);
 }
 
 #define SPVD_TRY(call)            \
@@ -155,6 +156,9 @@ static int plan_range(const float* pc, int n_points, int n_batch, int max_cloud_
     for (int i = level_begin; i < level_end; ++i) {
       const spvd_plan_level_t& L = levels[i];
       if (L.kmap3) SPVD_TRY(spvd_kmap_subm3(L.coords, n_points, L.count, L.keys, L.vals, L.capacity, L.kmap3, ld, L.mask3, stream));
+      if (L.kmap3 && L.kmap3_sorted && L.mask3_sorted && L.perm3 && L.sort_ws)   // mask-sorted view for the persistent conv
+        SPVD_TRY(spvd_kmap_sort(L.kmap3, ld, n_points, L.count, 27, L.kmap3_sorted, L.mask3_sorted, L.perm3, L.sort_ws,
+                                (size_t)L.sort_ws_bytes, stream));
       if (L.kmap3 && L.pair_in && L.pair_out && L.pair_tile_k && L.pair_counts && L.pair_scratch)
         SPVD_TRY(spvd_kmap_pairs(L.kmap3, ld, n_points, L.count, 27, L.pair_tile_cap, L.pair_in, L.pair_out, L.pair_tile_k,
                                  L.pair_counts, L.pair_counts + 1, L.pair_scratch, stream));

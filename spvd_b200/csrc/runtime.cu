@@ -232,6 +232,7 @@ int spvd_conv_fwd_pairs(const float*, const float*, const int32_t*, const int32_
                         int, const float*, const float*, float*, int, spvd_stream_t);
 int spvd_conv_fwd_pairs_simt(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int,
                              int, int, const float*, float*, spvd_stream_t);
+int spvd_conv_sp_f16(const spvd_conv_sp_args_t*, int, int, spvd_stream_t);
 }
 
 extern "C" int spvd_film_affine_fwd(const float* x, const float* tt, int ldt, const int32_t* coords,
@@ -403,8 +404,9 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
       set_error("spvd_program_run: op %d has a bad row space", i);
       return SPVD_ERR_INVALID;
     }
-    const long long need = o.dst + rout * (long long)((o.op == SPVD_OP_CAT || o.op == SPVD_OP_CAT_AFFINE) ? o.c0 + o.c1 : o.c1) * 4;  // c1 = output channels
-    if (o.dst < 0 || (size_t)need > arena_bytes) {
+    const long long out_bytes = rout * (long long)((o.op == SPVD_OP_CAT || o.op == SPVD_OP_CAT_AFFINE) ? o.c0 + o.c1 : o.c1) * 4;  // c1 = output channels
+    const long long need = (o.dst >= 0 ? o.dst : o.aux) + out_bytes;
+    if ((o.dst < 0 && !(o.op == SPVD_OP_CONV_SP && o.aux >= 0)) || (size_t)need > arena_bytes) {
       set_error("spvd_program_run: op %d writes past the arena (%lld > %zu)", i, need, arena_bytes);
       return SPVD_ERR_WORKSPACE;
     }
@@ -460,6 +462,44 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
         else
           rc = spvd_conv_fwd_simt(at(o.src0), o.w, map, ld, mask, (int)rout, o.kvol, o.c0, o.c1, o.bias, at(o.src1),
                                   at(o.dst), stream);
+        if (conv_events) SPVD_CUDA(cudaEventRecord((cudaEvent_t)conv_events[2 * conv_index + 1], (cudaStream_t)stream));
+        ++conv_index;
+        break;
+      }
+      case SPVD_OP_CONV_SP: {
+        spvd_conv_sp_args_t a = {};
+        a.in = at(o.src0);
+        a.w = o.w_packed;
+        if (o.map_kind == SPVD_MAP_K3) {
+          SPVD_CHECK_ARG(lv && lv->kmap3, "op %d: level %d lacks the 3^3 kernel map", i, o.level);
+          if (lv->kmap3_sorted && lv->mask3_sorted && lv->perm3) {
+            a.map_t = lv->kmap3_sorted; a.tile_mask = lv->mask3_sorted; a.out_rows = lv->perm3;
+          } else {
+            a.map_t = lv->kmap3; a.tile_mask = lv->mask3;
+          }
+          a.ld = lv->ld3;
+        } else {
+          SPVD_CHECK_ARG(o.map_kind == SPVD_MAP_NONE, "op %d: the sorted-tile convolution takes 3^3 or identity maps", i);
+        }
+        a.in2 = at(o.src2);
+        a.w2 = o.w2_packed;
+        a.cin2 = o.c2;
+        a.bias = o.bias;
+        a.residual = at(o.src1);
+        if (o.src3 >= 0) {
+          SPVD_CHECK_ARG(lv && lv->coords, "op %d: FiLM epilogue without level coordinates", i);
+          a.film = at(o.src3) + o.i1;
+          a.film_ld = o.i0;
+          a.coords = lv->coords;
+        }
+        a.aff_scale = o.p0;
+        a.aff_shift = o.p1;
+        a.act = (o.flags & SPVD_FLAG_SILU) ? 1 : 0;
+        a.out32 = at(o.dst);
+        a.out16 = o.aux >= 0 ? (void*)at(o.aux) : nullptr;
+        a.n_out = (int)rout; a.n_in = (int)rin; a.kvol = o.kvol; a.cin = o.c0; a.cout = o.c1;
+        if (conv_events) SPVD_CUDA(cudaEventRecord((cudaEvent_t)conv_events[2 * conv_index], (cudaStream_t)stream));
+        rc = spvd_conv_sp_f16(&a, 0, 0, stream);
         if (conv_events) SPVD_CUDA(cudaEventRecord((cudaEvent_t)conv_events[2 * conv_index + 1], (cudaStream_t)stream));
         ++conv_index;
         break;

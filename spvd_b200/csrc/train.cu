@@ -1,0 +1,769 @@
+// Training-mode kernels of the denoiser's glue (row TR of the scope table): everything between the sparse convolutions of
+// EmbResBlock / PointBlock / SparseAttention that the forward + backward pass needs, so that a training step runs no
+// library (cuBLAS / cuDNN / ATen) kernel:
+//   * BatchNorm1d with batch statistics (+ SiLU), forward and backward           models/ddpm_unet_attn.py:24-28
+//   * FiLM backward (per-cloud segmented reduction of the scale / shift gradients) models/modules/graph.py:19-41
+//   * LayerNorm forward (saving mean / rstd) and backward                         models/modules/transformer.py:102-125
+//   * per-cloud multi-head attention backward                                     models/modules/transformer.py:40-67
+//   * channel split (backward of torchsparse.cat), SiLU, column sums (bias gradients), embedding-row scatter,
+//     sinusoidal timestep embedding, fused MSE loss + gradient                    models/spvd.py:232,380-392; models/utils.py:15-19
+// All HBM-bound row-major [rows, C] passes: 128-bit accesses where C % 4 == 0, fp32 partial sums per CTA, fp64 atomics for
+// the per-channel totals (65k rows of fp32 squares would otherwise lose the last digits of the variance).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace spvd {
+
+__device__ __forceinline__ float sigmoid_f(float v) { return 1.f / (1.f + __expf(-v)); }
+__device__ __forceinline__ float silu_t(float v) { return v * sigmoid_f(v); }
+__device__ __forceinline__ float dsilu_t(float v) {
+  const float s = sigmoid_f(v);
+  return s * (1.f + v * (1.f - s));
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-channel reduction skeleton over a row-major [rows, c] matrix: every thread owns one channel (thread t -> channel
+// t % c of row lane t / c) and walks the rows of its CTA's chunk; the row lanes are then combined in shared memory and
+// the CTA adds its partial sums to fp64 totals.  f(row, ch, &a, &b) yields the two summands.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRedThreads = 256;
+constexpr int kRedRows = 128;   // rows per CTA
+
+template <typename F>
+__device__ __forceinline__ void col_reduce2(long long rows, int c, double* __restrict__ tot, F f) {
+  __shared__ float sa[kRedThreads], sb[kRedThreads];
+  const long long r_begin = (long long)blockIdx.x * kRedRows;
+  const long long r_end = min(rows, r_begin + kRedRows);
+  for (int c0 = 0; c0 < c; c0 += kRedThreads) {            // channel chunks of up to 256 (one pass for every SPVD width)
+    const int cw = min(kRedThreads, c - c0);
+    const int lanes = kRedThreads / cw;                    // row lanes
+    const int ch = threadIdx.x % cw, lane = threadIdx.x / cw;
+    float a = 0.f, b = 0.f;
+    if (lane < lanes)
+      for (long long r = r_begin + lane; r < r_end; r += lanes) f(r, c0 + ch, &a, &b);
+    sa[threadIdx.x] = a;
+    sb[threadIdx.x] = b;
+    __syncthreads();
+    if (threadIdx.x < cw) {
+      for (int l = 1; l < lanes; ++l) {
+        a += sa[threadIdx.x + l * cw];
+        b += sb[threadIdx.x + l * cw];
+      }
+      atomicAdd(tot + c0 + ch, (double)a);
+      atomicAdd(tot + c + c0 + ch, (double)b);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ BatchNorm (train)
+__global__ void __launch_bounds__(kRedThreads) k_bn_stats(const float* __restrict__ x, long long rows, int c,
+                                                          double* __restrict__ tot) {
+  col_reduce2(rows, c, tot, [&](long long r, int ch, float* a, float* b) {
+    const float v = x[r * c + ch];
+    *a += v;
+    *b = fmaf(v, v, *b);
+  });
+}
+
+// mean / biased variance -> scale, shift of the normalising affine; running statistics as nn.BatchNorm1d updates them
+// (momentum, unbiased variance); the totals are cleared for the next user of the workspace
+__global__ void k_bn_finalize(double* __restrict__ tot, long long rows, int c, const float* __restrict__ gamma,
+                              const float* __restrict__ beta, float eps, float momentum, float* __restrict__ running_mean,
+                              float* __restrict__ running_var, float* __restrict__ save_mean, float* __restrict__ save_invstd,
+                              float* __restrict__ scale, float* __restrict__ shift) {
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  const double n = (double)rows;
+  const double mean = tot[ch] / n;
+  double var = tot[c + ch] / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  const float invstd = (float)(1.0 / sqrt(var + (double)eps));
+  const float g = gamma ? gamma[ch] : 1.f, b = beta ? beta[ch] : 0.f;
+  save_mean[ch] = (float)mean;
+  save_invstd[ch] = invstd;
+  scale[ch] = g * invstd;
+  shift[ch] = b - (float)mean * g * invstd;
+  if (running_mean) running_mean[ch] = (1.f - momentum) * running_mean[ch] + momentum * (float)mean;
+  if (running_var) {
+    const double unbiased = rows > 1 ? var * n / (n - 1.0) : var;
+    running_var[ch] = (1.f - momentum) * running_var[ch] + momentum * (float)unbiased;
+  }
+  tot[ch] = 0.0;
+  tot[c + ch] = 0.0;
+}
+
+// totals of dz and dz * xhat, dz = gy * silu'(z) (z = x * scale + shift) when the forward applied SiLU
+__global__ void __launch_bounds__(kRedThreads) k_bn_bwd_reduce(const float* __restrict__ x, const float* __restrict__ gy,
+                                                               long long rows, int c, const float* __restrict__ mean,
+                                                               const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                               const float* __restrict__ beta, int act, double* __restrict__ tot) {
+  col_reduce2(rows, c, tot, [&](long long r, int ch, float* a, float* b) {
+    const float xh = (x[r * c + ch] - mean[ch]) * invstd[ch];
+    float dz = gy[r * c + ch];
+    if (act & 1) dz *= dsilu_t(fmaf(xh, gamma ? gamma[ch] : 1.f, beta ? beta[ch] : 0.f));
+    *a += dz;
+    *b = fmaf(dz, xh, *b);
+  });
+}
+
+// gx = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat));  CTA 0 also writes the parameter gradients
+__global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ gy, long long rows,
+                                                      int c, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                      const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                                      const double* __restrict__ tot, float* __restrict__ gx,
+                                                      float* __restrict__ ggamma, float* __restrict__ gbeta) {
+  const long long total = rows * c;
+  const double inv_n = 1.0 / (double)rows;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const int ch = (int)(t % c);
+    const float g = gamma ? gamma[ch] : 1.f;
+    const float xh = (x[t] - mean[ch]) * invstd[ch];
+    float dz = gy[t];
+    if (act & 1) dz *= dsilu_t(fmaf(xh, g, beta ? beta[ch] : 0.f));
+    const float m1 = (float)(tot[ch] * inv_n), m2 = (float)(tot[c + ch] * inv_n);
+    gx[t] = g * invstd[ch] * (dz - m1 - xh * m2);
+  }
+  if (blockIdx.x == 0)
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      if (gbeta) gbeta[ch] = (float)tot[ch];
+      if (ggamma) ggamma[ch] = (float)tot[c + ch];
+    }
+}
+
+__global__ void k_clear_f64(double* p, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ column sums
+__global__ void __launch_bounds__(kRedThreads) k_colsum(const float* __restrict__ g, long long rows, int c, double* __restrict__ tot) {
+  col_reduce2(rows, c, tot, [&](long long r, int ch, float* a, float* b) {
+    *a += g[r * c + ch];
+    (void)b;
+  });
+}
+__global__ void k_f64_to_f32(double* __restrict__ tot, int n, int clear_n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = (float)tot[i];
+  if (i < clear_n) tot[i] = 0.0;
+}
+
+// ------------------------------------------------------------------------------------------------ FiLM backward
+// gx = (1 + scale[b]) * gy;   gtt[b, c] += sum_rows gy * x,  gtt[b, C + c] += sum_rows gy   (rows of cloud b)
+__global__ void __launch_bounds__(256) k_film_bwd(const float* __restrict__ x, const float* __restrict__ gy,
+                                                  const float* __restrict__ tt, int ldt, const int* __restrict__ offsets, int c,
+                                                  int rows_per_cta, float* __restrict__ gx, float* __restrict__ gtt, int ldg) {
+  __shared__ float sa[256], sb[256];
+  const int b = blockIdx.y;
+  const int r0 = offsets[b] + blockIdx.x * rows_per_cta;
+  const int r1 = min(offsets[b + 1], r0 + rows_per_cta);
+  if (r0 >= r1) return;
+  const float* trow = tt + (size_t)b * ldt;
+  for (int c0 = 0; c0 < c; c0 += 256) {
+    const int cw = min(256, c - c0), lanes = 256 / cw;
+    const int ch = threadIdx.x % cw, lane = threadIdx.x / cw;
+    float a = 0.f, s = 0.f;
+    if (lane < lanes) {
+      const float sc = 1.f + trow[c0 + ch];
+      for (int r = r0 + lane; r < r1; r += lanes) {
+        const size_t i = (size_t)r * c + c0 + ch;
+        const float g = gy[i];
+        gx[i] = sc * g;
+        a = fmaf(g, x[i], a);
+        s += g;
+      }
+    }
+    sa[threadIdx.x] = a;
+    sb[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < cw) {
+      for (int l = 1; l < lanes; ++l) {
+        a += sa[threadIdx.x + l * cw];
+        s += sb[threadIdx.x + l * cw];
+      }
+      atomicAdd(gtt + (size_t)b * ldg + c0 + ch, a);
+      atomicAdd(gtt + (size_t)b * ldg + c + c0 + ch, s);
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ LayerNorm
+// one warp per row; writes y and (optionally) the row statistics the backward needs
+__global__ void k_layernorm_train(const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                                  int rows, int c, float eps, float* __restrict__ y, float* __restrict__ mean_out,
+                                  float* __restrict__ rstd_out) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* xr = x + (size_t)row * c;
+  float s = 0.f;
+  for (int i = lane; i < c; i += 32) s += xr[i];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / c;
+  float v = 0.f;
+  for (int i = lane; i < c; i += 32) {
+    const float d = xr[i] - mean;
+    v = fmaf(d, d, v);
+  }
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const float rstd = rsqrtf(v / c + eps);
+  for (int i = lane; i < c; i += 32) y[(size_t)row * c + i] = (xr[i] - mean) * rstd * gamma[i] + beta[i];
+  if (lane == 0) {
+    if (mean_out) mean_out[row] = mean;
+    if (rstd_out) rstd_out[row] = rstd;
+  }
+}
+
+// gx = rstd * (g' - mean(g') - xhat * mean(g' * xhat)),  g' = gy * gamma
+__global__ void k_layernorm_bwd_x(const float* __restrict__ x, const float* __restrict__ gy, const float* __restrict__ gamma,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd, int rows, int c,
+                                  float* __restrict__ gx) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float mu = mean[row], rs = rstd[row];
+  const float* xr = x + (size_t)row * c;
+  const float* gr = gy + (size_t)row * c;
+  float s1 = 0.f, s2 = 0.f;
+  for (int i = lane; i < c; i += 32) {
+    const float gp = gr[i] * gamma[i];
+    s1 += gp;
+    s2 = fmaf(gp, (xr[i] - mu) * rs, s2);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+  }
+  s1 /= c;
+  s2 /= c;
+  for (int i = lane; i < c; i += 32) {
+    const float xh = (xr[i] - mu) * rs;
+    gx[(size_t)row * c + i] = rs * (gr[i] * gamma[i] - s1 - xh * s2);
+  }
+}
+
+__global__ void __launch_bounds__(kRedThreads) k_layernorm_bwd_params(const float* __restrict__ x, const float* __restrict__ gy,
+                                                                      const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                                      long long rows, int c, double* __restrict__ tot) {
+  col_reduce2(rows, c, tot, [&](long long r, int ch, float* a, float* b) {
+    const float g = gy[r * c + ch];
+    *a = fmaf(g, (x[r * c + ch] - mean[r]) * rstd[r], *a);    // d gamma
+    *b += g;                                                  // d beta
+  });
+}
+
+// ------------------------------------------------------------------------------------------------ attention (train)
+// Forward with the log-sum-exp of every (row, head) saved; same layout and tiling as k_attention (runtime.cu):
+// qkv [rows, 3C] = q | k | v with channel head*D + d, rows of a cloud contiguous, 4 lanes per query.
+template <int D>
+__global__ void __launch_bounds__(128) k_attention_train(const float* __restrict__ qkv, const int* __restrict__ offsets, int C,
+                                                         int heads, float scale, float* __restrict__ out, float* __restrict__ lse) {
+  constexpr int KB = D <= 32 ? 128 : 64;
+  constexpr int QB = 32, S = 4;
+  __shared__ float4 Ks[KB][D / 4];
+  __shared__ float4 Vs[KB][D / 4];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int r0 = offsets[b], L = offsets[b + 1] - r0;
+  if ((int)blockIdx.x * QB >= L) return;
+  const int slice = threadIdx.x & (S - 1);
+  const int qi = blockIdx.x * QB + (threadIdx.x >> 2);
+  const bool valid = qi < L;
+  float q[D], acc[D];
+  {
+    const float4* qp = reinterpret_cast<const float4*>(qkv + (size_t)(r0 + (valid ? qi : 0)) * 3 * C + h * D);
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+      const float4 t = qp[i];
+      q[4 * i] = t.x * scale; q[4 * i + 1] = t.y * scale; q[4 * i + 2] = t.z * scale; q[4 * i + 3] = t.w * scale;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = 0.f;
+  }
+  float m = -INFINITY, l = 0.f;
+  for (int k0 = 0; k0 < L; k0 += KB) {
+    __syncthreads();
+    const int nk = min(KB, L - k0);
+    for (int e = threadIdx.x; e < nk * (D / 4); e += 128) {
+      const int j = e / (D / 4), i = e % (D / 4);
+      const float4* kp = reinterpret_cast<const float4*>(qkv + (size_t)(r0 + k0 + j) * 3 * C + C + h * D);
+      Ks[j][i] = kp[i];
+      Vs[j][i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(kp) + C)[i];
+    }
+    __syncthreads();
+    for (int j = slice; j < nk; j += S) {
+      float d = 0.f;
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i) {
+        const float4 k4 = Ks[j][i];
+        d = fmaf(q[4 * i], k4.x, d); d = fmaf(q[4 * i + 1], k4.y, d); d = fmaf(q[4 * i + 2], k4.z, d); d = fmaf(q[4 * i + 3], k4.w, d);
+      }
+      const float mn = fmaxf(m, d);
+      const float alpha = __expf(m - mn), p = __expf(d - mn);
+      m = mn;
+      l = l * alpha + p;
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i) {
+        const float4 v4 = Vs[j][i];
+        acc[4 * i] = fmaf(p, v4.x, acc[4 * i] * alpha);
+        acc[4 * i + 1] = fmaf(p, v4.y, acc[4 * i + 1] * alpha);
+        acc[4 * i + 2] = fmaf(p, v4.z, acc[4 * i + 2] * alpha);
+        acc[4 * i + 3] = fmaf(p, v4.w, acc[4 * i + 3] * alpha);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < S; o <<= 1) {
+    const float m_o = __shfl_xor_sync(0xffffffffu, m, o), l_o = __shfl_xor_sync(0xffffffffu, l, o);
+    const float mn = fmaxf(m, m_o);
+    const float wa = m == -INFINITY ? 0.f : __expf(m - mn), wb = m_o == -INFINITY ? 0.f : __expf(m_o - mn);
+    l = l * wa + l_o * wb;
+#pragma unroll
+    for (int i = 0; i < D; ++i) acc[i] = acc[i] * wa + __shfl_xor_sync(0xffffffffu, acc[i], o) * wb;
+    m = mn;
+  }
+  if (valid) {
+    const float inv = 1.f / l;
+    float4* op = reinterpret_cast<float4*>(out + (size_t)(r0 + qi) * C + h * D);
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+      if ((i & (S - 1)) != slice) continue;
+      op[i] = make_float4(acc[4 * i] * inv, acc[4 * i + 1] * inv, acc[4 * i + 2] * inv, acc[4 * i + 3] * inv);
+    }
+    if (slice == 0 && lse) lse[(size_t)(r0 + qi) * heads + h] = m + __logf(l);
+  }
+}
+
+// dQ and delta = dO . O per (row, head): 4 lanes per query, keys / values staged in shared memory
+template <int D>
+__global__ void __launch_bounds__(128) k_attention_bwd_q(const float* __restrict__ qkv, const float* __restrict__ out,
+                                                         const float* __restrict__ gout, const float* __restrict__ lse,
+                                                         const int* __restrict__ offsets, int C, int heads, float scale,
+                                                         float* __restrict__ gqkv, float* __restrict__ delta) {
+  constexpr int KB = D <= 32 ? 128 : 64;
+  constexpr int QB = 32, S = 4;
+  __shared__ float4 Ks[KB][D / 4];
+  __shared__ float4 Vs[KB][D / 4];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int r0 = offsets[b], L = offsets[b + 1] - r0;
+  if ((int)blockIdx.x * QB >= L) return;
+  const int slice = threadIdx.x & (S - 1);
+  const int qi = blockIdx.x * QB + (threadIdx.x >> 2);
+  const bool valid = qi < L;
+  const size_t row = (size_t)(r0 + (valid ? qi : 0));
+  float q[D], go[D], dq[D];
+  float dl = 0.f;
+  {
+    const float4* qp = reinterpret_cast<const float4*>(qkv + row * 3 * C + h * D);
+    const float4* gp = reinterpret_cast<const float4*>(gout + row * C + h * D);
+    const float4* op = reinterpret_cast<const float4*>(out + row * C + h * D);
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+      const float4 t = qp[i], g = gp[i], o = op[i];
+      q[4 * i] = t.x * scale; q[4 * i + 1] = t.y * scale; q[4 * i + 2] = t.z * scale; q[4 * i + 3] = t.w * scale;
+      go[4 * i] = g.x; go[4 * i + 1] = g.y; go[4 * i + 2] = g.z; go[4 * i + 3] = g.w;
+      dl += g.x * o.x + g.y * o.y + g.z * o.z + g.w * o.w;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) dq[i] = 0.f;
+  }
+  const float ls = valid ? lse[row * heads + h] : 0.f;
+  for (int k0 = 0; k0 < L; k0 += KB) {
+    __syncthreads();
+    const int nk = min(KB, L - k0);
+    for (int e = threadIdx.x; e < nk * (D / 4); e += 128) {
+      const int j = e / (D / 4), i = e % (D / 4);
+      const float4* kp = reinterpret_cast<const float4*>(qkv + (size_t)(r0 + k0 + j) * 3 * C + C + h * D);
+      Ks[j][i] = kp[i];
+      Vs[j][i] = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(kp) + C)[i];
+    }
+    __syncthreads();
+    for (int j = slice; j < nk; j += S) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i) {
+        const float4 k4 = Ks[j][i], v4 = Vs[j][i];
+        s = fmaf(q[4 * i], k4.x, s); s = fmaf(q[4 * i + 1], k4.y, s); s = fmaf(q[4 * i + 2], k4.z, s); s = fmaf(q[4 * i + 3], k4.w, s);
+        dp = fmaf(go[4 * i], v4.x, dp); dp = fmaf(go[4 * i + 1], v4.y, dp); dp = fmaf(go[4 * i + 2], v4.z, dp); dp = fmaf(go[4 * i + 3], v4.w, dp);
+      }
+      const float ds = __expf(s - ls) * (dp - dl);
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i) {
+        const float4 k4 = Ks[j][i];
+        dq[4 * i] = fmaf(ds, k4.x, dq[4 * i]); dq[4 * i + 1] = fmaf(ds, k4.y, dq[4 * i + 1]);
+        dq[4 * i + 2] = fmaf(ds, k4.z, dq[4 * i + 2]); dq[4 * i + 3] = fmaf(ds, k4.w, dq[4 * i + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < S; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < D; ++i) dq[i] += __shfl_xor_sync(0xffffffffu, dq[i], o);
+  if (valid) {
+    float4* gq = reinterpret_cast<float4*>(gqkv + row * 3 * C + h * D);
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+      if ((i & (S - 1)) != slice) continue;
+      gq[i] = make_float4(dq[4 * i] * scale, dq[4 * i + 1] * scale, dq[4 * i + 2] * scale, dq[4 * i + 3] * scale);
+    }
+    if (slice == 0) delta[row * heads + h] = dl;
+  }
+}
+
+// dK and dV: 4 lanes per key, queries (scaled q, dO, lse, delta) staged in shared memory
+template <int D>
+__global__ void __launch_bounds__(128) k_attention_bwd_kv(const float* __restrict__ qkv, const float* __restrict__ gout,
+                                                          const float* __restrict__ lse, const float* __restrict__ delta,
+                                                          const int* __restrict__ offsets, int C, int heads, float scale,
+                                                          float* __restrict__ gqkv) {
+  constexpr int QT = D <= 32 ? 128 : 64;   // queries per shared-memory tile
+  constexpr int KBLK = 32, S = 4;
+  __shared__ float4 Qs[QT][D / 4];
+  __shared__ float4 Gs[QT][D / 4];
+  __shared__ float Ls[QT], Ds[QT];
+  const int b = blockIdx.z, h = blockIdx.y;
+  const int r0 = offsets[b], L = offsets[b + 1] - r0;
+  if ((int)blockIdx.x * KBLK >= L) return;
+  const int slice = threadIdx.x & (S - 1);
+  const int kj = blockIdx.x * KBLK + (threadIdx.x >> 2);
+  const bool valid = kj < L;
+  const size_t row = (size_t)(r0 + (valid ? kj : 0));
+  float k[D], v[D], dk[D], dv[D];
+  {
+    const float4* kp = reinterpret_cast<const float4*>(qkv + row * 3 * C + C + h * D);
+    const float4* vp = reinterpret_cast<const float4*>(qkv + row * 3 * C + 2 * C + h * D);
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+      const float4 a = kp[i], c4 = vp[i];
+      k[4 * i] = a.x; k[4 * i + 1] = a.y; k[4 * i + 2] = a.z; k[4 * i + 3] = a.w;
+      v[4 * i] = c4.x; v[4 * i + 1] = c4.y; v[4 * i + 2] = c4.z; v[4 * i + 3] = c4.w;
+    }
+#pragma unroll
+    for (int i = 0; i < D; ++i) dk[i] = dv[i] = 0.f;
+  }
+  for (int q0 = 0; q0 < L; q0 += QT) {
+    __syncthreads();
+    const int nq = min(QT, L - q0);
+    for (int e = threadIdx.x; e < nq * (D / 4); e += 128) {
+      const int j = e / (D / 4), i = e % (D / 4);
+      float4 t = reinterpret_cast<const float4*>(qkv + (size_t)(r0 + q0 + j) * 3 * C + h * D)[i];
+      t.x *= scale; t.y *= scale; t.z *= scale; t.w *= scale;
+      Qs[j][i] = t;
+      Gs[j][i] = reinterpret_cast<const float4*>(gout + (size_t)(r0 + q0 + j) * C + h * D)[i];
+    }
+    for (int j = threadIdx.x; j < nq; j += 128) {
+      Ls[j] = lse[(size_t)(r0 + q0 + j) * heads + h];
+      Ds[j] = delta[(size_t)(r0 + q0 + j) * heads + h];
+    }
+    __syncthreads();
+    for (int j = slice; j < nq; j += S) {
+      float s = 0.f, dp = 0.f;
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i) {
+        const float4 q4 = Qs[j][i], g4 = Gs[j][i];
+        s = fmaf(q4.x, k[4 * i], s); s = fmaf(q4.y, k[4 * i + 1], s); s = fmaf(q4.z, k[4 * i + 2], s); s = fmaf(q4.w, k[4 * i + 3], s);
+        dp = fmaf(g4.x, v[4 * i], dp); dp = fmaf(g4.y, v[4 * i + 1], dp); dp = fmaf(g4.z, v[4 * i + 2], dp); dp = fmaf(g4.w, v[4 * i + 3], dp);
+      }
+      const float p = __expf(s - Ls[j]);
+      const float ds = p * (dp - Ds[j]);
+#pragma unroll
+      for (int i = 0; i < D / 4; ++i) {
+        const float4 q4 = Qs[j][i], g4 = Gs[j][i];
+        dv[4 * i] = fmaf(p, g4.x, dv[4 * i]); dv[4 * i + 1] = fmaf(p, g4.y, dv[4 * i + 1]);
+        dv[4 * i + 2] = fmaf(p, g4.z, dv[4 * i + 2]); dv[4 * i + 3] = fmaf(p, g4.w, dv[4 * i + 3]);
+        dk[4 * i] = fmaf(ds, q4.x, dk[4 * i]); dk[4 * i + 1] = fmaf(ds, q4.y, dk[4 * i + 1]);     // q4 carries the scale
+        dk[4 * i + 2] = fmaf(ds, q4.z, dk[4 * i + 2]); dk[4 * i + 3] = fmaf(ds, q4.w, dk[4 * i + 3]);
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < S; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < D; ++i) {
+      dk[i] += __shfl_xor_sync(0xffffffffu, dk[i], o);
+      dv[i] += __shfl_xor_sync(0xffffffffu, dv[i], o);
+    }
+  if (valid) {
+    float4* gk = reinterpret_cast<float4*>(gqkv + row * 3 * C + C + h * D);
+    float4* gv = reinterpret_cast<float4*>(gqkv + row * 3 * C + 2 * C + h * D);
+#pragma unroll
+    for (int i = 0; i < D / 4; ++i) {
+      if ((i & (S - 1)) != slice) continue;
+      gk[i] = make_float4(dk[4 * i], dk[4 * i + 1], dk[4 * i + 2], dk[4 * i + 3]);
+      gv[i] = make_float4(dv[4 * i], dv[4 * i + 1], dv[4 * i + 2], dv[4 * i + 3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ small elementwise
+__global__ void k_split(const float* __restrict__ g, long long rows, int ca, int cb, float* __restrict__ ga, float* __restrict__ gb) {
+  const long long total = rows * (ca + cb);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / (ca + cb);
+    const int q = (int)(t % (ca + cb));
+    if (q < ca) ga[r * ca + q] = g[t];
+    else gb[r * cb + (q - ca)] = g[t];
+  }
+}
+__global__ void k_cat(const float* __restrict__ a, const float* __restrict__ b, long long rows, int ca, int cb, float* __restrict__ y) {
+  const long long total = rows * (ca + cb);
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long long)gridDim.x * blockDim.x) {
+    const long long r = t / (ca + cb);
+    const int q = (int)(t % (ca + cb));
+    y[t] = q < ca ? a[r * ca + q] : b[r * cb + (q - ca)];
+  }
+}
+__global__ void k_silu_fwd(const float* __restrict__ x, long long n, float* __restrict__ y) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) y[t] = silu_t(x[t]);
+}
+__global__ void k_silu_bwd(const float* __restrict__ x, const float* __restrict__ gy, long long n, float* __restrict__ gx) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x)
+    gx[t] = gy[t] * dsilu_t(x[t]);
+}
+// y = a + b (gradient accumulation / residual sums on the training path)
+__global__ void k_add(const float* __restrict__ a, const float* __restrict__ b, long long n, float* __restrict__ y) {
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) y[t] = a[t] + b[t];
+}
+// out[b, :] = table[idx[b], :] (+ base[b, :]);  backward: gtable[idx[b], :] += g[b, :]
+__global__ void k_embedding_fwd(const float* __restrict__ table, const long long* __restrict__ idx, const float* __restrict__ base,
+                                int e, float* __restrict__ out) {
+  const int b = blockIdx.x;
+  const float* row = table + (size_t)idx[b] * e;
+  for (int i = threadIdx.x; i < e; i += blockDim.x) out[(size_t)b * e + i] = row[i] + (base ? base[(size_t)b * e + i] : 0.f);
+}
+__global__ void k_embedding_bwd(const float* __restrict__ g, const long long* __restrict__ idx, int e, float* __restrict__ gtable) {
+  const int b = blockIdx.x;
+  float* row = gtable + (size_t)idx[b] * e;
+  for (int i = threadIdx.x; i < e; i += blockDim.x) atomicAdd(row + i, g[(size_t)b * e + i]);
+}
+// models/utils.py:15-19: exponent = -ln(1e4) * linspace(0, 1, d/2); emb = [sin(t * e^exponent), cos(t * e^exponent)]
+__global__ void k_timestep_embedding(const long long* __restrict__ t, int d, float* __restrict__ out) {
+  const int b = blockIdx.x, half = d / 2;
+  const float tv = (float)t[b];
+  for (int i = threadIdx.x; i < half; i += blockDim.x) {
+    const float lin = half > 1 ? (float)i / (float)(half - 1) : 0.f;
+    const float e = tv * expf(-logf(10000.f) * lin);
+    out[(size_t)b * d + i] = sinf(e);
+    out[(size_t)b * d + half + i] = cosf(e);
+  }
+}
+// loss = mean((p - t)^2), gp = 2 (p - t) / n * gscale
+__global__ void __launch_bounds__(256) k_mse(const float* __restrict__ p, const float* __restrict__ t, long long n, float gscale,
+                                             float* __restrict__ gp, double* __restrict__ tot) {
+  __shared__ float sm[8];
+  float a = 0.f;
+  const float k = 2.f * gscale / (float)n;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float d = p[i] - t[i];
+    a = fmaf(d, d, a);
+    if (gp) gp[i] = k * d;
+  }
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = a;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < 8; ++w) a += sm[w];
+    atomicAdd(tot, (double)a);
+  }
+}
+__global__ void k_mse_finalize(double* __restrict__ tot, long long n, float* __restrict__ loss) {
+  loss[0] = (float)(tot[0] / (double)n);
+  tot[0] = 0.0;
+}
+
+static inline int grid_for(long long n, int per = 256, int cap = 148 * 16) {
+  long long g = (n + per - 1) / per;
+  return (int)(g < 1 ? 1 : g > cap ? cap : g);
+}
+
+}  // namespace spvd
+
+using namespace spvd;
+
+extern "C" int spvd_bn_silu_fwd(const float*, const float*, const float*, long long, int, int, float*, spvd_stream_t);
+
+extern "C" int spvd_bn_train_fwd(const float* x, long long rows, int c, const float* gamma, const float* beta, float eps,
+                                 float momentum, float* running_mean, float* running_var, float* save_mean,
+                                 float* save_invstd, float* scale, float* shift, int act, float* y, double* workspace,
+                                 spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && save_mean && save_invstd && scale && shift && y && workspace && rows > 0 && c > 0,
+                 "spvd_bn_train_fwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  k_bn_stats<<<cdiv(rows, kRedRows), kRedThreads, 0, s>>>(x, rows, c, workspace);
+  k_bn_finalize<<<cdiv(c, 128), 128, 0, s>>>(workspace, rows, c, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
+                                             save_invstd, scale, shift);
+  SPVD_LAUNCH_CHECK();
+  return spvd_bn_silu_fwd(x, scale, shift, rows, c, act & 1, y, stream);
+}
+
+extern "C" int spvd_bn_train_bwd(const float* x, const float* gy, long long rows, int c, const float* gamma, const float* beta,
+                                 const float* save_mean, const float* save_invstd, int act, float* gx, float* ggamma,
+                                 float* gbeta, double* workspace, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && gy && save_mean && save_invstd && gx && workspace && rows > 0 && c > 0, "spvd_bn_train_bwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  k_bn_bwd_reduce<<<cdiv(rows, kRedRows), kRedThreads, 0, s>>>(x, gy, rows, c, save_mean, save_invstd, gamma, beta, act, workspace);
+  k_bn_bwd_apply<<<grid_for(rows * c), 256, 0, s>>>(x, gy, rows, c, save_mean, save_invstd, gamma, beta, act, workspace, gx, ggamma,
+                                                    gbeta);
+  k_clear_f64<<<cdiv(2 * c, 256), 256, 0, s>>>(workspace, 2 * c);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_colsum(const float* g, long long rows, int c, float* out, double* workspace, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(g && out && workspace && rows >= 0 && c > 0, "spvd_colsum: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rows > 0) k_colsum<<<cdiv(rows, kRedRows), kRedThreads, 0, s>>>(g, rows, c, workspace);
+  k_f64_to_f32<<<cdiv(2 * c, 256), 256, 0, s>>>(workspace, c, 2 * c, out);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_film_bwd(const float* x, const float* gy, const float* tt, int ldt, const int32_t* batch_offsets, int n_batch,
+                             int max_rows_per_cloud, int c, float* gx, float* gtt, int ldg, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && gy && tt && batch_offsets && gx && gtt && n_batch > 0 && c > 0 && ldt >= 2 * c && ldg >= 2 * c,
+                 "spvd_film_bwd: bad arguments");
+  if (max_rows_per_cloud <= 0) return SPVD_OK;
+  const int rows_per_cta = 64;
+  dim3 grid(cdiv(max_rows_per_cloud, rows_per_cta), n_batch);
+  k_film_bwd<<<grid, 256, 0, (cudaStream_t)stream>>>(x, gy, tt, ldt, batch_offsets, c, rows_per_cta, gx, gtt, ldg);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_layernorm_train_fwd(const float* x, const float* gamma, const float* beta, int rows, int c, float eps,
+                                        float* y, float* mean, float* rstd, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && gamma && beta && y && rows >= 0 && c > 0, "spvd_layernorm_train_fwd: bad arguments");
+  if (rows == 0) return SPVD_OK;
+  k_layernorm_train<<<cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(x, gamma, beta, rows, c, eps, y, mean, rstd);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_layernorm_bwd(const float* x, const float* gy, const float* gamma, const float* mean, const float* rstd,
+                                  int rows, int c, float* gx, float* ggamma, float* gbeta, double* workspace,
+                                  spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && gy && gamma && mean && rstd && gx && workspace && rows >= 0 && c > 0, "spvd_layernorm_bwd: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (rows > 0) {
+    k_layernorm_bwd_x<<<cdiv(rows, 8), 256, 0, s>>>(x, gy, gamma, mean, rstd, rows, c, gx);
+    if (ggamma || gbeta) k_layernorm_bwd_params<<<cdiv(rows, kRedRows), kRedThreads, 0, s>>>(x, gy, mean, rstd, rows, c, workspace);
+  }
+  if (ggamma) k_f64_to_f32<<<cdiv(c, 256), 256, 0, s>>>(workspace, c, c, ggamma);
+  if (gbeta) k_f64_to_f32<<<cdiv(c, 256), 256, 0, s>>>(workspace + c, c, c, gbeta);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+#define SPVD_ATTN_DISPATCH(D_, CALL)                              \
+  switch (D_) {                                                   \
+    case 8: { constexpr int D = 8; CALL; } break;                 \
+    case 16: { constexpr int D = 16; CALL; } break;               \
+    case 24: { constexpr int D = 24; CALL; } break;               \
+    case 32: { constexpr int D = 32; CALL; } break;               \
+    case 48: { constexpr int D = 48; CALL; } break;               \
+    case 64: { constexpr int D = 64; CALL; } break;               \
+    default:                                                      \
+      set_error("attention: head dim %d is not instantiated (8,16,24,32,48,64)", D_); \
+      return SPVD_ERR_INVALID;                                    \
+  }
+
+extern "C" int spvd_attention_train_fwd(const float* qkv, const int32_t* batch_offsets, int n_batch, int max_len, int c, int heads,
+                                        float* out, float* lse, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(qkv && batch_offsets && out && lse && n_batch > 0 && heads > 0 && c % heads == 0, "spvd_attention_train_fwd: bad arguments");
+  if (max_len <= 0) return SPVD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int d = c / heads;
+  const float scale = 1.0f / sqrtf((float)d);
+  dim3 grid(cdiv(max_len, 32), heads, n_batch);
+  SPVD_ATTN_DISPATCH(d, (k_attention_train<D><<<grid, 128, 0, s>>>(qkv, batch_offsets, c, heads, scale, out, lse)));
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_attention_bwd(const float* qkv, const float* out, const float* gout, const float* lse,
+                                  const int32_t* batch_offsets, int n_batch, int max_len, int c, int heads, float* gqkv,
+                                  float* delta, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(qkv && out && gout && lse && batch_offsets && gqkv && delta && n_batch > 0 && heads > 0 && c % heads == 0,
+                 "spvd_attention_bwd: bad arguments");
+  if (max_len <= 0) return SPVD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int d = c / heads;
+  const float scale = 1.0f / sqrtf((float)d);
+  dim3 grid(cdiv(max_len, 32), heads, n_batch);
+  SPVD_ATTN_DISPATCH(d, (k_attention_bwd_q<D><<<grid, 128, 0, s>>>(qkv, out, gout, lse, batch_offsets, c, heads, scale, gqkv, delta)));
+  SPVD_ATTN_DISPATCH(d, (k_attention_bwd_kv<D><<<grid, 128, 0, s>>>(qkv, gout, lse, delta, batch_offsets, c, heads, scale, gqkv)));
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_split_fwd(const float* g, long long rows, int ca, int cb, float* ga, float* gb, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(g && ga && gb && rows >= 0 && ca > 0 && cb > 0, "spvd_split_fwd: bad arguments");
+  if (rows == 0) return SPVD_OK;
+  k_split<<<grid_for(rows * (ca + cb)), 256, 0, (cudaStream_t)stream>>>(g, rows, ca, cb, ga, gb);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_cat_any_fwd(const float* a, const float* b, long long rows, int ca, int cb, float* y, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(a && b && y && rows >= 0 && ca > 0 && cb > 0, "spvd_cat_any_fwd: bad arguments");
+  if (rows == 0) return SPVD_OK;
+  k_cat<<<grid_for(rows * (ca + cb)), 256, 0, (cudaStream_t)stream>>>(a, b, rows, ca, cb, y);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_silu_fwd(const float* x, long long n, float* y, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && y && n >= 0, "spvd_silu_fwd: bad arguments");
+  if (n == 0) return SPVD_OK;
+  k_silu_fwd<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, n, y);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_silu_bwd(const float* x, const float* gy, long long n, float* gx, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && gy && gx && n >= 0, "spvd_silu_bwd: bad arguments");
+  if (n == 0) return SPVD_OK;
+  k_silu_bwd<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(x, gy, n, gx);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_add_fwd(const float* a, const float* b, long long n, float* y, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(a && b && y && n >= 0, "spvd_add_fwd: bad arguments");
+  if (n == 0) return SPVD_OK;
+  k_add<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(a, b, n, y);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_embedding_fwd(const float* table, const int64_t* idx, const float* base, int n_batch, int e, float* out,
+                                  spvd_stream_t stream) {
+  SPVD_CHECK_ARG(table && idx && out && n_batch > 0 && e > 0, "spvd_embedding_fwd: bad arguments");
+  k_embedding_fwd<<<n_batch, 128, 0, (cudaStream_t)stream>>>(table, (const long long*)idx, base, e, out);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_embedding_bwd(const float* g, const int64_t* idx, int n_batch, int e, float* gtable, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(g && idx && gtable && n_batch > 0 && e > 0, "spvd_embedding_bwd: bad arguments");
+  k_embedding_bwd<<<n_batch, 128, 0, (cudaStream_t)stream>>>(g, (const long long*)idx, e, gtable);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_timestep_embedding(const int64_t* t, int n_batch, int d, float* out, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(t && out && n_batch > 0 && d > 0 && d % 2 == 0, "spvd_timestep_embedding: bad arguments");
+  k_timestep_embedding<<<n_batch, 64, 0, (cudaStream_t)stream>>>((const long long*)t, d, out);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_mse_loss(const float* pred, const float* target, long long n, float grad_scale, float* loss, float* gpred,
+                             double* workspace, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(pred && target && loss && workspace && n > 0, "spvd_mse_loss: bad arguments");
+  cudaStream_t s = (cudaStream_t)stream;
+  k_mse<<<grid_for(n, 1024, 296), 256, 0, s>>>(pred, target, n, grad_scale, gpred, workspace);
+  k_mse_finalize<<<1, 1, 0, s>>>(workspace, n, loss);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}

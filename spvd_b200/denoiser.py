@@ -41,8 +41,8 @@ class Conv3d(nn.Module):
         self._packed = SF.PackedWeight()
         self.impl = ops.CONV_AUTO
 
-    def forward(self, feats, kmap, a_tf32=False):
-        return SF.sparse_conv(feats, self.kernel, self.bias, kmap, self._packed, self.impl, a_tf32)
+    def forward(self, feats, kmap, a_tf32=False, residual=None):
+        return SF.sparse_conv(feats, self.kernel, self.bias, kmap, self._packed, self.impl, a_tf32, residual)
 
     def extra_repr(self):
         return (f"{self.in_channels}, {self.out_channels}, kernel_size={self.kernel_size}, stride={self.stride}, "
@@ -175,6 +175,8 @@ class SPVUnet(nn.Module):
         self.out_conv = _bn_silu_linear(c_out, point_channels, bias=False)
         self._plan = self._make_plan(down_blocks, up_blocks)
         self._folded = {}
+        self._lin_cache = {}         # id(nn.Linear) -> SF.LinearCache (transposed weight + tile image of the op-by-op path)
+        self._impl = ops.CONV_AUTO
         self._programs = {}          # (n_points, n_batch) -> runtime.Program (native inference executor)
         self.use_executor = True
         self._plan_ws = {}           # (n_points, n_batch, device) -> [PlanWorkspace pool, cursor]
@@ -188,6 +190,8 @@ class SPVUnet(nn.Module):
         # tensor-core operand format of the executor: "f16" = IEEE half operands (the 11-bit significand of TF32, fp32
         # accumulation, twice the issue rate and half the operand bytes) or "tf32"; training always uses TF32
         self.executor_operands = os.environ.get("SPVD_EXEC_OPERANDS", "f16")
+        # strides whose 3^3 maps also get a mask-sorted view (spvd_kmap_sort) for the executor's sorted-tile convolutions
+        self.sort_strides = tuple(1 << int(v) for v in os.environ.get("SPVD_SORT_LEVELS", "").split(",") if v != "")
 
     # -- static description of which strides need which maps (so Geometry can build all of them up front)
     @staticmethod
@@ -215,6 +219,7 @@ class SPVUnet(nn.Module):
     def invalidate_programs(self):
         self._programs.clear()
         self._folded.clear()
+        self.__dict__.pop("_stamp_tensors", None)
 
     def train(self, mode=True):
         self.invalidate_programs()
@@ -231,10 +236,17 @@ class SPVUnet(nn.Module):
     def set_conv_impl(self, impl):
         self.invalidate_programs()
         self.use_executor = impl == ops.CONV_AUTO
+        self._impl = impl
         for m in self.modules():
             if isinstance(m, Conv3d):
                 m.impl = impl
         return self
+
+    def _param_stamp(self):
+        ps = self.__dict__.get("_stamp_tensors")
+        if ps is None:
+            ps = self.__dict__["_stamp_tensors"] = list(self.parameters()) + list(self.buffers())
+        return sum(p._version for p in ps), sum(p.data_ptr() for p in ps[:8])
 
     def num_params(self):
         return sum(p.numel() for p in self.parameters())
@@ -245,8 +257,9 @@ class SPVUnet(nn.Module):
 
     def _bn_act(self, bn: nn.BatchNorm1d, x, act=True, tf32=False):
         """BatchNorm1d (+ SiLU).  Inference: one fused kernel on the folded affine; ``tf32`` also rounds the
-        result to TF32 there, so that the convolution consuming it can gather with cp.async."""
-        if self._fast():
+        result to TF32 there, so that the convolution consuming it can gather with cp.async.  Training: batch statistics,
+        forward and backward on the library's own kernels (csrc/train.cu)."""
+        if self._fast() or not bn.training:
             key = id(bn)
             ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version)
             hit = self._folded.get(key)
@@ -255,36 +268,42 @@ class SPVUnet(nn.Module):
                 shift = bn.bias.detach() - bn.running_mean * scale
                 hit = (ver, scale.contiguous(), shift.contiguous())
                 self._folded[key] = hit
-            return ops.affine_act(x.contiguous(), hit[1], hit[2], (1 if act else 0) | (2 if tf32 else 0))
-        y = bn(x)
-        return F.silu(y) if act else y
+            if self._fast():
+                return ops.affine_act(x.contiguous(), hit[1], hit[2], (1 if act else 0) | (2 if tf32 else 0))
+            y = x * hit[1] + hit[2]                      # eval mode with autograd (frozen statistics): plain torch
+            return F.silu(y) if act else y
+        return SF.batch_norm_act(x, bn, act)
+
+    def _linear(self, lin: nn.Linear, x, residual=None):
+        """nn.Linear as a kernel-size-1 convolution of the library (tcgen05 TF32 / fp32 SIMT), forward and backward"""
+        cache = self._lin_cache.get(id(lin))
+        if cache is None:
+            cache = self._lin_cache[id(lin)] = SF.LinearCache()
+        return SF.linear(x, lin.weight, lin.bias, cache, self._impl, residual)
 
     def _point_block(self, pb: PointBlock, z1, z):
-        return z1 + pb.conv[2](self._bn_act(pb.conv[0], z))
+        return self._linear(pb.conv[2], self._bn_act(pb.conv[0], z), residual=z1)
 
     def _attention(self, blk: SparseAttention, x, geo: Geometry, s):
-        dense_idx, mask, nb, nmax = geo.dense_layout(s)
-        C = x.shape[1]
-        h = blk.attn.num_heads
-        dense = x.new_zeros((nb * nmax, C)).index_copy_(0, dense_idx, x).view(nb, nmax, C)
-        y = blk.norm1(dense)
-        qkv = blk.attn.qkv(y).view(nb, nmax, 3, h, C // h).permute(2, 0, 3, 1, 4)
-        o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2], attn_mask=mask[:, None, None, :])
-        o = blk.attn.proj(o.transpose(1, 2).reshape(nb, nmax, C))
-        return (dense + o).view(nb * nmax, C).index_select(0, dense_idx)
+        """models/modules/transformer.py:118-125: x + proj(attention(qkv(LayerNorm(x)))) per cloud -- rows of a level are
+        batch-major, so the padded [B, Nmax] layout of the reference is replaced by per-cloud row ranges"""
+        lv = geo.level(s)
+        y = SF.layer_norm(x, blk.norm1)
+        qkv = self._linear(blk.attn.qkv, y)
+        o = SF.attention(qkv, geo.batch_offsets(s), len(lv.batch_counts_host), max(lv.batch_counts_host), blk.attn.num_heads)
+        return self._linear(blk.attn.proj, o, residual=x)
 
     def _res_block(self, blk: EmbResBlock, x_in, emb_act, geo: Geometry, s):
         lv = geo.level(s)
         fast = self._fast()
         x = blk.conv1[2](self._bn_act(blk.conv1[0], x_in, tf32=fast), lv.kmap3, fast)
-        tt = blk.t_emb.proj_mlp(emb_act)                                    # [B, 2C]
+        tt = self._linear(blk.t_emb.proj_mlp, emb_act)                      # [B, 2C]
         if fast:
             x = ops.film(x, tt.contiguous(), lv.coords)
         else:
-            scale, shift = torch.chunk(tt[geo.batch_index(s)], 2, dim=-1)
-            x = (1 + scale) * x + shift
-        x = blk.conv2[2](self._bn_act(blk.conv2[0], x, tf32=fast), lv.kmap3, fast)
-        x = x + (blk.idconv(x_in) if hasattr(blk, "idconv") else x_in)
+            x = SF.film(x, tt, lv.coords, geo.batch_offsets(s), max(lv.batch_counts_host))
+        res = self._linear(blk.idconv, x_in) if hasattr(blk, "idconv") else x_in
+        x = blk.conv2[2](self._bn_act(blk.conv2[0], x, tf32=fast), lv.kmap3, fast, residual=res)
         if hasattr(blk, "attn"):
             x = self._attention(blk.attn, x, geo, s)
         return x
@@ -304,7 +323,8 @@ class SPVUnet(nn.Module):
             # training: pair lists at every level (the weight gradient reduces over them); inference: only where the
             # executor can choose pair-major convolutions
             pool[0].append(PlanWorkspace(pc.shape[0], n_batch, p["strides"], p["strides"], p["p2v"], p["devox"], pc.device,
-                                         pair_strides=None if self.training else (1, 2)))
+                                         pair_strides=None if self.training else (1, 2),
+                                         sort_strides=() if self.training else self.sort_strides))
             ws = pool[0][-1]
         else:
             pool[1] = (pool[1] + 1) % len(pool[0])
@@ -333,8 +353,12 @@ class SPVUnet(nn.Module):
             from .runtime import Program
             key = (feats.shape[0], t.shape[0], self.executor_operands)
             prog = self._programs.get(key)
-            if prog is None:
+            # a compiled program holds derived copies of the parameters (packed tile images, folded BatchNorm): rebuild it
+            # when any parameter or buffer was modified in place since (optimizer / EMA step, manual edits in eval mode)
+            stamp = self._param_stamp()
+            if prog is None or prog.stamp != stamp:
                 prog = self._programs[key] = Program(self, *key[:2])
+                prog.stamp = stamp
             if (geometry is None and getattr(self, "profile_sink", None) is None and self.plan_split_level not in (0, (0,))
                     and self.side_prologue):
                 # timestep-only ops run on a side stream beside the geometry planning
@@ -355,7 +379,7 @@ class SPVUnet(nn.Module):
                 e.record()                      # materialises the cudaEvent_t handles
             out = prog.run(geo, feats.contiguous().float(), t, conv_events=[e.cuda_event for e in evs], cls=cls)
             pairs = {}
-            for (kvol, cin, cout, rows_out, level, map_kind, kind) in prog.conv_meta:
+            for (kvol, cin, cout, rows_out, level, map_kind, kind, cin2) in prog.conv_meta:
                 if map_kind and (level, map_kind) not in pairs:
                     lv = geo.level(prog.strides[level])
                     km = {1: lv.kmap3, 2: lv.kmap_down, 3: lv.kmap_up}[map_kind]
@@ -364,14 +388,12 @@ class SPVUnet(nn.Module):
             sink.append((evs, prog.conv_meta, {k: int(v.item()) for k, v in pairs.items()}, sizes))
             return out
         # timestep embedding (models/utils.py:15-19; linspace(0,1,d/2) includes 1.0) + MLP
-        exponent = -math.log(10000) * torch.linspace(0, 1, self.n_temb // 2, device=t.device)
-        e = t[:, None].float() * exponent.exp()[None, :]
-        e = torch.cat([e.sin(), e.cos()], dim=-1)
-        emb = self.emb_mlp[0][2](F.silu(self.emb_mlp[0][0](e)))
-        emb = self.emb_mlp[1][1](F.silu(emb))
+        e = ops.timestep_embedding(t.long().contiguous(), self.n_temb)
+        emb = self._linear(self.emb_mlp[0][2], self._bn_act(self.emb_mlp[0][0], e))
+        emb = self._linear(self.emb_mlp[1][1], SF.silu(emb))
         if cls is not None:
-            emb = emb + self.cond_emb(cls)
-        emb_act = F.silu(emb)                      # every TimeEmbeddingBlock starts with SiLU(emb)
+            emb = SF.embedding_add(emb, self.cond_emb.weight, cls.long().contiguous())
+        emb_act = SF.silu(emb)                     # every TimeEmbeddingBlock starts with SiLU(emb)
 
         def v2p(x, s):
             idx8, w8 = geo.devox[s]
@@ -406,7 +428,7 @@ class SPVUnet(nn.Module):
         for si, stage in enumerate(self.up_stages):
             for blk in stage.ups:
                 for r in blk.resnets:
-                    x = self._res_block(r, torch.cat([x, saved.pop()], dim=1), emb_act, geo, s)
+                    x = self._res_block(r, SF.cat(x, saved.pop()), emb_act, geo, s)
                 if blk.add_up:
                     s //= 2
                     x = blk.up(x, geo.level(s).kmap_up)
@@ -415,7 +437,7 @@ class SPVUnet(nn.Module):
             z = self._point_block(stage.point_block, v2p(x, s), z)
             if si + 1 < len(self.up_stages):
                 x = p2v(z, s)            # the reference's last point_to_voxel is dead work (models/spvd.py:269)
-        return self.out_conv[2](self._bn_act(self.out_conv[0], z))
+        return self._linear(self.out_conv[2], self._bn_act(self.out_conv[0], z))
 
 
 # models/__init__.py:9-38

@@ -23,7 +23,7 @@ class PackedWeight:
 
 class _SparseConv(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, weight, bias, kmap, cache, impl, a_tf32=False):
+    def forward(ctx, x, weight, bias, kmap, cache, impl, a_tf32=False, residual=None):
         w3 = weight if weight.dim() == 3 else weight.unsqueeze(0)
         w3 = w3.contiguous()
         wp = cache.get(w3) if (cache is not None and impl != ops.CONV_SIMT) else None
@@ -32,7 +32,8 @@ class _SparseConv(torch.autograd.Function):
         n_out = kmap.n_out if kmap is not None else x.shape[0]
         x = x.contiguous()
         out = ops.conv_fwd(x, w3, wp, kmap.map_t if kmap is not None else None,
-                           kmap.mask if kmap is not None else None, n_out, bias, impl, a_tf32=a_tf32)
+                           kmap.mask if kmap is not None else None, n_out, bias, impl, a_tf32=a_tf32,
+                           residual=residual.contiguous() if residual is not None else None)
         ctx.save_for_backward(x, weight)
         ctx.kmap, ctx.impl, ctx.has_bias = kmap, impl, bias is not None
         return out
@@ -63,14 +64,14 @@ class _SparseConv(torch.autograd.Function):
             else:
                 gw = ops.conv_wgrad(x, g, kmap.map_t if kmap is not None else None, n_out, kvol).view_as(weight)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = g.sum(0)
-        return gx, gw, gb, None, None, None, None
+            gb = ops.colsum(g)
+        return gx, gw, gb, None, None, None, None, (g if ctx.needs_input_grad[7] else None)
 
 
-def sparse_conv(x, weight, bias, kmap, cache=None, impl=ops.CONV_AUTO, a_tf32=False):
-    """out[o] = sum_k x[kmap[k][o]] @ weight[k] (+ bias); kmap None = kernel size 1.  ``a_tf32``: the caller
-    guarantees x is already TF32-representable (enables the cp.async gather of the tcgen05 path)."""
-    return _SparseConv.apply(x, weight, bias, kmap, cache, impl, a_tf32)
+def sparse_conv(x, weight, bias, kmap, cache=None, impl=ops.CONV_AUTO, a_tf32=False, residual=None):
+    """out[o] = sum_k x[kmap[k][o]] @ weight[k] (+ bias) (+ residual[o]); kmap None = kernel size 1.  ``a_tf32``: the
+    caller guarantees x is already TF32-representable (enables the cp.async gather of the tcgen05 path)."""
+    return _SparseConv.apply(x, weight, bias, kmap, cache, impl, a_tf32, residual)
 
 
 class _ScatterMean(torch.autograd.Function):
@@ -110,3 +111,220 @@ class _Devoxelize(torch.autograd.Function):
 def devoxelize(feats, idx8, w8):
     """torchsparse.nn.functional.spdevoxelize (models/sparse_utils.py:119,128)."""
     return _Devoxelize.apply(feats, idx8, w8)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Training-mode glue on the library's own kernels (csrc/train.cu): with these, a training step of the denoiser
+# launches no ATen / cuBLAS / cuDNN kernel between the sparse convolutions.
+# ------------------------------------------------------------------------------------------------------------------
+class LinearCache:
+    """[1, in, out] transpose of an nn.Linear weight + its tensor-core tile image, rebuilt when the parameter changes"""
+
+    def __init__(self):
+        self.key, self.w3, self.packed = None, None, None
+
+    def get(self, weight, want_packed):
+        key = (weight.data_ptr(), weight._version)
+        if key != self.key:
+            self.w3 = ops.transpose_weights(weight.detach().unsqueeze(0).contiguous(), False)      # [1, out, in] -> [1, in, out]
+            self.packed, self.key = None, key
+        if want_packed and self.packed is None and ops.umma_supported(*self.w3.shape):
+            self.packed = ops.pack_weights(self.w3)
+        return self.w3, (self.packed if want_packed else None)
+
+
+class _Linear(torch.autograd.Function):
+    """nn.Linear (weight [out, in]) as a kernel-size-1 convolution: forward / data gradient on the conv kernels (tcgen05 TF32
+    where the widths allow, fp32 SIMT otherwise), weight gradient = transposed conv weight gradient, bias gradient = column
+    sum; an optional residual rides on the epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, cache, impl, residual):
+        x = x.contiguous()
+        umma = impl != ops.CONV_SIMT and ops.umma_supported(1, weight.shape[1], weight.shape[0])
+        w3, wp = cache.get(weight, umma)
+        out = ops.conv_fwd(x, w3, wp, None, None, x.shape[0], bias, ops.CONV_AUTO if umma else ops.CONV_SIMT,
+                           residual=residual.contiguous() if residual is not None else None)
+        ctx.save_for_backward(x, weight)
+        ctx.impl, ctx.has_bias = impl, bias is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        x, weight = ctx.saved_tensors
+        g = g.contiguous()
+        cout, cin = weight.shape
+        gx = gw = gb = None
+        if ctx.needs_input_grad[0]:
+            wt = weight.detach().unsqueeze(0).contiguous()                         # [1, out, in]: the transposed conv weight
+            umma = ctx.impl != ops.CONV_SIMT and ops.umma_supported(1, cout, cin)
+            gx = ops.conv_fwd(g, wt, ops.pack_weights(wt) if umma else None, None, None, g.shape[0], None,
+                              ops.CONV_AUTO if umma else ops.CONV_SIMT)
+        if ctx.needs_input_grad[1]:
+            if ctx.impl != ops.CONV_SIMT and ops.umma_supported(1, cin, cout):
+                gw3 = ops.conv_wgrad_umma(ops.round_tf32(x), ops.round_tf32(g), None, x.shape[0], 1)
+            else:
+                gw3 = ops.conv_wgrad(x, g, None, x.shape[0], 1)
+            gw = ops.transpose_weights(gw3, False)[0]                              # [in, out] -> [out, in]
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            gb = ops.colsum(g)
+        return gx, gw, gb, None, None, (g if ctx.needs_input_grad[5] else None)
+
+
+def linear(x, weight, bias, cache, impl=ops.CONV_AUTO, residual=None):
+    return _Linear.apply(x, weight, bias, cache, impl, residual)
+
+
+class _BatchNormAct(torch.autograd.Function):
+    """nn.BatchNorm1d with batch statistics (+ SiLU); updates the running statistics like torch."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, eps, momentum, act):
+        x = x.contiguous()
+        y, stats = ops.bn_train_fwd(x, gamma, beta, eps, momentum, running_mean, running_var, act)
+        ctx.save_for_backward(x, gamma, beta, stats)
+        ctx.act = act
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, beta, stats = ctx.saved_tensors
+        gx, gg, gb = ops.bn_train_bwd(x, gy.contiguous(), gamma, beta, stats, ctx.act)
+        return gx, gg, gb, None, None, None, None, None
+
+
+def batch_norm_act(x, bn, act=True):
+    return _BatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
+                               bn.momentum if bn.momentum is not None else 0.1, 1 if act else 0)
+
+
+class _FiLM(torch.autograd.Function):
+    """(1 + scale[b]) * x + shift[b], [scale | shift] = tt[b] (models/modules/graph.py:35-41); rows of a cloud contiguous"""
+
+    @staticmethod
+    def forward(ctx, x, tt, coords, offsets, max_rows):
+        x, tt = x.contiguous(), tt.contiguous()
+        ctx.save_for_backward(x, tt, offsets)
+        ctx.max_rows = max_rows
+        return ops.film(x, tt, coords)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, tt, offsets = ctx.saved_tensors
+        gx, gtt = ops.film_bwd(x, gy.contiguous(), tt, offsets, ctx.max_rows)
+        return gx, gtt, None, None, None
+
+
+def film(x, tt, coords, offsets, max_rows):
+    return _FiLM.apply(x, tt, coords, offsets, max_rows)
+
+
+class _LayerNorm(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps):
+        x = x.contiguous()
+        y, st = ops.layernorm_train_fwd(x, gamma, beta, eps)
+        ctx.save_for_backward(x, gamma, st)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, gamma, st = ctx.saved_tensors
+        gx, gg, gb = ops.layernorm_bwd(x, gy.contiguous(), gamma, st)
+        return gx, gg, gb, None
+
+
+def layer_norm(x, ln):
+    return _LayerNorm.apply(x, ln.weight, ln.bias, ln.eps)
+
+
+class _Attention(torch.autograd.Function):
+    """per-cloud multi-head softmax attention over qkv [rows, 3C] (models/modules/transformer.py:54-67)"""
+
+    @staticmethod
+    def forward(ctx, qkv, offsets, n_batch, max_len, heads):
+        qkv = qkv.contiguous()
+        out, lse = ops.attention_train_fwd(qkv, offsets, n_batch, max_len, heads)
+        ctx.save_for_backward(qkv, out, lse, offsets)
+        ctx.meta = (n_batch, max_len, heads)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        qkv, out, lse, offsets = ctx.saved_tensors
+        return ops.attention_bwd(qkv, out, gout.contiguous(), lse, offsets, *ctx.meta), None, None, None, None
+
+
+def attention(qkv, offsets, n_batch, max_len, heads):
+    return _Attention.apply(qkv, offsets, n_batch, max_len, heads)
+
+
+class _Cat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.ca = a.shape[1]
+        return ops.cat_any(a.contiguous(), b.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        return ops.split(g.contiguous(), ctx.ca)
+
+
+def cat(a, b):
+    return _Cat.apply(a, b)
+
+
+class _SiLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x):
+        x = x.contiguous()
+        ctx.save_for_backward(x)
+        return ops.silu_fwd(x)
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        return ops.silu_bwd(x, gy.contiguous())
+
+
+def silu(x):
+    return _SiLU.apply(x)
+
+
+class _EmbeddingAdd(torch.autograd.Function):
+    """base + table[idx] (the class embedding added to the time embedding)"""
+
+    @staticmethod
+    def forward(ctx, base, table, idx):
+        ctx.save_for_backward(idx)
+        ctx.n = table.shape[0]
+        return ops.embedding_fwd(table, idx, base.contiguous())
+
+    @staticmethod
+    def backward(ctx, g):
+        (idx,) = ctx.saved_tensors
+        g = g.contiguous()
+        return g, ops.embedding_bwd(g, idx, ctx.n), None
+
+
+def embedding_add(base, table, idx):
+    return _EmbeddingAdd.apply(base, table, idx)
+
+
+class _MSELoss(torch.autograd.Function):
+    """nn.MSELoss()(pred, target): loss and its gradient from one pass"""
+
+    @staticmethod
+    def forward(ctx, pred, target):
+        loss, gp = ops.mse_loss(pred.contiguous(), target.contiguous(), want_grad=True)
+        ctx.save_for_backward(gp)
+        return loss.view(())
+
+    @staticmethod
+    def backward(ctx, g):
+        (gp,) = ctx.saved_tensors
+        return gp * g, None
+
+
+def mse_loss(pred, target):
+    return _MSELoss.apply(pred, target)

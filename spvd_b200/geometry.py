@@ -209,8 +209,11 @@ class _PlanLevel(_C.Structure):
                                            "kmap_up", "mask_up", "p2v", "devox_idx", "devox_w", "batch_counts",
                                            "batch_offsets", "pair_in", "pair_out", "pair_tile_k", "pair_counts",
                                            "pair_scratch", "dpair_in", "dpair_out", "dpair_tile_k", "dpair_counts",
-                                           "p2v_w", "p2v_cnt", "p2v_start", "p2v_cursor", "p2v_order", "p2v_units")] + \
-               [("capacity", _C.c_int32), ("pair_tile_cap", _C.c_int32), ("dpair_tile_cap", _C.c_int32), ("pad", _C.c_int32)]
+                                           "p2v_w", "p2v_cnt", "p2v_start", "p2v_cursor", "p2v_order", "p2v_units",
+                                           "kmap3_sorted", "mask3_sorted", "perm3", "kmap_down_sorted", "mask_down_sorted",
+                                           "perm_down", "kmap_up_sorted", "mask_up_sorted", "perm_up", "sort_ws")] + \
+               [("capacity", _C.c_int32), ("pair_tile_cap", _C.c_int32), ("dpair_tile_cap", _C.c_int32),
+                ("sort_ws_bytes", _C.c_int32)]
 
 
 class _Table:
@@ -226,8 +229,11 @@ class PlanWorkspace:
     """All buffers of one Geometry for a fixed (n_points, n_batch, plan), allocated once; ``build`` fills them
     with one C call and returns a Geometry that VIEWS them (valid until the workspace is built again)."""
 
-    def __init__(self, n_points, n_batch, strides, k3_strides, p2v_strides, devox_strides, device, pair_strides=None):
+    def __init__(self, n_points, n_batch, strides, k3_strides, p2v_strides, devox_strides, device, pair_strides=None,
+                 sort_strides=()):
         self.n_points, self.n_batch, self.strides = n_points, n_batch, tuple(strides)
+        # mask-sorted views of the 3^3 maps (spvd_kmap_sort) for the persistent sorted-tile convolution of the executor
+        self.sort_strides = tuple(s for s in sort_strides if s in k3_strides)
         # pair lists at every level: the executor picks pair-major or dense per level from the pair count, the training path's
         # weight gradient reduces over them
         self.pair_strides = tuple(s for s in (k3_strides if pair_strides is None else pair_strides) if s in k3_strides)
@@ -257,6 +263,10 @@ class PlanWorkspace:
                      batch_offsets=torch.zeros(n_batch + 1, **i32))
             if s in k3_strides:
                 b["kmap3"], b["mask3"] = torch.empty((27, ld), **i32), torch.empty(ld // 128, **i32)
+            if s in self.sort_strides:
+                b["kmap3_sorted"], b["mask3_sorted"] = torch.empty((27, ld), **i32), torch.empty(ld // 128, **i32)
+                b["perm3"] = torch.empty(ld, **i32)
+                b["sort_ws"] = torch.empty(_lib.spvd_kmap_sort_workspace_bytes(n_points), dtype=torch.uint8, device=device)
             if i + 1 < nl:
                 b["kmap_down"], b["mask_down"] = torch.empty((8, ld), **i32), torch.empty(ld // 128, **i32)
                 b["kmap_up"], b["mask_up"] = torch.empty((8, ld), **i32), torch.empty(ld // 128, **i32)
@@ -292,12 +302,13 @@ class PlanWorkspace:
             for name, t in b.items():
                 setattr(L, name, t.data_ptr())
             L.capacity = 2 * n_points
+            L.sort_ws_bytes = b["sort_ws"].numel() if "sort_ws" in b else 0
             L.pair_tile_cap = tile_cap
             L.dpair_tile_cap = dcap
         self.status = self.summary[nl: nl + 1]
         # kernels launched by one build (ops.stats accounting)
         self.n_kernels = (1 + 22 + 23 * (nl - 1) + nl + (nl - 1) + len(k3_strides) + 2 * len(p2v_strides) + len(devox_strides) +
-                          2 * nl + 3 * len(self.pair_strides) + 3 * (nl - 1))
+                          2 * nl + 3 * len(self.pair_strides) + 3 * (nl - 1) + 13 * len(self.sort_strides))
 
     def build(self, pc, pres, voxel_size, scale_mode="mul", downsample_mode="spconv", max_cloud_rows=0, split_level=0,
               side_stream=None):
@@ -423,6 +434,8 @@ class PlanWorkspace:
             if "kmap3" in b:
                 lv.kmap3 = KernelMap(b["kmap3"], b["mask3"], lv.n, lv.n, 27, flip=True)
                 lv.kmap3.grad = lv.kmap3
+                if "kmap3_sorted" in b:
+                    lv.kmap3_sorted = (b["kmap3_sorted"], b["mask3_sorted"], b["perm3"])
                 if "pair_in" in b:       # the weight-gradient kernel reduces over the planner's pair list: no lazy build, no sync
                     lv.kmap3._pairs = lv.pairs[:4]
         for i in range(max(lo - 1, 0), hi - 1):           # stride-2 maps between level i and i + 1 (planned with level i + 1)

@@ -435,3 +435,169 @@ def conv_sp(x16, w_packed, kvol, cin, cout, n_out, map_t=None, tile_mask=None, o
     a.n_in = x16.shape[0]
     check(lib.spvd_conv_sp_f16(ctypes.byref(a), int(bn), int(stages), _s()))
     return out32, out16
+
+
+# ------------------------------------------------------------------------------------ training-mode glue (csrc/train.cu)
+_K.update({"bn_train_fwd": 3, "bn_train_bwd": 3, "colsum": 2, "film_bwd": 1, "layernorm_train": 1, "layernorm_bwd": 4,
+           "attention_train": 1, "attention_bwd": 2, "cat_any": 1, "split": 1, "silu": 1, "add": 1, "embedding": 1,
+           "timestep_embedding": 1, "mse": 2})
+_TRAIN_WS = {}
+
+
+def train_ws(device):
+    """fp64 scratch of the per-channel reductions (zero on entry, left zero by every kernel that uses it)"""
+    ws = _TRAIN_WS.get(device)
+    if ws is None:
+        ws = _TRAIN_WS[device] = torch.zeros(8192, dtype=torch.float64, device=device)
+    return ws
+
+
+def bn_train_fwd(x, gamma, beta, eps, momentum, running_mean, running_var, act=1):
+    """-> y, (save_mean, save_invstd); running statistics updated in place"""
+    _count("bn_train_fwd")
+    rows, c = x.shape
+    dev = x.device
+    stats = torch.empty((4, c), dtype=torch.float32, device=dev)       # mean | invstd | scale | shift
+    y = torch.empty_like(x)
+    check(lib.spvd_bn_train_fwd(_p(x, torch.float32), rows, c, _p(gamma), _p(beta), float(eps), float(momentum),
+                                _p(running_mean), _p(running_var), _p(stats[0]), _p(stats[1]), _p(stats[2]), _p(stats[3]),
+                                int(act), _p(y), _p(train_ws(dev)), _s()))
+    return y, stats
+
+
+def bn_train_bwd(x, gy, gamma, beta, stats, act=1):
+    _count("bn_train_bwd")
+    rows, c = x.shape
+    gx = torch.empty_like(x)
+    gg = torch.empty(c, dtype=torch.float32, device=x.device)
+    gb = torch.empty(c, dtype=torch.float32, device=x.device)
+    check(lib.spvd_bn_train_bwd(_p(x, torch.float32), _p(gy, torch.float32), rows, c, _p(gamma), _p(beta), _p(stats[0]),
+                                _p(stats[1]), int(act), _p(gx), _p(gg), _p(gb), _p(train_ws(x.device)), _s()))
+    return gx, gg, gb
+
+
+def colsum(g):
+    _count("colsum")
+    rows, c = g.shape
+    out = torch.empty(c, dtype=torch.float32, device=g.device)
+    check(lib.spvd_colsum(_p(g, torch.float32), rows, c, _p(out), _p(train_ws(g.device)), _s()))
+    return out
+
+
+def film_bwd(x, gy, tt, offsets, max_rows):
+    _count("film_bwd")
+    rows, c = x.shape
+    gx = torch.empty_like(x)
+    gtt = torch.zeros_like(tt)
+    check(lib.spvd_film_bwd(_p(x, torch.float32), _p(gy, torch.float32), _p(tt, torch.float32), tt.shape[1], _p(offsets, torch.int32),
+                            tt.shape[0], int(max_rows), c, _p(gx), _p(gtt), gtt.shape[1], _s()))
+    return gx, gtt
+
+
+def layernorm_train_fwd(x, gamma, beta, eps):
+    _count("layernorm_train")
+    rows, c = x.shape
+    y = torch.empty_like(x)
+    st = torch.empty((2, max(rows, 1)), dtype=torch.float32, device=x.device)
+    check(lib.spvd_layernorm_train_fwd(_p(x, torch.float32), _p(gamma), _p(beta), rows, c, float(eps), _p(y), _p(st[0]), _p(st[1]), _s()))
+    return y, st
+
+
+def layernorm_bwd(x, gy, gamma, st):
+    _count("layernorm_bwd")
+    rows, c = x.shape
+    gx = torch.empty_like(x)
+    gg = torch.empty(c, dtype=torch.float32, device=x.device)
+    gb = torch.empty(c, dtype=torch.float32, device=x.device)
+    check(lib.spvd_layernorm_bwd(_p(x, torch.float32), _p(gy, torch.float32), _p(gamma), _p(st[0]), _p(st[1]), rows, c, _p(gx),
+                                 _p(gg), _p(gb), _p(train_ws(x.device)), _s()))
+    return gx, gg, gb
+
+
+def attention_train_fwd(qkv, offsets, n_batch, max_len, heads):
+    _count("attention_train")
+    rows, c3 = qkv.shape
+    c = c3 // 3
+    out = torch.empty((rows, c), dtype=torch.float32, device=qkv.device)
+    lse = torch.empty((rows, heads), dtype=torch.float32, device=qkv.device)
+    check(lib.spvd_attention_train_fwd(_p(qkv, torch.float32), _p(offsets, torch.int32), n_batch, int(max_len), c, heads, _p(out),
+                                       _p(lse), _s()))
+    return out, lse
+
+
+def attention_bwd(qkv, out, gout, lse, offsets, n_batch, max_len, heads):
+    _count("attention_bwd")
+    rows, c3 = qkv.shape
+    gqkv = torch.empty_like(qkv)
+    delta = torch.empty_like(lse)
+    check(lib.spvd_attention_bwd(_p(qkv, torch.float32), _p(out, torch.float32), _p(gout, torch.float32), _p(lse), _p(offsets, torch.int32),
+                                 n_batch, int(max_len), c3 // 3, heads, _p(gqkv), _p(delta), _s()))
+    return gqkv
+
+
+def cat_any(a, b):
+    _count("cat_any")
+    y = torch.empty((a.shape[0], a.shape[1] + b.shape[1]), dtype=torch.float32, device=a.device)
+    check(lib.spvd_cat_any_fwd(_p(a, torch.float32), _p(b, torch.float32), a.shape[0], a.shape[1], b.shape[1], _p(y), _s()))
+    return y
+
+
+def split(g, ca):
+    _count("split")
+    rows, c = g.shape
+    ga = torch.empty((rows, ca), dtype=torch.float32, device=g.device)
+    gb = torch.empty((rows, c - ca), dtype=torch.float32, device=g.device)
+    check(lib.spvd_split_fwd(_p(g, torch.float32), rows, ca, c - ca, _p(ga), _p(gb), _s()))
+    return ga, gb
+
+
+def silu_fwd(x):
+    _count("silu")
+    y = torch.empty_like(x)
+    check(lib.spvd_silu_fwd(_p(x, torch.float32), x.numel(), _p(y), _s()))
+    return y
+
+
+def silu_bwd(x, gy):
+    _count("silu")
+    gx = torch.empty_like(x)
+    check(lib.spvd_silu_bwd(_p(x, torch.float32), _p(gy, torch.float32), x.numel(), _p(gx), _s()))
+    return gx
+
+
+def add(a, b):
+    _count("add")
+    y = torch.empty_like(a)
+    check(lib.spvd_add_fwd(_p(a, torch.float32), _p(b, torch.float32), a.numel(), _p(y), _s()))
+    return y
+
+
+def embedding_fwd(table, idx, base=None):
+    _count("embedding")
+    out = torch.empty((idx.shape[0], table.shape[1]), dtype=torch.float32, device=table.device)
+    check(lib.spvd_embedding_fwd(_p(table, torch.float32), _p(idx, torch.int64), _p(base), idx.shape[0], table.shape[1], _p(out), _s()))
+    return out
+
+
+def embedding_bwd(g, idx, n_rows):
+    _count("embedding")
+    gt = torch.zeros((n_rows, g.shape[1]), dtype=torch.float32, device=g.device)
+    check(lib.spvd_embedding_bwd(_p(g, torch.float32), _p(idx, torch.int64), idx.shape[0], g.shape[1], _p(gt), _s()))
+    return gt
+
+
+def timestep_embedding(t, d):
+    _count("timestep_embedding")
+    out = torch.empty((t.shape[0], d), dtype=torch.float32, device=t.device)
+    check(lib.spvd_timestep_embedding(_p(t, torch.int64), t.shape[0], d, _p(out), _s()))
+    return out
+
+
+def mse_loss(pred, target, want_grad=True, grad_scale=1.0):
+    """-> (loss [1], d loss / d pred or None)"""
+    _count("mse")
+    loss = torch.empty(1, dtype=torch.float32, device=pred.device)
+    gp = torch.empty_like(pred) if want_grad else None
+    check(lib.spvd_mse_loss(_p(pred, torch.float32), _p(target, torch.float32), pred.numel(), float(grad_scale), _p(loss), _p(gp),
+                            _p(train_ws(pred.device)), _s()))
+    return loss, gp

@@ -11,6 +11,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 import time
 
 import torch
@@ -20,12 +21,12 @@ from . import ops
 from ._C import check, lib
 from .geometry import Geometry
 
-OP_SCATTER_MEAN, OP_DEVOX, OP_CONV, OP_AFFINE, OP_FILM_AFFINE, OP_CAT, OP_LAYERNORM, OP_ATTENTION, OP_TIME_EMBED, OP_CAT_AFFINE = range(10)
+OP_SCATTER_MEAN, OP_DEVOX, OP_CONV, OP_AFFINE, OP_FILM_AFFINE, OP_CAT, OP_LAYERNORM, OP_ATTENTION, OP_TIME_EMBED, OP_CAT_AFFINE, OP_CONV_SP = range(11)
 MAP_NONE, MAP_K3, MAP_DOWN, MAP_UP = range(4)
 ROWS_POINTS, ROWS_BATCH = -1, -2
 FLAG_SILU, FLAG_ROUND, FLAG_A_TF32, FLAG_SIMT, FLAG_F16 = 1, 2, 4, 8, 16
 KERNELS_PER_OP = {OP_SCATTER_MEAN: 2, OP_DEVOX: 1, OP_CONV: 1, OP_AFFINE: 1, OP_FILM_AFFINE: 1, OP_CAT: 1,
-                  OP_LAYERNORM: 1, OP_ATTENTION: 1, OP_TIME_EMBED: 1, OP_CAT_AFFINE: 1}
+                  OP_LAYERNORM: 1, OP_ATTENTION: 1, OP_TIME_EMBED: 1, OP_CAT_AFFINE: 1, OP_CONV_SP: 1}
 
 
 class LevelGeom(C.Structure):
@@ -35,6 +36,9 @@ class LevelGeom(C.Structure):
                 ("pair_in", C.c_void_p), ("pair_out", C.c_void_p), ("pair_tile_k", C.c_void_p),
                 ("dpair_in", C.c_void_p), ("dpair_out", C.c_void_p), ("dpair_tile_k", C.c_void_p), ("p2v_w", C.c_void_p),
                 ("p2v_cnt", C.c_void_p), ("p2v_start", C.c_void_p), ("p2v_order", C.c_void_p), ("p2v_units", C.c_void_p),
+                ("kmap3_sorted", C.c_void_p), ("mask3_sorted", C.c_void_p), ("perm3", C.c_void_p),
+                ("kmap_down_sorted", C.c_void_p), ("mask_down_sorted", C.c_void_p), ("perm_down", C.c_void_p),
+                ("kmap_up_sorted", C.c_void_p), ("mask_up_sorted", C.c_void_p), ("perm_up", C.c_void_p),
                 ("n", C.c_int32), ("ld3", C.c_int32), ("ld_down", C.c_int32), ("ld_up", C.c_int32),
                 ("max_per_batch", C.c_int32), ("n_pair_tiles", C.c_int32), ("n_dpair_tiles", C.c_int32), ("pad", C.c_int32)]
 
@@ -45,7 +49,8 @@ class Op(C.Structure):
                 ("c0", C.c_int32), ("c1", C.c_int32), ("kvol", C.c_int32), ("i0", C.c_int32), ("i1", C.c_int32),
                 ("pad", C.c_int32),
                 ("src0", C.c_int64), ("src1", C.c_int64), ("dst", C.c_int64), ("aux", C.c_int64),
-                ("w", C.c_void_p), ("w_packed", C.c_void_p), ("bias", C.c_void_p), ("p0", C.c_void_p), ("p1", C.c_void_p)]
+                ("w", C.c_void_p), ("w_packed", C.c_void_p), ("bias", C.c_void_p), ("p0", C.c_void_p), ("p1", C.c_void_p),
+                ("src2", C.c_int64), ("src3", C.c_int64), ("w2_packed", C.c_void_p), ("c2", C.c_int32), ("pad2", C.c_int32)]
 
 
 class _Reg:
@@ -71,6 +76,11 @@ class Program:
         self.strides = list(model._plan["strides"])
         # tensor-core operands of the executor: "f16" (IEEE half, TF32's 11-bit significand, kind::f16) or "tf32"
         self.f16 = getattr(model, "executor_operands", "f16") == "f16"
+        # levels whose 3^3 convolutions run on the persistent sorted-tile kernel with fused epilogues (spvd_conv_sp_f16):
+        # the fine, many-tile levels; the coarse ones (tens of tiles) keep the split-K kernel
+        sp = os.environ.get("SPVD_SP_LEVELS", "1")
+        self.sp_levels = {int(v) for v in sp.split(",") if v != ""} if self.f16 else set()
+        self._safe_cache, self.tf32_fallbacks = {}, []     # per-layer operand format guard (_f16_safe)
         self._emit()
         self._allocate()
         self._finalize()
@@ -86,16 +96,35 @@ class Program:
         self.keep.append(t)
         return t
 
-    def _conv_params(self, w3, bias, force_simt=False):
+    def _f16_safe(self, w):
+        """May this layer's weights be fed to the tensor cores as IEEE half?  Half keeps TF32's 11-bit significand but only 5
+        exponent bits: an output channel whose largest weight is below ~2^-12 would be stored in subnormals (or flushed), one
+        above ~3e4 would saturate.  Such layers (none with the reference's initialisation; a guard for odd checkpoints)
+        fall back to TF32 operands, and their producers keep fp32 activations.  Decided once per compiled program."""
+        key = (w.data_ptr(), w._version)
+        hit = self._safe_cache.get(key)
+        if hit is None:
+            w3 = w.detach()
+            w3 = w3 if w3.dim() == 3 else (w3.t().unsqueeze(0) if w3.dim() == 2 else w3.reshape(1, 1, -1))
+            col = w3.abs().amax(dim=(0, 1))
+            hit = bool((col.min() >= 2.0 ** -12) & (col.max() <= 3.0e4))
+            self._safe_cache[key] = hit
+            if not hit:
+                self.tf32_fallbacks.append(tuple(w3.shape))
+        return hit
+
+    def _conv_params(self, w3, bias, force_simt=False, safe=None):
+        """safe: the f16 verdict of the ORIGINAL parameter (when w3 is a derived view of it); None = judge w3 itself"""
         w3 = self._hold(w3)
         wp = None
         if not force_simt and ops.umma_supported(*w3.shape):
-            wp = ops.pack_weights_f16(w3) if self.f16 else ops.pack_weights(w3)
+            f16 = self.f16 and (self._f16_safe(w3) if safe is None else safe)
+            wp = ops.pack_weights_f16(w3) if f16 else ops.pack_weights(w3)
             self.keep.append(wp)
         return w3, wp, (self._hold(bias) if bias is not None else None)
 
     def _linear_params(self, lin):
-        return self._conv_params(lin.weight.detach().t().unsqueeze(0), lin.bias)
+        return self._conv_params(lin.weight.detach().t().unsqueeze(0), lin.bias, safe=self._f16_safe(lin.weight))
 
     def _bn(self, bn):
         scale = bn.weight.detach() * torch.rsqrt(bn.running_var + bn.eps)
@@ -112,19 +141,41 @@ class Program:
         self.recs.append(dict(op=op, dst=dst, src0=src0, src1=src1, aux=aux, **kw))
         return dst
 
-    def _half(self, cin, cout, kvol=1):
-        """should the producer of a [.., cin] tensor write it as f16?  (its only consumer is that tensor-core conv)"""
-        return self.f16 and bool(ops.umma_supported(kvol, cin, cout))
+    def _half(self, cin, cout, kvol=1, w=None):
+        """should the producer of a [.., cin] tensor write it as f16?  (its only consumer is that tensor-core conv, whose
+        weights ``w`` must be representable in half: _f16_safe)"""
+        return self.f16 and bool(ops.umma_supported(kvol, cin, cout)) and (w is None or self._f16_safe(w))
 
     def conv(self, x, params, kvol, map_kind, level, rows_out, cout, residual=None, a_tf32=False):
         w3, wp, bias = params
         if x.half and wp is None:
             raise RuntimeError("an f16 activation reached a convolution without a tensor-core path")
-        pre = x.half if self.f16 else a_tf32            # src0 already in the operand format of the tensor-core kernel
-        flags = (FLAG_A_TF32 if (pre and wp is not None) else 0) | (FLAG_SIMT if wp is None else 0) | \
-                (FLAG_F16 if (self.f16 and wp is not None) else 0)
+        is16 = wp is not None and wp.dtype == torch.float16
+        if x.half and not is16:
+            raise RuntimeError("an f16 activation reached a convolution whose weights are not in the f16 image")
+        pre = x.half if is16 else a_tf32                # src0 already in the operand format of the tensor-core kernel
+        flags = (FLAG_A_TF32 if (pre and wp is not None) else 0) | (FLAG_SIMT if wp is None else 0) | (FLAG_F16 if is16 else 0)
         return self.op(OP_CONV, self.reg(rows_out, cout), x, residual, flags=flags, level=level, map_kind=map_kind,
                        rows_in=x.rows, rows_out=rows_out, c0=x.ch, c1=cout, kvol=kvol, w=w3, w_packed=wp, bias=bias)
+
+    def conv_sp(self, x, params, kvol, map_kind, level, rows_out, cout, residual=None, src2=None, w2=None, film=None,
+                aff=None, silu=False, want32=True, want16=False):
+        """spvd_conv_sp_f16 record: x (f16) [+ src2 (f16) @ w2] -> fp32 dst (want32) and / or f16 aux = act(v * aff)."""
+        w3, wp, bias = params
+        assert x.half and wp is not None
+        dst = self.reg(rows_out, cout) if want32 else None
+        aux = self.reg(rows_out, cout) if want16 else None
+        if aux is not None:
+            aux.half = True
+        kw = dict(flags=(FLAG_SILU if silu else 0) | FLAG_F16, level=level, map_kind=map_kind, rows_in=x.rows, rows_out=rows_out,
+                  c0=x.ch, c1=cout, kvol=kvol, w=w3, w_packed=wp, bias=bias, src2=src2, w2_packed=w2,
+                  c2=src2.ch if src2 is not None else 0)
+        if film is not None:
+            kw.update(src3=film[0], i0=film[1], i1=film[2])
+        if aff is not None:
+            kw.update(p0=aff[0], p1=aff[1])
+        self.recs.append(dict(op=OP_CONV_SP, dst=dst, src0=x, src1=residual, aux=aux, **kw))
+        return dst, aux
 
     def linear(self, x, lin, residual=None, a_tf32=False):
         return self.conv(x, self._linear_params(lin), 1, MAP_NONE, -1, x.rows, lin.out_features, residual, a_tf32)
@@ -145,7 +196,7 @@ class Program:
     def point_block(self, pb, z1, z):
         lin = pb.conv[2]
         rnd = self._umma_ok(lin.in_features, lin.out_features)
-        a = self.affine(z, pb.conv[0], True, rnd, rnd and self._half(lin.in_features, lin.out_features))
+        a = self.affine(z, pb.conv[0], True, rnd, rnd and self._half(lin.in_features, lin.out_features, 1, lin.weight))
         return self.linear(a, lin, residual=z1, a_tf32=rnd)
 
     def res_block(self, blk, x, lvl, pre=None):
@@ -155,24 +206,42 @@ class Program:
         if pre is not None:
             a1, x = pre
         else:
-            a1 = self.affine(x, blk.conv1[0], True, True, self._half(x.ch, nf, 27))
+            a1 = self.affine(x, blk.conv1[0], True, True, self._half(x.ch, nf, 27, c1.kernel))
+        half2 = self._half(nf, nf, 27, c2.kernel)
+        if lvl in self.sp_levels and a1.half and half2 and not hasattr(blk, "attn") and \
+                (not hasattr(blk, "idconv") or x.half):
+            # fused block: conv1 -> (FiLM, BN2, SiLU in its epilogue) -> f16 operand of conv2; the 1x1 shortcut runs as extra
+            # K slabs of conv2 (its bias joins conv2's), an identity shortcut as the epilogue's residual
+            s2, b2 = self._bn(blk.conv2[0])
+            _, a2 = self.conv_sp(a1, self._conv_params(c1.kernel, c1.bias), 27, MAP_K3, lvl, lvl, nf,
+                                 film=(self.tt, self.tt_width, self.tt_offsets[id(blk)]), aff=(s2, b2), silu=True,
+                                 want32=False, want16=True)
+            p2 = self._conv_params(c2.kernel, c2.bias)
+            if hasattr(blk, "idconv"):
+                w2 = ops.pack_weights_f16(self._hold(blk.idconv.weight.detach().t().unsqueeze(0)))      # (x.half: judged safe)
+                self.keep.append(w2)
+                bias = self._hold(c2.bias.detach() + blk.idconv.bias.detach())
+                h2, _ = self.conv_sp(a2, (p2[0], p2[1], bias), 27, MAP_K3, lvl, lvl, nf, src2=x, w2=w2)
+            else:
+                h2, _ = self.conv_sp(a2, p2, 27, MAP_K3, lvl, lvl, nf, residual=x)
+            return h2
         h1 = self.conv(a1, self._conv_params(c1.kernel, c1.bias), 27, MAP_K3, lvl, lvl, nf, a_tf32=True)
         s2, b2 = self._bn(blk.conv2[0])
         off = self.tt_offsets[id(blk)]
-        a2 = self.op(OP_FILM_AFFINE, self.reg(lvl, nf), h1, self.tt, flags=FLAG_SILU | self._fmt(True, self._half(nf, nf, 27)),
+        a2 = self.op(OP_FILM_AFFINE, self.reg(lvl, nf), h1, self.tt, flags=FLAG_SILU | self._fmt(True, half2),
                      level=lvl, rows_in=lvl, rows_out=lvl, c0=nf, c1=nf, i0=self.tt_width, i1=off, p0=s2, p1=b2)
-        a2.half = self._half(nf, nf, 27)
+        a2.half = half2
         res = self.linear(x, blk.idconv) if hasattr(blk, "idconv") else x
         h2 = self.conv(a2, self._conv_params(c2.kernel, c2.bias), 27, MAP_K3, lvl, lvl, nf, residual=res, a_tf32=True)
         if hasattr(blk, "attn"):
             at = blk.attn
-            ln = self.op(OP_LAYERNORM, self.reg(lvl, nf), h2, flags=self._fmt(True, self._half(nf, 3 * nf)), level=-1,
+            ln = self.op(OP_LAYERNORM, self.reg(lvl, nf), h2, flags=self._fmt(True, self._half(nf, 3 * nf, 1, at.attn.qkv.weight)), level=-1,
                          rows_in=lvl, rows_out=lvl, c0=nf, c1=nf, p0=self._hold(at.norm1.weight), p1=self._hold(at.norm1.bias))
-            ln.half = self._half(nf, 3 * nf)
+            ln.half = self._half(nf, 3 * nf, 1, at.attn.qkv.weight)
             qkv = self.linear(ln, at.attn.qkv, a_tf32=True)
-            ao = self.op(OP_ATTENTION, self.reg(lvl, nf), qkv, flags=self._fmt(True, self._half(nf, nf)), level=lvl,
+            ao = self.op(OP_ATTENTION, self.reg(lvl, nf), qkv, flags=self._fmt(True, self._half(nf, nf, 1, at.attn.proj.weight)), level=lvl,
                          rows_in=lvl, rows_out=lvl, c0=3 * nf, c1=nf, i0=at.attn.num_heads)
-            ao.half = self._half(nf, nf)
+            ao.half = self._half(nf, nf, 1, at.attn.proj.weight)
             h2 = self.linear(ao, at.attn.proj, residual=h2, a_tf32=True)
             self.attn_levels.add(lvl)
         return h2
@@ -218,7 +287,7 @@ class Program:
         st = m.stem_conv
         c0, c3 = st.voxel_conv[0], st.voxel_conv[3]
         x = self.conv(x, self._conv_params(c0.kernel, c0.bias), 27, MAP_K3, 0, 0, c0.out_channels)
-        x = self.affine(x, st.voxel_conv[1], True, True, self._half(c3.in_channels, c3.out_channels, 27))
+        x = self.affine(x, st.voxel_conv[1], True, True, self._half(c3.in_channels, c3.out_channels, 27, c3.kernel))
         x = self.conv(x, self._conv_params(c3.kernel, c3.bias), 27, MAP_K3, 0, 0, c3.out_channels, a_tf32=True)
         z = self.point_block(st.point_conv, devox(x, 0), z)
         x = scatter(z, 0)
@@ -242,7 +311,7 @@ class Program:
                 for r in blk.resnets:
                     skip = saved.pop()
                     cc, nf = x.ch + skip.ch, r.conv1[2].out_channels
-                    if hasattr(r, "idconv") and self._half(cc, nf, 27) and self._half(cc, nf, 1):
+                    if hasattr(r, "idconv") and self._half(cc, nf, 27, r.conv1[2].kernel) and self._half(cc, nf, 1, r.idconv.weight):
                         # cat + BN + SiLU in one pass, both results as f16: the block reads the concatenation only through
                         # its two tensor-core convolutions (first 3^3 conv, 1x1 shortcut)
                         s1, b1 = self._bn(r.conv1[0])
@@ -276,8 +345,8 @@ class Program:
 
     def _allocate(self):
         for i, rec in enumerate(self.recs):
-            for k in ("src0", "src1", "aux", "dst"):
-                if rec[k] is not None:
+            for k in ("src0", "src1", "src2", "src3", "aux", "dst"):
+                if rec.get(k) is not None:
                     rec[k].last = i
         self.in_feats.last = max(self.in_feats.last, 0)
         self.out.last = len(self.recs) + 1
@@ -315,7 +384,7 @@ class Program:
                 r = rec[k]
                 if r is not None and r.offset < 0:
                     alloc(r)
-            for r in {id(rec[k]): rec[k] for k in ("src0", "src1", "aux", "dst") if rec[k] is not None}.values():
+            for r in {id(rec[k]): rec[k] for k in ("src0", "src1", "src2", "src3", "aux", "dst") if rec.get(k) is not None}.values():
                 if r.last == i and r is not self.out:
                     release(r)
         self.arena_bytes = top + 256
@@ -332,15 +401,20 @@ class Program:
             o.c0, o.c1, o.kvol, o.i0, o.i1 = rec["c0"], rec["c1"], rec.get("kvol", 0), rec.get("i0", 0), rec.get("i1", 0)
             o.src0 = rec["src0"].offset if rec["src0"] is not None else -1
             o.src1 = rec["src1"].offset if rec["src1"] is not None else -1
-            o.dst = rec["dst"].offset
+            o.dst = rec["dst"].offset if rec["dst"] is not None else -1
             o.aux = rec["aux"].offset if rec["aux"] is not None else -1
-            for k in ("w", "w_packed", "bias", "p0", "p1"):
+            o.src2 = rec["src2"].offset if rec.get("src2") is not None else -1
+            o.src3 = rec["src3"].offset if rec.get("src3") is not None else -1
+            o.c2 = rec.get("c2", 0)
+            for k in ("w", "w_packed", "bias", "p0", "p1", "w2_packed"):
                 t = rec.get(k)
                 setattr(o, k, t.data_ptr() if t is not None else None)
             self.n_kernels += KERNELS_PER_OP[rec["op"]]
-            if rec["op"] == OP_CONV:
+            if rec["op"] in (OP_CONV, OP_CONV_SP):
+                # (kvol, cin [+ cin2 of the folded shortcut], cout, rows, level, map kind, kernel family)
                 self.conv_meta.append((rec["kvol"], rec["c0"], rec["c1"], rec["rows_out"], rec["level"], rec["map_kind"],
-                                       "umma" if (rec.get("w_packed") is not None) else "simt"))
+                                       "sp" if rec["op"] == OP_CONV_SP else "umma" if (rec.get("w_packed") is not None) else "simt",
+                                       rec.get("c2", 0)))
         # finest level an op can run with: it needs every level up to max(level, rows_in, rows_out) planned; the stride-2
         # maps / pair lists of level l are planned together with level l + 1
         self.op_max_level, self.convs_before, nconv = [], [], 0
@@ -348,7 +422,7 @@ class Program:
             top = max(rec.get("level", -1), rec["rows_in"], rec["rows_out"])
             self.op_max_level.append(top)
             self.convs_before.append(nconv)
-            nconv += rec["op"] == OP_CONV
+            nconv += rec["op"] in (OP_CONV, OP_CONV_SP)
         self.arena = torch.empty(self.arena_bytes, dtype=torch.uint8, device=self.dev)
         self.arena_f = self.arena.view(torch.float32)
         # leading ops that read nothing but the timestep / class ids: time embedding and the FiLM projection GEMM
@@ -384,6 +458,8 @@ class Program:
             g.coords, g.n = lv.coords_cap.data_ptr(), lv.n
             if lv.kmap3 is not None:
                 g.kmap3, g.mask3, g.ld3 = lv.kmap3.map_t.data_ptr(), lv.kmap3.mask.data_ptr(), lv.kmap3.map_t.shape[1]
+            srt = getattr(lv, "kmap3_sorted", None)
+            g.kmap3_sorted, g.mask3_sorted, g.perm3 = [t.data_ptr() for t in srt] if srt is not None else [None] * 3
             g.p2v = geo.p2v[s].data_ptr() if s in geo.p2v else None
             pw = getattr(geo, "p2v_w", None)
             g.p2v_w = pw[s].data_ptr() if pw and s in pw else None

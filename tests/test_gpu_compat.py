@@ -84,3 +84,49 @@ def test_reference_call_sequences(ts):
     assert v.shape[0] == x2.C.shape[0]
     cat = ts.cat([x2, x2])
     assert cat.F.shape[1] == 128 and cat._caches is x2._caches
+
+
+def test_reference_unmodified_model_through_plugin(ts):
+    """The reference's OWN models/spvd.py, models/sparse_utils.py and utils/schedulers.py (unmodified copies staged by
+    __graft_entry__.build() into the git-ignored baseline/_ref/; absent -> skip) running on the plugin surface
+    (compat.install(): torchsparse / torch_scatter names backed by libspvd_b200.so), against spvd_b200.SPVUnet's native
+    executor on the same weights and input.  Reference call path: utils/schedulers.py:249-257 -> models/spvd.py:432-457."""
+    import os
+    import sys
+    import spvd_b200
+    from oracle import model as om
+    ref_root = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+    if not os.path.exists(os.path.join(ref_root, "models", "spvd.py")):
+        pytest.skip("baseline/_ref/models is not staged (run __graft_entry__.build() where /root/reference exists)")
+    sys.path.insert(0, ref_root)
+    try:
+        for name in [k for k in sys.modules if k == "models" or k.startswith("models.") or k == "utils" or k.startswith("utils.")]:
+            del sys.modules[name]
+        import models.spvd as ref_spvd
+        from utils.schedulers import DDPMSparseSchedulerGPU as RefScheduler
+    finally:
+        sys.path.remove(ref_root)
+    for preset, B, N in (("SPVD_TINY", 2, 512), ("SPVD", 2, 1024)):
+        cfg = om.get_config(preset)
+        sd = om.make_state_dict(preset, seed=7)
+        ref = ref_spvd.SPVUnet(point_channels=cfg["point_channels"], voxel_size=cfg["voxel_size"], down_blocks=cfg["down_blocks"],
+                               up_blocks=cfg["up_blocks"], num_layers=cfg["num_layers"], pres=cfg["pres"])
+        assert sum(p.numel() for p in ref.parameters()) == om.num_params(preset)
+        missing = ref.load_state_dict(sd, strict=True)
+        assert not missing.missing_keys and not missing.unexpected_keys
+        ref = ref.cuda().eval()
+        ours = spvd_b200.build_model(preset)
+        ours.load_state_dict(sd, strict=True)
+        ours = ours.cuda().eval()
+        g = torch.Generator().manual_seed(21)
+        pts = torch.randn(B, N, 3, generator=g).clamp(-3, 3).cuda()
+        t = torch.tensor([999, 123][:B]).cuda()
+        with torch.no_grad():
+            xt = RefScheduler().torch2sparse(pts, (B, N, 3))          # the reference's re-sparsification (ravel-hash order)
+            y_ref = ref((xt, t))                                       # the reference's forward on the plugin kernels
+            y_ours = ours((spvd_b200.SparseTensor(xt.F.clone(), xt.C.clone()), t))   # native executor, same rows
+            coords, feats = xt.C.cpu(), xt.F.cpu()
+            want = om.forward(sd, preset, coords, feats, t.cpu()).numpy()
+        assert y_ref.shape == y_ours.shape == (coords.shape[0], 3)
+        assert rel_err(y_ref.cpu().numpy(), want) < 1e-3               # reference code + plugin vs CPU oracle
+        assert rel_err(y_ours.cpu().numpy(), y_ref.cpu().numpy()) < 1e-3

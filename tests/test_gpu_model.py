@@ -81,7 +81,8 @@ def test_config1_b4x2048_vs_oracle(sp, mode):
         m.set_conv_impl(sp.ops.CONV_SIMT)
         y32 = m((sp.SparseTensor(feats.cuda(), coords.cuda()), t.cuda())).cpu().numpy()
     assert rel_err(y32, want.numpy()) < 2e-5                 # fp32 kernels vs fp32 oracle
-    assert rel_err(y, want_tf32.numpy()) < 1e-4              # tensor-core path vs TF32-emulating oracle
+    assert rel_err(y, want_tf32.numpy()) < 5e-4              # tensor-core path vs TF32-emulating oracle (round 2: the nn.Linear
+                                                             # layers also run as TF32 k=1 convs; the oracle emulates the convs only)
     assert rel_err(y, want.numpy()) < 1e-3                   # and within the stated tolerance of plain fp32
     assert rel_err(y_exec, want.numpy()) < 1e-3              # executor: nn.Linear layers also run as TF32 k=1 convs
 
@@ -108,7 +109,7 @@ def test_native_executor_matches_python_path_and_oracle(sp):
             want32 = om.forward(sd, preset, coords, feats, t).numpy()
         assert rel_err(y_exec, y_py) < 1e-3        # Linear layers run as TF32 k=1 convs in the executor
         assert rel_err(y_exec, want32) < 1e-3
-        assert rel_err(y_py, want) < 1e-4
+        assert rel_err(y_py, want) < 5e-4          # (nn.Linear layers are TF32 k=1 convs on this path too since round 2)
 
 
 def test_split_planning_matches_one_shot_planning(sp):

@@ -661,3 +661,103 @@ def test_fused_ddpm_step_matches_reference_formulas(sp):
 def test_cpu_tensors_are_refused(sp):
     with pytest.raises(RuntimeError):
         sp.ops.point_voxel_coords(torch.zeros(4, 4), 1e-5, 0.1)
+
+
+# ------------------------------------------------------------------------------------------------ round 2
+def _level_maps(sp, B=6, N=2048, seed=3):
+    from oracle import model as om
+    g = torch.Generator().manual_seed(seed)
+    pts = torch.randn(B, N, 3, generator=g).clamp(-3, 3)
+    coords, feats, _ = om.torch2sparse(pts)
+    geo = sp.Geometry(coords.cuda().float(), 1e-5, 0.1, strides=(1, 2, 4), p2v_strides=(1,), devox_strides=(1,), n_batch=B)
+    return geo
+
+
+def test_kmap_sort_matches_host_sort():
+    """spvd_kmap_sort: rows ordered by their active-offset bit set (stable), map / tile masks / permutation bit-exact
+    against a torch argsort of the same masks -- for the 3^3 map and both stride-2 maps."""
+    import spvd_b200 as sp
+    from spvd_b200 import ops
+    geo = _level_maps(sp)
+    for s in (1, 2, 4):
+        lv = geo.level(s)
+        for km, kvol in ((lv.kmap3, 27), (lv.kmap_down, 8), (lv.kmap_up, 8)):
+            if km is None:
+                continue
+            n = km.n_out
+            ms, tm, perm = ops.kmap_sort(km.map_t, n, kvol)
+            ks = torch.arange(kvol, device="cuda")
+            mask = ((km.map_t[:, :n] >= 0).long() << ks[:, None]).sum(0)
+            hp = torch.argsort(mask, stable=True)
+            assert torch.equal(perm[:n].long(), hp) and bool((perm[n:] == -1).all())
+            assert torch.equal(ms[:, :n], km.map_t[:, hp]) and bool((ms[:, n:] == -1).all())
+            pm = torch.zeros(km.map_t.shape[1], dtype=torch.int64, device="cuda")
+            pm[:n] = mask[hp]
+            want = pm.view(-1, 128).cpu().numpy()
+            want = np.bitwise_or.reduce(want, axis=1)
+            assert np.array_equal(tm.cpu().numpy().astype(np.int64) & 0xffffffff, want)
+
+
+@pytest.mark.parametrize("srt", [False, True])
+@pytest.mark.parametrize("bn", [0, 64])
+def test_conv_sp_fused_epilogue(srt, bn):
+    """spvd_conv_sp_f16 (persistent sorted-tile kernel): conv + second K source + bias + residual + FiLM, fp32 result and the
+    f16 BN+SiLU operand, against the one-tile tcgen05 kernel + torch glue on the same f16 operands; repeated to catch
+    pipeline races (the map-row ring once let a few rows per launch gather a refilled segment)."""
+    import spvd_b200 as sp
+    from spvd_b200 import ops
+    geo = _level_maps(sp, B=8)
+    lv = geo.level(2)
+    km, n = lv.kmap3, lv.n
+    cin, cout, cin2 = 96, 128, 160
+    g = torch.Generator(device="cuda").manual_seed(0)
+    w = torch.randn(27, cin, cout, device="cuda", generator=g) / (27 * cin) ** 0.5
+    w2 = torch.randn(1, cin2, cout, device="cuda", generator=g) / cin2 ** 0.5
+    wp, wp2 = ops.pack_weights_f16(w), ops.pack_weights_f16(w2)
+    x, x2 = torch.randn(n, cin, device="cuda", generator=g).half(), torch.randn(n, cin2, device="cuda", generator=g).half()
+    bias, res = torch.randn(cout, device="cuda", generator=g), torch.randn(n, cout, device="cuda", generator=g)
+    film = torch.randn(8, 2 * cout + 64, device="cuda", generator=g)[:, 32:32 + 2 * cout]
+    sc, sh = torch.rand(cout, device="cuda", generator=g) + 0.5, torch.randn(cout, device="cuda", generator=g)
+    ref = ops.conv_fwd(x, w, wp, km.map_t, km.mask, n, bias, ops.CONV_UMMA, mt=3)
+    ref = ref + ops.conv_fwd(x2, w2, wp2, None, None, n, None, ops.CONV_UMMA) + res
+    fv = film[lv.coords[:, 0].long()]
+    ref32 = (1 + fv[:, :cout]) * ref + fv[:, cout:]
+    ref16 = torch.nn.functional.silu(ref32 * sc + sh)
+    kw = dict(map_t=km.map_t, tile_mask=km.mask)
+    if srt:
+        ms, tm, perm = ops.kmap_sort(km.map_t, n, 27)
+        kw = dict(map_t=ms, tile_mask=tm, out_rows=perm)
+    for rep in range(12):
+        o32, o16 = ops.conv_sp(x, wp, 27, cin, cout, n, bias=bias, residual=res, in2=x2, w2_packed=wp2, film=film,
+                               coords=lv.coords_cap, aff=(sc, sh), silu=True, want32=True, want16=True, bn=bn, stages=(0, 2, 3)[rep % 3], **kw)
+        assert rel_err(o32.cpu().numpy(), ref32.cpu().numpy()) < 1e-5
+        assert rel_err(o16.float().cpu().numpy(), ref16.cpu().numpy()) < 1e-3
+        assert float((o32 - ref32).abs().max()) < 1e-3 * float(ref32.abs().max())      # no stray rows
+    # identity (kernel size 1) and f16-only output
+    wl = torch.randn(1, cin, cout, device="cuda", generator=g) / cin ** 0.5
+    _, o16 = ops.conv_sp(x, ops.pack_weights_f16(wl), 1, cin, cout, n, bias=bias, want32=False, want16=True)
+    want = x.float() @ wl[0].half().float() + bias
+    assert rel_err(o16.float().cpu().numpy(), want.cpu().numpy()) < 1e-3
+
+
+def test_executor_rebuilds_after_inplace_parameter_update():
+    """a compiled program holds packed copies of the weights; an in-place update in eval mode must not leave it
+    stale."""
+    import spvd_b200 as sp
+    from oracle import model as om
+    m = sp.build_model("SPVD_TINY")
+    m.load_state_dict(om.make_state_dict("SPVD_TINY", seed=0))
+    m = m.cuda().eval()
+    g = torch.Generator().manual_seed(1)
+    pts = torch.randn(2, 512, 3, generator=g).clamp(-3, 3)
+    coords, feats, _ = om.torch2sparse(pts)
+    x, t = sp.SparseTensor(feats.cuda(), coords.cuda()), torch.tensor([500, 20]).cuda()
+    with torch.no_grad():
+        y0 = m((x, t)).clone()
+        m.stem_conv.voxel_conv[3].kernel.mul_(1.5)
+        m.out_conv[0].running_var.mul_(2.0)
+        y1 = m((x, t)).clone()
+        m.use_executor = False
+        y2 = m((x, t))
+    assert rel_err(y1.cpu().numpy(), y0.cpu().numpy()) > 1e-2           # the update is visible ...
+    assert rel_err(y1.cpu().numpy(), y2.cpu().numpy()) < 1e-3           # ... and matches the op-by-op path on the new weights
