@@ -49,6 +49,8 @@ def parse():
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=6, help="timed steps of the training sub-record (0 = skip)")
+    ap.add_argument("--no-tf32-leg", action="store_true")
     return ap.parse_args()
 
 
@@ -233,15 +235,17 @@ def run_b200(args):
         except Exception:
             pass
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "conv_umma_traffic.json")))["dram_bytes_per_launch"]
+        traffic, traffic_src = None, None
+        try:        # mean DRAM bytes per launch of the tcgen05 conv kernels only, from the committed ncu --set full capture
+            tj = json.load(open(os.path.join(ROOT, "profiles", "conv_umma_traffic.json")))
+            traffic = tj.get("dram_bytes_per_umma_launch", tj.get("dram_bytes_per_launch"))
+            traffic_src = tj.get("source", "profiles/conv_umma_traffic.json")
         except Exception:
             pass
         ach = flops / (ms * 1e-3) / 1e12 if ms > 0 else 0.0
         f16 = model.executor_operands == "f16"
         roof = {"bound": "tensor", "kernel": "k_conv_fwd_umma (tcgen05 kind::%s)" % ("f16" if f16 else "tf32"), "achieved": round(ach, 2),
-                "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic,
+                "peak": peak, "unit": "TFLOP/s", "frac": round(ach / peak, 4), "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained" if peaks else "fallback 1.4 PF sustained",
                 "note": ("f16 operands (same tensor-core rate as the bf16 peak), fp32 accumulate; " if f16 else
                          "TF32 operands (kind::tf32 runs at half the bf16 rate, so frac <= 0.5 by construction); ") + "durations from "
@@ -249,6 +253,63 @@ def run_b200(args):
                 "launches": n, "avg_launch_us": round(ms * 1e3 / max(n, 1), 2),
                 "algorithmic_gflop_per_step": round(flops / K / 1e9, 1),
                 "conv_share_of_step": round(ms / total_ms, 3) if total_ms else None}
+
+    # ---- second roofline entry: the worst HBM-bound kernel of the path (devoxelize, C = 256 from the coarsest level),
+    #      algorithmic bytes (Np*64 + Nv*4C + Np*4C) / CUDA-event time, cold L2
+    roof_hbm = None
+    if rank == 0:
+        try:
+            st = sched.torch2sparse(xs_dev[W], shape)
+            geo = model.plan_geometry(st.coords_float, B, N).finish()
+            s_top = max(geo.devox)
+            idx8, w8 = geo.devox[s_top]
+            nv, C = geo.level(s_top).n, 256
+            xv = torch.randn(nv, C, device=dev)
+            ops.devoxelize_fwd(xv, idx8, w8)
+            dts = []
+            for _ in range(10):
+                if flush is not None:
+                    flush.fill_(3)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                ops.devoxelize_fwd(xv, idx8, w8)
+                b.record()
+                torch.cuda.synchronize()
+                dts.append(a.elapsed_time(b))
+            nbytes = B * N * 64 + nv * 4 * C + B * N * 4 * C
+            hbm_peak = float(peaks.get("hbm_gbs", 6400.0))
+            gbs = nbytes / (statistics.median(dts) * 1e-3) / 1e9
+            roof_hbm = {"bound": "hbm", "kernel": f"k_devox_fwd4 (C={C}, stride {s_top} -> points)", "achieved": round(gbs, 1),
+                        "peak": hbm_peak, "unit": "GB/s", "frac": round(gbs / hbm_peak, 4), "algorithmic_bytes": nbytes,
+                        "note": "includes the wrapper's output allocation; median of 10 cold-L2 launches"}
+        except Exception as e:          # a measurement aid must never take the bench line down
+            roof_hbm = {"error": str(e)[:200]}
+
+    # ---- the same device-resident leg with TF32 operands (the reference's precision class), for comparison
+    value_tf32 = None
+    if not args.no_tf32_leg:
+        model.executor_operands = "tf32"
+        with torch.no_grad():
+            for j in range(W):
+                step_device(xs_dev[j], ts[j], j)
+            torch.cuda.synchronize()
+            ev2 = []
+            for j in range(W, W + K):
+                if flush is not None:
+                    flush.fill_(j & 0xFF)
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                step_device(xs_dev[j], ts[j], j)
+                b.record()
+                ev2.append((a, b))
+            torch.cuda.synchronize()
+        t32 = sum(a.elapsed_time(b) for a, b in ev2)
+        if world > 1:
+            tt = torch.tensor([t32], device=dev, dtype=torch.float64)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            t32 = float(tt.item())
+        value_tf32 = round(world * K / (t32 * 1e-3), 3)
+        model.executor_operands = "f16"
 
     # ---- end-to-end leg through the public API with host buffers
     pin_in = [x.pin_memory() for x in xs]
@@ -274,6 +335,8 @@ def run_b200(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_s = float(tt.item())
 
+    train = run_train_leg(args, dev, world, rank, xs_dev, flush) if args.train_steps > 0 else None
+
     out = None
     if rank == 0:
         nbytes = B * N * 3 * 4
@@ -287,17 +350,89 @@ def run_b200(args):
                           "l2": "256 MiB flush write between timed steps" if flush is not None else "no flush (per-step working set > L2)"},
                "e2e": {"value": round(world * K / e2e_s, 3), "unit": UNIT, "h2d_bytes_per_step": nbytes,
                        "d2h_bytes_per_step": nbytes},
-               "gpu_launches": launches, "clocks": clk, "roofline": roof}
-    return out, rank, world
+               "gpu_launches": launches, "clocks": clk, "roofline": roof, "roofline_hbm": roof_hbm,
+               "value_tf32_operands": value_tf32, "train": train}
+    return out, rank, world, dict(model=model, dev=dev, sched=sched)
+
+
+def run_train_leg(args, dev, world, rank, xs_dev, flush):
+    """BASELINE config 3 as a sub-record: one optimisation step = forward + MSE + backward + NCCL gradient all-reduce
+    (bucketed, launched from backward hooks) + clip_grad_norm_(10) + Adam, B per GPU as in the sampling leg
+    (train_generation.py:98-112, utils/callbacks.py:58-63).  Device-timed, max over ranks."""
+    import torch.distributed as dist
+    import spvd_b200
+    from spvd_b200.parallel import GradientAllReduce, train_step
+    from spvd_b200.sampler import torch2sparse
+    B, N, K, W = args.batch, args.points, args.train_steps, 2
+    torch.manual_seed(0)
+    model = spvd_b200.build_model(args.preset, downsample_mode=args.downsample_mode).to(dev).train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
+    red = GradientAllReduce(model.parameters())
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    ev, ar_ms = [], 0.0
+    for j in range(W + K):
+        x = xs_dev[j % len(xs_dev)]
+        st = torch2sparse(x)
+        t = torch.randint(0, 1000, (B,), device=dev, generator=g)
+        eps = torch.randn(st.F.shape, device=dev, generator=g)
+        if flush is not None:
+            flush.fill_(j & 0xFF)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if j == W:
+            torch.cuda.synchronize()
+            if world > 1:
+                dist.barrier()
+        a.record()
+        train_step(model, opt, (st, t, eps), red)
+        b.record()
+        if j >= W:
+            ev.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    total = sum(a.elapsed_time(b) for a, b in ev)
+    # exposed all-reduce time: the same steps with the collective switched off (identical kernels otherwise)
+    exposed = None
+    if world > 1:
+        red_group_active = red._active
+        red._active = lambda: False
+        ev2 = []
+        for j in range(K):
+            st = torch2sparse(xs_dev[j % len(xs_dev)])
+            t = torch.randint(0, 1000, (B,), device=dev, generator=g)
+            eps = torch.randn(st.F.shape, device=dev, generator=g)
+            if flush is not None:
+                flush.fill_(j & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            train_step(model, opt, (st, t, eps), red)
+            b.record()
+            ev2.append((a, b))
+        torch.cuda.synchronize()
+        red._active = red_group_active
+        local = sum(a.elapsed_time(b) for a, b in ev2)
+        tt = torch.tensor([total, local], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total, local = float(tt[0]), float(tt[1])
+        exposed = round(max(0.0, (total - local) / K), 3)
+    if rank != 0:
+        return None
+    return {"metric": "SPVD training steps/s (fwd + bwd + gradient all-reduce + clip + Adam), B=%dx%d per GPU" % (B, N),
+            "steps_per_s": round(K / (total * 1e-3), 3), "clouds_per_s": round(world * B * K / (total * 1e-3), 1),
+            "ms_per_step": round(total / K, 3), "steps": K, "warmup": W, "n_gpus": world,
+            "allreduce": {"bytes": int(red.flat.numel() * 4), "buckets": len(red.buckets), "exposed_ms_per_step": exposed,
+                          "how": "step time with the NCCL all-reduce minus step time without it (same kernels), max over ranks"},
+            "dtype": "f32 activations, tf32 tensor-core operands (forward, dgrad, wgrad), f32 accumulate"}
 
 
 # -------------------------------------------------------------------------------- CPU oracle arm
-def cpu_steps(args, n_steps, warmup, seed=1234):
-    """The reference algorithm restated on the CPU (oracle/), timed on the host cores."""
+def cpu_steps(args, n_steps, warmup, seed=1234, sd=None, keep=None):
+    """The reference algorithm restated on the CPU (oracle/), timed on the host cores.  ``sd``: weights to use (default: the
+    oracle's own seeded initialisation); ``keep``: list that receives (coords, feats, t, eps) of the first timed step."""
     from oracle import model as om
     B, N = args.batch, args.points
     strat, xs, ts = make_workload(n_steps + warmup, B, N, seed)
-    sd = om.make_state_dict(args.preset, seed=0)
+    sd = om.make_state_dict(args.preset, seed=0) if sd is None else sd
     times = []
     with torch.no_grad():
         for j in range(n_steps + warmup):
@@ -311,6 +446,8 @@ def cpu_steps(args, n_steps, warmup, seed=1234):
             dt = time.perf_counter() - t0
             if j >= warmup:
                 times.append(dt)
+                if keep is not None and not keep:
+                    keep.append((coords, feats, ts[j], eps))
     return times
 
 
@@ -347,14 +484,30 @@ def main():
     if args.impl == "reference":
         out, rank, world = run_reference(args)
     else:
-        out, rank, world = run_b200(args)
+        out, rank, world, ctx = run_b200(args)
         if rank == 0 and world == 1 and not args.no_cpu_baseline:
             n = max(1, args.cpu_baseline_steps)
-            times = cpu_steps(args, n, 0)
+            # the CPU leg runs the GPU arm's own weights, so its first step doubles as the parity check of what was timed
+            model, dev = ctx["model"], ctx["dev"]
+            sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+            keep = []
+            times = cpu_steps(args, n, 0, sd=sd, keep=keep)
             out["cpu_baseline"] = {"value": round(n / sum(times), 4), "unit": UNIT, "cores": torch.get_num_threads(),
                                    "kind": "port",
                                    "sample": f"{n} full-size steps (t spread over 999..0) of the same workload on the "
                                              f"CPU oracle (oracle/model.py), os.cpu_count()={os.cpu_count()}"}
+            coords, feats, t0, eps_cpu = keep[0]
+            import spvd_b200
+            with torch.no_grad():
+                x = spvd_b200.SparseTensor(feats.to(dev), coords.to(dev))
+                x.points_per_cloud = args.points
+                eps_gpu = model((x, torch.full((args.batch,), t0, device=dev, dtype=torch.long))).cpu()
+            err = float((eps_gpu - eps_cpu).norm() / eps_cpu.norm())
+            out["parity_rel_err"] = round(err, 6)
+            out["parity"] = {"against": "CPU oracle forward on the first timed step's input, same weights", "tolerance": 1e-3,
+                             "ok": err < 1e-3}
+            if err >= 1e-3:
+                print(f"bench.py: PARITY FAILURE rel err {err:.3e} >= 1e-3", file=sys.stderr)
         elif rank == 0:
             out["cpu_baseline"] = None
     if rank == 0 and out is not None:

@@ -211,16 +211,15 @@ int spvd_conv_fwd_simt(const float* in, const float* w, const int32_t* map_t, in
  * a_is_tf32 != 0 promises that `in` is already TF32-representable (spvd_round_tf32, or a producer
  * that rounds, e.g. spvd_bn_silu_fwd with act & 2): the gather then runs as cp.async with kStages
  * slabs in flight instead of through registers with cvt.rna;
- * mt = 128-row output tiles per CTA sharing each weight tile (1 or 2; 0 = choose; 2 needs a_is_tf32).
+ * mt = tile configuration: 0 / 3 = one 128-row tile per CTA, two CTAs per SM (the product path); 1 = one CTA per SM with a
+ * four-stage ring.  (Cluster multicast of the weight tile and two tiles per CTA exist behind -DSPVD_EXPERIMENTAL: correct,
+ * measured no faster; the round-1 stream-K and CTA-pair kernels were removed)
  *
  * f16 operands (a_is_tf32 = SPVD_A_F32_TO_F16 or SPVD_A_F16): same tiles with A and B in IEEE half -- an 11-bit
  * significand, i.e. TF32's precision, fp32 accumulation -- on tcgen05.mma.kind::f16: twice the TF32 issue rate and 64
  * input channels per 128-byte slab, so half the iterations and half the operand bytes.  w_packed must then be the
  * spvd_conv_pack_weights_f16 image; `in` is fp32 (converted on the fly, clamped to the finite half range) for
- * SPVD_A_F32_TO_F16, or an f16 [rows, cin] tensor (a producer with act & 4) for SPVD_A_F16; mt is ignored, except
- * mt = 6 with SPVD_A_F16 and a map: the experimental persistent stream-K kernel (equal iteration shares per CTA);
- * mt = 7 with SPVD_A_F16: CTA pairs (tcgen05 cta_group::2, M = 256 over two SMs, each CTA loads half of every weight tile).
- * Both are correct and tested but slower than the default on the SPVD shapes. */
+ * SPVD_A_F32_TO_F16, or an f16 [rows, cin] tensor (a producer with act & 4) for SPVD_A_F16. */
 #define SPVD_A_F32 0        /* fp32 rows, rounded to TF32 while gathered          */
 #define SPVD_A_TF32 1       /* fp32 rows that are already TF32-representable      */
 #define SPVD_A_F32_TO_F16 2 /* fp32 rows, converted to f16 while gathered         */

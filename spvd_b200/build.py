@@ -44,11 +44,29 @@ def _digest() -> str:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
+    """Compile (if stale) and return the library path.  Safe under torchrun: ranks serialise on a lock file, the first one
+    builds into temporary names and renames atomically, the others find the fresh stamp."""
+    import fcntl
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.stamp")
     digest = _digest()
-    if not force and os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest:
+
+    def fresh():
+        return os.path.exists(LIB) and os.path.exists(stamp) and open(stamp).read().strip() == digest
+
+    if not force and fresh():
         return LIB
+    with open(os.path.join(LIBDIR, "build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and fresh():           # another rank built it while we waited
+                return LIB
+            return _build_locked(digest, stamp, verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(digest: str, stamp: str, verbose: bool) -> str:
     nvcc = _nvcc()
     srcs = [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
     objs = []
@@ -65,11 +83,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
         objs = list(ex.map(compile_one, srcs))
-    r = subprocess.run([nvcc, "-shared", "-o", LIB, *objs, "-lcudart"], capture_output=True, text=True)
+    tmp = LIB + f".tmp{os.getpid()}"
+    r = subprocess.run([nvcc, "-shared", "-o", tmp, *objs, "-lcudart"], capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(stamp, "w") as f:
+    os.replace(tmp, LIB)                         # atomic: nobody ever dlopens a half-written library
+    with open(stamp + ".tmp", "w") as f:
         f.write(digest)
+    os.replace(stamp + ".tmp", stamp)
     return LIB
 
 

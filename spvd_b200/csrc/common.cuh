@@ -36,6 +36,13 @@ void set_error(const char* fmt, ...);
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+// index of the current device for per-device one-time setup flags (cudaFuncSetAttribute is per device)
+static inline int current_device_slot() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 0;
+  return dev;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Programmatic dependent launch.  The feature-path kernels (convolutions and the elementwise glue)
 // are launched with programmaticStreamSerialization: each one lets its successor start early

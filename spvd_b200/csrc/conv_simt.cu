@@ -109,7 +109,7 @@ __global__ void __launch_bounds__(256) k_conv_fwd_small_cin(const float* __restr
       if (r[j] < 0) continue;
       const float* x = in + (size_t)r[j] * cin;
       const float* wk = s_w + ((k0 + j) * cin) * cout + c;
-      for (int ci = 0; ci < cin; ++ci) acc = fmaf(__ldg(x + ci), wk[ci * cout], acc);
+      for (int ci = 0; ci < cin; ++ci) acc = fmaf(x[ci], wk[ci * cout], acc);
     }
   }
   out[t] = acc;
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) k_linear_small_cin4(const float* __restri
     acc.x += r.x; acc.y += r.y; acc.z += r.z; acc.w += r.w;
   }
   for (int ci = 0; ci < cin; ++ci) {
-    const float x = __ldg(in + (size_t)o * cin + ci);
+    const float x = in[(size_t)o * cin + ci];
     const float4 wv = s_w4[ci * cout4 + q];
     acc.x = fmaf(x, wv.x, acc.x); acc.y = fmaf(x, wv.y, acc.y); acc.z = fmaf(x, wv.z, acc.z); acc.w = fmaf(x, wv.w, acc.w);
   }
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(128) k_conv_fwd_small_cin_pairs(const float* _
   // every lane fetches the input row of ITS pair (32 independent loads in flight), then the warp walks the 32 pairs
   float mx[4] = {0.f, 0.f, 0.f, 0.f};
   if (my_in >= 0)
-    for (int ci = 0; ci < cin; ++ci) mx[ci] = __ldg(in + (size_t)my_in * cin + ci);
+    for (int ci = 0; ci < cin; ++ci) mx[ci] = in[(size_t)my_in * cin + ci];
   for (int j = 0; j < 32; ++j) {
     const int ro = __shfl_sync(0xffffffffu, my_in < 0 ? -1 : my_out, j);
     float x[4];

@@ -65,6 +65,9 @@ extern "C" int spvd_conv_fwd_umma_rows(const float* in, const float* w_packed, c
   // weight tile (tools/conv_bench.py)
   if (mt <= 0) mt = 3;
   if (!aa && (mt == 2 || mt >= 4)) mt = mt == 2 ? 1 : 3;
+#ifndef SPVD_EXPERIMENTAL
+  if (mt == 2 || mt >= 4) mt = 3;
+#endif
   if (nsplit <= 0) nsplit = pick_split(cdiv(n_out, BM * (mt == 2 ? 2 : 1)) * (cout / bn), max_iters);
   if (nsplit > max_iters) nsplit = max_iters;
   switch (bn) {

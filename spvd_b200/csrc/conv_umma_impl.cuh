@@ -382,8 +382,8 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
           v[2 * i] = v[2 * i + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (rows[i] >= 0 && ch < cin) {
             const float4* p = reinterpret_cast<const float4*>(in + (size_t)rows[i] * cin + ch);
-            v[2 * i] = __ldg(p);
-            v[2 * i + 1] = __ldg(p + 1);
+            v[2 * i] = *p;          // (plain loads: the predecessor grid wrote these under PDL)
+            v[2 * i + 1] = *(p + 1);
           }
         }
       };
@@ -429,7 +429,7 @@ __global__ void __launch_bounds__(kUmmaThreads) k_conv_fwd_umma(const float* __r
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (rows[i] >= 0) v[i] = __ldg(reinterpret_cast<const float4*>(in + (size_t)rows[i] * cin + c * BK) + chunk16);
+          if (rows[i] >= 0) v[i] = *(reinterpret_cast<const float4*>(in + (size_t)rows[i] * cin + c * BK) + chunk16);
         }
       };
       if (num_iters > 0) issue_loads(it_begin);
@@ -642,7 +642,8 @@ static int launch_umma(const float* in, const float* wp, const int32_t* map_t, i
                        int n_out, int kvol, int cin, int cout, const float* bias, const float* residual, float* out,
                        int nsplit, cudaStream_t s, const int32_t* out_rows = nullptr) {
   using Cfg = UmmaCfg<BN, MT, false, kLite>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the attribute is per device: one flag per device, not per process
+  bool& configured = configured_dev[current_device_slot()];
   if (!configured) {
     SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN, MT, kAsyncA, false, kLite, 1, kF16>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -661,7 +662,8 @@ static int launch_umma_pairs_a(const float* in, const float* wp, const int32_t* 
                                const int32_t* tile_k, int n_pair_tiles, int center_k, int n_out, int kvol, int cin, int cout,
                                const float* bias, const float* residual, float* out, cudaStream_t s) {
   using Cfg = UmmaCfg<BN, 1, true>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the attribute is per device: one flag per device, not per process
+  bool& configured = configured_dev[current_device_slot()];
   if (!configured) {
     SPVD_CUDA(cudaFuncSetAttribute(k_conv_fwd_umma<BN, 1, kAsyncA, true, false, 1, kF16>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
@@ -693,7 +695,8 @@ static int launch_umma_cluster(const float* in, const float* wp, const int32_t* 
                                int nsplit, cudaStream_t s, const int32_t* out_rows = nullptr) {
   using Cfg = UmmaCfg<BN, 1, false, true>;
   auto kern = k_conv_fwd_umma<BN, 1, true, false, true, kCluster, kF16>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the attribute is per device: one flag per device, not per process
+  bool& configured = configured_dev[current_device_slot()];
   if (!configured) {
     SPVD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
     configured = true;
@@ -728,14 +731,16 @@ static int launch_umma_bn(bool async_a, int mt, const float* in, const float* wp
       return launch_umma<BN, 1, false, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
     return launch_umma<BN, 1, false>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
   }
+#ifdef SPVD_EXPERIMENTAL   // cluster multicast of the weight tile / two tiles per CTA: correct, measured no faster
   if (mt == 4)   // lite + weight tiles multicast across a cluster of 2 CTAs
     return launch_umma_cluster<BN, 2>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
   if (mt == 5)
     return launch_umma_cluster<BN, 4>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
-  if (mt == 3)   // one tile per CTA, two stages: small enough for two CTAs per SM
-    return launch_umma<BN, 1, true, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
-  if (mt >= 2)
+  if (mt == 2)
     return launch_umma<BN, 2, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
+#endif
+  if (mt >= 2)   // one tile per CTA, two stages: small enough for two CTAs per SM
+    return launch_umma<BN, 1, true, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
   return launch_umma<BN, 1, true>(in, wp, map_t, ld, tile_mask, n_out, kvol, cin, cout, bias, residual, out, nsplit, s, out_rows);
 }
 

@@ -228,7 +228,8 @@ template <int BN>
 static int launch(const float* x, const float* g, const int32_t* pin, const int32_t* pout, const int32_t* tk, int n_tiles,
                   int n_identity, int cin, int cout, float* gw, cudaStream_t s) {
   using C = Cfg<BN>;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the attribute is per device: one flag per device, not per process
+  bool& configured = configured_dev[current_device_slot()];
   if (!configured) {
     SPVD_CUDA(cudaFuncSetAttribute(k_conv_wgrad_umma<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmemBytes));
     configured = true;

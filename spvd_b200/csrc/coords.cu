@@ -592,7 +592,8 @@ static int seg_sorted_unique(const int4* coords, int n_cap, const int* n_dev, in
                              int* batch_offsets, int* status, cudaStream_t s) {
   const int cap = next_pow2(max_cloud_rows);
   const size_t smem = (size_t)cap * 8;
-  static bool configured = false;
+  static bool configured_dev[64] = {};   // the attribute is per device: one flag per device, not per process
+  bool& configured = configured_dev[current_device_slot()];
   if (!configured) {
     SPVD_CUDA(cudaFuncSetAttribute(k_seg_sort, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
     configured = true;

@@ -82,7 +82,7 @@ __global__ void k_film4(const float4* __restrict__ x, const float* __restrict__ 
   int row = (int)(t / c4), q = (int)(t % c4);
   int b = coords[row].x;
   const float4* tb = reinterpret_cast<const float4*>(tt + (size_t)b * c4 * 8);
-  float4 v = x[t], sc = __ldg(tb + q), sh = __ldg(tb + c4 + q);
+  float4 v = x[t], sc = tb[q], sh = tb[c4 + q];     // (the FiLM table is an activation: plain loads under PDL)
   v.x = fmaf(1.f + sc.x, v.x, sh.x);
   v.y = fmaf(1.f + sc.y, v.y, sh.y);
   v.z = fmaf(1.f + sc.z, v.z, sh.z);

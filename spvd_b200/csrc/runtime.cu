@@ -6,6 +6,7 @@
 // per-cloud attention (models/modules/transformer.py:40-67,118-125), FiLM fused with the following
 // BatchNorm+SiLU (models/modules/graph.py:35-41 + models/ddpm_unet_attn.py:57), channel concat.
 #include <math.h>
+#include <string.h>
 
 #include <cuda_fp16.h>
 #include "common.cuh"
@@ -31,7 +32,7 @@ __global__ void k_film_affine4(const float4* __restrict__ x, const float* __rest
   int row = (int)(t / c4), q = (int)(t % c4);
   int b = coords[row].x;
   const float4* tb = reinterpret_cast<const float4*>(tt + (size_t)b * ldt);
-  float4 v = x[t], sc = __ldg(tb + q), sh = __ldg(tb + c4 + q);
+  float4 v = x[t], sc = tb[q], sh = tb[c4 + q];     // (the FiLM table is an activation: plain loads under PDL)
   float4 s = __ldg(scale + q), o = __ldg(shift + q);
   v.x = fmaf(fmaf(1.f + sc.x, v.x, sh.x), s.x, o.x);
   v.y = fmaf(fmaf(1.f + sc.y, v.y, sh.y), s.y, o.y);
@@ -519,9 +520,12 @@ extern "C" int spvd_program_run(const spvd_op_t* ops, int n_ops, const spvd_leve
         SPVD_CHECK_ARG(o.aux >= 0 && o.p0 && o.p1, "op %d: cat+affine needs the second output and the affine", i);
         rc = spvd_cat_affine_f16_fwd(at(o.src0), at(o.src1), rin, o.c0, o.c1, o.p0, o.p1, o.flags & 1, at(o.aux), at(o.dst), stream);
         break;
-      case SPVD_OP_LAYERNORM:
-        rc = spvd_layernorm_fwd(at(o.src0), o.p0, o.p1, (int)rin, o.c0, 1e-5f, (o.flags & 3) | ((o.flags & SPVD_FLAG_F16) ? 4 : 0), at(o.dst), stream);
+      case SPVD_OP_LAYERNORM: {
+        float ln_eps;
+        memcpy(&ln_eps, &o.i0, sizeof(float));       // the module's own epsilon (float bits in i0)
+        rc = spvd_layernorm_fwd(at(o.src0), o.p0, o.p1, (int)rin, o.c0, ln_eps, (o.flags & 3) | ((o.flags & SPVD_FLAG_F16) ? 4 : 0), at(o.dst), stream);
         break;
+      }
       case SPVD_OP_ATTENTION:
         SPVD_CHECK_ARG(lv && lv->batch_offsets, "op %d: level %d has no per-cloud offsets", i, o.level);
         rc = spvd_attention_fwd(at(o.src0), lv->batch_offsets, n_batch, lv->max_per_batch, o.c1, o.i0, (o.flags & 3) | ((o.flags & SPVD_FLAG_F16) ? 4 : 0),

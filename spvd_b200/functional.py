@@ -42,6 +42,8 @@ class _SparseConv(torch.autograd.Function):
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
         kmap, impl = ctx.kmap, ctx.impl
+        if kmap is not None:
+            kmap.check_current()
         g = g.contiguous()
         w3 = (weight if weight.dim() == 3 else weight.unsqueeze(0)).contiguous()
         kvol, cin, cout = w3.shape

@@ -18,12 +18,21 @@ class KernelMap:
     """Offset-major map [kvol, ld] (+ per-128-row-tile offset mask) of one sparse convolution and the
     map of its data gradient."""
 
-    __slots__ = ("map_t", "mask", "n_out", "n_in", "kvol", "grad", "flip", "_pairs")
+    __slots__ = ("map_t", "mask", "n_out", "n_in", "kvol", "grad", "flip", "_pairs", "_ws", "_gen")
 
     def __init__(self, map_t, mask, n_out, n_in, kvol, flip):
         self.map_t, self.mask, self.n_out, self.n_in, self.kvol, self.flip = map_t, mask, n_out, n_in, kvol, flip
         self.grad = None   # KernelMap that produces d(in) from d(out)
         self._pairs = None
+        self._ws, self._gen = None, 0     # PlanWorkspace whose buffers this map views, and its build generation
+
+    def check_current(self):
+        """Maps planned by a PlanWorkspace are VIEWS of its persistent buffers: a later build of the same workspace
+        overwrites them.  Raise instead of computing gradients on somebody else's geometry."""
+        if self._ws is not None and self._ws.generation != self._gen:
+            raise RuntimeError("this kernel map was overwritten by a later forward pass that reused its geometry workspace "
+                               "(more forwards than model.geometry_pool between a forward and its backward): raise "
+                               "model.geometry_pool")
 
     def pairs(self):
         """pair-major view (pair_in, pair_out, tile_k, n_tiles) of this map, built on first use (the weight-gradient
@@ -322,6 +331,7 @@ class PlanWorkspace:
         nl = len(self.strides)
 
         ops.stats.launches += self.n_kernels if not max_cloud_rows else self.n_kernels - 20 * nl
+        self.generation = getattr(self, "generation", 0) + 1
         geo = Geometry.__new__(Geometry)
         geo.n_points, geo.mode, geo.status = self.n_points, downsample_mode, self.status
         geo.fcoords, geo.levels, geo.p2v, geo.devox, geo.p2v_w, geo.p2v_groups = self.fcoords, {}, {}, {}, {}, {}
@@ -434,6 +444,7 @@ class PlanWorkspace:
             if "kmap3" in b:
                 lv.kmap3 = KernelMap(b["kmap3"], b["mask3"], lv.n, lv.n, 27, flip=True)
                 lv.kmap3.grad = lv.kmap3
+                lv.kmap3._ws, lv.kmap3._gen = self, self.generation
                 if "kmap3_sorted" in b:
                     lv.kmap3_sorted = (b["kmap3_sorted"], b["mask3_sorted"], b["perm3"])
                 if "pair_in" in b:       # the weight-gradient kernel reduces over the planner's pair list: no lazy build, no sync
@@ -447,6 +458,8 @@ class PlanWorkspace:
                 lv.kmap_down = KernelMap(b["kmap_down"], b["mask_down"], c.n, lv.n, 8, flip=False)
                 lv.kmap_up = KernelMap(b["kmap_up"], b["mask_up"], lv.n, c.n, 8, flip=False)
                 lv.kmap_down.grad, lv.kmap_up.grad = lv.kmap_up, lv.kmap_down
+                for km in (lv.kmap_down, lv.kmap_up):
+                    km._ws, km._gen = self, self.generation
                 if "dpair_in" in b:      # one (fine, coarse) pair list serves the strided conv and, roles swapped, its transpose
                     dp = lv.dpairs
                     lv.kmap_down._pairs = (dp[0], dp[1], dp[2], dp[3])

@@ -5,6 +5,12 @@ gradient clipping so the clip sees the global gradient (utils/callbacks.py:62-63
 The reference has no distributed code; this is the only strategy the path needs:
 nothing in the forward is coupled across clouds except BatchNorm statistics, which stay per-rank exactly like
 the single-GPU reference (no SyncBN).  Sampling needs no collective at all.
+
+Layout: every gradient lives in ONE pre-allocated flat fp32 buffer (``p.grad`` are views into it, so there is no
+concatenation and no copy-back), cut into contiguous buckets in reverse parameter order -- the order in which backward
+finishes them.  A post-accumulate hook per parameter launches a bucket's all-reduce on the NCCL stream as soon as its
+last gradient is final, i.e. while the rest of backward is still running; ``finish()`` waits for the stragglers and
+the 1 / world average is folded into the clipping scale (one pass over the flat buffer).
 """
 from __future__ import annotations
 
@@ -20,62 +26,122 @@ def shard_clouds(n_clouds: int, rank: int, world: int):
 
 
 class GradientAllReduce:
-    """Flat-bucket gradient all-reduce.  Gradients are copied into a few large contiguous buckets
-    (default 64 MiB: NVSwitch makes the cost latency- not link-bound, so few big messages win), reduced
-    asynchronously on the NCCL stream and copied back; ``average`` divides by the world size."""
-
-    def __init__(self, params, bucket_bytes: int = 64 << 20, average: bool = True, group=None):
+    def __init__(self, params, bucket_bytes: int = 32 << 20, average: bool = True, group=None, overlap: bool = True):
         self.params = [p for p in params if p.requires_grad]
         self.average, self.group = average, group
-        self.buckets, cur, size = [], [], 0
-        for p in self.params:
-            n = p.numel() * p.element_size()
-            if cur and size + n > bucket_bytes:
-                self.buckets.append(cur)
-                cur, size = [], 0
-            cur.append(p)
-            size += n
-        if cur:
-            self.buckets.append(cur)
-        self._flat = [None] * len(self.buckets)
+        if not self.params:
+            raise ValueError("no parameters to reduce")
+        dev, dt = self.params[0].device, self.params[0].dtype
+        order = list(reversed(self.params))                      # backward produces the last layers' gradients first
+        self.flat = torch.zeros(sum(p.numel() for p in order), dtype=dt, device=dev)
+        self.buckets, self._bucket_of = [], {}                   # bucket = [lo, hi, pending, n_params, work]
+        off, lo, size = 0, 0, 0
+        for p in order:
+            n = p.numel()
+            view = self.flat[off: off + n].view_as(p)
+            if p.grad is not None:
+                view.copy_(p.grad)
+            p.grad = view
+            self._bucket_of[id(p)] = len(self.buckets)
+            off += n
+            size += n * p.element_size()
+            if size >= bucket_bytes:
+                self.buckets.append([lo, off, 0, 0, None])
+                lo, size = off, 0
+        if off > lo:
+            self.buckets.append([lo, off, 0, 0, None])
+        for p in order:
+            self.buckets[min(self._bucket_of[id(p)], len(self.buckets) - 1)][3] += 1
+            self._bucket_of[id(p)] = min(self._bucket_of[id(p)], len(self.buckets) - 1)
+        self._hooks = []
+        if overlap and hasattr(torch.Tensor, "register_post_accumulate_grad_hook"):
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._ready))
+        self.reset()
+
+    # -- per step -------------------------------------------------------------------------------------------------
+    def reset(self):
+        for b in self.buckets:
+            b[2], b[4] = b[3], None
+
+    def zero_grad(self):
+        """instead of optimizer.zero_grad(): one memset; the views stay attached"""
+        self.flat.zero_()
+        self.reset()
+
+    def _active(self):
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1
+
+    def _launch(self, b):
+        if b[4] is None and self._active():
+            b[4] = dist.all_reduce(self.flat[b[0]: b[1]], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+
+    def _ready(self, p):
+        if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + self._offset_of(p):
+            return                                               # someone replaced .grad (set_to_none): fall back to finish()
+        b = self.buckets[self._bucket_of[id(p)]]
+        b[2] -= 1
+        if b[2] == 0:
+            self._launch(b)
+
+    def _offset_of(self, p):
+        off = self.__dict__.setdefault("_offsets", {})
+        if not off:
+            o = 0
+            for q in reversed(self.params):
+                off[id(q)] = o * q.element_size()
+                o += q.numel()
+        return off[id(p)]
+
+    def finish(self):
+        """All buckets reduced (launching those whose hooks did not fire); returns the factor still owed (1 / world when
+        averaging) -- apply it with ``scale_`` or fold it into the clip."""
+        if not self._active():
+            self.reset()
+            return 1.0
+        for p in self.params:                                    # gradients that were re-created outside the flat buffer
+            if p.grad is not None and p.grad.data_ptr() != self.flat.data_ptr() + self._offset_of(p):
+                view = self.flat[self._offset_of(p) // p.element_size():][: p.numel()].view_as(p)
+                view.copy_(p.grad)
+                p.grad = view
+        for b in self.buckets:
+            self._launch(b)
+        for b in self.buckets:
+            b[4].wait()
+        self.reset()
+        return 1.0 / dist.get_world_size(self.group) if self.average else 1.0
 
     def __call__(self):
-        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
-            return
-        world = dist.get_world_size(self.group)
-        works = []
-        for i, bucket in enumerate(self.buckets):
-            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
-            flat = torch.cat([g.reshape(-1) for g in grads])
-            self._flat[i] = (flat, grads)
-            works.append(dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True))
-        for i, (w, bucket) in enumerate(zip(works, self.buckets)):
-            w.wait()
-            flat, grads = self._flat[i]
-            if self.average:
-                flat.div_(world)
-            off = 0
-            for p, g in zip(bucket, grads):
-                n = g.numel()
-                if p.grad is None:
-                    p.grad = flat[off: off + n].view_as(p).clone()
-                else:
-                    p.grad.copy_(flat[off: off + n].view_as(p))
-                off += n
-            self._flat[i] = None
+        """synchronous form: reduce now and apply the average"""
+        s = self.finish()
+        if s != 1.0:
+            self.flat.mul_(s)
+
+    def clip_(self, max_norm: float, pending_scale: float = 1.0):
+        """clip_grad_norm_ over the flat buffer with the owed average folded in: one norm, one multiply"""
+        norm = torch.linalg.vector_norm(self.flat) * pending_scale
+        scale = torch.clamp(max_norm / (norm + 1e-6), max=1.0) * pending_scale
+        self.flat.mul_(scale)
+        return norm
 
 
 def train_step(model, optimizer, batch, reducer: GradientAllReduce = None, clip: float = 10.0, scheduler=None):
     """One optimisation step of train_generation.py:98-112: MSE(model((x_t, t)), eps), backward, gradient
-    all-reduce (data parallel), clip_grad_norm_(10), optimizer (+ LR scheduler) step.  ``batch`` = (SparseTensor, t, eps)."""
+    all-reduce (data parallel, overlapped with backward), clip_grad_norm_(10), optimizer (+ LR scheduler) step.
+    ``batch`` = (SparseTensor, t, eps)."""
+    from . import functional as SF
     x, t, target = batch
-    optimizer.zero_grad(set_to_none=True)
+    if reducer is not None:
+        reducer.zero_grad()
+    else:
+        optimizer.zero_grad(set_to_none=True)
     pred = model((x, t))
-    loss = torch.nn.functional.mse_loss(pred, target)
+    loss = SF.mse_loss(pred, target) if pred.is_cuda else torch.nn.functional.mse_loss(pred, target)
     loss.backward()
     if reducer is not None:
-        reducer()
-    torch.nn.utils.clip_grad_norm_(model.parameters(), clip)
+        reducer.clip_(clip, reducer.finish())
+    else:
+        torch.nn.utils.clip_grad_norm_(model.parameters(), clip)
     optimizer.step()
     if scheduler is not None:
         scheduler.step()

@@ -236,7 +236,8 @@ class Program:
         if hasattr(blk, "attn"):
             at = blk.attn
             ln = self.op(OP_LAYERNORM, self.reg(lvl, nf), h2, flags=self._fmt(True, self._half(nf, 3 * nf, 1, at.attn.qkv.weight)), level=-1,
-                         rows_in=lvl, rows_out=lvl, c0=nf, c1=nf, p0=self._hold(at.norm1.weight), p1=self._hold(at.norm1.bias))
+                         rows_in=lvl, rows_out=lvl, c0=nf, c1=nf, p0=self._hold(at.norm1.weight), p1=self._hold(at.norm1.bias),
+                         i0=C.c_int32.from_buffer(C.c_float(at.norm1.eps)).value)
             ln.half = self._half(nf, 3 * nf, 1, at.attn.qkv.weight)
             qkv = self.linear(ln, at.attn.qkv, a_tf32=True)
             ao = self.op(OP_ATTENTION, self.reg(lvl, nf), qkv, flags=self._fmt(True, self._half(nf, nf, 1, at.attn.proj.weight)), level=lvl,

@@ -340,7 +340,7 @@ def test_conv_forward_tcgen05_f16_operands(sp, kind, cin, cout, pre):
     wp = sp.ops.pack_weights_f16(w.cuda())
     xd = x.cuda().half() if pre else x.cuda()
     # mt = 6: the persistent stream-K kernel, mt = 7: CTA pairs (cta_group::2); both for f16 rows only
-    for nsplit, mt in ((0, 0), (1, 0), (5, 0), (0, 6), (0, 7), (1, 7), (3, 7)):
+    for nsplit, mt in ((0, 0), (1, 0), (5, 0), (0, 1), (3, 3)):
         got = sp.ops.conv_fwd(xd, w.cuda(), wp, km.map_t if km is not None else None, km.mask if km is not None else None,
                               n_out, b.cuda(), sp.ops.CONV_UMMA, nsplit=nsplit, mt=mt).cpu().numpy()
         assert rel_err(got, want_f16.numpy()) < 2e-5        # same operand rounding as the emulation
@@ -375,11 +375,10 @@ def test_conv_backward(sp, kind, cin, cout, impl):
     assert rel_err(bb.grad.cpu().numpy(), ba.grad.numpy()) < 1e-5
 
 
-@pytest.mark.parametrize("mt", [1, 2, 3, 4, 5])
+@pytest.mark.parametrize("mt", [1, 3])
 @pytest.mark.parametrize("cout", [32, 128, 192, 256])
 def test_conv_tcgen05_tile_configs(sp, mt, cout):
-    """mt: 1 = one tile/CTA, 2 = two tiles share each weight tile, 3 = lite (2 stages, 2 CTAs/SM), 4 / 5 = lite + weight
-    tiles multicast across a cluster of 2 / 4 CTAs"""
+    """mt: 1 = one tile per CTA with a four-stage ring, 3 = lite (2-3 stages, two CTAs per SM: the product default)"""
     x, w, b, m, n_out, km, oo = _conv_case(sp, "k3", 64, cout, 29)
     want = oo.conv_gather_gemm_scatter(x, w, m, n_out, b, emulate_tf32=True)
     xd = sp.ops.round_tf32(x.cuda())

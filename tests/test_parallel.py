@@ -29,12 +29,25 @@ def _worker(rank, world, port, out):
     loss = ((net(data[lo:hi]) - target[lo:hi]) ** 2).sum() * world / 10
     loss.backward()
     GradientAllReduce(net.parameters(), bucket_bytes=256)()      # tiny buckets: several messages
+    ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.SiLU(), torch.nn.Linear(16, 3))
+    ref.load_state_dict(net.state_dict())
+    (((ref(data) - target) ** 2).sum() / 10).backward()
+    err = max(float((a.grad - b.grad).abs().max()) for a, b in zip(net.parameters(), ref.parameters()))
+    # second scenario: the reducer exists before backward (gradients accumulate into its flat buffer, the per-parameter
+    # hooks launch the buckets during backward), the 1 / world average is folded into the clip
+    red = GradientAllReduce(net.parameters(), bucket_bytes=256)
+    for _ in range(2):                                           # two steps: the buffer and the hooks are reusable
+        red.zero_grad()
+        (((net(data[lo:hi]) - target[lo:hi]) ** 2).sum() * world / 10 * 50).backward()
+        assert all(p.grad.data_ptr() == red.flat.data_ptr() + red._offset_of(p) for p in net.parameters())
+        norm = red.clip_(1.0, red.finish())
+    ref.zero_grad()
+    (((ref(data) - target) ** 2).sum() / 10 * 50).backward()
+    want_norm = torch.nn.utils.clip_grad_norm_(ref.parameters(), 1.0)
+    err2 = max(float((a.grad - b.grad).abs().max()) for a, b in zip(net.parameters(), ref.parameters()))
+    err2 = max(err2, abs(float(norm) - float(want_norm)) / float(want_norm))
     if rank == 0:
-        ref = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.SiLU(), torch.nn.Linear(16, 3))
-        ref.load_state_dict(net.state_dict())
-        (((ref(data) - target) ** 2).sum() / 10).backward()
-        err = max(float((a.grad - b.grad).abs().max()) for a, b in zip(net.parameters(), ref.parameters()))
-        out.put(err)
+        out.put(max(err, err2))
     dist.barrier()
     dist.destroy_process_group()
 
