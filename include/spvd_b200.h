@@ -575,6 +575,34 @@ int spvd_attention_train_fwd(const float* qkv, const int32_t* batch_offsets, int
                              float* out, float* lse, spvd_stream_t stream);
 int spvd_attention_bwd(const float* qkv, const float* out, const float* gout, const float* lse, const int32_t* batch_offsets,
                        int n_batch, int max_len, int c, int heads, float* gqkv, float* delta, spvd_stream_t stream);
+/* The whole backward of one sparse convolution (or nn.Linear = kernel size 1, map NULL) from one call: gx = data gradient
+ * (the forward kernels on the transposed weights and the gradient map gmap_t: same map with flipped offsets for a
+ * submanifold conv (flip = 1), the transposed map for strided convs), gw = weight gradient (tcgen05 over the pair lists
+ * pair_in / pair_out / pair_tile_k of spvd_kmap_pairs -- NULL with kvol == 1: identity pairs -- or the fp32 SIMT kernel on
+ * map_t when the widths are not multiples of 32 / allow_tensor_cores == 0), gbias = column sums of g.  Any of gx / gw /
+ * gbias may be NULL.  x_is_tf32: the forward input is already TF32-representable; gw_transposed: write gw as
+ * [kvol, cout, cin] (the layout of nn.Linear.weight).  workspace >= spvd_conv_bwd_workspace_bytes(...);
+ * red_workspace = the zeroed fp64 scratch of this section (>= 2 * cout doubles). */
+typedef struct spvd_conv_bwd_args {
+  const float* x;        /* [n_in, cin] forward input */
+  const float* g;        /* [n_out, cout] gradient of the output */
+  const float* w;        /* [kvol, cin, cout] forward weights */
+  const int32_t* map_t;  /* forward map [kvol, map_ld] (SIMT weight gradient) or NULL */
+  const int32_t* gmap_t; /* gradient map [kvol, gmap_ld] or NULL (kernel size 1) */
+  const uint32_t* gmap_mask;
+  const int32_t* pair_in;
+  const int32_t* pair_out;
+  const int32_t* pair_tile_k;
+  float* gx;
+  float* gw;
+  float* gbias;
+  void* workspace;
+  double* red_workspace;
+  size_t workspace_bytes;
+  int32_t map_ld, gmap_ld, n_pair_tiles, n_in, n_out, kvol, cin, cout, flip, x_is_tf32, gw_transposed, allow_tensor_cores;
+} spvd_conv_bwd_args_t;
+size_t spvd_conv_bwd_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout);
+int spvd_conv_bwd(const spvd_conv_bwd_args_t* args, spvd_stream_t stream);
 /* torchsparse.cat (models/spvd.py:232) for any channel counts, and its backward (channel split) */
 int spvd_cat_any_fwd(const float* a, const float* b, long long rows, int ca, int cb, float* y, spvd_stream_t stream);
 int spvd_split_fwd(const float* g, long long rows, int ca, int cb, float* ga, float* gb, spvd_stream_t stream);

@@ -76,6 +76,8 @@ SIGNATURES = {
     "spvd_embedding_bwd": (_i, [_p, _p, _i, _i, _p, _p]),
     "spvd_timestep_embedding": (_i, [_p, _i, _i, _p, _p]),
     "spvd_mse_loss": (_i, [_p, _p, _ll, _f, _p, _p, _p, _p]),
+    "spvd_conv_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "spvd_conv_bwd": (_i, [_p, _p]),
     "spvd_kmap_pairs": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),
     "spvd_conv_fwd_pairs": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _p, _i, _p]),
     "spvd_conv_wgrad_umma": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p, _p]),

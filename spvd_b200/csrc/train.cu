@@ -28,20 +28,35 @@ __device__ __forceinline__ float dsilu_t(float v) {
 // the CTA adds its partial sums to fp64 totals.  f(row, ch, &a, &b) yields the two summands.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRedThreads = 256;
-constexpr int kRedRows = 128;   // rows per CTA
+constexpr int kRedMaxCtas = 592;   // 4 per SM: the fp64 atomics of a launch stay at a few hundred per channel
+
+static inline int red_rows_per_cta(long long rows) {
+  long long per = (rows + kRedMaxCtas - 1) / kRedMaxCtas;
+  if (per < 32) per = 32;
+  return (int)per;
+}
 
 template <typename F>
-__device__ __forceinline__ void col_reduce2(long long rows, int c, double* __restrict__ tot, F f) {
+__device__ __forceinline__ void col_reduce2(long long rows, int c, int rows_per_cta, double* __restrict__ tot, F f) {
   __shared__ float sa[kRedThreads], sb[kRedThreads];
-  const long long r_begin = (long long)blockIdx.x * kRedRows;
-  const long long r_end = min(rows, r_begin + kRedRows);
+  const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+  const long long r_end = min(rows, r_begin + rows_per_cta);
   for (int c0 = 0; c0 < c; c0 += kRedThreads) {            // channel chunks of up to 256 (one pass for every SPVD width)
     const int cw = min(kRedThreads, c - c0);
     const int lanes = kRedThreads / cw;                    // row lanes
     const int ch = threadIdx.x % cw, lane = threadIdx.x / cw;
-    float a = 0.f, b = 0.f;
-    if (lane < lanes)
-      for (long long r = r_begin + lane; r < r_end; r += lanes) f(r, c0 + ch, &a, &b);
+    float a0 = 0.f, b0 = 0.f, a1 = 0.f, b1 = 0.f, a2 = 0.f, b2 = 0.f, a3 = 0.f, b3 = 0.f;
+    if (lane < lanes) {
+      long long r = r_begin + lane;
+      for (; r + 3 * lanes < r_end; r += 4 * lanes) {      // four independent rows in flight per thread
+        f(r, c0 + ch, &a0, &b0);
+        f(r + lanes, c0 + ch, &a1, &b1);
+        f(r + 2 * lanes, c0 + ch, &a2, &b2);
+        f(r + 3 * lanes, c0 + ch, &a3, &b3);
+      }
+      for (; r < r_end; r += lanes) f(r, c0 + ch, &a0, &b0);
+    }
+    float a = (a0 + a1) + (a2 + a3), b = (b0 + b1) + (b2 + b3);
     sa[threadIdx.x] = a;
     sb[threadIdx.x] = b;
     __syncthreads();
@@ -58,9 +73,9 @@ __device__ __forceinline__ void col_reduce2(long long rows, int c, double* __res
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm (train)
-__global__ void __launch_bounds__(kRedThreads) k_bn_stats(const float* __restrict__ x, long long rows, int c,
+__global__ void __launch_bounds__(kRedThreads) k_bn_stats(const float* __restrict__ x, long long rows, int c, int rpc,
                                                           double* __restrict__ tot) {
-  col_reduce2(rows, c, tot, [&](long long r, int ch, float* a, float* b) {
+  col_reduce2(rows, c, rpc, tot, [&](long long r, int ch, float* a, float* b) {
     const float v = x[r * c + ch];
     *a += v;
     *b = fmaf(v, v, *b);
@@ -98,8 +113,9 @@ __global__ void k_bn_finalize(double* __restrict__ tot, long long rows, int c, c
 __global__ void __launch_bounds__(kRedThreads) k_bn_bwd_reduce(const float* __restrict__ x, const float* __restrict__ gy,
                                                                long long rows, int c, const float* __restrict__ mean,
                                                                const float* __restrict__ invstd, const float* __restrict__ gamma,
-                                                               const float* __restrict__ beta, int act, double* __restrict__ tot) {
-  col_reduce2(rows, c, tot, [&](long long r, int ch, float* a, float* b) {
+                                                               const float* __restrict__ beta, int act, int rpc,
+                                                               double* __restrict__ tot) {
+  col_reduce2(rows, c, rpc, tot, [&](long long r, int ch, float* a, float* b) {
     const float xh = (x[r * c + ch] - mean[ch]) * invstd[ch];
     float dz = gy[r * c + ch];
     if (act & 1) dz *= dsilu_t(fmaf(xh, gamma ? gamma[ch] : 1.f, beta ? beta[ch] : 0.f));
@@ -138,8 +154,9 @@ __global__ void k_clear_f64(double* p, int n) {
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
-__global__ void __launch_bounds__(kRedThreads) k_colsum(const float* __restrict__ g, long long rows, int c, double* __restrict__ tot) {
-  col_reduce2(rows, c, tot, [&](long long r, int ch, float* a, float* b) {
+__global__ void __launch_bounds__(kRedThreads) k_colsum(const float* __restrict__ g, long long rows, int c, int rpc,
+                                                        double* __restrict__ tot) {
+  col_reduce2(rows, c, rpc, tot, [&](long long r, int ch, float* a, float* b) {
     *a += g[r * c + ch];
     (void)b;
   });
@@ -245,8 +262,8 @@ __global__ void k_layernorm_bwd_x(const float* __restrict__ x, const float* __re
 
 __global__ void __launch_bounds__(kRedThreads) k_layernorm_bwd_params(const float* __restrict__ x, const float* __restrict__ gy,
                                                                       const float* __restrict__ mean, const float* __restrict__ rstd,
-                                                                      long long rows, int c, double* __restrict__ tot) {
-  col_reduce2(rows, c, tot, [&](long long r, int ch, float* a, float* b) {
+                                                                      long long rows, int c, int rpc, double* __restrict__ tot) {
+  col_reduce2(rows, c, rpc, tot, [&](long long r, int ch, float* a, float* b) {
     const float g = gy[r * c + ch];
     *a = fmaf(g, (x[r * c + ch] - mean[r]) * rstd[r], *a);    // d gamma
     *b += g;                                                  // d beta
@@ -589,11 +606,12 @@ extern "C" int spvd_bn_train_fwd(const float* x, long long rows, int c, const fl
   SPVD_CHECK_ARG(x && save_mean && save_invstd && scale && shift && y && workspace && rows > 0 && c > 0,
                  "spvd_bn_train_fwd: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-  k_bn_stats<<<cdiv(rows, kRedRows), kRedThreads, 0, s>>>(x, rows, c, workspace);
+  const int rpc = red_rows_per_cta(rows);
+  k_bn_stats<<<cdiv(rows, rpc), kRedThreads, 0, s>>>(x, rows, c, rpc, workspace);
   k_bn_finalize<<<cdiv(c, 128), 128, 0, s>>>(workspace, rows, c, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
                                              save_invstd, scale, shift);
   SPVD_LAUNCH_CHECK();
-  return spvd_bn_silu_fwd(x, scale, shift, rows, c, act & 1, y, stream);
+  return spvd_bn_silu_fwd(x, scale, shift, rows, c, act & 3, y, stream);   // bit 1: round y to TF32 (operand of a tensor-core conv)
 }
 
 extern "C" int spvd_bn_train_bwd(const float* x, const float* gy, long long rows, int c, const float* gamma, const float* beta,
@@ -601,7 +619,8 @@ extern "C" int spvd_bn_train_bwd(const float* x, const float* gy, long long rows
                                  float* gbeta, double* workspace, spvd_stream_t stream) {
   SPVD_CHECK_ARG(x && gy && save_mean && save_invstd && gx && workspace && rows > 0 && c > 0, "spvd_bn_train_bwd: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-  k_bn_bwd_reduce<<<cdiv(rows, kRedRows), kRedThreads, 0, s>>>(x, gy, rows, c, save_mean, save_invstd, gamma, beta, act, workspace);
+  const int rpc = red_rows_per_cta(rows);
+  k_bn_bwd_reduce<<<cdiv(rows, rpc), kRedThreads, 0, s>>>(x, gy, rows, c, save_mean, save_invstd, gamma, beta, act, rpc, workspace);
   k_bn_bwd_apply<<<grid_for(rows * c), 256, 0, s>>>(x, gy, rows, c, save_mean, save_invstd, gamma, beta, act, workspace, gx, ggamma,
                                                     gbeta);
   k_clear_f64<<<cdiv(2 * c, 256), 256, 0, s>>>(workspace, 2 * c);
@@ -612,7 +631,8 @@ extern "C" int spvd_bn_train_bwd(const float* x, const float* gy, long long rows
 extern "C" int spvd_colsum(const float* g, long long rows, int c, float* out, double* workspace, spvd_stream_t stream) {
   SPVD_CHECK_ARG(g && out && workspace && rows >= 0 && c > 0, "spvd_colsum: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
-  if (rows > 0) k_colsum<<<cdiv(rows, kRedRows), kRedThreads, 0, s>>>(g, rows, c, workspace);
+  const int rpc = red_rows_per_cta(rows);
+  if (rows > 0) k_colsum<<<cdiv(rows, rpc), kRedThreads, 0, s>>>(g, rows, c, rpc, workspace);
   k_f64_to_f32<<<cdiv(2 * c, 256), 256, 0, s>>>(workspace, c, 2 * c, out);
   SPVD_LAUNCH_CHECK();
   return SPVD_OK;
@@ -646,7 +666,8 @@ extern "C" int spvd_layernorm_bwd(const float* x, const float* gy, const float* 
   cudaStream_t s = (cudaStream_t)stream;
   if (rows > 0) {
     k_layernorm_bwd_x<<<cdiv(rows, 8), 256, 0, s>>>(x, gy, gamma, mean, rstd, rows, c, gx);
-    if (ggamma || gbeta) k_layernorm_bwd_params<<<cdiv(rows, kRedRows), kRedThreads, 0, s>>>(x, gy, mean, rstd, rows, c, workspace);
+    const int rpc = red_rows_per_cta(rows);
+    if (ggamma || gbeta) k_layernorm_bwd_params<<<cdiv(rows, rpc), kRedThreads, 0, s>>>(x, gy, mean, rstd, rows, c, rpc, workspace);
   }
   if (ggamma) k_f64_to_f32<<<cdiv(c, 256), 256, 0, s>>>(workspace, c, c, ggamma);
   if (gbeta) k_f64_to_f32<<<cdiv(c, 256), 256, 0, s>>>(workspace + c, c, c, gbeta);
@@ -766,4 +787,86 @@ extern "C" int spvd_mse_loss(const float* pred, const float* target, long long n
   k_mse_finalize<<<1, 1, 0, s>>>(workspace, n, loss);
   SPVD_LAUNCH_CHECK();
   return SPVD_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Whole backward of one sparse convolution / nn.Linear from ONE host call: TF32 rounding of the output gradient, weight
+// transpose + tile image, data gradient (the forward kernels on the transposed weights and the gradient map), weight
+// gradient (tcgen05 over the pair lists, fp32 SIMT fallback) and the bias gradient -- nine launches that the autograd
+// functions used to issue one Python -> C call at a time (the training step was host-bound on exactly that).
+// ------------------------------------------------------------------------------------------------
+extern "C" {
+int spvd_round_tf32(const float*, float*, long long, spvd_stream_t);
+int spvd_conv_transpose_weights(const float*, int, int, int, int, float*, spvd_stream_t);
+int spvd_conv_pack_weights(const float*, int, int, int, float*, spvd_stream_t);
+int spvd_conv_umma_supported(int, int, int);
+int spvd_conv_fwd_umma(const float*, const float*, const int32_t*, int, const uint32_t*, int, int, int, int, const float*,
+                       const float*, float*, int, int, int, int, spvd_stream_t);
+int spvd_conv_fwd_simt(const float*, const float*, const int32_t*, int, const uint32_t*, int, int, int, int, const float*,
+                       const float*, float*, spvd_stream_t);
+int spvd_conv_wgrad_umma(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int,
+                         float*, spvd_stream_t);
+int spvd_conv_wgrad(const float*, const float*, const int32_t*, int, int, int, int, int, float*, spvd_stream_t);
+}
+
+static inline size_t al256(size_t b) { return (b + 255) / 256 * 256; }
+
+extern "C" size_t spvd_conv_bwd_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout) {
+  return al256((size_t)n_out * cout * 4) + al256((size_t)n_in * cin * 4) + 3 * al256((size_t)kvol * cin * cout * 4) + 1024;
+}
+
+extern "C" int spvd_conv_bwd(const spvd_conv_bwd_args_t* args, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(args, "spvd_conv_bwd: NULL arguments");
+  const spvd_conv_bwd_args_t& a = *args;
+  SPVD_CHECK_ARG(a.g && a.w && a.workspace && a.red_workspace && a.kvol >= 1 && a.cin >= 1 && a.cout >= 1 && a.n_in >= 0 && a.n_out >= 0,
+                 "spvd_conv_bwd: bad arguments");
+  SPVD_CHECK_ARG(a.workspace_bytes >= spvd_conv_bwd_workspace_bytes(a.n_in, a.n_out, a.kvol, a.cin, a.cout),
+                 "spvd_conv_bwd: workspace too small");
+  SPVD_CHECK_ARG(!a.gw || a.x, "spvd_conv_bwd: the weight gradient needs the forward input");
+  char* ws = (char*)(((size_t)a.workspace + 255) / 256 * 256);
+  float* gr = (float*)ws;                                   ws += al256((size_t)a.n_out * a.cout * 4);
+  float* xr = (float*)ws;                                   ws += al256((size_t)a.n_in * a.cin * 4);
+  float* wt = (float*)ws;                                   ws += al256((size_t)a.kvol * a.cin * a.cout * 4);
+  float* wtp = (float*)ws;                                  ws += al256((size_t)a.kvol * a.cin * a.cout * 4);
+  float* gw3 = (float*)ws;
+  const bool tc = a.allow_tensor_cores != 0;
+  const bool umma_d = tc && a.gx && spvd_conv_umma_supported(a.kvol, a.cout, a.cin);
+  const bool umma_w = tc && a.gw && spvd_conv_umma_supported(a.kvol, a.cin, a.cout);
+  int rc = SPVD_OK;
+  const float* g_tc = a.g;
+  if ((umma_d || umma_w) && a.n_out > 0) {
+    if ((rc = spvd_round_tf32(a.g, gr, (long long)a.n_out * a.cout, stream)) != SPVD_OK) return rc;
+    g_tc = gr;
+  }
+  if (a.gx) {
+    // data gradient: out' = in, W'[k'] = W[k]^T (k' = K-1-k for submanifold maps), map = the gradient map
+    if ((rc = spvd_conv_transpose_weights(a.w, a.kvol, a.cin, a.cout, a.flip, wt, stream)) != SPVD_OK) return rc;
+    if (umma_d) {
+      if ((rc = spvd_conv_pack_weights(wt, a.kvol, a.cout, a.cin, wtp, stream)) != SPVD_OK) return rc;
+      rc = spvd_conv_fwd_umma(g_tc, wtp, a.gmap_t, a.gmap_ld, a.gmap_mask, a.n_in, a.kvol, a.cout, a.cin, nullptr, nullptr, a.gx, 0, 0,
+                              SPVD_A_TF32, 0, stream);
+    } else {
+      rc = spvd_conv_fwd_simt(a.g, wt, a.gmap_t, a.gmap_ld, a.gmap_mask, a.n_in, a.kvol, a.cout, a.cin, nullptr, nullptr, a.gx, stream);
+    }
+    if (rc != SPVD_OK) return rc;
+  }
+  if (a.gw) {
+    float* dst = a.gw_transposed ? gw3 : a.gw;
+    if (umma_w) {
+      const float* x_tc = a.x;
+      if (!a.x_is_tf32 && a.n_in > 0) {
+        if ((rc = spvd_round_tf32(a.x, xr, (long long)a.n_in * a.cin, stream)) != SPVD_OK) return rc;
+        x_tc = xr;
+      }
+      rc = spvd_conv_wgrad_umma(x_tc, g_tc, a.pair_in, a.pair_out, a.pair_tile_k, a.n_pair_tiles, a.pair_in ? 0 : a.n_out, a.kvol,
+                                a.cin, a.cout, dst, stream);
+    } else {
+      rc = spvd_conv_wgrad(a.x, a.g, a.map_t, a.map_ld, a.n_out, a.kvol, a.cin, a.cout, dst, stream);
+    }
+    if (rc != SPVD_OK) return rc;
+    if (a.gw_transposed)     // nn.Linear keeps [out, in]: [1, in, out] -> [1, out, in]
+      if ((rc = spvd_conv_transpose_weights(gw3, a.kvol, a.cin, a.cout, 0, a.gw, stream)) != SPVD_OK) return rc;
+  }
+  if (a.gbias) rc = spvd_colsum(a.g, a.n_out, a.cout, a.gbias, a.red_workspace, stream);
+  return rc;
 }

@@ -272,17 +272,23 @@ class SPVUnet(nn.Module):
                 return ops.affine_act(x.contiguous(), hit[1], hit[2], (1 if act else 0) | (2 if tf32 else 0))
             y = x * hit[1] + hit[2]                      # eval mode with autograd (frozen statistics): plain torch
             return F.silu(y) if act else y
-        return SF.batch_norm_act(x, bn, act)
+        return SF.batch_norm_act(x, bn, act, round_tf32=tf32)
 
-    def _linear(self, lin: nn.Linear, x, residual=None):
+    def _linear(self, lin: nn.Linear, x, residual=None, a_tf32=False):
         """nn.Linear as a kernel-size-1 convolution of the library (tcgen05 TF32 / fp32 SIMT), forward and backward"""
         cache = self._lin_cache.get(id(lin))
         if cache is None:
             cache = self._lin_cache[id(lin)] = SF.LinearCache()
-        return SF.linear(x, lin.weight, lin.bias, cache, self._impl, residual)
+        return SF.linear(x, lin.weight, lin.bias, cache, self._impl, residual, a_tf32)
+
+    def _tc(self):
+        """do the convolutions of this call run on the tensor cores (then their BatchNorm producers round to TF32)"""
+        return self._impl != ops.CONV_SIMT
 
     def _point_block(self, pb: PointBlock, z1, z):
-        return self._linear(pb.conv[2], self._bn_act(pb.conv[0], z), residual=z1)
+        lin = pb.conv[2]
+        tc = self._tc() and self.training and bool(ops.umma_supported(1, lin.in_features, lin.out_features))
+        return self._linear(lin, self._bn_act(pb.conv[0], z, tf32=tc), residual=z1, a_tf32=tc)
 
     def _attention(self, blk: SparseAttention, x, geo: Geometry, s):
         """models/modules/transformer.py:118-125: x + proj(attention(qkv(LayerNorm(x)))) per cloud -- rows of a level are
@@ -296,14 +302,17 @@ class SPVUnet(nn.Module):
     def _res_block(self, blk: EmbResBlock, x_in, emb_act, geo: Geometry, s):
         lv = geo.level(s)
         fast = self._fast()
-        x = blk.conv1[2](self._bn_act(blk.conv1[0], x_in, tf32=fast), lv.kmap3, fast)
+        # BatchNorm rounds its output to TF32 for the tensor-core conv that consumes it (inference kernels and the
+        # training-mode kernels do; the plain-torch eval-with-autograd branch of _bn_act does not)
+        tc = fast or (self._tc() and self.training)
+        x = blk.conv1[2](self._bn_act(blk.conv1[0], x_in, tf32=tc), lv.kmap3, tc)
         tt = self._linear(blk.t_emb.proj_mlp, emb_act)                      # [B, 2C]
         if fast:
             x = ops.film(x, tt.contiguous(), lv.coords)
         else:
             x = SF.film(x, tt, lv.coords, geo.batch_offsets(s), max(lv.batch_counts_host))
         res = self._linear(blk.idconv, x_in) if hasattr(blk, "idconv") else x_in
-        x = blk.conv2[2](self._bn_act(blk.conv2[0], x, tf32=fast), lv.kmap3, fast, residual=res)
+        x = blk.conv2[2](self._bn_act(blk.conv2[0], x, tf32=tc), lv.kmap3, tc, residual=res)
         if hasattr(blk, "attn"):
             x = self._attention(blk.attn, x, geo, s)
         return x
@@ -407,8 +416,9 @@ class SPVUnet(nn.Module):
         x = p2v(z, 1)                                                        # initial_voxelize
         st = self.stem_conv
         x = st.voxel_conv[0](x, geo.level(1).kmap3)
-        x = self._bn_act(st.voxel_conv[1], x, tf32=self._fast())
-        x = st.voxel_conv[3](x, geo.level(1).kmap3, self._fast())
+        tc = self._fast() or (self._tc() and self.training)
+        x = self._bn_act(st.voxel_conv[1], x, tf32=tc)
+        x = st.voxel_conv[3](x, geo.level(1).kmap3, tc)
         z = self._point_block(st.point_conv, v2p(x, 1), z)
         x = p2v(z, 1)
         saved = [x]

@@ -35,7 +35,7 @@ class _SparseConv(torch.autograd.Function):
                            kmap.mask if kmap is not None else None, n_out, bias, impl, a_tf32=a_tf32,
                            residual=residual.contiguous() if residual is not None else None)
         ctx.save_for_backward(x, weight)
-        ctx.kmap, ctx.impl, ctx.has_bias = kmap, impl, bias is not None
+        ctx.kmap, ctx.impl, ctx.has_bias, ctx.a_tf32 = kmap, impl, bias is not None, bool(a_tf32)
         return out
 
     @staticmethod
@@ -44,29 +44,16 @@ class _SparseConv(torch.autograd.Function):
         kmap, impl = ctx.kmap, ctx.impl
         if kmap is not None:
             kmap.check_current()
-        g = g.contiguous()
         w3 = (weight if weight.dim() == 3 else weight.unsqueeze(0)).contiguous()
-        kvol, cin, cout = w3.shape
-        gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            flip = kmap.flip if kmap is not None else False
-            wt = ops.transpose_weights(w3, flip)                       # [kvol, cout, cin]
-            use_umma = impl != ops.CONV_SIMT and ops.umma_supported(kvol, cout, cin)
-            wtp = ops.pack_weights(wt) if use_umma else None
-            gm = kmap.grad if kmap is not None else None
-            n_in = kmap.n_in if kmap is not None else g.shape[0]
-            gx = ops.conv_fwd(g, wt, wtp, gm.map_t if gm is not None else None, gm.mask if gm is not None else None,
-                              n_in, None, ops.CONV_AUTO if use_umma else ops.CONV_SIMT)
-        if ctx.needs_input_grad[1]:
-            n_out = kmap.n_out if kmap is not None else x.shape[0]
-            if impl != ops.CONV_SIMT and ops.umma_supported(kvol, cin, cout):
-                # tensor cores: reduction over the pair lists, TF32 operands (rounded here), fp32 accumulation
-                gw = ops.conv_wgrad_umma(ops.round_tf32(x), ops.round_tf32(g), kmap.pairs() if kmap is not None else None,
-                                         n_out, kvol).view_as(weight)
-            else:
-                gw = ops.conv_wgrad(x, g, kmap.map_t if kmap is not None else None, n_out, kvol).view_as(weight)
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = ops.colsum(g)
+        n_out = kmap.n_out if kmap is not None else x.shape[0]
+        n_in = kmap.n_in if kmap is not None else g.shape[0]
+        # one C call: TF32-rounded gradient -> data gradient (cp.async gather) + weight gradient (tcgen05 over the pair
+        # lists; x was rounded by its producer when the forward ran with a_tf32) + bias gradient
+        gx, gw, gb = ops.conv_bwd(x, g.contiguous(), w3, kmap, n_in, n_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                  ctx.has_bias and ctx.needs_input_grad[2], x_is_tf32=ctx.a_tf32,
+                                  tensor_cores=impl != ops.CONV_SIMT)
+        if gw is not None:
+            gw = gw.view_as(weight)
         return gx, gw, gb, None, None, None, None, (g if ctx.needs_input_grad[7] else None)
 
 
@@ -141,40 +128,30 @@ class _Linear(torch.autograd.Function):
     sum; an optional residual rides on the epilogue."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, cache, impl, residual):
+    def forward(ctx, x, weight, bias, cache, impl, residual, a_tf32=False):
         x = x.contiguous()
         umma = impl != ops.CONV_SIMT and ops.umma_supported(1, weight.shape[1], weight.shape[0])
         w3, wp = cache.get(weight, umma)
         out = ops.conv_fwd(x, w3, wp, None, None, x.shape[0], bias, ops.CONV_AUTO if umma else ops.CONV_SIMT,
-                           residual=residual.contiguous() if residual is not None else None)
-        ctx.save_for_backward(x, weight)
-        ctx.impl, ctx.has_bias = impl, bias is not None
+                           a_tf32=bool(a_tf32) and umma, residual=residual.contiguous() if residual is not None else None)
+        ctx.save_for_backward(x, weight, w3)
+        ctx.impl, ctx.has_bias, ctx.a_tf32 = impl, bias is not None, bool(a_tf32)
         return out
 
     @staticmethod
     def backward(ctx, g):
-        x, weight = ctx.saved_tensors
-        g = g.contiguous()
-        cout, cin = weight.shape
-        gx = gw = gb = None
-        if ctx.needs_input_grad[0]:
-            wt = weight.detach().unsqueeze(0).contiguous()                         # [1, out, in]: the transposed conv weight
-            umma = ctx.impl != ops.CONV_SIMT and ops.umma_supported(1, cout, cin)
-            gx = ops.conv_fwd(g, wt, ops.pack_weights(wt) if umma else None, None, None, g.shape[0], None,
-                              ops.CONV_AUTO if umma else ops.CONV_SIMT)
-        if ctx.needs_input_grad[1]:
-            if ctx.impl != ops.CONV_SIMT and ops.umma_supported(1, cin, cout):
-                gw3 = ops.conv_wgrad_umma(ops.round_tf32(x), ops.round_tf32(g), None, x.shape[0], 1)
-            else:
-                gw3 = ops.conv_wgrad(x, g, None, x.shape[0], 1)
-            gw = ops.transpose_weights(gw3, False)[0]                              # [in, out] -> [out, in]
-        if ctx.has_bias and ctx.needs_input_grad[2]:
-            gb = ops.colsum(g)
-        return gx, gw, gb, None, None, (g if ctx.needs_input_grad[5] else None)
+        x, weight, w3 = ctx.saved_tensors                                       # w3 = [1, in, out] (the conv layout)
+        gx, gw, gb = ops.conv_bwd(x, g.contiguous(), w3, None, x.shape[0], x.shape[0], ctx.needs_input_grad[0],
+                                  ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2], x_is_tf32=ctx.a_tf32,
+                                  gw_transposed=True, tensor_cores=ctx.impl != ops.CONV_SIMT)
+        if gw is not None:
+            gw = gw[0]                                                           # [out, in], nn.Linear's layout
+        return gx, gw, gb, None, None, (g if ctx.needs_input_grad[5] else None), None
 
 
-def linear(x, weight, bias, cache, impl=ops.CONV_AUTO, residual=None):
-    return _Linear.apply(x, weight, bias, cache, impl, residual)
+def linear(x, weight, bias, cache, impl=ops.CONV_AUTO, residual=None, a_tf32=False):
+    """a_tf32: x is already TF32-representable (its producer rounded it)"""
+    return _Linear.apply(x, weight, bias, cache, impl, residual, a_tf32)
 
 
 class _BatchNormAct(torch.autograd.Function):
@@ -195,9 +172,12 @@ class _BatchNormAct(torch.autograd.Function):
         return gx, gg, gb, None, None, None, None, None
 
 
-def batch_norm_act(x, bn, act=True):
+def batch_norm_act(x, bn, act=True, round_tf32=False):
+    """round_tf32: also round the result to TF32 (it is the operand of a tensor-core convolution, which would round it in
+    its gather anyway: the forward value is the same, the gather becomes a plain cp.async and the weight gradient can use
+    the saved tensor as it is)"""
     return _BatchNormAct.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, bn.eps,
-                               bn.momentum if bn.momentum is not None else 0.1, 1 if act else 0)
+                               bn.momentum if bn.momentum is not None else 0.1, (1 if act else 0) | (2 if round_tf32 else 0))
 
 
 class _FiLM(torch.autograd.Function):

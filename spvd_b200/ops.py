@@ -601,3 +601,48 @@ def mse_loss(pred, target, want_grad=True, grad_scale=1.0):
     check(lib.spvd_mse_loss(_p(pred, torch.float32), _p(target, torch.float32), pred.numel(), float(grad_scale), _p(loss), _p(gp),
                             _p(train_ws(pred.device)), _s()))
     return loss, gp
+
+
+class ConvBwdArgs(ctypes.Structure):
+    """spvd_conv_bwd_args_t (include/spvd_b200.h)"""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("x", "g", "w", "map_t", "gmap_t", "gmap_mask", "pair_in", "pair_out", "pair_tile_k",
+                                               "gx", "gw", "gbias", "workspace", "red_workspace")] + \
+               [("workspace_bytes", ctypes.c_size_t)] + \
+               [(n, ctypes.c_int32) for n in ("map_ld", "gmap_ld", "n_pair_tiles", "n_in", "n_out", "kvol", "cin", "cout", "flip",
+                                              "x_is_tf32", "gw_transposed", "allow_tensor_cores")]
+
+
+_K["conv_bwd"] = 8
+_BWD_WS = {}
+
+
+def conv_bwd(x, g, w3, kmap, n_in, n_out, want_gx, want_gw, want_gb, x_is_tf32=False, gw_transposed=False, tensor_cores=True):
+    """The whole backward of a sparse convolution / Linear in one C call (spvd_conv_bwd).  w3 [kvol, cin, cout];
+    kmap = geometry.KernelMap of the forward conv or None (kernel size 1).  -> (gx, gw, gbias), None where not wanted;
+    gw is [kvol, cin, cout], or [kvol, cout, cin] with gw_transposed."""
+    _count("conv_bwd")
+    kvol, cin, cout = w3.shape
+    dev = g.device
+    a = ConvBwdArgs()
+    need = lib.spvd_conv_bwd_workspace_bytes(int(n_in), int(n_out), kvol, cin, cout)
+    ws = _BWD_WS.get(dev)
+    if ws is None or ws.numel() < need:             # one scratch per device, grown to the largest layer (stream-ordered reuse)
+        ws = _BWD_WS[dev] = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=dev)
+    gx = torch.empty((n_in, cin), dtype=torch.float32, device=dev) if want_gx else None
+    gw = torch.empty((kvol, cout, cin) if gw_transposed else (kvol, cin, cout), dtype=torch.float32, device=dev) if want_gw else None
+    gb = torch.empty(cout, dtype=torch.float32, device=dev) if want_gb else None
+    a.x, a.g, a.w = _p(x), _p(g, torch.float32), _p(w3, torch.float32)
+    if kmap is not None:
+        gm = kmap.grad
+        a.map_t, a.map_ld = _p(kmap.map_t), kmap.map_t.shape[1]
+        a.gmap_t, a.gmap_mask, a.gmap_ld = _p(gm.map_t), _p(gm.mask), gm.map_t.shape[1]
+        a.flip = 1 if kmap.flip else 0
+        if want_gw and tensor_cores and umma_supported(kvol, cin, cout):
+            pin, pout, tk, nt = kmap.pairs()
+            a.pair_in, a.pair_out, a.pair_tile_k, a.n_pair_tiles = _p(pin), _p(pout), _p(tk), int(nt)
+    a.gx, a.gw, a.gbias = _p(gx), _p(gw), _p(gb)
+    a.workspace, a.workspace_bytes, a.red_workspace = _p(ws), ws.numel(), _p(train_ws(dev))
+    a.n_in, a.n_out, a.kvol, a.cin, a.cout = int(n_in), int(n_out), kvol, cin, cout
+    a.x_is_tf32, a.gw_transposed, a.allow_tensor_cores = int(bool(x_is_tf32)), int(bool(gw_transposed)), int(bool(tensor_cores))
+    check(lib.spvd_conv_bwd(ctypes.byref(a), _s()))
+    return gx, gw, gb
