@@ -49,7 +49,7 @@ def parse():
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-flush", action="store_true")
-    ap.add_argument("--train-steps", type=int, default=6, help="timed steps of the training sub-record (0 = skip)")
+    ap.add_argument("--train-steps", type=int, default=8, help="timed steps of the training sub-record (0 = skip)")
     ap.add_argument("--no-tf32-leg", action="store_true")
     return ap.parse_args()
 
@@ -363,7 +363,7 @@ def run_train_leg(args, dev, world, rank, xs_dev, flush):
     import spvd_b200
     from spvd_b200.parallel import GradientAllReduce, train_step
     from spvd_b200.sampler import torch2sparse
-    B, N, K, W = args.batch, args.points, args.train_steps, 2
+    B, N, K, W = args.batch, args.points, args.train_steps, 4     # (the first NCCL all-reduces of a new buffer set up connections)
     torch.manual_seed(0)
     model = spvd_b200.build_model(args.preset, downsample_mode=args.downsample_mode).to(dev).train()
     opt = torch.optim.Adam(model.parameters(), lr=1e-4)
@@ -391,6 +391,8 @@ def run_train_leg(args, dev, world, rank, xs_dev, flush):
     if world > 1:
         dist.barrier()
     total = sum(a.elapsed_time(b) for a, b in ev)
+    if os.environ.get("SPVD_BENCH_VERBOSE"):
+        print(f"[train rank {rank}] per-step ms: " + " ".join(f"{a.elapsed_time(b):.1f}" for a, b in ev), file=sys.stderr)
     # exposed all-reduce time: the same steps with the collective switched off (identical kernels otherwise)
     exposed = None
     if world > 1:

@@ -270,7 +270,9 @@ class SPVUnet(nn.Module):
                 self._folded[key] = hit
             if self._fast():
                 return ops.affine_act(x.contiguous(), hit[1], hit[2], (1 if act else 0) | (2 if tf32 else 0))
-            y = x * hit[1] + hit[2]                      # eval mode with autograd (frozen statistics): plain torch
+            # eval mode with autograd (frozen statistics, trainable affine): plain torch, gradients reach weight / bias
+            scale = bn.weight * torch.rsqrt(bn.running_var + bn.eps)
+            y = x * scale + (bn.bias - bn.running_mean * scale)
             return F.silu(y) if act else y
         return SF.batch_norm_act(x, bn, act, round_tf32=tf32)
 

@@ -1,0 +1,44 @@
+"""Kernel-time breakdown of one sampling step (SPVD, B=32x2048, executor): torch profiler, CUDA activity.
+usage: python tools/step_profile.py"""
+import os, sys, collections, time
+import torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench, spvd_b200
+from spvd_b200.sampler import DDPMSparseSchedulerGPU
+from torch.profiler import ProfilerActivity, profile
+
+dev = torch.device("cuda", 0)
+torch.manual_seed(0)
+model = spvd_b200.build_model("SPVD").to(dev).eval()
+sched = DDPMSparseSchedulerGPU()
+B, N = 32, 2048
+strat, xs, ts = bench.make_workload(12, B, N, 1234)
+xs = [x.to(dev) for x in xs]
+def step(j):
+    st = sched.torch2sparse(xs[j], (B, N, 3))
+    tb = torch.full((B,), ts[j], device=dev, dtype=torch.long)
+    eps = model((st, tb))
+    return sched.update_rule(st, eps, ts[j], j, (B, N, 3), dev)
+with torch.no_grad():
+    for j in range(4):
+        step(j)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for j in range(4, 8):
+        step(j)
+    torch.cuda.synchronize()
+    print("wall ms/step", (time.perf_counter() - t0) * 1e3 / 4)
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        step(8)
+        torch.cuda.synchronize()
+ev = [e for e in prof.events() if "cuda" in str(getattr(e, "device_type", "")).lower()]
+tot = collections.defaultdict(lambda: [0, 0.0])
+for e in ev:
+    k = e.name.split("(")[0][:80]
+    tot[k][0] += 1
+    tot[k][1] += e.device_time
+all_us = sum(v[1] for v in tot.values())
+t_lo = min(e.time_range.start for e in ev); t_hi = max(e.time_range.end for e in ev)
+print(f"GPU kernel time {all_us/1e3:.3f} ms in {len(ev)} launches; first-to-last {(t_hi - t_lo)/1e3:.3f} ms")
+for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])[:45]:
+    print(f"{v[1]/1e3:8.3f} ms {v[0]:5d}  {k}")

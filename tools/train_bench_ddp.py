@@ -16,7 +16,7 @@ if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0); model = spvd_b200.build_model("SPVD"); model = model.to(dev).train()
 opt = torch.optim.Adam(model.parameters(), lr=1e-4)
-red = GradientAllReduce(model.parameters()) if world > 1 else None
+red = GradientAllReduce(model.parameters(), overlap=os.environ.get('SPVD_DDP_OVERLAP', '1') == '1')
 W = 3
 strat, xs, ts = bench.make_workload(steps + W, 32, 2048, 7 + rank)
 times = []
