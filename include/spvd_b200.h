@@ -600,6 +600,7 @@ typedef struct spvd_conv_bwd_args {
   double* red_workspace;
   size_t workspace_bytes;
   int32_t map_ld, gmap_ld, n_pair_tiles, n_in, n_out, kvol, cin, cout, flip, x_is_tf32, gw_transposed, allow_tensor_cores;
+  int32_t n_pairs, pad; /* valid pairs in the lists (0 = unknown): the data gradient runs pair-major when n_pairs < 10 n_in */
 } spvd_conv_bwd_args_t;
 size_t spvd_conv_bwd_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout);
 int spvd_conv_bwd(const spvd_conv_bwd_args_t* args, spvd_stream_t stream);

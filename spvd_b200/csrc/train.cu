@@ -789,6 +789,37 @@ extern "C" int spvd_mse_loss(const float* pred, const float* target, long long n
   return SPVD_OK;
 }
 
+// y = x rounded to TF32 (cvt.rna) and, in the same pass, the column sums of x (bias gradient)
+__global__ void __launch_bounds__(kRedThreads) k_round_colsum(const float* __restrict__ x, long long rows, int c, int rpc,
+                                                              float* __restrict__ y, double* __restrict__ tot) {
+  col_reduce2(rows, c, rpc, tot, [&](long long r, int ch, float* a, float* b) {
+    const float v = x[r * c + ch];
+    unsigned q;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q) : "f"(v));
+    y[r * c + ch] = __uint_as_float(q);
+    *a += v;
+    (void)b;
+  });
+}
+
+// tensor-core tile image (K-major SWIZZLE_128B, TF32-rounded: the layout of spvd_conv_pack_weights) of the TRANSPOSED
+// weights W'[k'][co][ci] = W[k][ci][co], k = K-1-k' when flip -- the data-gradient weights, without materialising W'
+__global__ void k_pack_weights_transposed(const float* __restrict__ w, int kvol, int cin, int cout, int flip,
+                                          float* __restrict__ wp) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)kvol * cin * cout) return;
+  const int n = (int)(t % cin);                 // output channel of the data gradient = input channel of the forward
+  const long long q = t / cin;
+  const int ci = (int)(q % cout);               // its input channel = forward output channel
+  const int kp = (int)(q / cout);
+  const int k = flip ? kvol - 1 - kp : kp;
+  const int c = ci / 32, kk = ci % 32;
+  const size_t dst = ((size_t)(kp * (cout / 32) + c) * cin + n) * 32 + ((((kk >> 2) ^ (n & 7)) << 2) | (kk & 3));
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(w[((size_t)k * cin + n) * cout + ci]));
+  wp[dst] = __uint_as_float(r);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Whole backward of one sparse convolution / nn.Linear from ONE host call: TF32 rounding of the output gradient, weight
 // transpose + tile image, data gradient (the forward kernels on the transposed weights and the gradient map), weight
@@ -807,6 +838,8 @@ int spvd_conv_fwd_simt(const float*, const float*, const int32_t*, int, const ui
 int spvd_conv_wgrad_umma(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int,
                          float*, spvd_stream_t);
 int spvd_conv_wgrad(const float*, const float*, const int32_t*, int, int, int, int, int, float*, spvd_stream_t);
+int spvd_conv_fwd_pairs(const float*, const float*, const int32_t*, const int32_t*, const int32_t*, int, int, int, int, int, int,
+                        const float*, const float*, float*, int, spvd_stream_t);
 }
 
 static inline size_t al256(size_t b) { return (b + 255) / 256 * 256; }
@@ -833,19 +866,38 @@ extern "C" int spvd_conv_bwd(const spvd_conv_bwd_args_t* args, spvd_stream_t str
   const bool umma_d = tc && a.gx && spvd_conv_umma_supported(a.kvol, a.cout, a.cin);
   const bool umma_w = tc && a.gw && spvd_conv_umma_supported(a.kvol, a.cin, a.cout);
   int rc = SPVD_OK;
+  cudaStream_t s = (cudaStream_t)stream;
   const float* g_tc = a.g;
+  bool bias_done = false;
   if ((umma_d || umma_w) && a.n_out > 0) {
-    if ((rc = spvd_round_tf32(a.g, gr, (long long)a.n_out * a.cout, stream)) != SPVD_OK) return rc;
+    if (a.gbias) {       // rounding pass and bias gradient share one read of g
+      const int rpc = red_rows_per_cta(a.n_out);
+      k_round_colsum<<<cdiv(a.n_out, rpc), kRedThreads, 0, s>>>(a.g, a.n_out, a.cout, rpc, gr, a.red_workspace);
+      k_f64_to_f32<<<cdiv(2 * a.cout, 256), 256, 0, s>>>(a.red_workspace, a.cout, 2 * a.cout, a.gbias);
+      SPVD_LAUNCH_CHECK();
+      bias_done = true;
+    } else if ((rc = spvd_round_tf32(a.g, gr, (long long)a.n_out * a.cout, stream)) != SPVD_OK) {
+      return rc;
+    }
     g_tc = gr;
   }
   if (a.gx) {
     // data gradient: out' = in, W'[k'] = W[k]^T (k' = K-1-k for submanifold maps), map = the gradient map
-    if ((rc = spvd_conv_transpose_weights(a.w, a.kvol, a.cin, a.cout, a.flip, wt, stream)) != SPVD_OK) return rc;
     if (umma_d) {
-      if ((rc = spvd_conv_pack_weights(wt, a.kvol, a.cout, a.cin, wtp, stream)) != SPVD_OK) return rc;
-      rc = spvd_conv_fwd_umma(g_tc, wtp, a.gmap_t, a.gmap_ld, a.gmap_mask, a.n_in, a.kvol, a.cout, a.cin, nullptr, nullptr, a.gx, 0, 0,
-                              SPVD_A_TF32, 0, stream);
+      // sparse levels (few active offsets per voxel): pair-major on the forward pair list with the roles swapped
+      const bool pairs = a.pair_in && a.pair_out && a.pair_tile_k && a.n_pair_tiles > 0 && a.n_pairs > 0 &&
+                         (long long)a.n_pairs < 10ll * a.n_in;
+      const long long total = (long long)a.kvol * a.cin * a.cout;
+      k_pack_weights_transposed<<<cdiv(total, 256), 256, 0, s>>>(a.w, a.kvol, a.cin, a.cout, pairs ? 0 : a.flip, wtp);
+      SPVD_LAUNCH_CHECK();
+      if (pairs)
+        rc = spvd_conv_fwd_pairs(g_tc, wtp, a.pair_out, a.pair_in, a.pair_tile_k, a.n_pair_tiles, -1, a.n_in, a.kvol, a.cout, a.cin,
+                                 nullptr, nullptr, a.gx, SPVD_A_TF32, stream);
+      else
+        rc = spvd_conv_fwd_umma(g_tc, wtp, a.gmap_t, a.gmap_ld, a.gmap_mask, a.n_in, a.kvol, a.cout, a.cin, nullptr, nullptr, a.gx, 0,
+                                0, SPVD_A_TF32, 0, stream);
     } else {
+      if ((rc = spvd_conv_transpose_weights(a.w, a.kvol, a.cin, a.cout, a.flip, wt, stream)) != SPVD_OK) return rc;
       rc = spvd_conv_fwd_simt(a.g, wt, a.gmap_t, a.gmap_ld, a.gmap_mask, a.n_in, a.kvol, a.cout, a.cin, nullptr, nullptr, a.gx, stream);
     }
     if (rc != SPVD_OK) return rc;
@@ -867,6 +919,6 @@ extern "C" int spvd_conv_bwd(const spvd_conv_bwd_args_t* args, spvd_stream_t str
     if (a.gw_transposed)     // nn.Linear keeps [out, in]: [1, in, out] -> [1, out, in]
       if ((rc = spvd_conv_transpose_weights(gw3, a.kvol, a.cin, a.cout, 0, a.gw, stream)) != SPVD_OK) return rc;
   }
-  if (a.gbias) rc = spvd_colsum(a.g, a.n_out, a.cout, a.gbias, a.red_workspace, stream);
+  if (a.gbias && !bias_done) rc = spvd_colsum(a.g, a.n_out, a.cout, a.gbias, a.red_workspace, stream);
   return rc;
 }

@@ -31,9 +31,15 @@ class _SparseConv(torch.autograd.Function):
             wp = ops.pack_weights(w3)
         n_out = kmap.n_out if kmap is not None else x.shape[0]
         x = x.contiguous()
-        out = ops.conv_fwd(x, w3, wp, kmap.map_t if kmap is not None else None,
-                           kmap.mask if kmap is not None else None, n_out, bias, impl, a_tf32=a_tf32,
-                           residual=residual.contiguous() if residual is not None else None)
+        res = residual.contiguous() if residual is not None else None
+        if (wp is not None and kmap is not None and kmap.n_pairs and kmap.n_pairs < 10 * n_out and kmap._pairs is not None
+                and (kmap.kvol % 2 == 1 or (bias is None and res is None))):
+            # sparse level (few active offsets per voxel): pair-major tensor-core kernel, as the inference executor chooses
+            pin, pout, tk, nt = kmap._pairs
+            out = ops.conv_fwd_pairs(x, w3, wp, pin, pout, tk, nt, n_out, bias, res, a_tf32=a_tf32)
+        else:
+            out = ops.conv_fwd(x, w3, wp, kmap.map_t if kmap is not None else None,
+                               kmap.mask if kmap is not None else None, n_out, bias, impl, a_tf32=a_tf32, residual=res)
         ctx.save_for_backward(x, weight)
         ctx.kmap, ctx.impl, ctx.has_bias, ctx.a_tf32 = kmap, impl, bias is not None, bool(a_tf32)
         return out

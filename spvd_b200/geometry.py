@@ -18,13 +18,14 @@ class KernelMap:
     """Offset-major map [kvol, ld] (+ per-128-row-tile offset mask) of one sparse convolution and the
     map of its data gradient."""
 
-    __slots__ = ("map_t", "mask", "n_out", "n_in", "kvol", "grad", "flip", "_pairs", "_ws", "_gen")
+    __slots__ = ("map_t", "mask", "n_out", "n_in", "kvol", "grad", "flip", "_pairs", "_ws", "_gen", "n_pairs")
 
     def __init__(self, map_t, mask, n_out, n_in, kvol, flip):
         self.map_t, self.mask, self.n_out, self.n_in, self.kvol, self.flip = map_t, mask, n_out, n_in, kvol, flip
         self.grad = None   # KernelMap that produces d(in) from d(out)
         self._pairs = None
         self._ws, self._gen = None, 0     # PlanWorkspace whose buffers this map views, and its build generation
+        self.n_pairs = 0                  # valid (in, out) pairs, when the planner counted them (pair-major kernels)
 
     def check_current(self):
         """Maps planned by a PlanWorkspace are VIEWS of its persistent buffers: a later build of the same workspace
@@ -449,6 +450,7 @@ class PlanWorkspace:
                     lv.kmap3_sorted = (b["kmap3_sorted"], b["mask3_sorted"], b["perm3"])
                 if "pair_in" in b:       # the weight-gradient kernel reduces over the planner's pair list: no lazy build, no sync
                     lv.kmap3._pairs = lv.pairs[:4]
+                    lv.kmap3.n_pairs = lv.pairs[4]
         for i in range(max(lo - 1, 0), hi - 1):           # stride-2 maps between level i and i + 1 (planned with level i + 1)
             b, lv, c = self.bufs[i], geo.levels[self.strides[i]], geo.levels[self.strides[i + 1]]
             if "dpair_in" in b:
@@ -464,3 +466,4 @@ class PlanWorkspace:
                     dp = lv.dpairs
                     lv.kmap_down._pairs = (dp[0], dp[1], dp[2], dp[3])
                     lv.kmap_up._pairs = (dp[1], dp[0], dp[2], dp[3])
+                    lv.kmap_down.n_pairs = lv.kmap_up.n_pairs = dp[4]

@@ -609,7 +609,7 @@ class ConvBwdArgs(ctypes.Structure):
                                                "gx", "gw", "gbias", "workspace", "red_workspace")] + \
                [("workspace_bytes", ctypes.c_size_t)] + \
                [(n, ctypes.c_int32) for n in ("map_ld", "gmap_ld", "n_pair_tiles", "n_in", "n_out", "kvol", "cin", "cout", "flip",
-                                              "x_is_tf32", "gw_transposed", "allow_tensor_cores")]
+                                              "x_is_tf32", "gw_transposed", "allow_tensor_cores", "n_pairs", "pad")]
 
 
 _K["conv_bwd"] = 8
@@ -637,9 +637,10 @@ def conv_bwd(x, g, w3, kmap, n_in, n_out, want_gx, want_gw, want_gb, x_is_tf32=F
         a.map_t, a.map_ld = _p(kmap.map_t), kmap.map_t.shape[1]
         a.gmap_t, a.gmap_mask, a.gmap_ld = _p(gm.map_t), _p(gm.mask), gm.map_t.shape[1]
         a.flip = 1 if kmap.flip else 0
-        if want_gw and tensor_cores and umma_supported(kvol, cin, cout):
+        if tensor_cores and ((want_gw and umma_supported(kvol, cin, cout)) or kmap.n_pairs):
             pin, pout, tk, nt = kmap.pairs()
             a.pair_in, a.pair_out, a.pair_tile_k, a.n_pair_tiles = _p(pin), _p(pout), _p(tk), int(nt)
+            a.n_pairs = int(kmap.n_pairs or 0)
     a.gx, a.gw, a.gbias = _p(gx), _p(gw), _p(gb)
     a.workspace, a.workspace_bytes, a.red_workspace = _p(ws), ws.numel(), _p(train_ws(dev))
     a.n_in, a.n_out, a.kvol, a.cin, a.cout = int(n_in), int(n_out), kvol, cin, cout
