@@ -35,8 +35,15 @@ for i, r in enumerate(data):
                     regs=int(g(r, 'launch__registers_per_thread')), smem_dyn_KB=round(sm, 1)))
     tot_t += dur_us
     tot_b += rd + wr
+tc = [o for o in out if any(k in o["kernel"] for k in ("k_conv_fwd_umma", "k_conv_pairs_persistent", "k_conv_sp_f16"))]
+tc_bytes = sum((o["dram_read_MB"] + o["dram_write_MB"]) * 1e6 for o in tc)
+date = sys.argv[3] if len(sys.argv) > 3 else "n/a"
 json.dump({"source": f"{name} (ncu --set full --clock-control none --import-source on, all conv launches of one SPVD denoising step "
-                     "B=32x2048, t=997 geometry, cold caches; f16-operand kernels: one-tile 2-CTA/SM, persistent pair-major, split-K)",
+                     f"B=32x2048, t=997 geometry, cold caches, captured {date}; f16-operand kernels: one-tile 2-CTA/SM, persistent "
+                     "pair-major, sorted-tile persistent with fused epilogue, split-K)",
            "dram_bytes_per_launch": int(tot_b / len(data)), "launches": len(data), "total_duration_us": round(tot_t, 1),
+           "dram_bytes_per_umma_launch": int(tc_bytes / max(len(tc), 1)), "umma_launches": len(tc),
+           "umma_total_duration_us": round(sum(o["duration_us"] for o in tc), 1),
            "per_launch": out}, open('profiles/conv_umma_traffic.json', 'w'), indent=1)
-print(len(data), "launches,", round(tot_t, 1), "us,", int(tot_b / len(data)), "DRAM bytes per launch")
+print(len(data), "launches,", round(tot_t, 1), "us,", int(tot_b / len(data)), "DRAM bytes per launch;", len(tc), "tcgen05 launches,",
+      int(tc_bytes / max(len(tc), 1)), "DRAM bytes per tcgen05 launch")
