@@ -7,6 +7,30 @@ import torch
 from . import ops
 
 
+# ------------------------------------------------------------------------------------------------------------------
+# In-place parameter gradients.  With a parallel.GradientAllReduce attached, every parameter's .grad is a slot of one flat
+# buffer that is zeroed once per step.  A backward below then lets its kernel write the parameter gradient straight into
+# that slot and returns None to autograd: no temporary, no AccumulateGrad add (one elementwise launch per parameter and
+# step, 276 for SPVD), and the reducer learns that the slot is final.  Only for a parameter used exactly once since the
+# last zero_grad() (a second use, or a second backward without zero_grad, goes through autograd's accumulation as usual).
+# ------------------------------------------------------------------------------------------------------------------
+def _use(p):
+    sink = getattr(p, "_spvd_sink", None)
+    if sink is not None:
+        sink.note_use(p)
+    return p
+
+
+def _claim(p, wanted=True):
+    sink = getattr(p, "_spvd_sink", None) if (wanted and p is not None) else None
+    return sink.claim(p) if sink is not None else None
+
+
+def _wrote(*ps):
+    for p in ps:
+        p._spvd_sink.wrote(p)
+
+
 class PackedWeight:
     """Tensor-core tile image of a conv weight, rebuilt when the parameter changes (optimizer step)."""
 
@@ -42,12 +66,16 @@ class _SparseConv(torch.autograd.Function):
                                kmap.mask if kmap is not None else None, n_out, bias, impl, a_tf32=a_tf32, residual=res)
         ctx.save_for_backward(x, weight)
         ctx.kmap, ctx.impl, ctx.has_bias, ctx.a_tf32 = kmap, impl, bias is not None, bool(a_tf32)
+        ctx.params = (_use(weight), _use(bias) if bias is not None else None)
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, weight = ctx.saved_tensors
         kmap, impl = ctx.kmap, ctx.impl
+        p_w, p_b = ctx.params
+        want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+        gw_out, gb_out = _claim(p_w, ctx.needs_input_grad[1]), _claim(p_b, want_gb)
         if kmap is not None:
             kmap.check_current()
         w3 = (weight if weight.dim() == 3 else weight.unsqueeze(0)).contiguous()
@@ -56,10 +84,15 @@ class _SparseConv(torch.autograd.Function):
         # one C call: TF32-rounded gradient -> data gradient (cp.async gather) + weight gradient (tcgen05 over the pair
         # lists; x was rounded by its producer when the forward ran with a_tf32) + bias gradient
         gx, gw, gb = ops.conv_bwd(x, g.contiguous(), w3, kmap, n_in, n_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                  ctx.has_bias and ctx.needs_input_grad[2], x_is_tf32=ctx.a_tf32,
-                                  tensor_cores=impl != ops.CONV_SIMT)
-        if gw is not None:
+                                  want_gb, x_is_tf32=ctx.a_tf32, tensor_cores=impl != ops.CONV_SIMT, gw_out=gw_out, gb_out=gb_out)
+        if gw_out is not None:
+            _wrote(p_w)
+            gw = None
+        elif gw is not None:
             gw = gw.view_as(weight)
+        if gb_out is not None:
+            _wrote(p_b)
+            gb = None
         return gx, gw, gb, None, None, None, None, (g if ctx.needs_input_grad[7] else None)
 
 
@@ -142,16 +175,26 @@ class _Linear(torch.autograd.Function):
                            a_tf32=bool(a_tf32) and umma, residual=residual.contiguous() if residual is not None else None)
         ctx.save_for_backward(x, weight, w3)
         ctx.impl, ctx.has_bias, ctx.a_tf32 = impl, bias is not None, bool(a_tf32)
+        ctx.params = (_use(weight), _use(bias) if bias is not None else None)
         return out
 
     @staticmethod
     def backward(ctx, g):
         x, weight, w3 = ctx.saved_tensors                                       # w3 = [1, in, out] (the conv layout)
+        p_w, p_b = ctx.params
+        want_gb = ctx.has_bias and ctx.needs_input_grad[2]
+        gw_out, gb_out = _claim(p_w, ctx.needs_input_grad[1]), _claim(p_b, want_gb)
         gx, gw, gb = ops.conv_bwd(x, g.contiguous(), w3, None, x.shape[0], x.shape[0], ctx.needs_input_grad[0],
-                                  ctx.needs_input_grad[1], ctx.has_bias and ctx.needs_input_grad[2], x_is_tf32=ctx.a_tf32,
-                                  gw_transposed=True, tensor_cores=ctx.impl != ops.CONV_SIMT)
-        if gw is not None:
+                                  ctx.needs_input_grad[1], want_gb, x_is_tf32=ctx.a_tf32,
+                                  gw_transposed=True, tensor_cores=ctx.impl != ops.CONV_SIMT, gw_out=gw_out, gb_out=gb_out)
+        if gw_out is not None:
+            _wrote(p_w)
+            gw = None
+        elif gw is not None:
             gw = gw[0]                                                           # [out, in], nn.Linear's layout
+        if gb_out is not None:
+            _wrote(p_b)
+            gb = None
         return gx, gw, gb, None, None, (g if ctx.needs_input_grad[5] else None), None
 
 
@@ -169,12 +212,24 @@ class _BatchNormAct(torch.autograd.Function):
         y, stats = ops.bn_train_fwd(x, gamma, beta, eps, momentum, running_mean, running_var, act)
         ctx.save_for_backward(x, gamma, beta, stats)
         ctx.act = act
+        ctx.params = (_use(gamma), _use(beta))
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, gamma, beta, stats = ctx.saved_tensors
-        gx, gg, gb = ops.bn_train_bwd(x, gy.contiguous(), gamma, beta, stats, ctx.act)
+        p_g, p_b = ctx.params
+        gg_out = gb_out = None
+        if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+            gg_out = _claim(p_g)
+            gb_out = _claim(p_b) if gg_out is not None else None
+        gx, gg, gb = ops.bn_train_bwd(x, gy.contiguous(), gamma, beta, stats, ctx.act, gg_out, gb_out)
+        if gg_out is not None:
+            _wrote(p_g)
+            gg = None
+        if gb_out is not None:
+            _wrote(p_b)
+            gb = None
         return gx, gg, gb, None, None, None, None, None
 
 
@@ -213,12 +268,24 @@ class _LayerNorm(torch.autograd.Function):
         x = x.contiguous()
         y, st = ops.layernorm_train_fwd(x, gamma, beta, eps)
         ctx.save_for_backward(x, gamma, st)
+        ctx.params = (_use(gamma), _use(beta))
         return y
 
     @staticmethod
     def backward(ctx, gy):
         x, gamma, st = ctx.saved_tensors
-        gx, gg, gb = ops.layernorm_bwd(x, gy.contiguous(), gamma, st)
+        p_g, p_b = ctx.params
+        gg_out = gb_out = None
+        if ctx.needs_input_grad[1] and ctx.needs_input_grad[2]:
+            gg_out = _claim(p_g)
+            gb_out = _claim(p_b) if gg_out is not None else None
+        gx, gg, gb = ops.layernorm_bwd(x, gy.contiguous(), gamma, st, gg_out, gb_out)
+        if gg_out is not None:
+            _wrote(p_g)
+            gg = None
+        if gb_out is not None:
+            _wrote(p_b)
+            gb = None
         return gx, gg, gb, None
 
 
@@ -286,13 +353,19 @@ class _EmbeddingAdd(torch.autograd.Function):
     def forward(ctx, base, table, idx):
         ctx.save_for_backward(idx)
         ctx.n = table.shape[0]
+        ctx.params = (_use(table),)
         return ops.embedding_fwd(table, idx, base.contiguous())
 
     @staticmethod
     def backward(ctx, g):
         (idx,) = ctx.saved_tensors
         g = g.contiguous()
-        return g, ops.embedding_bwd(g, idx, ctx.n), None
+        out = _claim(ctx.params[0], ctx.needs_input_grad[1])
+        gt = ops.embedding_bwd(g, idx, ctx.n, out)
+        if out is not None:
+            _wrote(ctx.params[0])
+            gt = None
+        return g, gt, None
 
 
 def embedding_add(base, table, idx):

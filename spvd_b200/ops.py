@@ -465,12 +465,13 @@ def bn_train_fwd(x, gamma, beta, eps, momentum, running_mean, running_var, act=1
     return y, stats
 
 
-def bn_train_bwd(x, gy, gamma, beta, stats, act=1):
+def bn_train_bwd(x, gy, gamma, beta, stats, act=1, gg_out=None, gb_out=None):
+    """gg_out / gb_out: write the parameter gradients there (a slot of the flat gradient buffer) instead of new tensors"""
     _count("bn_train_bwd")
     rows, c = x.shape
     gx = torch.empty_like(x)
-    gg = torch.empty(c, dtype=torch.float32, device=x.device)
-    gb = torch.empty(c, dtype=torch.float32, device=x.device)
+    gg = gg_out if gg_out is not None else torch.empty(c, dtype=torch.float32, device=x.device)
+    gb = gb_out if gb_out is not None else torch.empty(c, dtype=torch.float32, device=x.device)
     check(lib.spvd_bn_train_bwd(_p(x, torch.float32), _p(gy, torch.float32), rows, c, _p(gamma), _p(beta), _p(stats[0]),
                                 _p(stats[1]), int(act), _p(gx), _p(gg), _p(gb), _p(train_ws(x.device)), _s()))
     return gx, gg, gb
@@ -503,12 +504,12 @@ def layernorm_train_fwd(x, gamma, beta, eps):
     return y, st
 
 
-def layernorm_bwd(x, gy, gamma, st):
+def layernorm_bwd(x, gy, gamma, st, gg_out=None, gb_out=None):
     _count("layernorm_bwd")
     rows, c = x.shape
     gx = torch.empty_like(x)
-    gg = torch.empty(c, dtype=torch.float32, device=x.device)
-    gb = torch.empty(c, dtype=torch.float32, device=x.device)
+    gg = gg_out if gg_out is not None else torch.empty(c, dtype=torch.float32, device=x.device)
+    gb = gb_out if gb_out is not None else torch.empty(c, dtype=torch.float32, device=x.device)
     check(lib.spvd_layernorm_bwd(_p(x, torch.float32), _p(gy, torch.float32), _p(gamma), _p(st[0]), _p(st[1]), rows, c, _p(gx),
                                  _p(gg), _p(gb), _p(train_ws(x.device)), _s()))
     return gx, gg, gb
@@ -579,9 +580,10 @@ def embedding_fwd(table, idx, base=None):
     return out
 
 
-def embedding_bwd(g, idx, n_rows):
+def embedding_bwd(g, idx, n_rows, out=None):
+    """out: a ZEROED [n_rows, d] tensor to accumulate into (a slot of the flat gradient buffer)"""
     _count("embedding")
-    gt = torch.zeros((n_rows, g.shape[1]), dtype=torch.float32, device=g.device)
+    gt = out if out is not None else torch.zeros((n_rows, g.shape[1]), dtype=torch.float32, device=g.device)
     check(lib.spvd_embedding_bwd(_p(g, torch.float32), _p(idx, torch.int64), idx.shape[0], g.shape[1], _p(gt), _s()))
     return gt
 
@@ -616,10 +618,12 @@ _K["conv_bwd"] = 8
 _BWD_WS = {}
 
 
-def conv_bwd(x, g, w3, kmap, n_in, n_out, want_gx, want_gw, want_gb, x_is_tf32=False, gw_transposed=False, tensor_cores=True):
+def conv_bwd(x, g, w3, kmap, n_in, n_out, want_gx, want_gw, want_gb, x_is_tf32=False, gw_transposed=False, tensor_cores=True,
+             gw_out=None, gb_out=None):
     """The whole backward of a sparse convolution / Linear in one C call (spvd_conv_bwd).  w3 [kvol, cin, cout];
     kmap = geometry.KernelMap of the forward conv or None (kernel size 1).  -> (gx, gw, gbias), None where not wanted;
-    gw is [kvol, cin, cout], or [kvol, cout, cin] with gw_transposed."""
+    gw is [kvol, cin, cout], or [kvol, cout, cin] with gw_transposed.  gw_out / gb_out: contiguous fp32 tensors of those
+    element counts to write the parameter gradients into (slots of the flat gradient buffer)."""
     _count("conv_bwd")
     kvol, cin, cout = w3.shape
     dev = g.device
@@ -629,8 +633,14 @@ def conv_bwd(x, g, w3, kmap, n_in, n_out, want_gx, want_gw, want_gb, x_is_tf32=F
     if ws is None or ws.numel() < need:             # one scratch per device, grown to the largest layer (stream-ordered reuse)
         ws = _BWD_WS[dev] = torch.empty(int(need * 1.25) + 4096, dtype=torch.uint8, device=dev)
     gx = torch.empty((n_in, cin), dtype=torch.float32, device=dev) if want_gx else None
-    gw = torch.empty((kvol, cout, cin) if gw_transposed else (kvol, cin, cout), dtype=torch.float32, device=dev) if want_gw else None
-    gb = torch.empty(cout, dtype=torch.float32, device=dev) if want_gb else None
+    gw = gb = None
+    if want_gw:
+        gw = gw_out if gw_out is not None else torch.empty((kvol, cout, cin) if gw_transposed else (kvol, cin, cout),
+                                                           dtype=torch.float32, device=dev)
+        if gw.numel() != kvol * cin * cout or not gw.is_contiguous() or gw.dtype != torch.float32:
+            raise ValueError("conv_bwd: gw_out must be a contiguous fp32 tensor of kvol*cin*cout elements")
+    if want_gb:
+        gb = gb_out if gb_out is not None else torch.empty(cout, dtype=torch.float32, device=dev)
     a.x, a.g, a.w = _p(x), _p(g, torch.float32), _p(w3, torch.float32)
     if kmap is not None:
         gm = kmap.grad

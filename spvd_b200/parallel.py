@@ -11,6 +11,10 @@ concatenation and no copy-back), cut into contiguous buckets in reverse paramete
 finishes them.  A post-accumulate hook per parameter launches a bucket's all-reduce on the NCCL stream as soon as its
 last gradient is final, i.e. while the rest of backward is still running; ``finish()`` waits for the stragglers and
 the 1 / world average is folded into the clipping scale (one pass over the flat buffer).
+
+The library's own backward functions (spvd_b200/functional.py) go one step further: for a parameter used once per step
+their kernels write the gradient straight INTO its slot (``claim`` / ``wrote`` below) and hand autograd nothing, so there
+is no temporary and no AccumulateGrad add per parameter either.
 """
 from __future__ import annotations
 
@@ -33,8 +37,10 @@ class GradientAllReduce:
             raise ValueError("no parameters to reduce")
         dev, dt = self.params[0].device, self.params[0].dtype
         order = list(reversed(self.params))                      # backward produces the last layers' gradients first
-        self.flat = torch.zeros(sum(p.numel() for p in order), dtype=dt, device=dev)
-        self.buckets, self._bucket_of = [], {}                   # bucket = [lo, hi, pending, n_params, work]
+        pad = lambda n: (n + 63) // 64 * 64                      # slots start on 256-byte boundaries: the backward kernels
+        self.flat = torch.zeros(sum(pad(p.numel()) for p in order), dtype=dt, device=dev)   # store float4s into them; the
+        self.buckets, self._bucket_of = [], {}                   # padding stays zero (neutral for the sum and the norm)
+        self._offsets = {}                                       # bucket = [lo, hi, pending, n_params, work]
         off, lo, size = 0, 0, 0
         for p in order:
             n = p.numel()
@@ -43,8 +49,9 @@ class GradientAllReduce:
                 view.copy_(p.grad)
             p.grad = view
             self._bucket_of[id(p)] = len(self.buckets)
-            off += n
-            size += n * p.element_size()
+            self._offsets[id(p)] = off * p.element_size()
+            off += pad(n)
+            size += pad(n) * p.element_size()
             if size >= bucket_bytes:
                 self.buckets.append([lo, off, 0, 0, None])
                 lo, size = off, 0
@@ -54,10 +61,34 @@ class GradientAllReduce:
             self.buckets[min(self._bucket_of[id(p)], len(self.buckets) - 1)][3] += 1
             self._bucket_of[id(p)] = min(self._bucket_of[id(p)], len(self.buckets) - 1)
         self._hooks = []
+        self.overlap = bool(overlap)
         if overlap and hasattr(torch.Tensor, "register_post_accumulate_grad_hook"):
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._ready))
+        self._uses, self._written = {}, set()
+        self.direct = True                                       # in-place parameter gradients (see claim)
+        for p in self.params:
+            p._spvd_sink = self
         self.reset()
+
+    # -- in-place parameter gradients (called by spvd_b200.functional) ---------------------------------------------
+    def note_use(self, p):
+        self._uses[id(p)] = self._uses.get(id(p), 0) + 1         # (forwards since zero_grad(); grad mode is off inside Function.forward)
+
+    def claim(self, p):
+        """The zeroed slot of ``p``'s gradient if the calling backward may write it in place: p is used once since
+        zero_grad(), nothing has been written yet and .grad still is the slot.  The caller MUST then write the full gradient
+        there, return None to autograd and call ``wrote(p)``."""
+        i = id(p)
+        if (not self.direct or self._uses.get(i, 0) != 1 or i in self._written or i not in self._bucket_of or p.grad is None
+                or p.grad.data_ptr() != self.flat.data_ptr() + self._offset_of(p)):
+            return None
+        self._written.add(i)
+        return p.grad
+
+    def wrote(self, p):
+        if self.overlap:
+            self._ready(p)
 
     # -- per step -------------------------------------------------------------------------------------------------
     def reset(self):
@@ -67,6 +98,8 @@ class GradientAllReduce:
     def zero_grad(self):
         """instead of optimizer.zero_grad(): one memset; the views stay attached"""
         self.flat.zero_()
+        self._uses.clear()
+        self._written.clear()
         self.reset()
 
     def _active(self):
@@ -85,13 +118,7 @@ class GradientAllReduce:
             self._launch(b)
 
     def _offset_of(self, p):
-        off = self.__dict__.setdefault("_offsets", {})
-        if not off:
-            o = 0
-            for q in reversed(self.params):
-                off[id(q)] = o * q.element_size()
-                o += q.numel()
-        return off[id(p)]
+        return self._offsets[id(p)]
 
     def finish(self):
         """All buckets reduced (launching those whose hooks did not fire); returns the factor still owed (1 / world when
