@@ -362,12 +362,13 @@ def run_train_leg(args, dev, world, rank, xs_dev, flush):
     import torch.distributed as dist
     import spvd_b200
     from spvd_b200.parallel import GradientAllReduce, train_step
+    from spvd_b200.optim import FlatAdam
     from spvd_b200.sampler import torch2sparse
     B, N, K, W = args.batch, args.points, args.train_steps, 4     # (the first NCCL all-reduces of a new buffer set up connections)
     torch.manual_seed(0)
     model = spvd_b200.build_model(args.preset, downsample_mode=args.downsample_mode).to(dev).train()
-    opt = torch.optim.Adam(model.parameters(), lr=1e-4)
     red = GradientAllReduce(model.parameters())
+    opt = FlatAdam(red, lr=1e-4)          # flat-buffer Adam + clip + average on the library's kernels
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     ev, ar_ms = [], 0.0
     for j in range(W + K):

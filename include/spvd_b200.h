@@ -621,6 +621,18 @@ int spvd_timestep_embedding(const int64_t* t, int n_batch, int d, float* out, sp
 int spvd_mse_loss(const float* pred, const float* target, long long n, float grad_scale, float* loss, float* gpred,
                   double* workspace, spvd_stream_t stream);
 
+/* Optimizer tail of train_generation.py:106-112 over flat fp32 buffers of n elements (n % 4 == 0, 16-byte aligned; the
+ * gradient buffer of spvd_b200.parallel.GradientAllReduce and the parameter / moment buffers of spvd_b200.optim.FlatAdam):
+ * spvd_sumsq: *acc = sum x^2 (fp64; zeroed by the call).
+ * spvd_adam_step: torch.optim.Adam (utils/... LearnerCallbacks use Adam; no amsgrad) at step `step` (1-based) on
+ * g' = g * scale, scale = pending_scale * min(1, max_norm / (pending_scale * sqrt(*sumsq) + 1e-6)) -- clip_grad_norm_
+ * (utils/callbacks.py:62-63) and the data-parallel 1/world average folded into the same pass; sumsq NULL or
+ * max_norm <= 0 = no clipping.  norm_out (may be NULL) receives the norm of the averaged gradient. */
+int spvd_sumsq(const float* x, long long n, double* acc, spvd_stream_t stream);
+int spvd_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                   float weight_decay, int step, const double* sumsq, float max_norm, float pending_scale, float* norm_out,
+                   spvd_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * N4  evaluation distances between point clouds xyz1 [B,n,3], xyz2 [B,m,3] (fp32, row-major).
  * Chamfer (metrics/chamfer_dist/chamfer.cu:15-229): dist1[b,i] = min_j |xyz1_i - xyz2_j|^2 with its first argmin idx1, and

@@ -76,6 +76,8 @@ SIGNATURES = {
     "spvd_embedding_bwd": (_i, [_p, _p, _i, _i, _p, _p]),
     "spvd_timestep_embedding": (_i, [_p, _i, _i, _p, _p]),
     "spvd_mse_loss": (_i, [_p, _p, _ll, _f, _p, _p, _p, _p]),
+    "spvd_sumsq": (_i, [_p, _ll, _p, _p]),
+    "spvd_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _p, _f, _f, _p, _p]),
     "spvd_conv_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "spvd_conv_bwd": (_i, [_p, _p]),
     "spvd_kmap_pairs": (_i, [_p, _i, _i, _p, _i, _i, _p, _p, _p, _p, _p, _p, _p]),

@@ -789,6 +789,81 @@ extern "C" int spvd_mse_loss(const float* pred, const float* target, long long n
   return SPVD_OK;
 }
 
+// ------------------------------------------------------------------------------------------------
+// Optimizer tail of a training step over the flat buffers of parallel.GradientAllReduce / optim.FlatAdam: one pass for the
+// gradient norm, one pass for clip + (data-parallel average) + Adam.  torch.optim.Adam semantics (no amsgrad, L2 weight
+// decay added to the gradient): m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;  p -= lr/(1-b1^t) * m / (sqrt(v)/sqrt(1-b2^t) + eps).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_sumsq(const float4* __restrict__ x, long long n4, double* __restrict__ acc) {
+  float s = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 v = x[i];
+    s += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;       // <= a few hundred terms per thread in fp32, then fp64
+  }
+  double d = (double)s;
+  for (int o = 16; o > 0; o >>= 1) d += __shfl_xor_sync(0xffffffffu, d, o);
+  __shared__ double ws[8];
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = d;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0;
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    atomicAdd(acc, t);
+  }
+}
+
+__global__ void __launch_bounds__(256) k_adam(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                              float4* __restrict__ v, long long n4, float lr_c, float b1, float b2, float eps,
+                                              float wd, float inv_bc2_sqrt, const double* __restrict__ sumsq, float max_norm,
+                                              float pending, float* __restrict__ norm_out) {
+  float scale = pending;
+  if (sumsq) {
+    const float norm = (float)sqrt(*sumsq) * pending;          // the norm of the averaged gradient
+    if (max_norm > 0.f) scale = fminf(max_norm / (norm + 1e-6f), 1.f) * pending;     // torch.nn.utils.clip_grad_norm_
+    if (norm_out && blockIdx.x == 0 && threadIdx.x == 0) *norm_out = norm;
+  }
+  const float c1 = 1.f - b1, c2 = 1.f - b2;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    float4 P = p[i], G = g[i], M = m[i], V = v[i];
+#define SPVD_ADAM1(f)                                      \
+  {                                                        \
+    float gg = G.f * scale;                                \
+    if (wd != 0.f) gg += wd * P.f;                         \
+    M.f = b1 * M.f + c1 * gg;                              \
+    V.f = b2 * V.f + c2 * gg * gg;                         \
+    P.f -= lr_c * (M.f / (sqrtf(V.f) * inv_bc2_sqrt + eps)); \
+  }
+    SPVD_ADAM1(x) SPVD_ADAM1(y) SPVD_ADAM1(z) SPVD_ADAM1(w)
+#undef SPVD_ADAM1
+    p[i] = P;
+    m[i] = M;
+    v[i] = V;
+  }
+}
+
+extern "C" int spvd_sumsq(const float* x, long long n, double* acc, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(x && acc && n > 0 && n % 4 == 0 && ((size_t)x & 15) == 0, "spvd_sumsq: bad arguments (n a multiple of 4, 16-byte aligned)");
+  cudaStream_t s = (cudaStream_t)stream;
+  SPVD_CUDA(cudaMemsetAsync(acc, 0, sizeof(double), s));
+  k_sumsq<<<grid_for(n / 4, 256 * 8, 148 * 8), 256, 0, s>>>(reinterpret_cast<const float4*>(x), n / 4, acc);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
+extern "C" int spvd_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2,
+                              float eps, float weight_decay, int step, const double* sumsq, float max_norm, float pending_scale,
+                              float* norm_out, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(p && g && m && v && n > 0 && n % 4 == 0 && step >= 1, "spvd_adam_step: bad arguments (n a multiple of 4, step >= 1)");
+  SPVD_CHECK_ARG((((size_t)p | (size_t)g | (size_t)m | (size_t)v) & 15) == 0, "spvd_adam_step: buffers must be 16-byte aligned");
+  const double bc1 = 1.0 - pow((double)beta1, (double)step), bc2 = 1.0 - pow((double)beta2, (double)step);
+  k_adam<<<grid_for(n / 4, 256 * 4, 148 * 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m), reinterpret_cast<float4*>(v),
+      n / 4, (float)((double)lr / bc1), beta1, beta2, eps, weight_decay, (float)(1.0 / sqrt(bc2)), sumsq, max_norm, pending_scale,
+      norm_out);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
 // y = x rounded to TF32 (cvt.rna) and, in the same pass, the column sums of x (bias gradient)
 __global__ void __launch_bounds__(kRedThreads) k_round_colsum(const float* __restrict__ x, long long rows, int c, int rpc,
                                                               float* __restrict__ y, double* __restrict__ tot) {

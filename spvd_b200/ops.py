@@ -657,3 +657,23 @@ def conv_bwd(x, g, w3, kmap, n_in, n_out, want_gx, want_gw, want_gb, x_is_tf32=F
     a.x_is_tf32, a.gw_transposed, a.allow_tensor_cores = int(bool(x_is_tf32)), int(bool(gw_transposed)), int(bool(tensor_cores))
     check(lib.spvd_conv_bwd(ctypes.byref(a), _s()))
     return gx, gw, gb
+
+
+# ------------------------------------------------------------------------------------------------ optimizer tail
+_K.update({"sumsq": 1, "adam_step": 1})
+
+
+def sumsq(flat, acc):
+    """acc[0] (float64, device) = sum flat^2"""
+    _count("sumsq")
+    check(lib.spvd_sumsq(_p(flat, torch.float32), flat.numel(), _p(acc, torch.float64), _s()))
+    return acc
+
+
+def adam_step(p, g, m, v, lr, beta1, beta2, eps, weight_decay, step, sumsq_acc=None, max_norm=0.0, pending_scale=1.0, norm_out=None):
+    """in place over flat fp32 buffers: clip (by the norm in sumsq_acc) + scale + Adam (spvd_adam_step)"""
+    _count("adam_step")
+    check(lib.spvd_adam_step(_p(p, torch.float32), _p(g, torch.float32), _p(m, torch.float32), _p(v, torch.float32), p.numel(),
+                             float(lr), float(beta1), float(beta2), float(eps), float(weight_decay), int(step),
+                             _p(sumsq_acc, torch.float64) if sumsq_acc is not None else None, float(max_norm), float(pending_scale),
+                             _p(norm_out), _s()))

@@ -165,11 +165,14 @@ def train_step(model, optimizer, batch, reducer: GradientAllReduce = None, clip:
     pred = model((x, t))
     loss = SF.mse_loss(pred, target) if pred.is_cuda else torch.nn.functional.mse_loss(pred, target)
     loss.backward()
-    if reducer is not None:
-        reducer.clip_(clip, reducer.finish())
+    if reducer is not None and hasattr(optimizer, "flat_p"):      # optim.FlatAdam: norm + clip + average + Adam in two launches
+        optimizer.step(max_norm=clip, pending_scale=reducer.finish())
     else:
-        torch.nn.utils.clip_grad_norm_(model.parameters(), clip)
-    optimizer.step()
+        if reducer is not None:
+            reducer.clip_(clip, reducer.finish())
+        else:
+            torch.nn.utils.clip_grad_norm_(model.parameters(), clip)
+        optimizer.step()
     if scheduler is not None:
         scheduler.step()
     return loss.detach()

@@ -288,3 +288,39 @@ def test_in_place_parameter_gradients_match_autograd_accumulation():
     adds = [n for n in names if "vectorized_elementwise_kernel" in n and "add" in n.lower()]
     if names:
         assert len(adds) < 0.25 * n_params, (len(adds), n_params)
+
+
+@pytest.mark.parametrize("wd,clip", [(0.0, 10.0), (0.01, 0.05), (0.0, 0.0)])
+def test_flat_adam_matches_torch_adam_and_clip(wd, clip):
+    """optim.FlatAdam (spvd_sumsq + spvd_adam_step over the flat buffers) against torch.optim.Adam after
+    torch.nn.utils.clip_grad_norm_ (train_generation.py:106-112), several steps, odd parameter sizes."""
+    from spvd_b200.optim import FlatAdam
+    from spvd_b200.parallel import GradientAllReduce
+    torch.manual_seed(3)
+    make = lambda: torch.nn.Sequential(torch.nn.Linear(7, 33), torch.nn.SiLU(), torch.nn.Linear(33, 130), torch.nn.SiLU(),
+                                       torch.nn.Linear(130, 3)).cuda()
+    a, b = make(), make()
+    b.load_state_dict(a.state_dict())
+    red = GradientAllReduce(a.parameters())
+    opt_a = FlatAdam(red, lr=3e-3, weight_decay=wd)
+    opt_b = torch.optim.Adam(b.parameters(), lr=3e-3, weight_decay=wd)
+    sched = torch.optim.lr_scheduler.StepLR(opt_a, 2, 0.5)
+    sched_b = torch.optim.lr_scheduler.StepLR(opt_b, 2, 0.5)
+    v0 = [p._version for p in a.parameters()]
+    for it in range(6):
+        x, y = torch.randn(64, 7, device="cuda") * (1 + it), torch.randn(64, 3, device="cuda")
+        opt_a.zero_grad()
+        F.mse_loss(a(x), y).backward()
+        opt_a.step(max_norm=clip)
+        sched.step()
+        opt_b.zero_grad()
+        F.mse_loss(b(x), y).backward()
+        nb = torch.nn.utils.clip_grad_norm_(b.parameters(), clip) if clip > 0 else None
+        opt_b.step()
+        sched_b.step()
+        if nb is not None:
+            assert abs(float(opt_a.grad_norm) - float(nb)) <= 1e-5 * float(nb)
+        for pa, pb in zip(a.parameters(), b.parameters()):
+            _cmp(pa, pb, 2e-6, f"step {it}")
+    assert all(p._version > v for p, v in zip(a.parameters(), v0))      # version-keyed caches see the in-place update
+    assert all(p.data_ptr() >= opt_a.flat_p.data_ptr() for p in a.parameters())

@@ -7,6 +7,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, spvd_b200
 from spvd_b200.sampler import torch2sparse
 from spvd_b200.parallel import GradientAllReduce, train_step
+from spvd_b200.optim import FlatAdam
 
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 8
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -15,8 +16,8 @@ dev = torch.device("cuda", local)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 torch.manual_seed(0); model = spvd_b200.build_model("SPVD"); model = model.to(dev).train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-4)
 red = GradientAllReduce(model.parameters(), overlap=os.environ.get('SPVD_DDP_OVERLAP', '1') == '1')
+opt = FlatAdam(red, lr=1e-4) if os.environ.get('SPVD_FLAT_ADAM', '1') == '1' else torch.optim.Adam(model.parameters(), lr=1e-4)
 W = 3
 strat, xs, ts = bench.make_workload(steps + W, 32, 2048, 7 + rank)
 times = []

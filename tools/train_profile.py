@@ -5,14 +5,15 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import bench, spvd_b200
 from spvd_b200.parallel import GradientAllReduce, train_step
+from spvd_b200.optim import FlatAdam
 from spvd_b200.sampler import torch2sparse
 from torch.profiler import ProfilerActivity, profile
 
 dev = torch.device("cuda", 0)
 torch.manual_seed(0)
 model = spvd_b200.build_model("SPVD").to(dev).train()
-opt = torch.optim.Adam(model.parameters(), lr=1e-4)
 red = GradientAllReduce(model.parameters())
+opt = FlatAdam(red, lr=1e-4)          # flat-buffer Adam + clip + average on the library's kernels
 strat, xs, ts = bench.make_workload(6, 32, 2048, 7)
 def step(j):
     st = torch2sparse(xs[j].to(dev))
