@@ -42,3 +42,19 @@ t_lo = min(e.time_range.start for e in ev); t_hi = max(e.time_range.end for e in
 print(f"GPU kernel time {all_us/1e3:.3f} ms in {len(ev)} launches; first-to-last {(t_hi - t_lo)/1e3:.3f} ms")
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1][1])[:45]:
     print(f"{v[1]/1e3:8.3f} ms {v[0]:5d}  {k}")
+
+# ---- timeline: when is NO kernel running, and between which kernels?
+iv = sorted(((e.time_range.start, e.time_range.end, e.name.split("(")[0][:60]) for e in ev), key=lambda x: x[0])
+busy_end, idle, gaps = iv[0][0], 0.0, []
+last_name = ""
+for s, e, nme in iv:
+    if s > busy_end:
+        idle += s - busy_end
+        gaps.append((s - busy_end, last_name, nme, s - t_lo))
+    if e > busy_end:
+        busy_end, last_name = e, nme
+print(f"idle (no kernel on any stream) {idle/1e3:.3f} ms of {(t_hi - t_lo)/1e3:.3f} ms in {len(gaps)} gaps")
+hist = collections.Counter(min(int(g[0]), 20) for g in gaps)
+print("gap histogram (us: count):", dict(sorted(hist.items())))
+for g in sorted(gaps, key=lambda g: -g[0])[:25]:
+    print(f"  {g[0]:7.1f} us at +{g[3]/1e3:6.3f} ms   {g[1]}  ->  {g[2]}")
