@@ -598,11 +598,19 @@ typedef struct spvd_conv_bwd_args {
   float* gbias;
   void* workspace;
   double* red_workspace;
+  const float* w_packed_t; /* optional: transposed tile image from spvd_conv_pack_weights_train (else built per call) */
   size_t workspace_bytes;
   int32_t map_ld, gmap_ld, n_pair_tiles, n_in, n_out, kvol, cin, cout, flip, x_is_tf32, gw_transposed, allow_tensor_cores;
-  int32_t n_pairs, pad; /* valid pairs in the lists (0 = unknown): the data gradient runs pair-major when n_pairs < 10 n_in */
+  int32_t n_pairs;         /* valid pairs in the lists (0 = unknown): the data gradient runs pair-major when n_pairs < 10 n_in */
+  int32_t w_packed_t_flip; /* the flip_t w_packed_t was built with; it is used only if that is what this call needs */
 } spvd_conv_bwd_args_t;
 size_t spvd_conv_bwd_workspace_bytes(int n_in, int n_out, int kvol, int cin, int cout);
+/* Training: every per-step derivative of one weight tensor in one launch -- the forward tile image wp_out (layout of
+ * spvd_conv_pack_weights), the transposed image wtp_out for the data gradient (offsets reversed when flip_t: the dense
+ * submanifold data gradient; 0 for the pair-major one and for strided maps) and, when w is an nn.Linear weight [cout, cin]
+ * (w_is_linear), its conv layout w3_out [1, cin, cout].  Any output may be NULL. */
+int spvd_conv_pack_weights_train(const float* w, int kvol, int cin, int cout, int w_is_linear, int flip_t, float* w3_out,
+                                 float* wp_out, float* wtp_out, spvd_stream_t stream);
 int spvd_conv_bwd(const spvd_conv_bwd_args_t* args, spvd_stream_t stream);
 /* torchsparse.cat (models/spvd.py:232) for any channel counts, and its backward (channel split) */
 int spvd_cat_any_fwd(const float* a, const float* b, long long rows, int ca, int cb, float* y, spvd_stream_t stream);

@@ -77,6 +77,7 @@ SIGNATURES = {
     "spvd_timestep_embedding": (_i, [_p, _i, _i, _p, _p]),
     "spvd_mse_loss": (_i, [_p, _p, _ll, _f, _p, _p, _p, _p]),
     "spvd_sumsq": (_i, [_p, _ll, _p, _p]),
+    "spvd_conv_pack_weights_train": (_i, [_p, _i, _i, _i, _i, _i, _p, _p, _p, _p]),
     "spvd_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _i, _p, _f, _f, _p, _p]),
     "spvd_conv_bwd_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "spvd_conv_bwd": (_i, [_p, _p]),

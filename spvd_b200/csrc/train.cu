@@ -895,6 +895,47 @@ __global__ void k_pack_weights_transposed(const float* __restrict__ w, int kvol,
   wp[dst] = __uint_as_float(r);
 }
 
+// Every per-step derivative of one weight tensor in ONE pass (training: the optimizer changed the weights): the forward
+// tile image (spvd_conv_pack_weights layout), the transposed image for the data gradient (k_pack_weights_transposed
+// layout, offsets flipped when `flip`) and, for an nn.Linear weight [cout, cin], its conv layout [1, cin, cout].
+__global__ void k_pack_weights_train(const float* __restrict__ w, int kvol, int cin, int cout, int linear, int flip,
+                                     float* __restrict__ w3, float* __restrict__ wp, float* __restrict__ wtp) {
+  const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (long long)kvol * cin * cout) return;
+  const int co = (int)(t % cout);
+  const long long q = t / cout;
+  const int ci = (int)(q % cin);
+  const int k = (int)(q / cin);
+  const float v = linear ? w[(size_t)co * cin + ci] : w[t];
+  if (w3) w3[t] = v;
+  unsigned r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  const float vr = __uint_as_float(r);
+  if (wp) {
+    const int c = ci / 32, kk = ci % 32;
+    wp[((size_t)(k * (cin / 32) + c) * cout + co) * 32 + ((((kk >> 2) ^ (co & 7)) << 2) | (kk & 3))] = vr;
+  }
+  if (wtp) {
+    const int kp = flip ? kvol - 1 - k : k;
+    const int c = co / 32, kk = co % 32;
+    wtp[((size_t)(kp * (cout / 32) + c) * cin + ci) * 32 + ((((kk >> 2) ^ (ci & 7)) << 2) | (kk & 3))] = vr;
+  }
+}
+
+extern "C" int spvd_conv_umma_supported(int, int, int);
+extern "C" int spvd_conv_pack_weights_train(const float* w, int kvol, int cin, int cout, int w_is_linear, int flip_t, float* w3_out,
+                                            float* wp_out, float* wtp_out, spvd_stream_t stream) {
+  SPVD_CHECK_ARG(w && kvol >= 1 && cin >= 1 && cout >= 1 && (w3_out || wp_out || wtp_out), "spvd_conv_pack_weights_train: bad arguments");
+  SPVD_CHECK_ARG(!w_is_linear || kvol == 1, "spvd_conv_pack_weights_train: an nn.Linear weight has kernel size 1");
+  SPVD_CHECK_ARG(!wp_out || spvd_conv_umma_supported(kvol, cin, cout), "spvd_conv_pack_weights_train: unsupported shape %dx%dx%d", kvol, cin, cout);
+  SPVD_CHECK_ARG(!wtp_out || spvd_conv_umma_supported(kvol, cout, cin), "spvd_conv_pack_weights_train: unsupported transposed shape %dx%dx%d",
+                 kvol, cout, cin);
+  const long long total = (long long)kvol * cin * cout;
+  k_pack_weights_train<<<cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(w, kvol, cin, cout, w_is_linear, flip_t, w3_out, wp_out, wtp_out);
+  SPVD_LAUNCH_CHECK();
+  return SPVD_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // Whole backward of one sparse convolution / nn.Linear from ONE host call: TF32 rounding of the output gradient, weight
 // transpose + tile image, data gradient (the forward kernels on the transposed weights and the gradient map), weight
@@ -962,9 +1003,14 @@ extern "C" int spvd_conv_bwd(const spvd_conv_bwd_args_t* args, spvd_stream_t str
       // sparse levels (few active offsets per voxel): pair-major on the forward pair list with the roles swapped
       const bool pairs = a.pair_in && a.pair_out && a.pair_tile_k && a.n_pair_tiles > 0 && a.n_pairs > 0 &&
                          (long long)a.n_pairs < 10ll * a.n_in;
-      const long long total = (long long)a.kvol * a.cin * a.cout;
-      k_pack_weights_transposed<<<cdiv(total, 256), 256, 0, s>>>(a.w, a.kvol, a.cin, a.cout, pairs ? 0 : a.flip, wtp);
-      SPVD_LAUNCH_CHECK();
+      const int need_flip = pairs ? 0 : (a.flip ? 1 : 0);
+      if (a.w_packed_t && a.w_packed_t_flip == need_flip) {      // prepared with the forward image (spvd_conv_pack_weights_train)
+        wtp = const_cast<float*>(a.w_packed_t);
+      } else {
+        const long long total = (long long)a.kvol * a.cin * a.cout;
+        k_pack_weights_transposed<<<cdiv(total, 256), 256, 0, s>>>(a.w, a.kvol, a.cin, a.cout, need_flip, wtp);
+        SPVD_LAUNCH_CHECK();
+      }
       if (pairs)
         rc = spvd_conv_fwd_pairs(g_tc, wtp, a.pair_out, a.pair_in, a.pair_tile_k, a.n_pair_tiles, -1, a.n_in, a.kvol, a.cout, a.cin,
                                  nullptr, nullptr, a.gx, SPVD_A_TF32, stream);

@@ -32,17 +32,34 @@ def _wrote(*ps):
 
 
 class PackedWeight:
-    """Tensor-core tile image of a conv weight, rebuilt when the parameter changes (optimizer step)."""
+    """Tensor-core tile image of a conv weight, rebuilt when the parameter changes (optimizer step).  With ``flip_t`` given
+    (a training forward whose input needs a gradient) the transposed image for the data gradient comes out of the same
+    launch (``packed_t``, built with ``t_flip``)."""
 
     def __init__(self):
-        self.key, self.packed = None, None
+        self.key, self.packed, self.packed_t, self.t_flip = None, None, None, 0
 
-    def get(self, w3: torch.Tensor):
+    def get(self, w3: torch.Tensor, flip_t=None):
         key = (w3.data_ptr(), w3._version, tuple(w3.shape))
-        if key != self.key:
-            self.packed = ops.pack_weights(w3.detach()) if ops.umma_supported(*w3.shape) else None
+        if key != self.key or (flip_t is not None and (self.packed_t is None or self.t_flip != flip_t)):
+            self.packed_t, self.t_flip = None, 0
+            if flip_t is None:
+                self.packed = ops.pack_weights(w3.detach()) if ops.umma_supported(*w3.shape) else None
+            else:
+                _, self.packed, self.packed_t = ops.pack_weights_train(w3.detach(), *w3.shape, flip_t=flip_t)
+                self.t_flip = flip_t
             self.key = key
         return self.packed
+
+
+def _dgrad_flip(kmap):
+    """the offset order the data gradient of a conv over ``kmap`` will want for its transposed weights (spvd_conv_bwd):
+    pair-major on sparse levels (no flip), dense with flipped offsets on submanifold maps"""
+    if kmap is None:
+        return 0
+    if kmap.n_pairs and kmap.n_pairs < 10 * kmap.n_in:
+        return 0
+    return 1 if kmap.flip else 0
 
 
 class _SparseConv(torch.autograd.Function):
@@ -50,9 +67,11 @@ class _SparseConv(torch.autograd.Function):
     def forward(ctx, x, weight, bias, kmap, cache, impl, a_tf32=False, residual=None):
         w3 = weight if weight.dim() == 3 else weight.unsqueeze(0)
         w3 = w3.contiguous()
-        wp = cache.get(w3) if (cache is not None and impl != ops.CONV_SIMT) else None
+        flip_t = _dgrad_flip(kmap) if (ctx.needs_input_grad[0] and weight.requires_grad) else None
+        wp = cache.get(w3, flip_t) if (cache is not None and impl != ops.CONV_SIMT) else None
         if impl == ops.CONV_UMMA and wp is None:
             wp = ops.pack_weights(w3)
+        ctx.cache = cache if flip_t is not None else None
         n_out = kmap.n_out if kmap is not None else x.shape[0]
         x = x.contiguous()
         res = residual.contiguous() if residual is not None else None
@@ -83,8 +102,13 @@ class _SparseConv(torch.autograd.Function):
         n_in = kmap.n_in if kmap is not None else g.shape[0]
         # one C call: TF32-rounded gradient -> data gradient (cp.async gather) + weight gradient (tcgen05 over the pair
         # lists; x was rounded by its producer when the forward ran with a_tf32) + bias gradient
+        wt, wt_flip = None, 0
+        c = ctx.cache
+        if c is not None and c.packed_t is not None and c.key == (w3.data_ptr(), w3._version, tuple(w3.shape)):
+            wt, wt_flip = c.packed_t, c.t_flip                     # (the weights have not changed since the forward)
         gx, gw, gb = ops.conv_bwd(x, g.contiguous(), w3, kmap, n_in, n_out, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
-                                  want_gb, x_is_tf32=ctx.a_tf32, tensor_cores=impl != ops.CONV_SIMT, gw_out=gw_out, gb_out=gb_out)
+                                  want_gb, x_is_tf32=ctx.a_tf32, tensor_cores=impl != ops.CONV_SIMT, gw_out=gw_out, gb_out=gb_out,
+                                  w_packed_t=wt, w_packed_t_flip=wt_flip)
         if gw_out is not None:
             _wrote(p_w)
             gw = None
@@ -149,13 +173,20 @@ class LinearCache:
     """[1, in, out] transpose of an nn.Linear weight + its tensor-core tile image, rebuilt when the parameter changes"""
 
     def __init__(self):
-        self.key, self.w3, self.packed = None, None, None
+        self.key, self.w3, self.packed, self.packed_t = None, None, None, None
 
-    def get(self, weight, want_packed):
+    def get(self, weight, want_packed, want_t=False):
+        """want_t: also the transposed tile image for the data gradient (same launch)"""
         key = (weight.data_ptr(), weight._version)
-        if key != self.key:
-            self.w3 = ops.transpose_weights(weight.detach().unsqueeze(0).contiguous(), False)      # [1, out, in] -> [1, in, out]
-            self.packed, self.key = None, key
+        cout, cin = weight.shape
+        if key != self.key or (want_t and self.packed_t is None and ops.umma_supported(1, cout, cin)):
+            if want_packed or want_t:            # conv layout + both tile images from one pass over the weight
+                self.w3, self.packed, self.packed_t = ops.pack_weights_train(weight.detach().contiguous(), 1, cin, cout, linear=True,
+                                                                             want_w3=True, want_t=want_t)
+            else:
+                self.w3 = ops.transpose_weights(weight.detach().unsqueeze(0).contiguous(), False)  # [1, out, in] -> [1, in, out]
+                self.packed, self.packed_t = None, None
+            self.key = key
         if want_packed and self.packed is None and ops.umma_supported(*self.w3.shape):
             self.packed = ops.pack_weights(self.w3)
         return self.w3, (self.packed if want_packed else None)
@@ -170,10 +201,12 @@ class _Linear(torch.autograd.Function):
     def forward(ctx, x, weight, bias, cache, impl, residual, a_tf32=False):
         x = x.contiguous()
         umma = impl != ops.CONV_SIMT and ops.umma_supported(1, weight.shape[1], weight.shape[0])
-        w3, wp = cache.get(weight, umma)
+        want_t = impl != ops.CONV_SIMT and ctx.needs_input_grad[0] and weight.requires_grad
+        w3, wp = cache.get(weight, umma, want_t)
         out = ops.conv_fwd(x, w3, wp, None, None, x.shape[0], bias, ops.CONV_AUTO if umma else ops.CONV_SIMT,
                            a_tf32=bool(a_tf32) and umma, residual=residual.contiguous() if residual is not None else None)
         ctx.save_for_backward(x, weight, w3)
+        ctx.cache = cache if want_t else None
         ctx.impl, ctx.has_bias, ctx.a_tf32 = impl, bias is not None, bool(a_tf32)
         ctx.params = (_use(weight), _use(bias) if bias is not None else None)
         return out
@@ -184,9 +217,12 @@ class _Linear(torch.autograd.Function):
         p_w, p_b = ctx.params
         want_gb = ctx.has_bias and ctx.needs_input_grad[2]
         gw_out, gb_out = _claim(p_w, ctx.needs_input_grad[1]), _claim(p_b, want_gb)
+        c = ctx.cache
+        wt = c.packed_t if (c is not None and c.key == (weight.data_ptr(), weight._version)) else None
         gx, gw, gb = ops.conv_bwd(x, g.contiguous(), w3, None, x.shape[0], x.shape[0], ctx.needs_input_grad[0],
                                   ctx.needs_input_grad[1], want_gb, x_is_tf32=ctx.a_tf32,
-                                  gw_transposed=True, tensor_cores=ctx.impl != ops.CONV_SIMT, gw_out=gw_out, gb_out=gb_out)
+                                  gw_transposed=True, tensor_cores=ctx.impl != ops.CONV_SIMT, gw_out=gw_out, gb_out=gb_out,
+                                  w_packed_t=wt, w_packed_t_flip=0)
         if gw_out is not None:
             _wrote(p_w)
             gw = None

@@ -609,18 +609,33 @@ def mse_loss(pred, target, want_grad=True, grad_scale=1.0):
 class ConvBwdArgs(ctypes.Structure):
     """spvd_conv_bwd_args_t (include/spvd_b200.h)"""
     _fields_ = [(n, ctypes.c_void_p) for n in ("x", "g", "w", "map_t", "gmap_t", "gmap_mask", "pair_in", "pair_out", "pair_tile_k",
-                                               "gx", "gw", "gbias", "workspace", "red_workspace")] + \
+                                               "gx", "gw", "gbias", "workspace", "red_workspace", "w_packed_t")] + \
                [("workspace_bytes", ctypes.c_size_t)] + \
                [(n, ctypes.c_int32) for n in ("map_ld", "gmap_ld", "n_pair_tiles", "n_in", "n_out", "kvol", "cin", "cout", "flip",
-                                              "x_is_tf32", "gw_transposed", "allow_tensor_cores", "n_pairs", "pad")]
+                                              "x_is_tf32", "gw_transposed", "allow_tensor_cores", "n_pairs", "w_packed_t_flip")]
 
 
 _K["conv_bwd"] = 8
 _BWD_WS = {}
 
 
+def pack_weights_train(w, kvol, cin, cout, linear=False, flip_t=0, want_w3=False, want_t=True):
+    """One launch for everything a training step derives from a weight tensor (spvd_conv_pack_weights_train):
+    -> (w3 [1, cin, cout] or None, forward tile image or None, transposed tile image or None)."""
+    _count("pack_weights")
+    dev = w.device
+    w3 = torch.empty((kvol, cin, cout), dtype=torch.float32, device=dev) if want_w3 else None
+    wp = torch.empty(kvol * cin * cout, dtype=torch.float32, device=dev) if umma_supported(kvol, cin, cout) else None
+    wtp = torch.empty(kvol * cin * cout, dtype=torch.float32, device=dev) if (want_t and umma_supported(kvol, cout, cin)) else None
+    if w3 is None and wp is None and wtp is None:
+        return None, None, None
+    check(lib.spvd_conv_pack_weights_train(_p(w, torch.float32), kvol, cin, cout, int(bool(linear)), int(flip_t), _p(w3), _p(wp),
+                                           _p(wtp), _s()))
+    return w3, wp, wtp
+
+
 def conv_bwd(x, g, w3, kmap, n_in, n_out, want_gx, want_gw, want_gb, x_is_tf32=False, gw_transposed=False, tensor_cores=True,
-             gw_out=None, gb_out=None):
+             gw_out=None, gb_out=None, w_packed_t=None, w_packed_t_flip=0):
     """The whole backward of a sparse convolution / Linear in one C call (spvd_conv_bwd).  w3 [kvol, cin, cout];
     kmap = geometry.KernelMap of the forward conv or None (kernel size 1).  -> (gx, gw, gbias), None where not wanted;
     gw is [kvol, cin, cout], or [kvol, cout, cin] with gw_transposed.  gw_out / gb_out: contiguous fp32 tensors of those
@@ -656,6 +671,7 @@ def conv_bwd(x, g, w3, kmap, n_in, n_out, want_gx, want_gw, want_gb, x_is_tf32=F
     a.workspace, a.workspace_bytes, a.red_workspace = _p(ws), ws.numel(), _p(train_ws(dev))
     a.n_in, a.n_out, a.kvol, a.cin, a.cout = int(n_in), int(n_out), kvol, cin, cout
     a.x_is_tf32, a.gw_transposed, a.allow_tensor_cores = int(bool(x_is_tf32)), int(bool(gw_transposed)), int(bool(tensor_cores))
+    a.w_packed_t, a.w_packed_t_flip = _p(w_packed_t), int(w_packed_t_flip)
     check(lib.spvd_conv_bwd(ctypes.byref(a), _s()))
     return gx, gw, gb
 
