@@ -364,30 +364,43 @@ def run_train_leg(args, dev, world, rank, xs_dev, flush):
     from spvd_b200.parallel import GradientAllReduce, train_step
     from spvd_b200.optim import FlatAdam
     from spvd_b200.sampler import torch2sparse
-    B, N, K, W = args.batch, args.points, args.train_steps, 4     # (the first NCCL all-reduces of a new buffer set up connections)
+    B, N, K, W = args.batch, args.points, args.train_steps, 6     # (the first NCCL all-reduces of a new buffer set up connections,
+                                                                  #  both geometry buffer sets capture their planner graphs)
     torch.manual_seed(0)
     model = spvd_b200.build_model(args.preset, downsample_mode=args.downsample_mode).to(dev).train()
     red = GradientAllReduce(model.parameters())
     opt = FlatAdam(red, lr=1e-4)          # flat-buffer Adam + clip + average on the library's kernels
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     ev, ar_ms = [], 0.0
-    for j in range(W + K):
-        x = xs_dev[j % len(xs_dev)]
-        st = torch2sparse(x)
-        t = torch.randint(0, 1000, (B,), device=dev, generator=g)
-        eps = torch.randn(st.F.shape, device=dev, generator=g)
-        if flush is not None:
-            flush.fill_(j & 0xFF)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        if j == W:
-            torch.cuda.synchronize()
-            if world > 1:
-                dist.barrier()
-        a.record()
-        train_step(model, opt, (st, t, eps), red)
-        b.record()
-        if j >= W:
-            ev.append((a, b))
+
+    def make_batch(j):            # what the data loader hands over (train_generation.py:98-103): noisy clouds, t, target noise
+        st = torch2sparse(xs_dev[j % len(xs_dev)])
+        return st, torch.randint(0, 1000, (B,), device=dev, generator=g), torch.randn(st.F.shape, device=dev, generator=g)
+
+    def run_steps(n, timed_from):
+        """batch j + 1 is produced, and its geometry planned on a side stream (model.prefetch_geometry), while step j runs"""
+        out = []
+        batch = make_batch(0)
+        geo = model.prefetch_geometry(batch[0], B)
+        for j in range(n):
+            if flush is not None:
+                flush.fill_(j & 0xFF)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if j == timed_from:
+                torch.cuda.synchronize()
+                if world > 1:
+                    dist.barrier()
+            a.record()
+            nxt = make_batch(j + 1) if j + 1 < n else None
+            geo_next = model.prefetch_geometry(nxt[0], B) if nxt is not None else None
+            train_step(model, opt, batch, red, geometry=geo)
+            b.record()
+            if j >= timed_from:
+                out.append((a, b))
+            batch, geo = nxt, geo_next
+        return out
+
+    ev = run_steps(W + K, W)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
@@ -399,18 +412,7 @@ def run_train_leg(args, dev, world, rank, xs_dev, flush):
     if world > 1:
         red_group_active = red._active
         red._active = lambda: False
-        ev2 = []
-        for j in range(K):
-            st = torch2sparse(xs_dev[j % len(xs_dev)])
-            t = torch.randint(0, 1000, (B,), device=dev, generator=g)
-            eps = torch.randn(st.F.shape, device=dev, generator=g)
-            if flush is not None:
-                flush.fill_(j & 0xFF)
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record()
-            train_step(model, opt, (st, t, eps), red)
-            b.record()
-            ev2.append((a, b))
+        ev2 = run_steps(K, 0)
         torch.cuda.synchronize()
         red._active = red_group_active
         local = sum(a.elapsed_time(b) for a, b in ev2)
@@ -422,7 +424,9 @@ def run_train_leg(args, dev, world, rank, xs_dev, flush):
         return None
     return {"metric": "SPVD training steps/s (fwd + bwd + gradient all-reduce + clip + Adam), B=%dx%d per GPU" % (B, N),
             "steps_per_s": round(K / (total * 1e-3), 3), "clouds_per_s": round(world * B * K / (total * 1e-3), 1),
-            "ms_per_step": round(total / K, 3), "steps": K, "warmup": W, "n_gpus": world,
+            "ms_per_step": round(total / K, 3), "ms_per_step_median": round(sorted(a.elapsed_time(b) for a, b in ev)[len(ev) // 2], 3),
+            "steps": K, "warmup": W, "n_gpus": world,
+            "pipeline": "batch j+1 (noise, t, re-sparsify) is produced and its geometry planned on a side stream while step j runs",
             "allreduce": {"bytes": int(red.flat.numel() * 4), "buckets": len(red.buckets), "exposed_ms_per_step": exposed,
                           "how": "step time with the NCCL all-reduce minus step time without it (same kernels), max over ranks"},
             "dtype": "f32 activations, tf32 tensor-core operands (forward, dgrad, wgrad), f32 accumulate"}

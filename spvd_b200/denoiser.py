@@ -185,6 +185,7 @@ class SPVUnet(nn.Module):
         # ops of the finer levels ("1,2" = level 0 | level 1 | the rest; "0" = plan everything up front)
         self.plan_split_level = tuple(int(v) for v in os.environ.get("SPVD_PLAN_SPLIT", "1,3").split(","))
         self._side_streams = {}
+        self._prefetch_streams = {}
         self._aux_streams = {}
         self.side_prologue = os.environ.get("SPVD_SIDE_PROLOGUE", "0") == "1"
         # tensor-core operand format of the executor: "f16" = IEEE half operands (the 11-bit significand of TF32, fp32
@@ -320,7 +321,7 @@ class SPVUnet(nn.Module):
         return x
 
     # -- forward -------------------------------------------------------------------------------
-    def plan_geometry(self, coords: torch.Tensor, n_batch: int, max_cloud_rows: int = 0, split_level=0) -> Geometry:
+    def plan_geometry(self, coords: torch.Tensor, n_batch: int, max_cloud_rows: int = 0, split_level=0, defer=False) -> Geometry:
         """Plan every coordinate structure of the forward with one C call into persistent buffers.  Two
         buffer sets alternate, so the geometry of the previous call stays valid while the next one is
         planned (``geometry_pool`` > 2 keeps more alive, e.g. when several forwards precede one backward)."""
@@ -345,7 +346,30 @@ class SPVUnet(nn.Module):
             side = self._side_streams.get(pc.device)
             if side is None:
                 side = self._side_streams[pc.device] = torch.cuda.Stream(device=pc.device, priority=-1)
-        return ws.build(pc, self.pres, self.voxel_size, self.scale_mode, self.downsample_mode, max_cloud_rows, split_level, side)
+        return ws.build(pc, self.pres, self.voxel_size, self.scale_mode, self.downsample_mode, max_cloud_rows, split_level, side,
+                        defer=defer)
+
+    def prefetch_geometry(self, x_in, n_batch: int) -> Geometry:
+        """Plan the geometry of a FUTURE batch now, on a side stream, without waiting for it: pass the result as
+        ``forward(inp, geometry=...)`` (or ``train_step(..., geometry=...)``) when that batch's turn comes.  The planner's
+        one host synchronisation (level sizes) otherwise sits at the start of every forward and drains the GPU: the host
+        cannot issue the next step while the device still runs the previous backward.  Call it for batch j + 1 BEFORE issuing
+        step j (what a data loader's prefetch would do): the side stream first waits for everything issued so far -- the
+        last user of the buffer set it is about to overwrite (two sets alternate) -- and then runs beside step j."""
+        coords = x_in.C if hasattr(x_in, "C") else x_in
+        cf = getattr(x_in, "coords_float", None)
+        if cf is not None and cf.shape[0] == coords.shape[0]:
+            coords = cf
+        dev = coords.device
+        ps = self._prefetch_streams.get(dev)
+        if ps is None:
+            ps = self._prefetch_streams[dev] = torch.cuda.Stream(device=dev)
+        pc = (coords.float() if coords.dtype != torch.float32 else coords).contiguous()
+        ps.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(ps):
+            geo = self.plan_geometry(pc, n_batch, int(getattr(x_in, "points_per_cloud", 0) or 0), 0, defer=True)
+        pc.record_stream(ps)
+        return geo
 
     def forward(self, inp, geometry: Geometry = None):
         x_in, t = inp[0], inp[1]
@@ -381,6 +405,8 @@ class SPVUnet(nn.Module):
         geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0],
                                                                        int(getattr(x_in, "points_per_cloud", 0) or 0),
                                                                        self.plan_split_level if executor else 0)
+        if geometry is not None and geo._pending:
+            geo.finish()                        # prefetched (prefetch_geometry): its planner finished long ago
         if executor:
             sink = getattr(self, "profile_sink", None)
             if sink is None:

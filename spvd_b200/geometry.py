@@ -148,6 +148,7 @@ class Geometry:
                 l.kmap_down.grad, l.kmap_up.grad = l.kmap_up, l.kmap_down
 
     _pending = None          # PlanWorkspace.build(split_level=...): [collect the next group of coarser levels, ...]
+    _keep = None
 
     def finish(self, upto=None):
         """Wait for (and collect) level groups that are still being planned on the side stream: all of them, or just
@@ -156,6 +157,7 @@ class Geometry:
             self._pending.pop(0)()
         if not self._pending:
             self._pending = None
+            self._keep = None
         return self
 
     @property
@@ -321,12 +323,14 @@ class PlanWorkspace:
                           2 * nl + 3 * len(self.pair_strides) + 3 * (nl - 1) + 13 * len(self.sort_strides))
 
     def build(self, pc, pres, voxel_size, scale_mode="mul", downsample_mode="spconv", max_cloud_rows=0, split_level=0,
-              side_stream=None):
+              side_stream=None, defer=False):
         """max_cloud_rows > 0: the points are batch-major with at most that many per cloud (what torch2sparse
         produces) -> per-cloud shared-memory sorts; 0: no assumption (global radix sort).
         split_level = k > 0 (or increasing cuts (k0, k1, ..)) with a side_stream: only the k finest levels are planned
         (and waited for) here; the coarser groups are planned on side_stream while the caller already works on the fine
-        ones, and ``Geometry.finish()`` (or the first access to a coarser level) collects them."""
+        ones, and ``Geometry.finish()`` (or the first access to a coarser level) collects them.
+        defer: do not wait for anything here -- the planner is only enqueued (on the current stream) and the caller collects
+        with ``Geometry.finish()`` before the first use: planning the NEXT batch on a side stream while this one trains."""
         if not pc.is_cuda or pc.dtype != torch.float32 or not pc.is_contiguous() or pc.shape != (self.n_points, 4):
             raise RuntimeError("PlanWorkspace.build needs a contiguous CUDA float32 [n_points,4] tensor")
         nl = len(self.strides)
@@ -371,6 +375,13 @@ class PlanWorkspace:
                 self.group_done[g].synchronize()
                 self._collect(geo, lo, hi, self.summary_hosts[g])
             pending.append(collect)
+        if defer:
+            def collect0(hi=bounds[1]):
+                self.group_done[0].synchronize()
+                self._collect(geo, 0, hi)
+            geo._pending = [collect0] + pending
+            geo._keep = pc                      # the planner reads it on this stream until then
+            return geo
         self.group_done[0].synchronize()
         if self.trace is not None:
             self.trace.append(("finest group done", time.perf_counter()))

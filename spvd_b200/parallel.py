@@ -152,17 +152,17 @@ class GradientAllReduce:
         return norm
 
 
-def train_step(model, optimizer, batch, reducer: GradientAllReduce = None, clip: float = 10.0, scheduler=None):
+def train_step(model, optimizer, batch, reducer: GradientAllReduce = None, clip: float = 10.0, scheduler=None, geometry=None):
     """One optimisation step of train_generation.py:98-112: MSE(model((x_t, t)), eps), backward, gradient
     all-reduce (data parallel, overlapped with backward), clip_grad_norm_(10), optimizer (+ LR scheduler) step.
-    ``batch`` = (SparseTensor, t, eps)."""
+    ``batch`` = (SparseTensor, t, eps).  ``geometry``: the batch's geometry planned ahead with ``model.prefetch_geometry``."""
     from . import functional as SF
     x, t, target = batch
     if reducer is not None:
         reducer.zero_grad()
     else:
         optimizer.zero_grad(set_to_none=True)
-    pred = model((x, t))
+    pred = model((x, t)) if geometry is None else model((x, t), geometry=geometry)
     loss = SF.mse_loss(pred, target) if pred.is_cuda else torch.nn.functional.mse_loss(pred, target)
     loss.backward()
     if reducer is not None and hasattr(optimizer, "flat_p"):      # optim.FlatAdam: norm + clip + average + Adam in two launches

@@ -324,3 +324,56 @@ def test_flat_adam_matches_torch_adam_and_clip(wd, clip):
             _cmp(pa, pb, 2e-6, f"step {it}")
     assert all(p._version > v for p, v in zip(a.parameters(), v0))      # version-keyed caches see the in-place update
     assert all(p.data_ptr() >= opt_a.flat_p.data_ptr() for p in a.parameters())
+
+
+def test_prefetched_geometry_gives_the_same_training_step():
+    """model.prefetch_geometry plans batch j + 1 on a side stream while step j is issued (no host wait until its first use);
+    the step computed on a prefetched geometry equals the step that plans its own, buffer sets alternate safely over
+    several steps, and a geometry whose buffer set was re-planned is refused in backward."""
+    import spvd_b200 as sp
+    from spvd_b200 import functional as SF
+    from oracle import model as om
+    m = sp.build_model("SPVD_TINY")
+    m.load_state_dict(om.make_state_dict("SPVD_TINY", seed=0))
+    m = m.cuda().train()
+    state = {k: v.clone() for k, v in m.state_dict().items()}
+    g = torch.Generator().manual_seed(5)
+    batches = []
+    for j in range(4):
+        pts = torch.randn(4, 384 + 64 * j, 3, generator=g).clamp(-3, 3)[:, :384]
+        coords, feats, _ = om.torch2sparse(pts)
+        batches.append((sp.SparseTensor(feats.cuda(), coords.cuda()), torch.tensor([999, 500, 20, 3]).cuda(),
+                        torch.randn(feats.shape[0], 3, device="cuda", generator=torch.Generator(device="cuda").manual_seed(j))))
+
+    def grads():
+        return torch.cat([p.grad.flatten() for p in m.parameters()]).clone()
+
+    ref = []
+    for x, t, tg in batches:
+        m.load_state_dict(state)
+        m.zero_grad()
+        loss = SF.mse_loss(m((x, t)), tg)
+        loss.backward()
+        ref.append((float(loss), grads()))
+    got = []
+    geo = m.prefetch_geometry(batches[0][0], 4)
+    for j, (x, t, tg) in enumerate(batches):
+        geo_next = m.prefetch_geometry(batches[j + 1][0], 4) if j + 1 < len(batches) else None
+        m.load_state_dict(state)
+        m.zero_grad()
+        loss = SF.mse_loss(m((x, t), geometry=geo), tg)
+        loss.backward()
+        got.append((float(loss), grads()))
+        geo = geo_next
+    torch.cuda.synchronize()
+    for (l0, g0), (l1, g1) in zip(ref, got):
+        assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
+        assert rel_err(g1.cpu().numpy(), g0.cpu().numpy()) < 2e-3       # run-to-run noise of the atomics (see the in-place test)
+    # a stale geometry (its buffer set has been planned again twice since) must not be used silently
+    x, t, tg = batches[0]
+    geo_old = m.prefetch_geometry(x, 4)
+    loss = SF.mse_loss(m((x, t), geometry=geo_old), tg)
+    m.prefetch_geometry(batches[1][0], 4).finish()
+    m.prefetch_geometry(batches[2][0], 4).finish()
+    with pytest.raises(RuntimeError):
+        loss.backward()

@@ -27,6 +27,34 @@ t1 = time.perf_counter()
 torch.cuda.synchronize()
 t2 = time.perf_counter()
 print(f"host issue time {1e3 * (t1 - t0) / 4:.2f} ms/step, with final sync {1e3 * (t2 - t0) / 4:.2f} ms/step")
+for rep in range(2):
+    t0 = time.perf_counter()
+    geo = model.prefetch_geometry(batches[0][0], 32)
+    for j in range(12):
+        geo_next = model.prefetch_geometry(batches[(j + 1) % 12][0], 32) if j + 1 < 12 else None
+        train_step(model, opt, batches[j], red, geometry=geo)
+        geo = geo_next
+    t1 = time.perf_counter()
+    torch.cuda.synchronize()
+    t2 = time.perf_counter()
+    print(f"with geometry prefetch: host issue time {1e3 * (t1 - t0) / 12:.2f} ms/step, with final sync {1e3 * (t2 - t0) / 12:.2f} ms/step")
+# host time per phase (no device syncs inside: what the Python thread spends issuing)
+from spvd_b200 import functional as SF
+ph = [0.0] * 5
+for j in range(4, 8):
+    x, t, target = batches[j]
+    a = time.perf_counter(); red.zero_grad()
+    b = time.perf_counter(); pred = model((x, t))
+    c = time.perf_counter(); loss = SF.mse_loss(pred, target)
+    d = time.perf_counter(); loss.backward()
+    e = time.perf_counter(); opt.step(max_norm=10.0, pending_scale=red.finish())
+    f = time.perf_counter()
+    for i, v in enumerate((b - a, c - b, d - c, e - d, f - e)):
+        ph[i] += v / 4
+torch.cuda.synchronize()
+print("host ms/step: zero_grad %.2f  forward %.2f  loss %.2f  backward %.2f  optimizer %.2f" % tuple(1e3 * v for v in ph))
+if hasattr(model, "_geo_trace"):
+    pass
 pr = cProfile.Profile()
 pr.enable()
 for j in range(8, 12):
