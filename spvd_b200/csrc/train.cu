@@ -72,6 +72,66 @@ __device__ __forceinline__ void col_reduce2(long long rows, int c, int rows_per_
   }
 }
 
+// The same with four channels per thread (c % 4 == 0, 16-byte aligned rows): thread t -> channels 4 * (t % (c/4)) .. +3 of
+// row lane t / (c/4), four rows in flight -> 64 bytes per thread instead of 16 outstanding (the scalar skeleton keeps
+// ~16 KB per SM in flight and reaches ~1.2 TB/s; HBM wants a few times that).  f(row, ch, a, b) adds to float4 sums.
+__device__ __forceinline__ void add4(float4& d, const float4& v) { d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w; }
+
+template <typename F>
+__device__ __forceinline__ void col_reduce4(long long rows, int c, int rows_per_cta, double* __restrict__ tot, F f) {
+  __shared__ float4 sa[kRedThreads], sb[kRedThreads];
+  const int c4 = c >> 2;
+  const long long r_begin = (long long)blockIdx.x * rows_per_cta;
+  const long long r_end = min(rows, r_begin + rows_per_cta);
+  for (int g0 = 0; g0 < c4; g0 += kRedThreads) {
+    const int gw = min(kRedThreads, c4 - g0);
+    const int lanes = kRedThreads / gw;
+    const int gi = threadIdx.x % gw, lane = threadIdx.x / gw;
+    const int ch = 4 * (g0 + gi);
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 a0 = z, b0 = z, a1 = z, b1 = z, a2 = z, b2 = z, a3 = z, b3 = z;
+    if (lane < lanes) {
+      long long r = r_begin + lane;
+      for (; r + 3 * lanes < r_end; r += 4 * lanes) {
+        f(r, ch, a0, b0);
+        f(r + lanes, ch, a1, b1);
+        f(r + 2 * lanes, ch, a2, b2);
+        f(r + 3 * lanes, ch, a3, b3);
+      }
+      for (; r < r_end; r += lanes) f(r, ch, a0, b0);
+    }
+    add4(a0, a1); add4(a2, a3); add4(a0, a2);
+    add4(b0, b1); add4(b2, b3); add4(b0, b2);
+    sa[threadIdx.x] = a0;
+    sb[threadIdx.x] = b0;
+    __syncthreads();
+    if (threadIdx.x < gw) {
+      for (int l = 1; l < lanes; ++l) {
+        add4(a0, sa[threadIdx.x + l * gw]);
+        add4(b0, sb[threadIdx.x + l * gw]);
+      }
+      atomicAdd(tot + ch, (double)a0.x); atomicAdd(tot + ch + 1, (double)a0.y);
+      atomicAdd(tot + ch + 2, (double)a0.z); atomicAdd(tot + ch + 3, (double)a0.w);
+      atomicAdd(tot + c + ch, (double)b0.x); atomicAdd(tot + c + ch + 1, (double)b0.y);
+      atomicAdd(tot + c + ch + 2, (double)b0.z); atomicAdd(tot + c + ch + 3, (double)b0.w);
+    }
+    __syncthreads();
+  }
+}
+
+// rows per CTA for the float4 skeleton: at least two full 4-row rounds of every row lane
+static inline int red_rows_per_cta4(long long rows, int c) {
+  const int c4 = c / 4, gw = c4 < kRedThreads ? c4 : kRedThreads, lanes = kRedThreads / (gw > 0 ? gw : 1);
+  long long per = (rows + kRedMaxCtas - 1) / kRedMaxCtas;
+  if (per < 8ll * lanes) per = 8ll * lanes;
+  return (int)per;
+}
+
+static inline bool vec4_ok(int c, const void* p0, const void* p1 = nullptr, const void* p2 = nullptr, const void* p3 = nullptr,
+                           const void* p4 = nullptr, const void* p5 = nullptr) {
+  return c % 4 == 0 && ((((size_t)p0 | (size_t)p1 | (size_t)p2 | (size_t)p3 | (size_t)p4 | (size_t)p5) & 15) == 0);
+}
+
 // ------------------------------------------------------------------------------------------------ BatchNorm (train)
 __global__ void __launch_bounds__(kRedThreads) k_bn_stats(const float* __restrict__ x, long long rows, int c, int rpc,
                                                           double* __restrict__ tot) {
@@ -79,6 +139,15 @@ __global__ void __launch_bounds__(kRedThreads) k_bn_stats(const float* __restric
     const float v = x[r * c + ch];
     *a += v;
     *b = fmaf(v, v, *b);
+  });
+}
+
+__global__ void __launch_bounds__(kRedThreads) k_bn_stats_v4(const float* __restrict__ x, long long rows, int c, int rpc,
+                                                             double* __restrict__ tot) {
+  col_reduce4(rows, c, rpc, tot, [&](long long r, int ch, float4& a, float4& b) {
+    const float4 v = *reinterpret_cast<const float4*>(x + r * c + ch);
+    a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    b.x = fmaf(v.x, v.x, b.x); b.y = fmaf(v.y, v.y, b.y); b.z = fmaf(v.z, v.z, b.z); b.w = fmaf(v.w, v.w, b.w);
   });
 }
 
@@ -124,6 +193,64 @@ __global__ void __launch_bounds__(kRedThreads) k_bn_bwd_reduce(const float* __re
   });
 }
 
+__global__ void __launch_bounds__(kRedThreads) k_bn_bwd_reduce_v4(const float* __restrict__ x, const float* __restrict__ gy,
+                                                                  long long rows, int c, const float* __restrict__ mean,
+                                                                  const float* __restrict__ invstd, const float* __restrict__ gamma,
+                                                                  const float* __restrict__ beta, int act, int rpc,
+                                                                  double* __restrict__ tot) {
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  col_reduce4(rows, c, rpc, tot, [&](long long r, int ch, float4& a, float4& b) {
+    const float4 xv = *reinterpret_cast<const float4*>(x + r * c + ch);
+    float4 dz = *reinterpret_cast<const float4*>(gy + r * c + ch);
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mean + ch)), is = __ldg(reinterpret_cast<const float4*>(invstd + ch));
+    const float4 xh = make_float4((xv.x - m.x) * is.x, (xv.y - m.y) * is.y, (xv.z - m.z) * is.z, (xv.w - m.w) * is.w);
+    if (act & 1) {
+      const float4 g = gamma ? __ldg(reinterpret_cast<const float4*>(gamma + ch)) : one;
+      const float4 bt = beta ? __ldg(reinterpret_cast<const float4*>(beta + ch)) : zero;
+      dz.x *= dsilu_t(fmaf(xh.x, g.x, bt.x)); dz.y *= dsilu_t(fmaf(xh.y, g.y, bt.y));
+      dz.z *= dsilu_t(fmaf(xh.z, g.z, bt.z)); dz.w *= dsilu_t(fmaf(xh.w, g.w, bt.w));
+    }
+    a.x += dz.x; a.y += dz.y; a.z += dz.z; a.w += dz.w;
+    b.x = fmaf(dz.x, xh.x, b.x); b.y = fmaf(dz.y, xh.y, b.y); b.z = fmaf(dz.z, xh.z, b.z); b.w = fmaf(dz.w, xh.w, b.w);
+  });
+}
+
+// the apply pass, four channels per thread
+__global__ void __launch_bounds__(256) k_bn_bwd_apply_v4(const float* __restrict__ x, const float* __restrict__ gy, long long rows,
+                                                         int c, const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta, int act,
+                                                         const double* __restrict__ tot, float* __restrict__ gx,
+                                                         float* __restrict__ ggamma, float* __restrict__ gbeta) {
+  const int c4 = c >> 2;
+  const long long total4 = rows * c4;
+  const double inv_n = 1.0 / (double)rows;
+  for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < total4; t += (long long)gridDim.x * blockDim.x) {
+    const int ch = 4 * (int)(t % c4);
+    const float4 xv = reinterpret_cast<const float4*>(x)[t];
+    const float4 gv = reinterpret_cast<const float4*>(gy)[t];
+    const float4 m = __ldg(reinterpret_cast<const float4*>(mean + ch)), is = __ldg(reinterpret_cast<const float4*>(invstd + ch));
+    const float4 g = gamma ? __ldg(reinterpret_cast<const float4*>(gamma + ch)) : make_float4(1.f, 1.f, 1.f, 1.f);
+    const float4 bt = beta ? __ldg(reinterpret_cast<const float4*>(beta + ch)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 o;
+#define SPVD_BN_APPLY1(f, i)                                                                 \
+  {                                                                                          \
+    const float xh = (xv.f - m.f) * is.f;                                                    \
+    float dz = gv.f;                                                                         \
+    if (act & 1) dz *= dsilu_t(fmaf(xh, g.f, bt.f));                                         \
+    const float m1 = (float)(tot[ch + i] * inv_n), m2 = (float)(tot[c + ch + i] * inv_n);    \
+    o.f = g.f * is.f * (dz - m1 - xh * m2);                                                  \
+  }
+    SPVD_BN_APPLY1(x, 0) SPVD_BN_APPLY1(y, 1) SPVD_BN_APPLY1(z, 2) SPVD_BN_APPLY1(w, 3)
+#undef SPVD_BN_APPLY1
+    reinterpret_cast<float4*>(gx)[t] = o;
+  }
+  if (blockIdx.x == 0)
+    for (int ch = threadIdx.x; ch < c; ch += blockDim.x) {
+      if (gbeta) gbeta[ch] = (float)tot[ch];
+      if (ggamma) ggamma[ch] = (float)tot[c + ch];
+    }
+}
+
 // gx = gamma * invstd * (dz - mean(dz) - xhat * mean(dz * xhat));  CTA 0 also writes the parameter gradients
 __global__ void __launch_bounds__(256) k_bn_bwd_apply(const float* __restrict__ x, const float* __restrict__ gy, long long rows,
                                                       int c, const float* __restrict__ mean, const float* __restrict__ invstd,
@@ -158,6 +285,13 @@ __global__ void __launch_bounds__(kRedThreads) k_colsum(const float* __restrict_
                                                         double* __restrict__ tot) {
   col_reduce2(rows, c, rpc, tot, [&](long long r, int ch, float* a, float* b) {
     *a += g[r * c + ch];
+    (void)b;
+  });
+}
+__global__ void __launch_bounds__(kRedThreads) k_colsum_v4(const float* __restrict__ g, long long rows, int c, int rpc,
+                                                           double* __restrict__ tot) {
+  col_reduce4(rows, c, rpc, tot, [&](long long r, int ch, float4& a, float4& b) {
+    add4(a, *reinterpret_cast<const float4*>(g + r * c + ch));
     (void)b;
   });
 }
@@ -607,7 +741,11 @@ extern "C" int spvd_bn_train_fwd(const float* x, long long rows, int c, const fl
                  "spvd_bn_train_fwd: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const int rpc = red_rows_per_cta(rows);
-  k_bn_stats<<<cdiv(rows, rpc), kRedThreads, 0, s>>>(x, rows, c, rpc, workspace);
+  if (vec4_ok(c, x)) {
+    const int rp4 = red_rows_per_cta4(rows, c);
+    k_bn_stats_v4<<<cdiv(rows, rp4), kRedThreads, 0, s>>>(x, rows, c, rp4, workspace);
+  }
+  else k_bn_stats<<<cdiv(rows, rpc), kRedThreads, 0, s>>>(x, rows, c, rpc, workspace);
   k_bn_finalize<<<cdiv(c, 128), 128, 0, s>>>(workspace, rows, c, gamma, beta, eps, momentum, running_mean, running_var, save_mean,
                                              save_invstd, scale, shift);
   SPVD_LAUNCH_CHECK();
@@ -620,9 +758,16 @@ extern "C" int spvd_bn_train_bwd(const float* x, const float* gy, long long rows
   SPVD_CHECK_ARG(x && gy && save_mean && save_invstd && gx && workspace && rows > 0 && c > 0, "spvd_bn_train_bwd: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const int rpc = red_rows_per_cta(rows);
-  k_bn_bwd_reduce<<<cdiv(rows, rpc), kRedThreads, 0, s>>>(x, gy, rows, c, save_mean, save_invstd, gamma, beta, act, rpc, workspace);
-  k_bn_bwd_apply<<<grid_for(rows * c), 256, 0, s>>>(x, gy, rows, c, save_mean, save_invstd, gamma, beta, act, workspace, gx, ggamma,
-                                                    gbeta);
+  if (vec4_ok(c, x, gy, save_mean, save_invstd, gamma, beta) && ((size_t)gx & 15) == 0) {
+    const int rp4 = red_rows_per_cta4(rows, c);
+    k_bn_bwd_reduce_v4<<<cdiv(rows, rp4), kRedThreads, 0, s>>>(x, gy, rows, c, save_mean, save_invstd, gamma, beta, act, rp4, workspace);
+    k_bn_bwd_apply_v4<<<grid_for(rows * (c / 4)), 256, 0, s>>>(x, gy, rows, c, save_mean, save_invstd, gamma, beta, act, workspace, gx,
+                                                             ggamma, gbeta);
+  } else {
+    k_bn_bwd_reduce<<<cdiv(rows, rpc), kRedThreads, 0, s>>>(x, gy, rows, c, save_mean, save_invstd, gamma, beta, act, rpc, workspace);
+    k_bn_bwd_apply<<<grid_for(rows * c), 256, 0, s>>>(x, gy, rows, c, save_mean, save_invstd, gamma, beta, act, workspace, gx, ggamma,
+                                                      gbeta);
+  }
   k_clear_f64<<<cdiv(2 * c, 256), 256, 0, s>>>(workspace, 2 * c);
   SPVD_LAUNCH_CHECK();
   return SPVD_OK;
@@ -632,7 +777,11 @@ extern "C" int spvd_colsum(const float* g, long long rows, int c, float* out, do
   SPVD_CHECK_ARG(g && out && workspace && rows >= 0 && c > 0, "spvd_colsum: bad arguments");
   cudaStream_t s = (cudaStream_t)stream;
   const int rpc = red_rows_per_cta(rows);
-  if (rows > 0) k_colsum<<<cdiv(rows, rpc), kRedThreads, 0, s>>>(g, rows, c, rpc, workspace);
+  if (rows > 0) {
+    const int rp4 = red_rows_per_cta4(rows, c);
+    if (vec4_ok(c, g)) k_colsum_v4<<<cdiv(rows, rp4), kRedThreads, 0, s>>>(g, rows, c, rp4, workspace);
+    else k_colsum<<<cdiv(rows, rpc), kRedThreads, 0, s>>>(g, rows, c, rpc, workspace);
+  }
   k_f64_to_f32<<<cdiv(2 * c, 256), 256, 0, s>>>(workspace, c, 2 * c, out);
   SPVD_LAUNCH_CHECK();
   return SPVD_OK;
@@ -877,6 +1026,21 @@ __global__ void __launch_bounds__(kRedThreads) k_round_colsum(const float* __res
   });
 }
 
+__global__ void __launch_bounds__(kRedThreads) k_round_colsum_v4(const float* __restrict__ x, long long rows, int c, int rpc,
+                                                                 float* __restrict__ y, double* __restrict__ tot) {
+  col_reduce4(rows, c, rpc, tot, [&](long long r, int ch, float4& a, float4& b) {
+    const float4 v = *reinterpret_cast<const float4*>(x + r * c + ch);
+    uint4 q;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q.x) : "f"(v.x));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q.y) : "f"(v.y));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q.z) : "f"(v.z));
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(q.w) : "f"(v.w));
+    *reinterpret_cast<uint4*>(y + r * c + ch) = q;
+    add4(a, v);
+    (void)b;
+  });
+}
+
 // tensor-core tile image (K-major SWIZZLE_128B, TF32-rounded: the layout of spvd_conv_pack_weights) of the TRANSPOSED
 // weights W'[k'][co][ci] = W[k][ci][co], k = K-1-k' when flip -- the data-gradient weights, without materialising W'
 __global__ void k_pack_weights_transposed(const float* __restrict__ w, int kvol, int cin, int cout, int flip,
@@ -988,7 +1152,9 @@ extern "C" int spvd_conv_bwd(const spvd_conv_bwd_args_t* args, spvd_stream_t str
   if ((umma_d || umma_w) && a.n_out > 0) {
     if (a.gbias) {       // rounding pass and bias gradient share one read of g
       const int rpc = red_rows_per_cta(a.n_out);
-      k_round_colsum<<<cdiv(a.n_out, rpc), kRedThreads, 0, s>>>(a.g, a.n_out, a.cout, rpc, gr, a.red_workspace);
+      const int rp4 = red_rows_per_cta4(a.n_out, a.cout);
+      if (vec4_ok(a.cout, a.g, gr)) k_round_colsum_v4<<<cdiv(a.n_out, rp4), kRedThreads, 0, s>>>(a.g, a.n_out, a.cout, rp4, gr, a.red_workspace);
+      else k_round_colsum<<<cdiv(a.n_out, rpc), kRedThreads, 0, s>>>(a.g, a.n_out, a.cout, rpc, gr, a.red_workspace);
       k_f64_to_f32<<<cdiv(2 * a.cout, 256), 256, 0, s>>>(a.red_workspace, a.cout, 2 * a.cout, a.gbias);
       SPVD_LAUNCH_CHECK();
       bias_done = true;

@@ -290,10 +290,11 @@ def test_in_place_parameter_gradients_match_autograd_accumulation():
         assert len(adds) < 0.25 * n_params, (len(adds), n_params)
 
 
-@pytest.mark.parametrize("wd,clip", [(0.0, 10.0), (0.01, 0.05), (0.0, 0.0)])
-def test_flat_adam_matches_torch_adam_and_clip(wd, clip):
+@pytest.mark.parametrize("wd,clip,pending", [(0.0, 10.0, 1.0), (0.01, 0.05, 1.0), (0.0, 0.0, 1.0), (0.0, 0.05, 0.125), (0.0, 0.0, 0.5)])
+def test_flat_adam_matches_torch_adam_and_clip(wd, clip, pending):
     """optim.FlatAdam (spvd_sumsq + spvd_adam_step over the flat buffers) against torch.optim.Adam after
-    torch.nn.utils.clip_grad_norm_ (train_generation.py:106-112), several steps, odd parameter sizes."""
+    torch.nn.utils.clip_grad_norm_ (train_generation.py:106-112), several steps, odd parameter sizes.  ``pending`` is the
+    factor still owed to the summed gradients (1 / world after the all-reduce): it must act before the clip."""
     from spvd_b200.optim import FlatAdam
     from spvd_b200.parallel import GradientAllReduce
     torch.manual_seed(3)
@@ -311,10 +312,12 @@ def test_flat_adam_matches_torch_adam_and_clip(wd, clip):
         x, y = torch.randn(64, 7, device="cuda") * (1 + it), torch.randn(64, 3, device="cuda")
         opt_a.zero_grad()
         F.mse_loss(a(x), y).backward()
-        opt_a.step(max_norm=clip)
+        opt_a.step(max_norm=clip, pending_scale=pending)
         sched.step()
         opt_b.zero_grad()
         F.mse_loss(b(x), y).backward()
+        for pb in b.parameters():
+            pb.grad.mul_(pending)
         nb = torch.nn.utils.clip_grad_norm_(b.parameters(), clip) if clip > 0 else None
         opt_b.step()
         sched_b.step()

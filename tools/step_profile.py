@@ -31,6 +31,11 @@ with torch.no_grad():
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
         step(8)
         torch.cuda.synchronize()
+    # steady state: three steps back to back (the host runs ahead of the device), the middle one analysed
+    with profile(activities=[ProfilerActivity.CUDA]) as prof3:
+        for j in (9, 10, 11):
+            step(j)
+        torch.cuda.synchronize()
 ev = [e for e in prof.events() if "cuda" in str(getattr(e, "device_type", "")).lower()]
 tot = collections.defaultdict(lambda: [0, 0.0])
 for e in ev:
@@ -58,3 +63,30 @@ hist = collections.Counter(min(int(g[0]), 20) for g in gaps)
 print("gap histogram (us: count):", dict(sorted(hist.items())))
 for g in sorted(gaps, key=lambda g: -g[0])[:25]:
     print(f"  {g[0]:7.1f} us at +{g[3]/1e3:6.3f} ms   {g[1]}  ->  {g[2]}")
+
+
+# ---- the same for a step in steady state (middle of three back-to-back steps)
+ev3 = sorted((e for e in prof3.events() if "cuda" in str(getattr(e, "device_type", "")).lower()), key=lambda e: e.time_range.start)
+upd = [i for i, e in enumerate(ev3) if "k_ddpm_update" in e.name]
+# a step ends with its k_ddpm_update_min launches; take the kernels between the end of step 9's update and step 10's
+ends = [i for i in upd if i + 1 >= len(ev3) or "k_ddpm_update" not in ev3[i + 1].name]
+if len(ends) >= 2:
+    lo, hi = ends[0] + 1, ends[1] + 1
+    win = ev3[lo:hi]
+    w0, w1 = win[0].time_range.start, max(e.time_range.end for e in win)
+    busy_end, idle, gaps, last = w0, 0.0, [], ""
+    for e in win:
+        s_, e_ = e.time_range.start, e.time_range.end
+        if s_ > busy_end:
+            idle += s_ - busy_end
+            gaps.append((s_ - busy_end, last, e.name.split("(")[0][:60], s_ - w0))
+        if e_ > busy_end:
+            busy_end, last = e_, e.name.split("(")[0][:60]
+    print(f"steady state: step window {(w1 - w0)/1e3:.3f} ms, {len(win)} launches, idle {idle/1e3:.3f} ms in {len(gaps)} gaps")
+    for g in sorted(gaps, key=lambda g: -g[0])[:12]:
+        print(f"  {g[0]:7.1f} us at +{g[3]/1e3:6.3f} ms   {g[1]}  ->  {g[2]}")
+    first_conv = next((e for e in win if "k_conv" in e.name), None)
+    if first_conv is not None:
+        print(f"first conv kernel at +{(first_conv.time_range.start - w0)/1e3:.3f} ms")
+    for e in win[:40]:
+        print(f"    +{(e.time_range.start - w0)/1e3:6.3f} {e.device_time:7.1f} us  {e.name.split('(')[0][:70]}")
