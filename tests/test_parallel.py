@@ -74,3 +74,60 @@ def test_gradient_allreduce_equals_full_batch_gradient():
         p.join(timeout=60)
         assert p.exitcode == 0
     assert err < 1e-6
+
+
+def test_flat_gradient_slots_and_in_place_claims():
+    """Host logic of the in-place parameter gradients (no kernels, CPU tensors): slots start on 256-byte boundaries and the
+    padding stays zero; a slot can be claimed once per step and only by a parameter used exactly once since zero_grad();
+    a direct write counts towards the bucket like an accumulate hook; everything else goes through autograd as before."""
+    from spvd_b200.parallel import GradientAllReduce
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(7, 5), torch.nn.SiLU(), torch.nn.Linear(5, 3))
+    red = GradientAllReduce(net.parameters(), bucket_bytes=64)
+    ps = list(net.parameters())
+    assert red.flat.numel() == sum((p.numel() + 63) // 64 * 64 for p in ps)
+    assert all(red._offset_of(p) % 256 == 0 for p in ps)
+    assert all(p.grad.data_ptr() == red.flat.data_ptr() + red._offset_of(p) and p.grad.shape == p.shape for p in ps)
+    assert all(getattr(p, "_spvd_sink") is red for p in ps)
+    w = ps[0]
+    red.zero_grad()
+    assert red.claim(w) is None                      # not used in a forward since zero_grad()
+    red.note_use(w)
+    slot = red.claim(w)
+    assert slot is not None and slot.data_ptr() == w.grad.data_ptr()
+    pending_before = red.buckets[red._bucket_of[id(w)]][2]
+    slot.copy_(torch.ones_like(w))                   # "the kernel writes the gradient"
+    red.wrote(w)
+    assert red.buckets[red._bucket_of[id(w)]][2] == pending_before - 1
+    assert red.claim(w) is None                      # once per step
+    red.zero_grad()
+    red.note_use(w); red.note_use(w)
+    assert red.claim(w) is None                      # used twice: autograd accumulates
+    red.zero_grad()
+    red.note_use(w)
+    w.grad = torch.zeros_like(w)                     # somebody replaced .grad: no claim, finish() would re-attach it
+    assert red.claim(w) is None
+    red.direct = False
+    red.zero_grad()
+    red.note_use(ps[1])
+    assert red.claim(ps[1]) is None
+    # the ordinary path still works with the padded layout: gradients land in the slots, padding stays zero
+    red2 = GradientAllReduce(net.parameters(), bucket_bytes=64)
+    red2.zero_grad()
+    net(torch.randn(4, 7)).sum().backward()
+    used = torch.zeros_like(red2.flat, dtype=torch.bool)
+    for p in ps:
+        o = red2._offset_of(p) // 4
+        used[o:o + p.numel()] = True
+        assert torch.equal(red2.flat[o:o + p.numel()].view_as(p), p.grad)
+    assert float(red2.flat[~used].abs().max()) == 0.0
+    assert float(red2.clip_(1e9)) > 0
+
+
+def test_flat_adam_refuses_cpu_parameters():
+    import pytest
+    from spvd_b200.optim import FlatAdam
+    from spvd_b200.parallel import GradientAllReduce
+    net = torch.nn.Linear(4, 4)
+    with pytest.raises(RuntimeError):
+        FlatAdam(GradientAllReduce(net.parameters()))
