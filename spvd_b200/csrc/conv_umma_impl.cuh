@@ -755,6 +755,12 @@ static int pick_bn(int cout, int n_tiles = 1 << 30, int kvol = 27) {
     for (int i = 5; i >= 0; --i)
       if (cout % widths[i] == 0 && widths[i] >= 64) return widths[i];
   }
+  if (n_tiles < 32) {
+    // a handful of tiles (stride 16): slices of at most 128 columns and more split-K fill the GPU better than one wide
+    // slice per tile (profiles/r02b_small_level_sweep.txt: 192->192 23.6 -> 19.2 us, 256->256 27.6 -> 23.6 us)
+    for (int w : widths)
+      if (w <= 128 && w >= 64 && cout % w == 0) return w;
+  }
   for (int w : widths)
     if (cout % w == 0) return w;
   return 32;
