@@ -30,6 +30,21 @@ def timeit(fn, reps=7):
     return sorted(ts)[len(ts) // 2]
 
 
+if "points" in sys.argv[2:]:
+    # the point-branch Linear layers: one row per POINT (65536), k = 1
+    n = 32 * 2048
+    for cin, cout in ((32, 256), (256, 192), (192, 32), (96, 64), (64, 32)):
+        w = torch.randn(1, cin, cout, device=dev) / cin ** 0.5
+        wp = ops.pack_weights_f16(w)
+        xin = torch.randn(n, cin, device=dev).half()
+        bias = torch.randn(cout, device=dev)
+        call = lambda bn, ns: ops.conv_fwd(xin, w, wp, None, None, n, bias, ops.CONV_UMMA, bn=bn, nsplit=ns)
+        auto = timeit(lambda: call(0, 0))
+        res = sorted((timeit(lambda: call(bn, 1), 5), bn) for bn in (32, 64, 96, 128, 192, 256) if cout % bn == 0)
+        mb = n * (cin * 2 + cout * 4) / 1e6
+        print(f"points n={n} k=1 {cin:3d}->{cout:3d} | {mb:5.1f} MB | auto {auto:6.1f} us ({mb / auto * 1e3 / 1e3:.2f} TB/s) | " +
+              "  ".join(f"{u:5.1f} (bn={b})" for u, b in res), flush=True)
+    sys.exit(0)
 layers = [(8, 27, 192, 192), (8, 27, 384, 192), (16, 27, 192, 192), (16, 27, 448, 256), (16, 27, 256, 256), (4, 27, 128, 128),
           (8, 1, 192, 576), (8, 1, 192, 192), (8, 1, 384, 192), (16, 1, 256, 768), (16, 1, 256, 256), (16, 1, 448, 256)]
 for s, kvol, cin, cout in layers:
