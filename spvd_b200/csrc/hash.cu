@@ -74,8 +74,9 @@ __global__ void k_hash_query(const int* __restrict__ query, int m, int order, in
   out[t] = find_coord(keys, vals, cap, c.x, c.y + dx, c.z + dy, c.w + dz);
 }
 
-// K1: one CTA = one 128-row output tile
-__global__ void __launch_bounds__(128) k_kmap_subm3(const int4* __restrict__ coords, int n_cap,
+// K1: one CTA = one 128-row output tile; three threads per voxel, each with the 9 probes of one dz plane in flight (the
+// kernel is a latency chain of L2-resident probes: three times the threads, a third of the chain per thread)
+__global__ void __launch_bounds__(384) k_kmap_subm3(const int4* __restrict__ coords, int n_cap,
                                                     const int* __restrict__ n_dev, const u64* __restrict__ keys,
                                                     const int* __restrict__ vals, unsigned cap,
                                                     int* __restrict__ map_t, int ld, unsigned* __restrict__ tile_mask) {
@@ -83,31 +84,29 @@ __global__ void __launch_bounds__(128) k_kmap_subm3(const int4* __restrict__ coo
   if (threadIdx.x == 0) s_mask = 0;
   __syncthreads();
   int n = resolve_n(n_dev, n_cap);
-  int o = blockIdx.x * 128 + threadIdx.x;
+  const int row = threadIdx.x & 127, k0 = 9 * (threadIdx.x >> 7);
+  int o = blockIdx.x * 128 + row;
   bool valid = o < n;
   int4 c = valid ? coords[o] : make_int4(0, 0, 0, 0);
   unsigned wmask = 0;
-#pragma unroll 1
-  for (int k0 = 0; k0 < 27; k0 += 9) {   // 9 independent probes in flight per thread
-    int r[9];
+  int r[9];
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      const int k = k0 + j;
-      r[j] = -1;
-      if (valid) {
-        if (k == 13) {
-          r[j] = o;
-        } else {
-          int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
-          r[j] = find_coord(keys, vals, cap, c.x, c.y + dx, c.z + dy, c.w + dz) - 1;
-        }
+  for (int j = 0; j < 9; ++j) {
+    const int k = k0 + j;
+    r[j] = -1;
+    if (valid) {
+      if (k == 13) {
+        r[j] = o;
+      } else {
+        int dx = k % 3 - 1, dy = (k / 3) % 3 - 1, dz = k / 9 - 1;
+        r[j] = find_coord(keys, vals, cap, c.x, c.y + dx, c.z + dy, c.w + dz) - 1;
       }
     }
+  }
 #pragma unroll
-    for (int j = 0; j < 9; ++j) {
-      if (o < ld) map_t[(size_t)(k0 + j) * ld + o] = r[j];
-      if (__ballot_sync(0xffffffffu, r[j] >= 0)) wmask |= 1u << (k0 + j);
-    }
+  for (int j = 0; j < 9; ++j) {
+    if (o < ld) map_t[(size_t)(k0 + j) * ld + o] = r[j];
+    if (__ballot_sync(0xffffffffu, r[j] >= 0)) wmask |= 1u << (k0 + j);
   }
   if ((threadIdx.x & 31) == 0 && wmask) atomicOr(&s_mask, wmask);
   __syncthreads();
@@ -356,7 +355,7 @@ extern "C" int spvd_kmap_subm3(const int32_t* coords, int n_cap, const int32_t* 
   SPVD_CHECK_ARG(coords && keys && vals && map_t && capacity > 0, "spvd_kmap_subm3: bad arguments");
   SPVD_CHECK_ARG(ld >= n_cap && ld % 128 == 0, "spvd_kmap_subm3: ld %d must be a multiple of 128 >= %d", ld, n_cap);
   if (ld == 0) return SPVD_OK;
-  k_kmap_subm3<<<ld / 128, 128, 0, (cudaStream_t)stream>>>((const int4*)coords, n_cap, n_dev, (const u64*)keys, vals,
+  k_kmap_subm3<<<ld / 128, 384, 0, (cudaStream_t)stream>>>((const int4*)coords, n_cap, n_dev, (const u64*)keys, vals,
                                                            (unsigned)capacity, map_t, ld, tile_mask);
   SPVD_LAUNCH_CHECK();
   return SPVD_OK;
