@@ -88,5 +88,5 @@ if len(ends) >= 2:
     first_conv = next((e for e in win if "k_conv" in e.name), None)
     if first_conv is not None:
         print(f"first conv kernel at +{(first_conv.time_range.start - w0)/1e3:.3f} ms")
-    for e in win[:40]:
+    for e in win[:int(os.environ.get("SPVD_TIMELINE_ROWS", "40"))]:
         print(f"    +{(e.time_range.start - w0)/1e3:6.3f} {e.device_time:7.1f} us  {e.name.split('(')[0][:70]}")
