@@ -401,6 +401,9 @@ class SPVUnet(nn.Module):
                 if aux is None:
                     aux = self._aux_streams[feats.device] = torch.cuda.Stream(device=feats.device, priority=-1)
                 prog.prologue(t, cls, aux)
+            if geometry is None:
+                feats = feats.contiguous().float()
+                prog.stage_input(feats)          # before the planner's host wait, not after it
         # executor: wait only for the finest levels; the coarser ones are planned on a side stream under the first ops
         geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0],
                                                                        int(getattr(x_in, "points_per_cloud", 0) or 0),
