@@ -437,10 +437,10 @@ class SPVUnet(nn.Module):
 
         def v2p(x, s):
             idx8, w8 = geo.devox[s]
-            return SF.devoxelize(x, idx8, w8)
+            return SF.devoxelize(x, idx8, w8, geo)
 
         def p2v(zf, s):
-            return SF.scatter_mean(zf, geo.p2v[s], geo.level(s).n)
+            return SF.scatter_mean(zf, geo.p2v[s], geo.level(s).n, geo)
 
         z = feats.contiguous().float()
         s = 1

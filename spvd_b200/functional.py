@@ -128,41 +128,46 @@ def sparse_conv(x, weight, bias, kmap, cache=None, impl=ops.CONV_AUTO, a_tf32=Fa
 
 class _ScatterMean(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, src, idx, nv):
+    def forward(ctx, src, idx, nv, guard=None):
         src = src.contiguous()
         out, counts = ops.scatter_mean_fwd(src, idx, nv)
         ctx.save_for_backward(idx, counts)
-        ctx.n = src.shape[0]
+        ctx.n, ctx.guard = src.shape[0], guard
         return out
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.guard is not None:
+            ctx.guard.check_current()            # idx is a view of a geometry workspace: refuse one that was re-planned
         idx, counts = ctx.saved_tensors
-        return ops.scatter_mean_bwd(g.contiguous(), idx, counts, ctx.n), None, None
+        return ops.scatter_mean_bwd(g.contiguous(), idx, counts, ctx.n), None, None, None
 
 
-def scatter_mean(src, idx, nv):
-    """torch_scatter.scatter_mean(src, idx, dim=0) with nv output rows (models/sparse_utils.py:69,94)."""
-    return _ScatterMean.apply(src, idx, nv)
+def scatter_mean(src, idx, nv, guard=None):
+    """torch_scatter.scatter_mean(src, idx, dim=0) with nv output rows (models/sparse_utils.py:69,94).  guard: the
+    Geometry that owns idx (its check_current() runs before the backward uses the indices)."""
+    return _ScatterMean.apply(src, idx, nv, guard)
 
 
 class _Devoxelize(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, feats, idx8, w8):
+    def forward(ctx, feats, idx8, w8, guard=None):
         feats = feats.contiguous()
         ctx.save_for_backward(idx8, w8)
-        ctx.nv = feats.shape[0]
+        ctx.nv, ctx.guard = feats.shape[0], guard
         return ops.devoxelize_fwd(feats, idx8, w8)
 
     @staticmethod
     def backward(ctx, g):
+        if ctx.guard is not None:
+            ctx.guard.check_current()
         idx8, w8 = ctx.saved_tensors
-        return ops.devoxelize_bwd(g.contiguous(), idx8, w8, ctx.nv), None, None
+        return ops.devoxelize_bwd(g.contiguous(), idx8, w8, ctx.nv), None, None, None
 
 
-def devoxelize(feats, idx8, w8):
-    """torchsparse.nn.functional.spdevoxelize (models/sparse_utils.py:119,128)."""
-    return _Devoxelize.apply(feats, idx8, w8)
+def devoxelize(feats, idx8, w8, guard=None):
+    """torchsparse.nn.functional.spdevoxelize (models/sparse_utils.py:119,128); guard as for scatter_mean."""
+    return _Devoxelize.apply(feats, idx8, w8, guard)
 
 
 # ------------------------------------------------------------------------------------------------------------------

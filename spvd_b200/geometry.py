@@ -149,6 +149,14 @@ class Geometry:
 
     _pending = None          # PlanWorkspace.build(split_level=...): [collect the next group of coarser levels, ...]
     _keep = None
+    _ws, _gen = None, 0      # the PlanWorkspace whose persistent buffers this geometry views, and its build generation
+
+    def check_current(self):
+        """Index tensors of a planned geometry (point -> voxel rows, devoxelize corners, kernel maps) are views of the
+        workspace's buffers: raise when a later build has overwritten them (see KernelMap.check_current)."""
+        if self._ws is not None and self._ws.generation != self._gen:
+            raise RuntimeError("this geometry was overwritten by a later forward pass that reused its workspace (more forwards "
+                               "than model.geometry_pool between a forward and its backward): raise model.geometry_pool")
 
     def finish(self, upto=None):
         """Wait for (and collect) level groups that are still being planned on the side stream: all of them, or just
@@ -338,6 +346,7 @@ class PlanWorkspace:
         ops.stats.launches += self.n_kernels if not max_cloud_rows else self.n_kernels - 20 * nl
         self.generation = getattr(self, "generation", 0) + 1
         geo = Geometry.__new__(Geometry)
+        geo._ws, geo._gen = self, self.generation
         geo.n_points, geo.mode, geo.status = self.n_points, downsample_mode, self.status
         geo.fcoords, geo.levels, geo.p2v, geo.devox, geo.p2v_w, geo.p2v_groups = self.fcoords, {}, {}, {}, {}, {}
         cur = torch.cuda.current_stream()
