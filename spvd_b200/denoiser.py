@@ -338,6 +338,7 @@ class SPVUnet(nn.Module):
                                          pair_strides=None if self.training else (1, 2),
                                          sort_strides=() if self.training else self.sort_strides))
             ws = pool[0][-1]
+            pool[1] = len(pool[0]) - 1           # the cursor follows the set just used: the next call takes the OTHER one
         else:
             pool[1] = (pool[1] + 1) % len(pool[0])
             ws = pool[0][pool[1]]

@@ -465,7 +465,7 @@ class PlanWorkspace:
             if "kmap3" in b:
                 lv.kmap3 = KernelMap(b["kmap3"], b["mask3"], lv.n, lv.n, 27, flip=True)
                 lv.kmap3.grad = lv.kmap3
-                lv.kmap3._ws, lv.kmap3._gen = self, self.generation
+                lv.kmap3._ws, lv.kmap3._gen = self, geo._gen
                 if "kmap3_sorted" in b:
                     lv.kmap3_sorted = (b["kmap3_sorted"], b["mask3_sorted"], b["perm3"])
                 if "pair_in" in b:       # the weight-gradient kernel reduces over the planner's pair list: no lazy build, no sync
@@ -481,7 +481,7 @@ class PlanWorkspace:
                 lv.kmap_up = KernelMap(b["kmap_up"], b["mask_up"], lv.n, c.n, 8, flip=False)
                 lv.kmap_down.grad, lv.kmap_up.grad = lv.kmap_up, lv.kmap_down
                 for km in (lv.kmap_down, lv.kmap_up):
-                    km._ws, km._gen = self, self.generation
+                    km._ws, km._gen = self, geo._gen
                 if "dpair_in" in b:      # one (fine, coarse) pair list serves the strided conv and, roles swapped, its transpose
                     dp = lv.dpairs
                     lv.kmap_down._pairs = (dp[0], dp[1], dp[2], dp[3])

@@ -358,6 +358,12 @@ def test_prefetched_geometry_gives_the_same_training_step():
         loss = SF.mse_loss(m((x, t)), tg)
         loss.backward()
         ref.append((float(loss), grads()))
+    # a FRESH model: its very first geometry builds are the prefetches (the buffer-set cursor must alternate from the
+    # first call on -- it once handed the second set out twice in a row at start-up)
+    m_ref = m
+    m = sp.build_model("SPVD_TINY")
+    m.load_state_dict(state)
+    m = m.cuda().train()
     got = []
     geo = m.prefetch_geometry(batches[0][0], 4)
     for j, (x, t, tg) in enumerate(batches):
@@ -369,6 +375,9 @@ def test_prefetched_geometry_gives_the_same_training_step():
         got.append((float(loss), grads()))
         geo = geo_next
     torch.cuda.synchronize()
+    sets = [ws for pool in m._plan_ws.values() for ws in pool[0]]
+    assert len(sets) == 2 and sorted(ws.generation for ws in sets) == [2, 2], [ws.generation for ws in sets]
+    del m_ref
     for (l0, g0), (l1, g1) in zip(ref, got):
         assert abs(l0 - l1) <= 1e-5 * abs(l0), (l0, l1)
         assert rel_err(g1.cpu().numpy(), g0.cpu().numpy()) < 2e-3       # run-to-run noise of the atomics (see the in-place test)
