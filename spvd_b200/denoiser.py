@@ -186,6 +186,7 @@ class SPVUnet(nn.Module):
         self.plan_split_level = tuple(int(v) for v in os.environ.get("SPVD_PLAN_SPLIT", "1,3").split(","))
         self._side_streams = {}
         self._prefetch_streams = {}
+        self._pre_plan_events = {}
         self._aux_streams = {}
         self.side_prologue = os.environ.get("SPVD_SIDE_PROLOGUE", "0") == "1"
         # tensor-core operand format of the executor: "f16" = IEEE half operands (the 11-bit significand of TF32, fp32
@@ -384,9 +385,21 @@ class SPVUnet(nn.Module):
         if cls is not None and not hasattr(self, "cond_emb"):
             raise RuntimeError("this model was built without n_classes; it takes (x, t)")
         executor = self.use_executor and self._fast()
-        prog = None
+        prog, geo = None, geometry
         if executor:
             from .runtime import Program
+            split = self.plan_split_level
+            early = geometry is None and getattr(self, "profile_sink", None) is None
+            before_plan = None
+            if early:
+                # the planner goes into the queue FIRST (it needs the coordinates only) and is collected after the host-side
+                # work below: program lookup / staleness stamp, the timestep-only ops on a side stream, staging the features.
+                # A caller that synchronises every step (host buffers in, host buffers out) no longer pays that work serially.
+                before_plan = self._pre_plan_events.get(feats.device)
+                if before_plan is None:
+                    before_plan = self._pre_plan_events[feats.device] = torch.cuda.Event()
+                before_plan.record()
+                geo = self.plan_geometry(coords, t.shape[0], int(getattr(x_in, "points_per_cloud", 0) or 0), split, defer=True)
             key = (feats.shape[0], t.shape[0], self.executor_operands)
             prog = self._programs.get(key)
             # a compiled program holds derived copies of the parameters (packed tile images, folded BatchNorm): rebuild it
@@ -395,20 +408,21 @@ class SPVUnet(nn.Module):
             if prog is None or prog.stamp != stamp:
                 prog = self._programs[key] = Program(self, *key[:2])
                 prog.stamp = stamp
-            if (geometry is None and getattr(self, "profile_sink", None) is None and self.plan_split_level not in (0, (0,))
-                    and self.side_prologue):
+            if early and split not in (0, (0,)) and self.side_prologue:
                 # timestep-only ops run on a side stream beside the geometry planning
                 aux = self._aux_streams.get(feats.device)
                 if aux is None:
                     aux = self._aux_streams[feats.device] = torch.cuda.Stream(device=feats.device, priority=-1)
-                prog.prologue(t, cls, aux)
+                prog.prologue(t, cls, aux, after=before_plan)
             if geometry is None:
                 feats = feats.contiguous().float()
                 prog.stage_input(feats)          # before the planner's host wait, not after it
-        # executor: wait only for the finest levels; the coarser ones are planned on a side stream under the first ops
-        geo = geometry if geometry is not None else self.plan_geometry(coords, t.shape[0],
-                                                                       int(getattr(x_in, "points_per_cloud", 0) or 0),
-                                                                       self.plan_split_level if executor else 0)
+            if early:
+                geo.finish(upto=1)               # the one host wait: the finest level group's sizes
+            elif geometry is None:
+                geo = self.plan_geometry(coords, t.shape[0], int(getattr(x_in, "points_per_cloud", 0) or 0), split)
+        elif geometry is None:
+            geo = self.plan_geometry(coords, t.shape[0], int(getattr(x_in, "points_per_cloud", 0) or 0), 0)
         if geometry is not None and geo._pending:
             geo.finish()                        # prefetched (prefetch_geometry): its planner finished long ago
         if executor:

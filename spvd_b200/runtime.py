@@ -488,14 +488,18 @@ class Program:
         te.bias = cls.data_ptr() if cls is not None else None
         self._time_keep = (t, cls)              # the op holds raw pointers
 
-    def prologue(self, t, cls, side_stream):
+    def prologue(self, t, cls, side_stream, after=None):
         """The ops that depend on the timestep only (embedding MLP, all FiLM projections) on a side stream, to run beside
-        the geometry planning instead of in front of the stem; ``run`` then starts behind them."""
+        the geometry planning instead of in front of the stem; ``run`` then starts behind them.  ``after``: an event on the
+        current stream to wait for instead of everything enqueued on it so far (the planner may already be in the queue)."""
         if self.n_prologue == 0:
             return
         self._bind_time(t, cls)
         cur = torch.cuda.current_stream()
-        side_stream.wait_stream(cur)            # the previous forward still reads the FiLM table
+        if after is not None:
+            side_stream.wait_event(after)
+        else:
+            side_stream.wait_stream(cur)        # the previous forward still reads the FiLM table
         check(lib.spvd_program_run(self.c_ops, self.n_prologue, self.c_levels, len(self.strides), self.n_points, self.n_batch,
                                    C.c_void_p(self.arena.data_ptr()), self.arena_bytes, None, C.c_void_p(side_stream.cuda_stream)))
         self.prologue_done.record(side_stream)
